@@ -1,0 +1,124 @@
+"""ctypes binding of libdasr_b200.so (C ABI declared in include/dasr.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or a tensor is not a contiguous CUDA
+tensor of the expected dtype, these wrappers raise.  Every launch goes to torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdasr_b200.so")
+
+# --- enums (include/dasr.h)
+EPI_STORE, EPI_STATS, EPI_SEAN, EPI_SHUFFLE2, EPI_NCHW_F32 = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+PACK_CONV, PACK_CONVT, PACK_STYLE = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("B", "H", "W", "Cin", "Cout", "ks", "epi", "act", "subsample", "clamp01", "inner_relu", "reserved")]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s")]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("v", "g", "alpha", "bias", "bias2", "dst", "dst_bias")] + \
+               [(n, C.c_int32) for n in ("dim0", "dim1", "ks", "mode", "alpha_mode", "shuffle_r", "row_offset",
+                                         "rows_per_tap")]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; fail loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libdasr_b200.so is missing (%s). Build it with `python __graft_entry__.py build` -- the B200 path has "
+            "no CPU/PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.dasr_last_error.restype = C.c_char_p
+    lib.dasr_version.restype = C.c_int
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    sigs = {
+        "dasr_check_device": [],
+        "dasr_conv_fwd": [C.POINTER(ConvDesc), C.POINTER(ConvArgs), vp],
+        "dasr_pack_weights": [C.POINTER(PackDesc), i32, vp, vp],
+        "dasr_conv_first": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_zero_insert2": [vp, vp, i32, i32, i32, i32, vp],
+        "dasr_add": [vp, vp, vp, i64, vp],
+        "dasr_region_pool_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "dasr_mask_labels": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_actv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_dynconv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dasr_instats_finalize": [vp, vp, i32, i32, i32, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_check_device", "dasr_conv_fwd", "dasr_pack_weights",
+            "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
+            "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize"]
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("libdasr_b200: %s (status %d)" % (load().dasr_last_error().decode(), rc))
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libdasr_b200 needs CUDA tensors (got %s); there is no CPU fallback" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("libdasr_b200 needs contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------ wrappers
+def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, *, Cout: int, ks: int,
+             epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
+             resid=None, stats=None, y=None, norm=None, gb_s=None) -> torch.Tensor:
+    """x: NHWC bf16 [B,H,W,Cin]."""
+    B, H, W, Cin = x.shape
+    d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, 0)
+    a = ConvArgs(ptr(x, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
+                 ptr(stats), ptr(y), ptr(norm), ptr(gb_s))
+    check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
+    return out
+
+
+def pack_weights(descs: Sequence[PackDesc], scratch: torch.Tensor) -> None:
+    arr = (PackDesc * len(descs))(*descs)
+    check(load().dasr_pack_weights(arr, len(descs), ptr(scratch, torch.float32), stream_ptr()))
+
+
+def pack_desc(v, dst, *, g=None, alpha=None, alpha_mode=0, bias=None, bias2=None, dst_bias=None, mode=PACK_CONV,
+              shuffle_r=0, row_offset=0, rows_per_tap=0) -> PackDesc:
+    return PackDesc(ptr(v, torch.float32), ptr(g, torch.float32), ptr(alpha, torch.float32), ptr(bias, torch.float32),
+                    ptr(bias2, torch.float32), ptr(dst, torch.bfloat16), ptr(dst_bias, torch.float32),
+                    v.shape[0], v.shape[1], v.shape[2], mode, alpha_mode, shuffle_r, row_offset, rows_per_tap)

@@ -1,0 +1,614 @@
+// K-CONV: stride-1 "same" convolution as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[pixel][cout] = sum_{tap,cin} A[pixel + tap][cin] * W[cout][tap][cin]      (bf16 x bf16 -> fp32)
+//
+// Design (B200-first, not a cuDNN translation):
+//  * HALO REUSE. One 4-D TMA box load brings a zero-padded (RB x Wp) pixel patch of KC channels into
+//    shared memory ONCE (128B/64B-swizzled rows, one row per pixel).  Output pixels are enumerated in
+//    "padded-flat" order q = h*Wp + w, so the A operand of tap (t,u) is the SAME smem tile viewed through
+//    a descriptor whose start address is shifted by (t*Wp+u) rows -- measured to be legal on sm_100a with
+//    base_offset = 0 (profiles/r01_umma_probe.md).  A 3x3 conv therefore reads each activation from L2
+//    ~1.3x instead of 9x (81x for the 9x9 output conv); the tensor pipe is no longer L2-bound at N=64.
+//    The price is (Wp-Wt)/Wp garbage rows (3% at W=64) that the epilogue discards.
+//  * Weights stay resident in shared memory for the whole persistent CTA when they fit (trunk 64->64:
+//    72 KB), otherwise they stream through a TMA ring (gamma/beta conv: 288 KB).
+//  * Warp roles: w0 = A producer (TMA), w3 = B producer (TMA), w1 = MMA issuer (one elected thread,
+//    tcgen05.mma cta_group::1, M=128), w2 = TMEM allocator, w4..7 = epilogue (tcgen05.ld -> fused
+//    epilogue -> vectorised NHWC bf16 stores).  Accumulators are double-buffered in TMEM so the epilogue
+//    of tile i overlaps the MMAs of tile i+1.
+//  * Fused epilogues: bias/activation/residual, InstanceNorm statistics (warp butterfly + fp32 atomics),
+//    the whole SEAN modulation (normalise, (1+gamma), beta, ReLU, residual), PixelShuffle(2) as store
+//    addressing, and the final clamp to NCHW fp32.
+//
+// Replaces: nn.Conv2d call sites codes/models/modules/sftmd_arch.py:743-749,812,819,862-864,891-910 and
+// codes/models/modules/normalization.py:41-42,87-89 of the reference.
+#include "dasr_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace dasr {
+
+constexpr int kMaxBStages = 96;
+constexpr int kMaxAStages = 4;
+constexpr int kThreads = 256;
+
+struct ConvK {
+    // geometry
+    int B, H, W, Cin, Cout;
+    int ks, pad, taps;
+    int Wt, Wp, RB;
+    int n_strips, tiles_per_strip, ntn, total_tiles;
+    int nch;                       // Cin / KC
+    int SA, SB, b_resident;
+    uint32_t a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+    // epilogue
+    int epi, act, subsample, clamp01, inner_relu;
+    int Ho, Wo;                    // output spatial size (after subsample / shuffle)
+    const float* bias;
+    __nv_bfloat16* out;
+    float* out_f32;
+    const __nv_bfloat16* resid;
+    float* stats;
+    const __nv_bfloat16* y;
+    const float* norm;
+    const __nv_bfloat16* gb_s;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == DASR_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == DASR_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+    return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ void load16(const __nv_bfloat16* p, float* f) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    unpack8(a, f);
+    unpack8(b, f + 8);
+}
+__device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = pack8(f);
+    q[1] = pack8(f + 8);
+}
+
+// Reduce 16 per-thread values over the 32 lanes of a warp (recursive halving).  On return lane L holds in
+// v[0] the warp-wide sum of column  8*b4 + 4*b3 + 2*b2 + b1  (bN = bit N of L); lanes L and L^1 agree.
+__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        bool hi = lane & 16;
+        float send = hi ? v[i] : v[i + 8];
+        float keep = hi ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        bool hi = lane & 8;
+        float send = hi ? v[i] : v[i + 4];
+        float keep = hi ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        bool hi = lane & 4;
+        float send = hi ? v[i] : v[i + 2];
+        float keep = hi ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        bool hi = lane & 2;
+        float send = hi ? v[0] : v[1];
+        float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int SWZ, int N_TILE, int NB>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const ConvK p) {
+    constexpr int KC = SWZ / 2;          // channels per K chunk (one swizzle span per pixel row)
+    constexpr int KSTEPS = SWZ / 32;     // UMMA K = 16 bf16 = 32 bytes
+    constexpr int ACC_COLS = NB * N_TILE;
+    constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    constexpr int TMEM_COLS = 512;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+    __shared__ uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+    __shared__ uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float norm_s[2 * 128];
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* a_smem = smem;
+    uint8_t* b_smem = smem + (size_t)p.SA * p.a_stage_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.SA; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < p.SB; i++) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int tiles_per_img = p.n_strips * p.tiles_per_strip * p.ntn;
+
+    if (warp == 0) {
+        // ===================================================== A producer: one halo box per K chunk
+        if (lane == 0) {
+            uint32_t a_it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int img = tile / tiles_per_img;
+                int r = tile - img * tiles_per_img;
+                const int strip = r / (p.tiles_per_strip * p.ntn);
+                r -= strip * (p.tiles_per_strip * p.ntn);
+                const int tps = r / p.ntn;
+                const int q0 = tps * (NB * 128);
+                const int r0 = q0 / p.Wp;
+                const int w0 = strip * p.Wt;
+                for (int c = 0; c < p.nch; c++) {
+                    const int sa = a_it % p.SA;
+                    const uint32_t ph = (a_it / p.SA) & 1;
+                    mbar_wait(&a_empty[sa], ph ^ 1);
+                    mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
+                    tma_load_4d(a_smem + (size_t)sa * p.a_stage_bytes, &mapA, &a_full[sa], c * KC,
+                                w0 - p.pad, r0 - p.pad, img);
+                    a_it++;
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================== B producer: weight tiles (tap, chunk)
+        if (lane == 0) {
+            uint32_t b_it = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.ntn;
+                if (p.b_resident && !first) continue;
+                for (int c = 0; c < p.nch; c++) {
+                    for (int tap = 0; tap < p.taps; tap++) {
+                        int sb;
+                        if (p.b_resident) {
+                            sb = c * p.taps + tap;
+                        } else {
+                            sb = b_it % p.SB;
+                            const uint32_t ph = (b_it / p.SB) & 1;
+                            mbar_wait(&b_empty[sb], ph ^ 1);
+                            b_it++;
+                        }
+                        mbar_expect_tx(&b_full[sb], p.b_tx_bytes);
+                        tma_load_2d(b_smem + (size_t)sb * p.b_stage_bytes, &mapB, &b_full[sb],
+                                    tap * p.Cin + c * KC, nt * N_TILE);
+                    }
+                }
+                first = false;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer (single thread)
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, N_TILE);
+            const uint64_t desc_hi = make_smem_desc<SWZ>(0, 0) & ~0x3FFFull;
+            uint32_t a_it = 0, b_it = 0, acc_it = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int r = tile % tiles_per_img;
+                r %= (p.tiles_per_strip * p.ntn);
+                const int tps = r / p.ntn;
+                const int q0 = tps * (NB * 128);
+                const int soff = q0 - (q0 / p.Wp) * p.Wp;  // first output row inside the smem patch
+                const int buf = acc_it % NACC;
+                const uint32_t aph = (acc_it / NACC) & 1;
+                mbar_wait(&acc_empty[buf], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+                for (int c = 0; c < p.nch; c++) {
+                    const int sa = a_it % p.SA;
+                    mbar_wait(&a_full[sa], (a_it / p.SA) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_smem + (size_t)sa * p.a_stage_bytes);
+                    for (int tap = 0; tap < p.taps; tap++) {
+                        int sb;
+                        if (p.b_resident) {
+                            sb = c * p.taps + tap;
+                            if (first) mbar_wait(&b_full[sb], 0);
+                        } else {
+                            sb = b_it % p.SB;
+                            mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
+                        }
+                        tc_fence_after();
+                        const uint32_t b_base = smem_u32(b_smem + (size_t)sb * p.b_stage_bytes);
+                        const int t = tap / p.ks, u = tap - t * p.ks;
+                        const uint32_t a_tap = a_base + (uint32_t)(soff + t * p.Wp + u) * SWZ;
+#pragma unroll
+                        for (int blk = 0; blk < NB; blk++) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; k++) {
+                                const uint64_t da = desc_hi | (((a_tap + blk * 128 * SWZ + k * 32) & 0x3FFFFu) >> 4);
+                                const uint64_t db = desc_hi | (((b_base + k * 32) & 0x3FFFFu) >> 4);
+                                umma_bf16(d_tmem + blk * N_TILE, da, db, idesc, (c | tap | k) != 0);
+                            }
+                        }
+                        if (!p.b_resident) {
+                            umma_commit(&b_empty[sb]);
+                            b_it++;
+                        }
+                    }
+                    umma_commit(&a_empty[sa]);
+                    a_it++;
+                }
+                umma_commit(&acc_full[buf]);
+                acc_it++;
+                first = false;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue warps
+        const int ew = warp & 3;              // TMEM lane group
+        const int m = ew * 32 + lane;         // accumulator row inside an M block
+        const int et = threadIdx.x - 128;     // 0..127
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int img = tile / tiles_per_img;
+            int r = tile - img * tiles_per_img;
+            const int strip = r / (p.tiles_per_strip * p.ntn);
+            r -= strip * (p.tiles_per_strip * p.ntn);
+            const int tps = r / p.ntn;
+            const int nt = r - tps * p.ntn;
+            const int q0 = tps * (NB * 128);
+            const int w0 = strip * p.Wt;
+            const int buf = acc_it % NACC;
+            const uint32_t aph = (acc_it / NACC) & 1;
+
+            if (p.epi == DASR_EPI_SEAN) {
+                // (mean, scale) of this image for the nf = N_TILE/2 normalised channels
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (et < N_TILE) norm_s[et] = __ldg(p.norm + (size_t)img * N_TILE + et);
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            }
+
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
+
+#pragma unroll 1
+            for (int blk = 0; blk < NB; blk++) {
+                const int q = q0 + blk * 128 + m;
+                const int h = q / p.Wp;
+                const int wl = q - h * p.Wp;
+                const int w = w0 + wl;
+                bool valid = (h < p.H) && (wl < p.Wt) && (w < p.W);
+                const uint32_t t_blk = t_acc + blk * N_TILE;
+
+                if (p.epi == DASR_EPI_STORE || p.epi == DASR_EPI_STATS) {
+                    int ho = h, wo = w;
+                    if (p.subsample == 2) {
+                        valid = valid && !(h & 1) && !(w & 1);
+                        ho = h >> 1;
+                        wo = w >> 1;
+                    }
+                    const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                    __nv_bfloat16* op = p.out + pix * p.Cout + nt * N_TILE;
+                    const __nv_bfloat16* rp = p.resid ? p.resid + pix * p.Cout + nt * N_TILE : nullptr;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(t_blk + c0, v);
+                        tmem_ld_wait();
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            f[j] = __uint_as_float(v[j]) + __ldg(p.bias + nt * N_TILE + c0 + j);
+                        if (p.epi == DASR_EPI_STORE) {
+                            if (rp && valid) {
+                                float rr[16];
+                                load16(rp + c0, rr);
+#pragma unroll
+                                for (int j = 0; j < 16; j++) f[j] += rr[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
+                            if (valid) store16(op + c0, f);
+                        } else {
+                            if (valid) store16(op + c0, f);
+                            float s1[16], s2[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                float x = valid ? f[j] : 0.f;
+                                s1[j] = x;
+                                s2[j] = x * x;
+                            }
+                            warp_colsum16(s1, lane);
+                            warp_colsum16(s2, lane);
+                            if (!(lane & 1)) {
+                                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
+                                                ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                                float* sp = p.stats + ((size_t)img * p.Cout + nt * N_TILE + c0 + col) * 2;
+                                atomicAdd(sp, s1[0]);
+                                atomicAdd(sp + 1, s2[0]);
+                            }
+                        }
+                    }
+                } else if (p.epi == DASR_EPI_SEAN) {
+                    constexpr int NF = N_TILE / 2;
+                    const size_t pix = ((size_t)img * p.H + h) * p.W + w;
+                    const __nv_bfloat16* yp = p.y + pix * NF;
+                    const __nv_bfloat16* sp = p.gb_s ? p.gb_s + pix * N_TILE : nullptr;
+                    const __nv_bfloat16* rp = p.resid ? p.resid + pix * NF : nullptr;
+                    __nv_bfloat16* op = p.out + pix * NF;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < NF; c0 += 16) {
+                        uint32_t vg[16], vb[16];
+                        tmem_ld16(t_blk + c0, vg);
+                        tmem_ld16(t_blk + NF + c0, vb);
+                        tmem_ld_wait();
+                        if (valid) {
+                            float yv[16], o[16];
+                            load16(yp + c0, yv);
+                            float gs[16], bs[16];
+                            if (sp) {
+                                load16(sp + c0, gs);
+                                load16(sp + NF + c0, bs);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; j++) gs[j] = bs[j] = 0.f;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const float g = __uint_as_float(vg[j]) + __ldg(p.bias + c0 + j) + gs[j];
+                                const float b = __uint_as_float(vb[j]) + __ldg(p.bias + NF + c0 + j) + bs[j];
+                                const float n = (yv[j] - norm_s[2 * (c0 + j)]) * norm_s[2 * (c0 + j) + 1];
+                                float t = fmaf(n, 1.f + g, b);
+                                if (p.inner_relu) t = fmaxf(t, 0.f);
+                                o[j] = t;
+                            }
+                            if (rp) {
+                                float rr[16];
+                                load16(rp + c0, rr);
+#pragma unroll
+                                for (int j = 0; j < 16; j++) o[j] += rr[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j++) o[j] = apply_act(o[j], p.act);
+                            store16(op + c0, o);
+                        }
+                    }
+                } else if (p.epi == DASR_EPI_SHUFFLE2) {
+                    const int Cq = p.Cout >> 2;  // channels after the shuffle
+#pragma unroll 1
+                    for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(t_blk + c0, v);
+                        tmem_ld_wait();
+                        if (valid) {
+                            const int n0 = nt * N_TILE + c0;  // permuted row: n0 = s*Cq + c
+                            const int s = n0 / Cq, c = n0 - s * Cq;
+                            const size_t pix = ((size_t)img * p.Ho + (2 * h + (s >> 1))) * p.Wo + (2 * w + (s & 1));
+                            float f[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                f[j] = apply_act(__uint_as_float(v[j]) + __ldg(p.bias + n0 + j), p.act);
+                            store16(p.out + pix * Cq + c, f);
+                        }
+                    }
+                } else {  // DASR_EPI_NCHW_F32
+#pragma unroll 1
+                    for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(t_blk + c0, v);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                const int co = nt * N_TILE + c0 + j;
+                                if (co < p.Cout) {
+                                    float f = apply_act(__uint_as_float(v[j]) + __ldg(p.bias + co), p.act);
+                                    if (p.clamp01) f = fminf(fmaxf(f, 0.f), 1.f);
+                                    p.out_f32[(((size_t)img * p.Cout + co) * p.H + h) * p.W + w] = f;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            acc_it++;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <int SWZ, int N_TILE, int NB>
+static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, size_t smem_bytes,
+                  cudaStream_t stream) {
+    auto fn = conv_halo_kernel<SWZ, N_TILE, NB>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    DASR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        configured[dev & 63] = true;
+    }
+    int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
+    fn<<<grid, kThreads, smem_bytes, stream>>>(mA, mB, k);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+template <int SWZ, int NB>
+static int dispatch_n(int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, size_t smem,
+                      cudaStream_t s) {
+    switch (n_tile) {
+        case 16: return launch<SWZ, 16, NB>(mA, mB, k, smem, s);
+        case 32: return launch<SWZ, 32, NB>(mA, mB, k, smem, s);
+        case 64: return launch<SWZ, 64, NB>(mA, mB, k, smem, s);
+        case 128: return launch<SWZ, 128, NB>(mA, mB, k, smem, s);
+    }
+    return fail(DASR_ERR_BAD_ARG, "unsupported N tile %d", n_tile);
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DASR_REQUIRE(d && a, "null descriptor");
+    DASR_REQUIRE(d->ks == 1 || d->ks == 3 || d->ks == 9, "ks must be 1, 3 or 9 (got %d)", d->ks);
+    DASR_REQUIRE(d->Cin % 32 == 0 && d->Cin >= 32, "Cin must be a multiple of 32 (got %d)", d->Cin);
+    DASR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "bad shape");
+    DASR_REQUIRE(a->x && a->w && a->bias && a->out, "null tensor pointer");
+
+    ConvK k;
+    memset(&k, 0, sizeof k);
+    k.B = d->B; k.H = d->H; k.W = d->W; k.Cin = d->Cin; k.Cout = d->Cout;
+    k.ks = d->ks; k.pad = d->ks / 2; k.taps = d->ks * d->ks;
+    k.epi = d->epi; k.act = d->act; k.subsample = d->subsample ? d->subsample : 1;
+    k.clamp01 = d->clamp01; k.inner_relu = d->inner_relu;
+
+    const int SWZ = (d->Cin % 64 == 0) ? 128 : 64;
+    const int KC = SWZ / 2;
+    k.nch = d->Cin / KC;
+
+    // N tiling
+    int n_tile;
+    if (d->epi == DASR_EPI_NCHW_F32) {
+        DASR_REQUIRE(d->Cout <= 16, "NCHW fp32 epilogue supports Cout <= 16");
+        n_tile = 16;
+        k.ntn = 1;
+    } else {
+        n_tile = d->Cout >= 128 ? 128 : d->Cout;
+        DASR_REQUIRE(n_tile == 16 || n_tile == 32 || n_tile == 64 || n_tile == 128,
+                     "Cout must be 16, 32, 64 or a multiple of 128 (got %d)", d->Cout);
+        DASR_REQUIRE(d->Cout % n_tile == 0, "Cout %d not a multiple of the N tile %d", d->Cout, n_tile);
+        k.ntn = d->Cout / n_tile;
+    }
+    if (d->epi == DASR_EPI_SEAN) {
+        DASR_REQUIRE(k.ntn == 1 && n_tile >= 32, "SEAN epilogue needs Cout = 2*nf in {64,128}");
+        DASR_REQUIRE(a->y && a->norm, "SEAN epilogue needs y and norm");
+    }
+    if (d->epi == DASR_EPI_STATS) DASR_REQUIRE(a->stats, "STATS epilogue needs a stats buffer");
+    if (d->epi == DASR_EPI_SHUFFLE2) DASR_REQUIRE(d->Cout % 64 == 0, "shuffle needs Cout multiple of 64");
+
+    // strips / tiles
+    const int NB = 2;
+    const int max_wt = 128;
+    k.n_strips = (d->W + max_wt - 1) / max_wt;
+    k.Wt = (d->W + k.n_strips - 1) / k.n_strips;
+    k.Wp = k.Wt + d->ks - 1;
+    const int span = (d->H - 1) * k.Wp + k.Wt;  // padded-flat positions that contain valid outputs
+    const int blocks = (span + 127) / 128;
+    k.tiles_per_strip = (blocks + NB - 1) / NB;
+    k.total_tiles = d->B * k.n_strips * k.tiles_per_strip * k.ntn;
+    k.RB = (k.Wp - 1 + NB * 128 + (d->ks - 1) * (k.Wp + 1) + k.Wp - 1) / k.Wp;
+    DASR_REQUIRE(k.RB <= 256 && k.Wp <= 256, "TMA box too large");
+
+    k.a_tx_bytes = (uint32_t)k.RB * k.Wp * SWZ;
+    k.a_stage_bytes = (k.a_tx_bytes + 1023u) & ~1023u;
+    k.b_tx_bytes = (uint32_t)n_tile * SWZ;
+    k.b_stage_bytes = (k.b_tx_bytes + 1023u) & ~1023u;
+
+    const size_t budget = 220 * 1024;
+    const size_t all_b = (size_t)k.nch * k.taps * k.b_stage_bytes;
+    k.SA = 2;
+    if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
+    DASR_REQUIRE((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes <= budget,
+                 "A tile (%u bytes) does not fit in shared memory", k.a_stage_bytes);
+    if (k.ntn == 1 && k.nch * k.taps <= kMaxBStages &&
+        (size_t)k.SA * k.a_stage_bytes + all_b <= budget) {
+        k.b_resident = 1;
+        k.SB = k.nch * k.taps;
+    } else if (k.ntn == 1 && k.nch * k.taps <= kMaxBStages && (size_t)k.a_stage_bytes + all_b <= budget) {
+        k.b_resident = 1;
+        k.SA = 1;
+        k.SB = k.nch * k.taps;
+    } else {
+        k.b_resident = 0;
+        size_t room = budget - (size_t)k.SA * k.a_stage_bytes;
+        int sb = (int)(room / k.b_stage_bytes);
+        if (sb > 8) sb = 8;
+        if (sb > k.nch * k.taps) sb = k.nch * k.taps;
+        k.SB = sb;
+        DASR_REQUIRE(sb >= 2, "not enough shared memory for the weight ring");
+    }
+    const size_t smem_bytes = (size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes + 1024;
+
+    // outputs
+    k.Ho = d->H; k.Wo = d->W;
+    if (k.subsample == 2) { k.Ho = (d->H + 1) / 2; k.Wo = (d->W + 1) / 2; }
+    if (d->epi == DASR_EPI_SHUFFLE2) { k.Ho = 2 * d->H; k.Wo = 2 * d->W; }
+    k.bias = a->bias;
+    k.out = (__nv_bfloat16*)a->out;
+    k.out_f32 = (float*)a->out;
+    k.resid = (const __nv_bfloat16*)a->resid;
+    k.stats = a->stats;
+    k.y = (const __nv_bfloat16*)a->y;
+    k.norm = a->norm;
+    k.gb_s = (const __nv_bfloat16*)a->gb_s;
+
+    // tensor maps
+    CUtensorMap mA, mB;
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {(uint32_t)KC, (uint32_t)k.Wp, (uint32_t)k.RB, 1};
+        int rc = encode_tmap_bf16(&mA, a->x, 4, dims, str, box, SWZ);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t ktot = (uint64_t)k.taps * d->Cin;
+        const uint64_t rows = (uint64_t)k.ntn * n_tile;
+        uint64_t dims[2] = {ktot, rows};
+        uint64_t str[1] = {ktot * 2};
+        uint32_t box[2] = {(uint32_t)KC, (uint32_t)n_tile};
+        int rc = encode_tmap_bf16(&mB, a->w, 2, dims, str, box, SWZ);
+        if (rc) return rc;
+    }
+    if (SWZ == 128) return dispatch_n<128, 2>(n_tile, mA, mB, k, smem_bytes, stream);
+    return dispatch_n<64, 2>(n_tile, mA, mB, k, smem_bytes, stream);
+}

@@ -1,0 +1,447 @@
+// Memory-bound kernels of the DepthNet hot path (CUDA cores, vectorised, coalesced):
+//   conv_first      encoder.layer1 (Cin=3) + LeakyReLU, NCHW fp32 -> NHWC bf16   (sftmd_arch.py:743,772,783)
+//   zero_insert2    zero-stuffed input of the transposed conv                    (sftmd_arch.py:748)
+//   add             feat_add1                                                    (sftmd_arch.py:931)
+//   region_pool     RegionWiseAvgPooling                                         (sftmd_arch.py:714-733)
+//   mask_labels     one-hot depth masks -> u8 label map (getDepthMask output, LQGTker_Depth_dataset.py:204-226)
+//   actv            SEAN mlp_mask: ReLU(conv3x3(depth, 1->C))                    (normalization.py:37-40,61)
+//   style_mix       SEAN A_i_j label mixing st' = A st + a                       (normalization.py:27,80)
+//   dynconv         K-DYN: depth-guided dynamic 3x3 convolution, apply step      (normalization.py:81-85 restated)
+//   instats_finalize double InstanceNorm closed form                             (sftmd_arch.py:813 + normalization.py:56)
+#include "dasr_internal.h"
+
+namespace dasr {
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+__device__ __forceinline__ uint4 pack8f(const float* f) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------ conv_first
+__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ v,
+                                                         const float* __restrict__ g, const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+    __shared__ float ws[27][32];  // [ci*9 + tap][co]
+    __shared__ float bs[32];
+    if (threadIdx.x < 32) {
+        const int co = threadIdx.x;
+        float ss = 0.f;
+        for (int i = 0; i < 27; i++) ss += v[co * 27 + i] * v[co * 27 + i];
+        const float sc = g ? g[co] / sqrtf(ss) : 1.f;
+        for (int i = 0; i < 27; i++) ws[i][co] = v[co * 27 + i] * sc;
+        bs[co] = bias[co];
+    }
+    __syncthreads();
+    const size_t npix = (size_t)B * H * W;
+    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+        const int w = pix % W;
+        const int h = (pix / W) % H;
+        const int b = pix / ((size_t)W * H);
+        float in[27];
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++)
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int hh = h + t - 1, ww = w + u - 1;
+                    in[ci * 9 + t * 3 + u] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                                                 ? __ldg(x + (((size_t)b * 3 + ci) * H + hh) * W + ww)
+                                                 : 0.f;
+                }
+        uint4* op = reinterpret_cast<uint4*>(out + pix * 32);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = bs[c0 + j];
+#pragma unroll
+            for (int i = 0; i < 27; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(in[i], ws[i][c0 + j], acc[j]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = lrelu02(acc[j]);
+            op[c0 / 8] = pack8f(acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ zero_insert2 / add
+__global__ void zero_insert2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    const int Ho = 2 * H - 1, Wo = 2 * W - 1;
+    const size_t total = (size_t)B * Ho * Wo * C8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % C8;
+        size_t pix = i / C8;
+        const int wo = pix % Wo;
+        const int ho = (pix / Wo) % Ho;
+        const int b = pix / ((size_t)Wo * Ho);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (!(ho & 1) && !(wo & 1)) v = __ldg(x + (((size_t)b * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c);
+        out[i] = v;
+    }
+}
+
+__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, size_t n8) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float fa[8], fb[8];
+        unpack8f(__ldg(a + i), fa);
+        unpack8f(__ldg(b + i), fb);
+#pragma unroll
+        for (int j = 0; j < 8; j++) fa[j] += fb[j];
+        out[i] = pack8f(fa);
+    }
+}
+
+// ------------------------------------------------------------------------------------ region pooling
+// one block per (b, k): threshold the bilinearly (align_corners=True) resized mask, then masked mean.
+constexpr int kPoolMaxPos = 8192;
+__global__ void __launch_bounds__(256) region_pool_kernel(const __nv_bfloat16* __restrict__ e5,
+                                                          const float* __restrict__ masks, float* __restrict__ vec,
+                                                          int hf, int wf, int C, int K, int H, int W) {
+    __shared__ float msel[kPoolMaxPos];
+    __shared__ float cnt_s;
+    const int b = blockIdx.x / K, k = blockIdx.x % K;
+    const float* mp = masks + ((size_t)b * K + k) * H * W;
+    const int P = hf * wf;
+    const bool resize = (H != hf) || (W != wf);
+    const float sh = (hf > 1) ? (float)(H - 1) / (float)(hf - 1) : 0.f;
+    const float sw = (wf > 1) ? (float)(W - 1) / (float)(wf - 1) : 0.f;
+    float local = 0.f;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        const int i = p / wf, j = p - i * wf;
+        float m;
+        if (!resize) {
+            m = mp[p];
+        } else {
+            // torch upsample_bilinear2d, align_corners=True: src = scale*dst, 2-tap lerp per axis
+            const float hr = __fmul_rn(sh, (float)i), wr = __fmul_rn(sw, (float)j);
+            const int h1 = (int)hr, w1 = (int)wr;
+            const int h1p = (h1 < H - 1) ? 1 : 0, w1p = (w1 < W - 1) ? 1 : 0;
+            const float h1l = __fsub_rn(hr, (float)h1), h0l = __fsub_rn(1.f, h1l);
+            const float w1l = __fsub_rn(wr, (float)w1), w0l = __fsub_rn(1.f, w1l);
+            const float v00 = mp[h1 * W + w1], v01 = mp[h1 * W + w1 + w1p];
+            const float v10 = mp[(h1 + h1p) * W + w1], v11 = mp[(h1 + h1p) * W + w1 + w1p];
+            const float t0 = __fadd_rn(__fmul_rn(w0l, v00), __fmul_rn(w1l, v01));
+            const float t1 = __fadd_rn(__fmul_rn(w0l, v10), __fmul_rn(w1l, v11));
+            const float val = __fadd_rn(__fmul_rn(h0l, t0), __fmul_rn(h1l, t1));
+            m = (val >= 0.5f) ? 1.f : 0.f;
+        }
+        msel[p] = m;
+        local += m;
+    }
+    __shared__ float red[8];
+    for (int off = 16; off; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+        cnt_s = t;
+    }
+    __syncthreads();
+    const float inv = 1.f / (cnt_s + 1e-10f);
+    const __nv_bfloat16* ep = e5 + (size_t)b * P * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < P; p++) {
+            const float m = msel[p];
+            if (m != 0.f) s = fmaf(m, __bfloat162float(ep[(size_t)p * C + c]), s);
+        }
+        vec[((size_t)b * K + k) * C + c] = s * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------ mask -> labels
+__global__ void mask_labels_kernel(const float* __restrict__ masks, uint8_t* __restrict__ labels,
+                                   int* __restrict__ flag, int B, int K, int HW) {
+    const size_t total = (size_t)B * HW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i / HW, p = i - (size_t)b * HW;
+        int lab = 255, nz = 0;
+        bool exact = true;
+        for (int k = 0; k < K; k++) {
+            const float m = __ldg(masks + ((size_t)b * K + k) * HW + p);
+            if (m != 0.f) {
+                nz++;
+                lab = k;
+                if (m != 1.f) exact = false;
+            }
+        }
+        if (nz > 1 || !exact) {
+            *flag = 1;
+            lab = 255;
+        }
+        labels[i] = (uint8_t)lab;
+    }
+}
+
+// ------------------------------------------------------------------------------------ actv
+// thread = (pixel, 8-channel group); out NHWC bf16.  Weights transposed to smem [9][C].
+__global__ void __launch_bounds__(256) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, uint4* __restrict__ out, int B,
+                                                   int H, int W, int C) {
+    extern __shared__ float sm[];
+    float* ws = sm;          // [9][C]
+    float* bs = sm + 9 * C;  // [C]
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+        const int c = i / 9, t = i - c * 9;
+        ws[t * C + c] = w[i];
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
+    __syncthreads();
+    const int G = C / 8;
+    const size_t total = (size_t)B * H * W * G;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int gch = i % G;
+        const size_t pix = i / G;
+        const int x = pix % W;
+        const int y = (pix / W) % H;
+        const int b = pix / ((size_t)W * H);
+        const float* dp = depth + (size_t)b * H * W;
+        float d[9];
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int yy = y + t - 1, xx = x + u - 1;
+                d[t * 3 + u] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dp + (size_t)yy * W + xx) : 0.f;
+            }
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = bs[gch * 8 + j];
+#pragma unroll
+        for (int t = 0; t < 9; t++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = fmaf(d[t], ws[t * C + gch * 8 + j], acc[j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
+        out[i] = pack8f(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------ style mix
+// stp[b][j][c] = sum_i A[j][i] st[b][i][c] + a[j]   -> bf16 (GEMM A operand of the table GEMM)
+__global__ void style_mix_kernel(const float* __restrict__ st, const float* __restrict__ A, const float* __restrict__ a,
+                                 __nv_bfloat16* __restrict__ stp, int B, int K, int L) {
+    const size_t total = (size_t)B * K * L;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % L;
+        const int j = (i / L) % K;
+        const int b = i / ((size_t)L * K);
+        float s = a[j];
+        for (int q = 0; q < K; q++) s = fmaf(A[j * K + q], st[((size_t)b * K + q) * L + c], s);
+        stp[i] = __float2bfloat16(s);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K-DYN apply
+// Block = one (image, 8-row band); table T[b] ([K][9][C2] bf16) and the label halo are staged in smem.
+// thread item = (pixel, 8-channel group): 9 label lookups + 9 16-byte smem reads + one 16-byte store.
+__global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16* __restrict__ table,
+                                                             const uint8_t* __restrict__ labels, uint4* __restrict__ out,
+                                                             int K, int H, int W, int C2, int rows_per_block) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    uint4* ts = reinterpret_cast<uint4*>(smraw);  // K*9*C2/8 uint4
+    const int G = C2 / 8;
+    const int tsz = K * 9 * G;
+    uint8_t* ls = smraw + (size_t)tsz * 16;  // (rows+2) x (W+2) labels
+    const int bands = (H + rows_per_block - 1) / rows_per_block;
+    const int b = blockIdx.x / bands, band = blockIdx.x % bands;
+    const int h0 = band * rows_per_block;
+    const int rows = min(rows_per_block, H - h0);
+    const uint4* tg = reinterpret_cast<const uint4*>(table + (size_t)b * K * 9 * C2);
+    for (int i = threadIdx.x; i < tsz; i += blockDim.x) ts[i] = __ldg(tg + i);
+    const int LW = W + 2;
+    for (int i = threadIdx.x; i < (rows + 2) * LW; i += blockDim.x) {
+        const int r = i / LW, c = i - r * LW;
+        const int hh = h0 + r - 1, ww = c - 1;
+        ls[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? labels[((size_t)b * H + hh) * W + ww] : (uint8_t)255;
+    }
+    __syncthreads();
+    const int items = rows * W * G;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int gch = it % G;
+        const int pl = it / G;
+        const int r = pl / W, c = pl - r * W;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int lab = ls[(r + t) * LW + c + u];
+                if (lab != 255) {
+                    float f[8];
+                    unpack8f(ts[(lab * 9 + t * 3 + u) * G + gch], f);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[j] += f[j];
+                }
+            }
+        out[(((size_t)b * H + h0 + r) * W + c) * G + gch] = pack8f(acc);
+    }
+}
+
+// general (non one-hot) masks: exact linear form, slow path kept for API completeness
+__global__ void dynconv_masks_kernel(const __nv_bfloat16* __restrict__ table, const float* __restrict__ masks,
+                                     uint4* __restrict__ out, int B, int K, int H, int W, int C2) {
+    const int G = C2 / 8;
+    const size_t total = (size_t)B * H * W * G;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int gch = i % G;
+        const size_t pix = i / G;
+        const int x = pix % W;
+        const int y = (pix / W) % H;
+        const int b = pix / ((size_t)W * H);
+        const uint4* tg = reinterpret_cast<const uint4*>(table + (size_t)b * K * 9 * C2);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+        for (int k = 0; k < K; k++)
+            for (int t = 0; t < 3; t++)
+                for (int u = 0; u < 3; u++) {
+                    const int yy = y + t - 1, xx = x + u - 1;
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    const float m = __ldg(masks + (((size_t)b * K + k) * H + yy) * W + xx);
+                    if (m != 0.f) {
+                        float f[8];
+                        unpack8f(__ldg(tg + (k * 9 + t * 3 + u) * G + gch), f);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) acc[j] = fmaf(m, f[j], acc[j]);
+                    }
+                }
+        out[i] = pack8f(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------ IN statistics
+__global__ void instats_finalize_kernel(const float* __restrict__ stats, float* __restrict__ norm, int n, float inv_hw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float mean = stats[2 * i] * inv_hw;
+    float var = stats[2 * i + 1] * inv_hw - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float eps = 1e-5f;
+    // IN(IN(y)) = (y - mean) * (var+eps)^-1/2 * (var/(var+eps) + eps)^-1/2
+    const float s1 = rsqrtf(var + eps);
+    const float s2 = rsqrtf(var * s1 * s1 + eps);
+    norm[2 * i] = mean;
+    norm[2 * i + 1] = s1 * s2;
+}
+
+static inline int grid_for(size_t n, int block, int cap = 148 * 16) {
+    size_t g = (n + block - 1) / block;
+    if (g > (size_t)cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" int dasr_conv_first(const float* x, const float* v, const float* g, const float* bias, void* out, int B,
+                               int H, int W, void* stream) {
+    DASR_REQUIRE(x && v && bias && out && B > 0 && H > 0 && W > 0, "bad arguments");
+    const size_t npix = (size_t)B * H * W;
+    conv_first_kernel<<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(x, v, g, bias, (__nv_bfloat16*)out, B, H, W);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_zero_insert2(const void* x, void* out, int B, int H, int W, int C, void* stream) {
+    DASR_REQUIRE(x && out && C % 8 == 0, "bad arguments (C must be a multiple of 8)");
+    const size_t total = (size_t)B * (2 * H - 1) * (2 * W - 1) * (C / 8);
+    zero_insert2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, B, H, W, C / 8);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
+    DASR_REQUIRE(a && b && out && n % 8 == 0, "bad arguments (n must be a multiple of 8)");
+    add_kernel<<<grid_for((size_t)n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, (size_t)n / 8);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_region_pool_fwd(const void* e5, const float* masks, float* depth_vec, int B, int hf, int wf, int C,
+                                    int K, int H, int W, void* stream) {
+    DASR_REQUIRE(e5 && masks && depth_vec, "null pointer");
+    DASR_REQUIRE(hf * wf <= kPoolMaxPos, "feature map %dx%d too large for region pooling (max %d positions)", hf, wf, kPoolMaxPos);
+    region_pool_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)e5, masks, depth_vec, hf, wf, C, K, H, W);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_mask_labels(const float* masks, uint8_t* labels, int32_t* flag, int B, int K, int H, int W,
+                                void* stream) {
+    DASR_REQUIRE(masks && labels && flag, "null pointer");
+    mask_labels_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(masks, labels, flag, B, K, H * W);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bias, void* out, int B, int H, int W,
+                             int C, void* stream) {
+    DASR_REQUIRE(depth && w && bias && out && C % 8 == 0, "bad arguments");
+    const size_t total = (size_t)B * H * W * (C / 8);
+    actv_kernel<<<grid_for(total, 256), 256, 10 * C * sizeof(float), (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, B, H, W, C);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_style_mix(const float* depth_vec, const float* A, const float* a, void* stp, int B, int K, int L,
+                              void* stream) {
+    DASR_REQUIRE(depth_vec && A && a && stp, "null pointer");
+    style_mix_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(depth_vec, A, a, (__nv_bfloat16*)stp, B, K, L);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, void* out, int B, int K,
+                                int H, int W, int nf2, void* stream) {
+    DASR_REQUIRE(table && out && (labels || masks), "null pointer");
+    DASR_REQUIRE(nf2 % 8 == 0, "2*nf must be a multiple of 8");
+    if (labels) {
+        const int rows = 8;
+        const size_t smem = (size_t)K * 9 * nf2 * 2 + (size_t)(rows + 2) * (W + 2);
+        DASR_REQUIRE(smem <= 200 * 1024, "image too wide for the label tile");
+        static bool configured[64] = {false};
+        int dev = 0;
+        DASR_CUDA_OK(cudaGetDevice(&dev));
+        if (!configured[dev & 63]) {
+            DASR_CUDA_OK(cudaFuncSetAttribute(dynconv_labels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured[dev & 63] = true;
+        }
+        const int bands = (H + rows - 1) / rows;
+        dynconv_labels_kernel<<<B * bands, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, labels, (uint4*)out, K, H, W, nf2, rows);
+    } else {
+        const size_t total = (size_t)B * H * W * (nf2 / 8);
+        dynconv_masks_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, masks, (uint4*)out, B, K, H, W, nf2);
+    }
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, void* stream) {
+    DASR_REQUIRE(stats && norm && HW > 0, "bad arguments");
+    const int n = B * C;
+    instats_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, norm, n, 1.f / (float)HW);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}

@@ -1,0 +1,162 @@
+/*
+ * dasr.h -- C ABI of libdasr_b200.so: the B200 (sm_100a) kernels behind the DepthNet hot path of
+ * CUHK-AIM-Group/Depth-Aware-Endoscopy-SR.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the boundary it offers
+ * is `models.networks.define_G(opt)` (codes/models/networks.py:15,41-49) returning an nn.Module whose
+ * arithmetic lives in torch ops.  Each entry point below replaces the torch op(s) cited next to it; the
+ * Python host (depth_aware_endoscopy_sr_b200/arch.py) binds them with ctypes exactly as INTEGRATION.md
+ * shows.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative dasr_status otherwise; dasr_last_error() returns
+ *    a thread-local message.  No exceptions cross the ABI, nothing falls back to the CPU.
+ *  - all pointers are DEVICE pointers borrowed for the call (owner: the caller / torch caching
+ *    allocator); the library allocates nothing persistent on the device.
+ *  - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no implicit sync.
+ *  - activations are NHWC bf16 ("act" tensors) unless stated; network inputs/outputs are NCHW fp32 like
+ *    the reference.
+ */
+#ifndef DASR_H_
+#define DASR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DASR_OK = 0,
+    DASR_ERR_BAD_ARG = -1,      /* shape / alignment / unsupported configuration */
+    DASR_ERR_ARCH = -2,         /* device is not sm_100 */
+    DASR_ERR_CUDA = -3,         /* launch or driver failure */
+    DASR_ERR_WORKSPACE = -4     /* workspace too small */
+} dasr_status;
+
+const char* dasr_last_error(void);
+int dasr_version(void);
+/* 0 if the current device is a B200-class (sm_100) part, DASR_ERR_ARCH otherwise */
+int dasr_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution (tcgen05 / TMEM / TMA), stride 1, square kernel ks in {1,3,9}, zero padding
+ * ks/2.  Replaces nn.Conv2d / weight-normed Conv2d / ConvTranspose2d-as-conv on the hot path
+ * (codes/models/modules/sftmd_arch.py:743-749,812,819,862-864,891-910; normalization.py:41-42).
+ * A: NHWC bf16 [B,H,W,Cin] (Cin multiple of 32).  Wp: packed weights bf16 [Npad][ks*ks*Cin]
+ * (dasr_pack_weights).  bias: fp32 [Npad].
+ * ------------------------------------------------------------------------------------------------ */
+enum {
+    DASR_EPI_STORE = 0,      /* out_bf16 NHWC = act(acc + bias [+ resid])                          */
+    DASR_EPI_STATS = 1,      /* out_bf16 NHWC = acc + bias ; stats[b][c][0..1] += sum, sum of squares */
+    DASR_EPI_SEAN = 2,       /* acc = [gamma_o | beta_o]; fused SEAN modulate (normalization.py:87-89) */
+    DASR_EPI_SHUFFLE2 = 3,   /* PixelShuffle(2) + act folded into the store (sftmd_arch.py:893-908)  */
+    DASR_EPI_NCHW_F32 = 4    /* out_f32 NCHW [B,Cout,H,W] = clamp?(acc + bias)  (sftmd_arch.py:948-950) */
+};
+enum { DASR_ACT_NONE = 0, DASR_ACT_RELU = 1, DASR_ACT_LRELU = 2 };
+
+typedef struct {
+    int32_t B, H, W, Cin, Cout;   /* Cout = real output channels                                   */
+    int32_t ks;                   /* 1, 3 or 9                                                     */
+    int32_t epi;                  /* DASR_EPI_*                                                    */
+    int32_t act;                  /* DASR_ACT_* applied last                                       */
+    int32_t subsample;            /* 1, or 2: keep even (h,w) only -> stride-2 conv output          */
+    int32_t clamp01;              /* DASR_EPI_NCHW_F32: clamp to [0,1]                              */
+    int32_t inner_relu;           /* DASR_EPI_SEAN: relu before the residual add (norm1 path)       */
+    int32_t reserved;
+} dasr_conv_desc;
+
+typedef struct {
+    const void* x;        /* A operand, NHWC bf16                                                   */
+    const void* w;        /* packed weights                                                         */
+    const float* bias;    /* [Npad]                                                                 */
+    void* out;            /* bf16 NHWC (or fp32 NCHW for DASR_EPI_NCHW_F32)                          */
+    const void* resid;    /* optional NHWC bf16 residual, same shape as out                         */
+    float* stats;         /* DASR_EPI_STATS: [B][Cout][2] accumulators (caller zeroes them)         */
+    const void* y;        /* DASR_EPI_SEAN: conv output to normalise, NHWC bf16 [B,H,W,Cout/2]      */
+    const float* norm;    /* DASR_EPI_SEAN: [B][Cout/2][2] = (mean, scale) from dasr_instats_finalize */
+    const void* gb_s;     /* DASR_EPI_SEAN: dynamic-conv term NHWC bf16 [B,H,W,Cout] (or NULL)       */
+} dasr_conv_args;
+
+int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight preparation: weight-norm (w = g*v/||v||, sftmd_arch.py:740,851), alpha folding and repacking
+ * of fp32 [O][I][ks][ks] conv weights into the bf16 K-major GEMM-B layout [rows][ks*ks*I'].
+ * ------------------------------------------------------------------------------------------------ */
+enum {
+    DASR_PACK_CONV = 0,        /* rows = O, K = (tap, I)                                             */
+    DASR_PACK_CONVT = 1,       /* source is ConvTranspose2d [I][O][ks][ks]; rows = O, taps flipped   */
+    DASR_PACK_STYLE = 2        /* source [O][I][ks][ks]; dst [taps*rows_per_tap][I], row = tap*rows_per_tap
+                                  + row_offset + o, K = I  (style-table GEMM B operand)             */
+};
+typedef struct {
+    const float* v;       /* weight or weight_v                                                      */
+    const float* g;       /* weight_g ([dim0]) or NULL                                               */
+    const float* alpha;   /* device scalar or NULL                                                   */
+    const float* bias;    /* [O] or NULL                                                             */
+    const float* bias2;   /* [O] or NULL: dst_bias = f*bias + (1-f)*bias2, f = the alpha factor      */
+    void* dst;            /* bf16 [rows_total][ks*ks*I]                                              */
+    float* dst_bias;      /* fp32 [rows_total] or NULL                                               */
+    int32_t dim0, dim1, ks;
+    int32_t mode;         /* DASR_PACK_*                                                             */
+    int32_t alpha_mode;   /* 0: none, 1: scale by alpha, 2: scale by (1-alpha)                       */
+    int32_t shuffle_r;    /* 0, or r: destination row = (i*r+j)*(O/r^2) + c for source row c*r^2+i*r+j */
+    int32_t row_offset;   /* destination row offset (stack several convs into one B matrix)          */
+    int32_t rows_per_tap; /* DASR_PACK_STYLE only                                                    */
+} dasr_pack_desc;
+/* descs: HOST array of n descriptors; scratch: device fp32 [sum of dim0] for the weight-norm scales */
+int dasr_pack_weights(const dasr_pack_desc* descs, int n, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout / small ops
+ * ------------------------------------------------------------------------------------------------ */
+/* encoder.layer1 (weight-normed 3x3 conv Cin=3 -> 32) + LeakyReLU(0.2): NCHW fp32 -> NHWC bf16
+ * (sftmd_arch.py:743,772,783).  v: fp32 [32][3][3][3] (weight_v), g: [32] (weight_g, NULL = plain
+ * weight), bias [32].                                                                              */
+int dasr_conv_first(const float* x_nchw, const float* v, const float* g, const float* bias,
+                    void* out_nhwc, int B, int H, int W, void* stream);
+/* zero-insertion upsample for the transposed conv (sftmd_arch.py:748): [B,H,W,C] -> [B,2H-1,2W-1,C]   */
+int dasr_zero_insert2(const void* x, void* out, int B, int H, int W, int C, void* stream);
+/* out = a + b (bf16 NHWC, n elements)  -- feat_add1 (sftmd_arch.py:931)                              */
+int dasr_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+
+/* RegionWiseAvgPooling (sftmd_arch.py:714-733): e5 NHWC bf16 [B,hf,wf,C], masks NCHW fp32 [B,K,H,W]
+ * -> depthVec fp32 [B,K,C]                                                                          */
+int dasr_region_pool_fwd(const void* e5, const float* masks, float* depth_vec, int B, int hf, int wf,
+                         int C, int K, int H, int W, void* stream);
+
+/* masks NCHW fp32 [B,K,H,W] -> labels u8 [B,H,W] (k if one-hot at k, 255 if all zero); *flag_not_onehot
+ * (device int, caller zeroes) is set when some pixel is neither                                      */
+int dasr_mask_labels(const float* masks, uint8_t* labels, int32_t* flag_not_onehot, int B, int K, int H,
+                     int W, void* stream);
+
+/* SEAN depth branch first layer (normalization.py:37-40,61): actv = ReLU(conv3x3(depth, 1->C) + b),
+ * depth NCHW fp32 [B,1,H,W], w fp32 [C][9], out NHWC bf16 [B,H,W,C]                                  */
+int dasr_actv_fwd(const float* depth, const float* w, const float* bias, void* out, int B, int H, int W,
+                  int C, void* stream);
+
+/* SEAN label mixing (normalization.py:27,80): stp[b][j][:] = sum_i A[j][i] depth_vec[b][i][:] + a[j]
+ * depth_vec fp32 [B,K,L] -> stp bf16 [B*K][L].  The style table (normalization.py:81-85 restated,
+ * SURVEY 8a-7b)  T[b][k][tap][o] = alpha_x * sum_c W_x[o][c][tap] stp[b][k][c]  is then ONE 1x1
+ * dasr_conv_fwd over the "image" [1,1,B*K,L] with weights packed by DASR_PACK_STYLE
+ * (rows = tap*2nf + o, gamma rows o in [0,nf), beta rows o in [nf,2nf)) -> T bf16 [B][K][9][2nf].     */
+int dasr_style_mix(const float* depth_vec, const float* A, const float* a, void* stp, int B, int K,
+                   int L, void* stream);
+
+/* K-DYN, the depth-guided dynamic convolution apply step:
+ *   gb_s[b,p,:] = sum_tap T[b][label(p+tap)][tap][:]          (one-hot masks, labels != NULL)
+ *   gb_s[b,p,:] = sum_{k,tap} mask[b,k,p+tap] T[b][k][tap][:]   (general masks, labels == NULL)
+ * equal to [mlp_gamma_s(style_map) ; mlp_beta_s(style_map)] without bias (bias is merged into the conv
+ * bias by dasr_pack_weights).  table bf16 [B][K][9][2nf]; out NHWC bf16 [B,H,W,2nf].                  */
+int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, void* out, int B,
+                     int K, int H, int W, int nf2, void* stream);
+
+/* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
+ * stats [B][C][2] (sum, sumsq over H*W) -> norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)  */
+int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASR_H_ */
