@@ -62,7 +62,7 @@ def load() -> C.CDLL:
         "dasr_mask_labels": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_actv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
-        "dasr_dynconv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_instats_finalize": [vp, vp, i32, i32, i32, vp],
     }
     for name, args in sigs.items():

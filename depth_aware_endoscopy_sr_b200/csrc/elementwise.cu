@@ -253,8 +253,10 @@ __global__ void style_mix_kernel(const float* __restrict__ st, const float* __re
 // Block = one (image, 8-row band); table T[b] ([K][9][C2] bf16) and the label halo are staged in smem.
 // thread item = (pixel, 8-channel group): 9 label lookups + 9 16-byte smem reads + one 16-byte store.
 __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16* __restrict__ table,
-                                                             const uint8_t* __restrict__ labels, uint4* __restrict__ out,
-                                                             int K, int H, int W, int C2, int rows_per_block) {
+                                                             const uint8_t* __restrict__ labels,
+                                                             const float* __restrict__ masks, const int* __restrict__ flag,
+                                                             uint4* __restrict__ out, int K, int H, int W, int C2,
+                                                             int rows_per_block) {
     extern __shared__ __align__(16) uint8_t smraw[];
     uint4* ts = reinterpret_cast<uint4*>(smraw);  // K*9*C2/8 uint4
     const int G = C2 / 8;
@@ -274,6 +276,33 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
     }
     __syncthreads();
     const int items = rows * W * G;
+    const bool general = (flag != nullptr) && (*flag != 0) && (masks != nullptr);
+    if (general) {
+        // masks are not one-hot: exact linear form  sum_{k,tap} mask * T  (slow path, same smem table)
+        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+            const int gch = it % G;
+            const int pl = it / G;
+            const int r = pl / W, c = pl - r * W;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = 0.f;
+            for (int k = 0; k < K; k++)
+                for (int t = 0; t < 3; t++)
+                    for (int u = 0; u < 3; u++) {
+                        const int yy = h0 + r + t - 1, xx = c + u - 1;
+                        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                        const float m = __ldg(masks + (((size_t)b * K + k) * H + yy) * W + xx);
+                        if (m != 0.f) {
+                            float f[8];
+                            unpack8f(ts[(k * 9 + t * 3 + u) * G + gch], f);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) acc[j] = fmaf(m, f[j], acc[j]);
+                        }
+                    }
+            out[(((size_t)b * H + h0 + r) * W + c) * G + gch] = pack8f(acc);
+        }
+        return;
+    }
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int gch = it % G;
         const int pl = it / G;
@@ -413,8 +442,8 @@ extern "C" int dasr_style_mix(const float* depth_vec, const float* A, const floa
     return DASR_OK;
 }
 
-extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, void* out, int B, int K,
-                                int H, int W, int nf2, void* stream) {
+extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, const int32_t* flag,
+                                void* out, int B, int K, int H, int W, int nf2, void* stream) {
     DASR_REQUIRE(table && out && (labels || masks), "null pointer");
     DASR_REQUIRE(nf2 % 8 == 0, "2*nf must be a multiple of 8");
     if (labels) {
@@ -429,7 +458,7 @@ extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const 
             configured[dev & 63] = true;
         }
         const int bands = (H + rows - 1) / rows;
-        dynconv_labels_kernel<<<B * bands, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, labels, (uint4*)out, K, H, W, nf2, rows);
+        dynconv_labels_kernel<<<B * bands, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, labels, masks, flag, (uint4*)out, K, H, W, nf2, rows);
     } else {
         const size_t total = (size_t)B * H * W * (nf2 / 8);
         dynconv_masks_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, masks, (uint4*)out, B, K, H, W, nf2);

@@ -1,0 +1,298 @@
+"""Host-side schedule of the DepthNet forward pass on libdasr_b200.so (C ABI: include/dasr.h).
+
+The engine owns (a) the packed bf16 GEMM-B copies of all convolution weights -- weight-norm, SEAN alpha
+folding, PixelShuffle row permutation and the ConvTranspose flip are applied by ``dasr_pack_weights`` -- and
+(b) the order of kernel launches that restates ``DepthNet.forward`` (reference codes/models/modules/
+sftmd_arch.py:912-950) and ``SEAN.forward`` (normalization.py:52-92):
+
+    per SEAN     actv   = ReLU(conv3x3(depth, 1->2nf))                       dasr_actv_fwd
+                 st'    = A_i_j(depthVec)                                    dasr_style_mix
+                 T      = alpha * W_s . st'   (table of per-image dynamic filters)   dasr_conv_fwd (1x1 GEMM)
+                 gb_s   = dynamic 3x3 conv of the depth mask with T          dasr_dynconv_fwd  (K-DYN)
+    per DGB conv y      = conv3x3(x) + b ; sum / sumsq per (image, channel)   dasr_conv_fwd EPI_STATS
+                 norm   = closed form of InstanceNorm applied twice          dasr_instats_finalize
+                 out    = act(IN(IN(y)) * (1 + gamma) + beta [+ x])          dasr_conv_fwd EPI_SEAN over actv
+                          with [gamma_o|beta_o] as the GEMM and gb_s, the blend and the modulation as epilogue
+
+Activations are NHWC bf16; network input / output are NCHW fp32 like the reference.  Everything is launched on
+torch's current stream; nothing here computes on the host or with torch ops.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+class _Packed:
+    """bf16 GEMM-B weights + fp32 bias of one convolution (device tensors owned by the engine)."""
+    __slots__ = ("w", "bias", "cout", "cin", "ks")
+
+    def __init__(self, w, bias, cout, cin, ks):
+        self.w, self.bias, self.cout, self.cin, self.ks = w, bias, cout, cin, ks
+
+
+class Engine:
+    def __init__(self, net):
+        self.net = net
+        self._key = None
+        self._packed: Dict[str, _Packed] = {}
+        self._descs: List[L.PackDesc] = []
+        self._scratch = None
+        self._zero_bias = None
+        self._device = None
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _named(self):
+        return dict(self.net.named_parameters()), dict(self.net.named_buffers())
+
+    def _build_pack_plan(self, device):
+        """Allocate destination buffers and descriptors for every convolution on the path."""
+        net = self.net
+        params, bufs = self._named()
+
+        def P(name):
+            return params[name] if name in params else bufs[name]
+
+        self._packed = {}
+        self._descs = []
+        self._keep = []   # tensors referenced by raw pointers in the descriptors
+        rows_total = 0
+
+        def add(name, v, g, bias, *, mode=L.PACK_CONV, shuffle_r=0, rows_pad=None):
+            nonlocal rows_total
+            cout = v.shape[0] if mode != L.PACK_CONVT else v.shape[1]
+            cin = v.shape[1] if mode != L.PACK_CONVT else v.shape[0]
+            ks = v.shape[2]
+            rows = rows_pad or cout
+            dst = torch.zeros(rows, ks * ks * cin, device=device, dtype=BF16)
+            dbias = torch.zeros(rows, device=device, dtype=torch.float32)
+            self._descs.append(L.pack_desc(v, dst, g=g, bias=bias, dst_bias=dbias, mode=mode, shuffle_r=shuffle_r))
+            rows_total += v.shape[0]
+            self._packed[name] = _Packed(dst, dbias, cout, cin, ks)
+
+        def add_wn(name, **kw):
+            add(name, P(name + ".weight_v"), P(name + ".weight_g"), P(name + ".bias"), **kw)
+
+        if not net.isBaseline:
+            add_wn("encoder.layer2")
+            add_wn("encoder.layer3")
+            add_wn("encoder.layer4", mode=L.PACK_CONVT)
+            add_wn("encoder.layer5")
+        add_wn("head.0")
+        add_wn("head.2")
+        for i, _pos in net.block_order():
+            blk = net.block(i)
+            if i in net.which_ResBlk_depth:
+                p = "depth-residual%d" % (i + 1)
+                nf = blk.nf
+                for j in (1, 2):
+                    add("%s.conv%d.0" % (p, j), P("%s.conv%d.0.weight" % (p, j)), None, P("%s.conv%d.0.bias" % (p, j)))
+                    n = "%s.norm%d" % (p, j)
+                    ag, ab = P(n + ".alpha_gamma"), P(n + ".alpha_beta")
+                    lat = blk.norm1.len_latent
+                    # [gamma_o | beta_o] stacked along N, scaled by (1 - alpha); bias = blend of both branches
+                    wo = torch.zeros(2 * nf, 9 * 2 * nf, device=device, dtype=BF16)
+                    bo = torch.zeros(2 * nf, device=device, dtype=torch.float32)
+                    for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
+                        self._descs.append(L.pack_desc(P("%s.mlp_%s_o.weight" % (n, x)), wo, alpha=al, alpha_mode=2,
+                                                       bias=P("%s.mlp_%s_o.bias" % (n, x)),
+                                                       bias2=P("%s.mlp_%s_s.bias" % (n, x)), dst_bias=bo,
+                                                       row_offset=off))
+                        rows_total += nf
+                    self._packed[n + ".gb_o"] = _Packed(wo, bo, 2 * nf, 2 * nf, 3)
+                    # style-table GEMM operand: rows = tap * 2nf + [gamma | beta], K = latent, scaled by alpha
+                    ws = torch.zeros(9 * 2 * nf, lat, device=device, dtype=BF16)
+                    for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
+                        self._descs.append(L.pack_desc(P("%s.mlp_%s_s.weight" % (n, x)), ws, alpha=al, alpha_mode=1,
+                                                       mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf))
+                        rows_total += nf
+                    self._packed[n + ".table"] = _Packed(ws, None, 9 * 2 * nf, lat, 1)
+            else:
+                p = "classic-residual%d" % (i + 1)
+                add_wn(p + ".block.0")
+                add_wn(p + ".block.2")
+        if net.scale == 8:
+            add_wn("upscale1.0", shuffle_r=2)
+            add_wn("upscale1.3")
+        if net.scale >= 4:
+            add_wn("upscale2.0", shuffle_r=2)
+            add_wn("upscale2.3")
+        add_wn("upscale3.0", shuffle_r=2)
+        add("conv_output", P("conv_output.weight"), None, P("conv_output.bias"), rows_pad=16)
+        self._scratch = torch.zeros(rows_total, device=device, dtype=torch.float32)
+        self._zero_bias = torch.zeros(9 * 2 * 64, device=device, dtype=torch.float32)
+        self._device = device
+
+    def _state_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.net.parameters())
+
+    def pack(self, force: bool = False):
+        """(Re)pack the weights when any parameter changed (optimizer step, load_state_dict, .to())."""
+        key = self._state_key()
+        if not force and key == self._key:
+            return
+        device = next(self.net.parameters()).device
+        ptrs = tuple(k[0] for k in key)
+        if self._device != device or getattr(self, "_ptrs", None) != ptrs:
+            self._build_pack_plan(device)
+            self._ptrs = ptrs
+        L.pack_weights(self._descs, self._scratch)
+        self._key = key
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _conv(self, x, name, *, epi=L.EPI_STORE, act=L.ACT_NONE, subsample=1, out=None, **kw):
+        pk = self._packed[name]
+        B, H, W, _ = x.shape
+        if out is None:
+            if epi == L.EPI_SHUFFLE2:
+                out = torch.empty(B, 2 * H, 2 * W, pk.cout // 4, device=x.device, dtype=BF16)
+            elif epi == L.EPI_SEAN:
+                out = torch.empty(B, H, W, pk.cout // 2, device=x.device, dtype=BF16)
+            elif subsample == 2:
+                out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=x.device, dtype=BF16)
+            else:
+                out = torch.empty(B, H, W, pk.cout, device=x.device, dtype=BF16)
+        return L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act, subsample=subsample, **kw)
+
+    def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, vec):
+        """actv and gb_s of one SEAN instance (they depend on the network inputs only, not on x)."""
+        lib = L.load()
+        B, _, H, W = depth.shape
+        nf2 = 2 * sean.norm_nc
+        K, lat = sean.label_nc, sean.len_latent
+        s = L.stream_ptr()
+        actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
+        L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias),
+                                  L.ptr(actv), B, H, W, nf2, s))
+        stp = torch.empty(1, 1, B * K, lat, device=depth.device, dtype=BF16)
+        L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias), L.ptr(stp), B, K,
+                                   lat, s))
+        pk = self._packed[n + ".table"]
+        table = torch.empty(1, 1, B * K, 9 * nf2, device=depth.device, dtype=BF16)
+        L.conv_fwd(stp, pk.w, self._zero_bias, table, Cout=9 * nf2, ks=1)
+        gb_s = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
+        L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W,
+                                     nf2, s))
+        return actv, gb_s
+
+    def _dgb(self, p: str, blk, x, depth, labels, masks, flag, vec):
+        """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834)."""
+        lib = L.load()
+        B, H, W, nf = x.shape
+        s = L.stream_ptr()
+        stats = torch.zeros(2, B, nf, 2, device=x.device, dtype=torch.float32)
+        norm = torch.empty(2, B, nf, 2, device=x.device, dtype=torch.float32)
+        cur = x
+        for j, sean in ((1, blk.norm1), (2, blk.norm2)):
+            n = "%s.norm%d" % (p, j)
+            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, vec)
+            y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats[j - 1])
+            L.check(lib.dasr_instats_finalize(L.ptr(stats[j - 1]), L.ptr(norm[j - 1]), B, nf, H * W, s))
+            if j == 1:
+                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
+            else:
+                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm[1], gb_s=gb_s,
+                                 resid=x)
+        return cur
+
+    def _classic(self, p: str, x):
+        """Classic_Residual_Block.forward (sftmd_arch.py:147-151)."""
+        f = self._conv(x, p + ".block.0", act=L.ACT_RELU)
+        return self._conv(f, p + ".block.2", act=L.ACT_RELU, resid=x)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, lq: torch.Tensor, depth: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        net = self.net
+        if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+            from . import autograd as _ag   # training path (forward + backward kernels)
+            return _ag.depthnet_apply(self, lq, depth, masks)
+        return self.infer(lq, depth, masks)
+
+    @torch.no_grad()
+    def infer(self, lq: torch.Tensor, depth: torch.Tensor, masks: torch.Tensor, cap: dict = None,
+              clamp: bool = True) -> torch.Tensor:
+        """Inference schedule.  ``cap`` (tests only) receives intermediate tensors in the engine's own layouts
+        (NHWC bf16 activations); ``clamp=False`` returns the pre-clamp output of conv_output."""
+        net = self.net
+        lib = L.load()
+        if not lq.is_cuda:
+            raise RuntimeError("DepthNet (B200) needs CUDA tensors; there is no CPU fallback")
+        lq = lq.contiguous().float()
+        depth = depth.contiguous().float()
+        masks = masks.contiguous().float()
+        B, _, h, w = lq.shape
+        K = masks.shape[1]
+        dev = lq.device
+        self.pack()
+        s = L.stream_ptr()
+
+        # ---- encoder (sftmd_arch.py:771-783)
+        enc = net.encoder
+        f0 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
+        L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g),
+                                    L.ptr(enc.layer1.bias), L.ptr(f0), B, h, w, s))
+        vec = labels = flag = None
+        if not net.isBaseline:
+            e2 = self._conv(f0, "encoder.layer2", subsample=2, act=L.ACT_LRELU)
+            e3 = self._conv(e2, "encoder.layer3", subsample=2, act=L.ACT_LRELU)
+            h3, w3 = e3.shape[1], e3.shape[2]
+            z = torch.empty(B, 2 * h3 - 1, 2 * w3 - 1, 128, device=dev, dtype=BF16)
+            L.check(lib.dasr_zero_insert2(L.ptr(e3), L.ptr(z), B, h3, w3, 128, s))
+            e4 = self._conv(z, "encoder.layer4", act=L.ACT_LRELU)
+            e5 = self._conv(e4, "encoder.layer5", subsample=2)
+            lat = e5.shape[3]
+            vec = torch.empty(B, K, lat, device=dev, dtype=torch.float32)
+            L.check(lib.dasr_region_pool_fwd(L.ptr(e5), L.ptr(masks), L.ptr(vec), B, e5.shape[1], e5.shape[2], lat, K,
+                                             h, w, s))
+            labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
+            flag = torch.zeros(1, device=dev, dtype=torch.int32)
+            L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
+            if cap is not None:
+                cap.update(e5=e5, depthVec=vec, labels=labels, flag=flag)
+
+        # ---- head + trunk (sftmd_arch.py:920-931)
+        fea_bef = self._conv(self._conv(f0, "head.0", act=L.ACT_LRELU), "head.2", act=L.ACT_LRELU)
+        x = fea_bef
+        order = net.block_order()
+
+        def run_block(i, x):
+            if i in net.which_ResBlk_depth:
+                if x.shape[1] != h or x.shape[2] != w:
+                    raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
+                                              "%d at x%d) are not implemented yet" % (i, net.scale))
+                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, depth, labels, masks, flag, vec)
+            return self._classic("classic-residual%d" % (i + 1), x)
+
+        for i, pos in order:
+            if pos == "trunk":
+                x = run_block(i, x)
+                if cap is not None:
+                    cap["block%d.out" % (i + 1)] = x
+        if cap is not None:
+            cap["fea_bef"] = fea_bef
+        add = torch.empty_like(x)
+        L.check(lib.dasr_add(L.ptr(x), L.ptr(fea_bef), L.ptr(add), x.numel(), s))
+        x = add
+
+        # ---- tail (sftmd_arch.py:932-950)
+        if net.scale == 8:
+            x = self._conv(x, "upscale1.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
+            x = self._conv(x, "upscale1.3", act=L.ACT_LRELU)
+        x = run_block(order[-2][0], x)
+        if net.scale >= 4:
+            x = self._conv(x, "upscale2.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
+            x = self._conv(x, "upscale2.3", act=L.ACT_LRELU)
+        x = run_block(order[-1][0], x)
+        x = self._conv(x, "upscale3.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
+        out = torch.empty(B, 3, x.shape[1], x.shape[2], device=dev, dtype=torch.float32)
+        if net.min != 0.0 or net.max != 1.0:
+            raise NotImplementedError("the fused output epilogue clamps to [0,1] (the only range define_G builds)")
+        if cap is not None:
+            cap["feat_up3"] = x
+        self._conv(x, "conv_output", epi=L.EPI_NCHW_F32, clamp01=1 if clamp else 0, out=out)
+        return out

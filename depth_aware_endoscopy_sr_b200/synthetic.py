@@ -10,7 +10,9 @@ tensors generated here from a seed (CPU generator => identical on every box).
 * ``synthetic_inputs`` follows SURVEY.md section 8(d): LQ in [0,1), depth in [0.01,10), GT in [0,1).
 * ``fill_state_dict`` fills a DepthNet ``state_dict`` *layout* (names + shapes) with seeded values.  It is
   deliberately harsher than the default init: ``weight_g != ||weight_v||`` so that the weight-norm path
-  matters, and the SEAN blend scalars are drawn from U[0,1) like the reference (normalization.py:31-32).
+  matters, the SEAN blend scalars are drawn from U[0,1) like the reference (normalization.py:31-32), and the
+  output convolution is centred on 0.5 so that the SR image fills [0,1] (with torch's default init the
+  reference's output sits in [0, 0.14] and the final clamp would hide most errors).
 """
 from __future__ import annotations
 
@@ -72,12 +74,16 @@ def fill_state_dict(layout: "OrderedDict[str, torch.Size]", seed: int = 0) -> "O
             t = 0.6 + 0.8 * torch.rand(shape, generator=g)
         elif leaf == "bias":
             t = (torch.rand(shape, generator=g) - 0.5) * 0.2
-        else:  # weight / weight_v : kaiming-uniform-like bound 1/sqrt(fan_in) ... times sqrt(3)
+        else:  # weight / weight_v: uniform, variance 0.64 / fan_in (activations neither vanish nor explode)
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            bound = math.sqrt(3.0 / max(fan_in, 1))
+            bound = 0.8 * math.sqrt(3.0 / max(fan_in, 1))
             t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        if name == "conv_output.weight":
+            t = t * 0.5
+        if name == "conv_output.bias":
+            t = t + 0.5  # centre the SR image inside [0,1] so that the clamp does not hide errors
         sd[name] = t.float()
     # weight_g := factor * ||weight_v|| (norm over all dims except 0, as torch weight_norm dim=0)
     for name in list(sd.keys()):

@@ -145,12 +145,13 @@ int dasr_style_mix(const float* depth_vec, const float* A, const float* a, void*
                    int L, void* stream);
 
 /* K-DYN, the depth-guided dynamic convolution apply step:
- *   gb_s[b,p,:] = sum_tap T[b][label(p+tap)][tap][:]          (one-hot masks, labels != NULL)
- *   gb_s[b,p,:] = sum_{k,tap} mask[b,k,p+tap] T[b][k][tap][:]   (general masks, labels == NULL)
+ *   gb_s[b,p,:] = sum_tap T[b][label(p+tap)][tap][:]          (one-hot masks: labels given, *flag == 0)
+ *   gb_s[b,p,:] = sum_{k,tap} mask[b,k,p+tap] T[b][k][tap][:]   (general masks: labels == NULL or *flag != 0;
+ *                                                              flag is the device int of dasr_mask_labels)
  * equal to [mlp_gamma_s(style_map) ; mlp_beta_s(style_map)] without bias (bias is merged into the conv
  * bias by dasr_pack_weights).  table bf16 [B][K][9][2nf]; out NHWC bf16 [B,H,W,2nf].                  */
-int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, void* out, int B,
-                     int K, int H, int W, int nf2, void* stream);
+int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, const int32_t* flag,
+                     void* out, int B, int K, int H, int W, int nf2, void* stream);
 
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
  * stats [B][C][2] (sum, sumsq over H*W) -> norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)  */

@@ -1,0 +1,129 @@
+"""Generate the golden vectors of tests/golden/*.npz by executing the REAL reference implementation.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+For every case it builds ``models.modules.sftmd_arch.DepthNet`` from /root/reference/codes with the yml's
+``network_G`` arguments, loads the seeded synthetic ``state_dict`` (depth_aware_endoscopy_sr_b200.synthetic.
+fill_state_dict -- a pure function of the key names/shapes and the seed, so nothing but the seed is stored),
+feeds the seeded synthetic inputs and records fp32 outputs, intermediate activations, the training loss of
+models/F_model_depthCond.py:163-190 (``nn.L1Loss`` + ``dynamic_weight_mask_loss``) and per-parameter gradient
+signatures.  The reference ships no tests or golden vectors of its own, so "the reference
+executed here" is the strongest pin available.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/codes")
+sys.dont_write_bytecode = True
+
+import models.modules.sftmd_arch as ref_arch  # noqa: E402  (the reference)
+from models.modules.mask_loss import dynamic_weight_mask_loss  # noqa: E402
+from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs  # noqa: E402
+
+CASES = {
+    # name: (scale, which, latent, B, h, w, seed, out_stride)
+    "x8_b2_16": (8, list(range(14)), 256, 2, 16, 16, 1, 1),
+    "x8_b1_64": (8, list(range(14)), 256, 1, 64, 64, 0, 3),
+    "x8_b1_24x40": (8, list(range(14)), 256, 1, 24, 40, 2, 2),
+    "x4_b1_24": (4, list(range(14)), 256, 1, 24, 24, 3, 1),
+    "x2_b1_32": (2, list(range(16)), 32, 1, 32, 32, 4, 1),
+}
+
+
+def grad_signature(name, g):
+    """4 numbers per gradient: sum, L1, L2 and a seeded random projection."""
+    gen = torch.Generator().manual_seed(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+    proj = torch.randn(g.numel(), generator=gen, dtype=torch.float64)
+    g64 = g.double().flatten()
+    return np.array([g64.sum().item(), g64.abs().sum().item(), g64.norm().item(), (g64 * proj).sum().item()])
+
+
+def run_case(name, scale, which, latent, B, h, w, seed, stride):
+    torch.manual_seed(0)
+    net = ref_arch.DepthNet(which_ResBlk_depth=which, in_nc=3, out_nc=3, nf=64, nb=16, scale=scale, input_para=10,
+                            depth_latent_ch=latent, depthRangeNum=10, norm_type="weight_norm",
+                            use_trainable_params=True, norm_gamma=0, norm_beta=0, ablate_depth_block=False,
+                            ablate_depth_matrix=False)
+    sd = fill_state_dict({k: v.shape for k, v in net.state_dict().items()}, seed=seed)
+    net.load_state_dict(sd, strict=True)
+    lq, depth, masks, gt = synthetic_inputs(B, h, w, scale=scale, seed=seed, with_gt=True)
+
+    cap = {}
+    hooks = []
+
+    def grab(key):
+        def fn(_m, _i, o):
+            cap[key] = (o[1] if isinstance(o, tuple) else o).detach()
+        return fn
+
+    hooks.append(net.encoder.register_forward_hook(grab("depthVec")))
+    hooks.append(net.head.register_forward_hook(grab("fea_bef")))
+    hooks.append(getattr(net, "depth-residual1").register_forward_hook(grab("dgb1_out")))
+    hooks.append(getattr(net, "depth-residual1").norm1.register_forward_hook(grab("dgb1_norm1_out")))
+    hooks.append(getattr(net, "depth-residual13").register_forward_hook(grab("dgb13_out")))
+    hooks.append(net.upscale3.register_forward_hook(grab("feat_up3")))
+    hooks.append(net.conv_output.register_forward_hook(grab("pre_clamp")))
+
+    net.train()
+    with torch.no_grad():
+        sr = net(lq, depth, masks)          # fp32, as the reference runs it
+    for hk in hooks:
+        hk.remove()
+    # loss + gradients in fp64 (the same reference modules, .double()): sums such as d(alpha) cancel heavily and
+    # their fp32 value depends on the summation order, so the pin for gradients is the fp64 value.
+    # Loss exactly as F_Model_depthCond.optimize_parameters builds it (pixel_weight 1, dynamic_weight 10).
+    net.double()
+    dyn = dynamic_weight_mask_loss({"dynamic_criterion": "smoothl1", "dynamic_weight": 10.0}, device="cpu").double()
+    sr64 = net(lq.double(), depth.double(), masks.double())
+    l_pix = 1.0 * torch.nn.L1Loss()(sr64, gt.double())
+    raw, _weighted, l_dyn, _sw = dyn(sr64, gt.double(), masks.double())
+    total = l_pix + l_dyn
+    total.backward()
+
+    out = {
+        "meta": np.array([scale, latent, B, h, w, seed, stride]),
+        "which": np.array(which),
+        "sr": sr.detach().numpy()[:, :, ::stride, ::stride],
+        "pre_clamp": cap["pre_clamp"].numpy()[:, :, ::stride, ::stride],
+        "depthVec": cap["depthVec"].numpy(),
+        "fea_bef": cap["fea_bef"].numpy()[:, ::4],
+        "dgb1_norm1_out": cap["dgb1_norm1_out"].numpy()[:, ::4],
+        "dgb1_out": cap["dgb1_out"].numpy()[:, ::4],
+        "dgb13_out": cap["dgb13_out"].numpy()[:, ::4],
+        "feat_up3": cap["feat_up3"].numpy()[:, ::8, ::max(stride, 2), ::max(stride, 2)],
+        "loss": np.array([total.item(), l_pix.item(), l_dyn.item()] + [r.item() for r in raw]),
+        "dyn_weight_grad": dyn.trainable_weight.grad.numpy(),
+    }
+    names, sigs = [], []
+    for k, p in net.named_parameters():
+        names.append(k)
+        sigs.append(grad_signature(k, p.grad) if p.grad is not None else np.full(4, np.nan))
+    out["grad_names"] = np.array(names)
+    out["grad_sig"] = np.stack(sigs)
+    out["sr64_absdiff_max"] = np.array([(sr64.detach().float() - sr).abs().max().item()])
+    # a few complete gradients (small tensors) for element-wise checks
+    params = dict(net.named_parameters())
+    for k in ("conv_output.bias", "depth-residual1.norm1.alpha_gamma", "depth-residual1.norm1.alpha_beta",
+              "depth-residual1.norm1.A_i_j.weight", "depth-residual7.conv2.0.bias", "encoder.layer5.bias",
+              "head.0.weight_g", "upscale3.0.bias", "depth-residual13.norm2.mlp_mask.0.weight"):
+        if k in params and params[k].grad is not None:
+            out["grad:" + k] = params[k].grad.numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-14s sr[min %.4f max %.4f] pre_clamp[min %.3f max %.3f] loss %.5f  -> %s (%.0f KB)" % (
+        name, sr.min().item(), sr.max().item(), cap["pre_clamp"].min().item(), cap["pre_clamp"].max().item(),
+        total.item(), os.path.basename(path), os.path.getsize(path) / 1024), flush=True)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    for name, args in CASES.items():
+        run_case(name, *args)

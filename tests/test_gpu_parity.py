@@ -1,0 +1,129 @@
+"""B200 parity tests: the CUDA path (through the C ABI of libdasr_b200.so) against the golden vectors of the
+real reference and against the CPU oracle on the same seeded inputs.
+
+Tolerances are the ones BASELINE.json's north_star states for the bf16 path: max-abs error <= 1e-2 on [0,1]
+pixels, PSNR delta <= 0.01 dB.
+"""
+import numpy as np
+import pytest
+import torch
+
+from common import CASES, case_tensors, load_golden, oracle, psnr
+
+pytestmark = pytest.mark.gpu
+
+TOL_PIX = 1e-2      # north_star: bf16, [0,1] pixels
+TOL_PSNR = 0.01     # dB
+
+
+def _build(meta, sd):
+    import depth_aware_endoscopy_sr_b200 as dasr
+    net = dasr.DepthNet(which_ResBlk_depth=list(meta["which"]), in_nc=3, out_nc=3, nf=64, nb=16, scale=meta["scale"],
+                        input_para=10, depth_latent_ch=meta["latent"], depthRangeNum=10, norm_type="weight_norm",
+                        use_trainable_params=True, norm_gamma=0, norm_beta=0)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    sd, (lq, depth, masks, gt) = case_tensors(meta)
+    net = _build(meta, sd)
+    cap = {}
+    with torch.no_grad():
+        sr = net.engine().infer(lq.cuda(), depth.cuda(), masks.cuda(), cap=cap)
+        pre = net.engine().infer(lq.cuda(), depth.cuda(), masks.cuda(), clamp=False)
+        sr2 = net(lq.cuda(), depth.cuda(), masks.cuda())          # the public call (define_G surface)
+    torch.cuda.synchronize()
+    assert sr.dtype == torch.float32 and tuple(sr.shape) == (meta["B"], 3, meta["scale"] * meta["h"],
+                                                             meta["scale"] * meta["w"])
+    assert torch.equal(sr, sr2)
+    st = meta["stride"]
+    sr_c, pre_c = sr.cpu(), pre.cpu()
+    # intermediates (looser: trunk activations are O(10), bf16 has 8 bits of mantissa)
+    np.testing.assert_allclose(cap["depthVec"].cpu().numpy(), z["depthVec"], atol=3e-2, rtol=2e-2)
+    fb = _nchw(cap["fea_bef"]).numpy()[:, ::4]
+    assert np.abs(fb - z["fea_bef"]).max() <= 2e-2 * max(1.0, np.abs(z["fea_bef"]).max())
+    d1 = _nchw(cap["block1.out"]).numpy()[:, ::4]
+    assert np.abs(d1 - z["dgb1_out"]).max() <= 3e-2 * max(1.0, np.abs(z["dgb1_out"]).max())
+    # final image against the REAL reference's output
+    err = np.abs(sr_c.numpy()[:, :, ::st, ::st] - z["sr"]).max()
+    err_pre = np.abs(pre_c.numpy()[:, :, ::st, ::st] - z["pre_clamp"]).max()
+    print("%s: max|sr-ref|=%.4g  max|pre_clamp-ref|=%.4g" % (name, err, err_pre))
+    assert err <= TOL_PIX, "max-abs error %.4g exceeds the bf16 tolerance" % err
+    assert err_pre <= 2 * TOL_PIX * max(1.0, np.abs(z["pre_clamp"]).max())
+
+
+@pytest.mark.parametrize("name", ["x8_b2_16", "x8_b1_24x40", "x4_b1_24", "x2_b1_32"])
+def test_forward_matches_oracle_full_frame(name):
+    """Full-resolution comparison + PSNR delta against the CPU oracle (itself pinned to the goldens)."""
+    _z, meta = load_golden(name)
+    sd, (lq, depth, masks, gt) = case_tensors(meta)
+    with torch.no_grad():
+        ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"])
+        sr = _build(meta, sd)(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+    err = (sr - ref).abs().max().item()
+    dp = abs(psnr(sr, gt) - psnr(ref, gt))
+    print("%s: max|sr-oracle|=%.4g  PSNR delta=%.5f dB" % (name, err, dp))
+    assert err <= TOL_PIX
+    assert dp <= TOL_PSNR
+
+
+def test_other_seeds_and_batch():
+    """Fresh seeds / batch 3 / non-square frame, oracle as the checker."""
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=8, latent=256, which=tuple(range(14)))
+    layout = oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10)
+    for seed, (B, h, w) in ((11, (3, 20, 36)), (12, (1, 33, 17))):
+        sd = fill_state_dict(layout, seed=seed)
+        lq, depth, masks = synthetic_inputs(B, h, w, scale=8, seed=seed)
+        with torch.no_grad():
+            ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=8, which=meta["which"])
+            sr = _build(meta, sd)(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+        err = (sr - ref).abs().max().item()
+        print("seed %d B%d %dx%d: max|sr-oracle|=%.4g" % (seed, B, h, w, err))
+        assert err <= TOL_PIX
+
+
+def test_images_are_independent():
+    """Size-independent property (no op couples batch elements): a batch of 8 frames equals the
+    8 frames run one by one -- bit-exact, since every reduction is per image."""
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=8, latent=256, which=tuple(range(14)))
+    sd = fill_state_dict(oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10), seed=5)
+    net = _build(meta, sd)
+    lq, depth, masks = [t.cuda() for t in synthetic_inputs(8, 64, 64, scale=8, seed=5)]
+    with torch.no_grad():
+        full = net(lq, depth, masks)
+        for b in (0, 3, 7):
+            one = net(lq[b:b + 1], depth[b:b + 1], masks[b:b + 1])
+            assert (one[0] - full[b]).abs().max().item() <= 2e-3   # atomics order in the IN statistics
+
+
+def test_non_onehot_masks_take_the_general_path():
+    """Overlapping / fractional masks: the dynamic conv must fall back to its exact linear form."""
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=8, latent=256, which=tuple(range(14)))
+    sd = fill_state_dict(oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10), seed=6)
+    lq, depth, masks = synthetic_inputs(1, 16, 16, scale=8, seed=6)
+    g = torch.Generator().manual_seed(1)
+    masks = masks * 0.5 + 0.25 * (torch.rand(masks.shape, generator=g) > 0.8).float()
+    with torch.no_grad():
+        ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=8, which=meta["which"])
+        sr = _build(meta, sd)(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+    assert (sr - ref).abs().max().item() <= TOL_PIX
+
+
+def test_cpu_tensors_are_rejected():
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=8, latent=256, which=tuple(range(14)))
+    sd = fill_state_dict(oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10), seed=0)
+    net = _build(meta, sd)
+    lq, depth, masks = synthetic_inputs(1, 16, 16, scale=8, seed=0)
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        net(lq, depth, masks)
