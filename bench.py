@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the DepthNet hot path (BASELINE.json: HR frames/s, x8 SR 64x64 -> 512x512).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+
+A "step" is one forward pass of the generator over one batch of synthetic frames (BASELINE.json configs[1]:
+x8 inference, batch 64 per GPU, 3x64x64 LR + 1x64x64 depth + 10 depth masks -> 3x512x512, bf16 tensor-core
+math with fp32 accumulation, random-init weights).  For N > 1 the frames are sharded by rank (no collective on
+the data path) and the rate is the whole-job aggregate (weak scaling).
+
+Prints ONE JSON line:
+  value      frames/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e        frames/s through the public call ``net(LQ, Depth, DepthMaskList)`` with pinned HOST buffers: the
+             host->device copies of the inputs and the device->host read of the SR frames are inside the timed
+             region
+  roofline   the dominant kernel family of the step, measured live with CUDA events in a separate
+             instrumented pass (achieved algorithmic TFLOP/s or GB/s against MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle port of the reference's forward (literal form: 256-channel style-map convs),
+             timed on this box's host cores on a bounded sample (rank 0, N == 1 only)
+
+``--impl reference`` times the reference's own CPU algorithm (the oracle port -- the reference is a Python
+code base that cannot travel to the GPU box) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCALE = 8
+LR = 64
+WHICH = tuple(range(14))
+METRIC = "hr_frames_per_sec_x8_sr_64to512"
+UNIT = "frames/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tc_burst=float(d["bf16_tflops"]),
+                    tc_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = max([float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()] or [0.0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def _make_state(seed=0):
+    """The reference's own random init (our DepthNet consumes the RNG like the reference constructor)."""
+    import torch
+    import depth_aware_endoscopy_sr_b200 as dasr
+    torch.manual_seed(seed)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = dasr.DepthNet(which_ResBlk_depth=list(WHICH), in_nc=3, out_nc=3, nf=64, nb=16, scale=SCALE,
+                            input_para=10, depth_latent_ch=256, depthRangeNum=10, norm_type="weight_norm",
+                            use_trainable_params=True, norm_gamma=0, norm_beta=0)
+    return net
+
+
+def cpu_reference_rate(seconds_budget=20.0, batch=1, warmup=1, min_iters=3):
+    """frames/s of the CPU oracle port (the reference's algorithm, fp32, all host threads) on B=`batch` frames."""
+    import torch
+    from oracle import depthnet_oracle as oracle     # the checker, allowed here as the cpu_baseline leg
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    net = _make_state(0)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    lq, depth, masks = synthetic_inputs(batch, LR, LR, scale=SCALE, seed=0)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            oracle.depthnet_forward(sd, lq, depth, masks, scale=SCALE, which=WHICH)
+        t_all = time.time()
+        while len(times) < min_iters or (time.time() - t_all) < seconds_budget:
+            t0 = time.time()
+            oracle.depthnet_forward(sd, lq, depth, masks, scale=SCALE, which=WHICH)
+            times.append(time.time() - t0)
+            if len(times) >= 200:
+                break
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    from oracle import depthnet_oracle as oracle
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    net = _make_state(0)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sample_b = 2       # frames per step of the bounded sample (the workload is 64 frames per step)
+    lq, depth, masks = synthetic_inputs(sample_b, LR, LR, scale=SCALE, seed=0)
+    with torch.no_grad():
+        for _ in range(max(W, 1)):
+            oracle.depthnet_forward(sd, lq, depth, masks, scale=SCALE, which=WHICH)
+        t0 = time.time()
+        for _ in range(K):
+            oracle.depthnet_forward(sd, lq, depth, masks, scale=SCALE, which=WHICH)
+        dt = time.time() - t0
+    fps = sample_b * K / dt
+    cores = torch.get_num_threads()
+    sample = "%d steps of %d frames (x8, 64x64 LR) out of the 64-frame batch" % (K, sample_b)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "depthNet_SEAN_depthMask x8 inference, 64x64 LR + depth -> 512x512, CPU oracle "
+                                   "port of the reference forward", "batch_per_step": sample_b, "lr": [LR, LR]},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from depth_aware_endoscopy_sr_b200 import _lib
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().dasr_check_device())
+
+    K, W, B = args.steps, max(args.warmup, 3), args.batch
+    net = _make_state(0).to(dev).eval()
+    eng = net.engine()
+
+    # a few different input batches (rank-specific seeds), resident in HBM and mirrored in pinned host memory
+    n_sets = 3
+    host_sets, dev_sets = [], []
+    for i in range(n_sets):
+        lq, depth, masks = synthetic_inputs(B, LR, LR, scale=SCALE, seed=1000 * rank + i)
+        host_sets.append(tuple(t.pin_memory() for t in (lq, depth, masks)))
+        dev_sets.append(tuple(t.to(dev) for t in (lq, depth, masks)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        # ------------------------------------------------ device-resident throughput
+        for i in range(W):
+            net(*dev_sets[i % n_sets])
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            net(*dev_sets[i % n_sets])
+        e1.record()
+        barrier()
+        launches = _lib.launch_count() - n0
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ------------------------------------------------ end to end through the public call, host buffers
+        out_host = torch.empty(B, 3, SCALE * LR, SCALE * LR, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+        d2h = out_host.numel() * out_host.element_size()
+
+        def e2e_step(i):
+            lq, depth, masks = (t.to(dev, non_blocking=True) for t in host_sets[i % n_sets])
+            sr = net(lq, depth, masks)
+            out_host.copy_(sr, non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(K):
+            e2e_step(i)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    value = B * world * K / (ms_total * 1e-3)
+    e2e = B * world * K / (ms_e2e * 1e-3)
+
+    roof = None
+    cpu = None
+    if rank == 0:
+        roof = roofline_pass(net, dev_sets, B)
+        if world == 1 and not args.no_cpu:
+            fps, iters, cores = cpu_reference_rate(seconds_budget=args.cpu_seconds)
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d forwards of 1 frame (x8, 64x64 LR -> 512x512), median" % iters}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "depthNet_SEAN_depthMask x8 inference, batch %d per GPU, synthetic 3x64x64 LR + "
+                                   "1x64x64 depth + 10 masks -> 3x512x512, random-init weights" % B,
+                       "batch_per_gpu": B, "lr": [LR, LR], "scale": SCALE, "sharding": "frames by rank, no collective",
+                       "l2": "no flush: one step streams ~3.5 GB of activations (>> 126 MB L2) and the input batch "
+                             "rotates over %d sets" % n_sets},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def roofline_pass(net, dev_sets, B):
+    """Instrumented pass: CUDA events around every kernel launch of the engine (on the launching stream),
+    grouped by kernel family; reports the family that takes the largest share of the step."""
+    import torch
+    eng = net.engine()
+    peaks = _peaks()
+    with torch.no_grad():
+        eng.profile = []
+        for i in range(2):
+            net(*dev_sets[i % len(dev_sets)])
+        torch.cuda.synchronize()
+        eng.profile = []
+        reps = 3
+        for i in range(reps):
+            net(*dev_sets[i % len(dev_sets)])
+        torch.cuda.synchronize()
+        recs = eng.profile
+        eng.profile = None
+    fam = {}
+    for r in recs:
+        f = fam.setdefault(r["family"], dict(ms=0.0, n=0, flops=0.0, bytes=0.0, bound=r["bound"]))
+        f["ms"] += r["e0"].elapsed_time(r["e1"])
+        f["n"] += 1
+        f["flops"] += r["flops"]
+        f["bytes"] += r["bytes"]
+    total = sum(f["ms"] for f in fam.values())
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    name, f = top
+    table = {k: {"share": v["ms"] / total, "ms_per_launch": v["ms"] / v["n"], "launches_per_step": v["n"] // reps,
+                 "achieved": (v["flops"] / v["ms"] / 1e9) if v["bound"] == "tensor" else (v["bytes"] / v["ms"] / 1e6),
+                 "unit": "TFLOP/s" if v["bound"] == "tensor" else "GB/s"}
+             for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    if f["bound"] == "tensor":
+        ach, peak, unit = f["flops"] / f["ms"] / 1e9, peaks["tc_sustained"], "TFLOP/s"
+    else:
+        ach, peak, unit = f["bytes"] / f["ms"] / 1e6, peaks["hbm"], "GB/s"
+    return {"kernel": name, "bound": "tensor" if f["bound"] == "tensor" else "hbm", "achieved": ach, "peak": peak,
+            "unit": unit, "frac": ach / peak, "traffic": None, "peak_source": peaks["src"],
+            "ms_per_launch": f["ms"] / f["n"], "share_of_step": f["ms"] / total, "families": table}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

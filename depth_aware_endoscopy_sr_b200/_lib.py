@@ -50,6 +50,7 @@ def load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     lib.dasr_last_error.restype = C.c_char_p
     lib.dasr_version.restype = C.c_int
+    lib.dasr_launch_count.restype = C.c_int64
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     sigs = {
         "dasr_check_device": [],
@@ -73,9 +74,13 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTED = ["dasr_last_error", "dasr_version", "dasr_check_device", "dasr_conv_fwd", "dasr_pack_weights",
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize"]
+
+
+def launch_count() -> int:
+    return int(load().dasr_launch_count())
 
 
 def check(rc: int) -> None:

@@ -1,5 +1,6 @@
 // Error plumbing, device check and TMA tensor-map encoding for libdasr_b200.so.
 #include "dasr_internal.h"
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
@@ -65,6 +66,9 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     return DASR_OK;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -80,6 +84,7 @@ int num_sms() {
 
 extern "C" const char* dasr_last_error(void) { return dasr::g_err; }
 extern "C" int dasr_version(void) { return 100; }
+extern "C" int64_t dasr_launch_count(void) { return (int64_t)dasr::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int dasr_check_device(void) {
     int dev = 0;

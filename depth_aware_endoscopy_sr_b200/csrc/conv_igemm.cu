@@ -574,7 +574,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         if (sb > 8) sb = 8;
         if (sb > k.nch * k.taps) sb = k.nch * k.taps;
         k.SB = sb;
-        DASR_REQUIRE(sb >= 2, "not enough shared memory for the weight ring");
+        DASR_REQUIRE(sb >= 1, "not enough shared memory for the weight ring");
     }
     const size_t smem_bytes = (size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes + 1024;
 

@@ -23,6 +23,7 @@ int fail(int code, const char* fmt, ...);
 
 #define DASR_LAUNCH_OK()                                                                    \
     do {                                                                                    \
+        ::dasr::count_launch();                                                             \
         cudaError_t e__ = cudaGetLastError();                                               \
         if (e__ != cudaSuccess)                                                             \
             return ::dasr::fail(DASR_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
@@ -39,5 +40,6 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 int num_sms();
+void count_launch();   // bumps the counter behind dasr_launch_count()
 
 }  // namespace dasr

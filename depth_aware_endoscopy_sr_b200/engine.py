@@ -45,6 +45,19 @@ class Engine:
         self._scratch = None
         self._zero_bias = None
         self._device = None
+        # bench.py's instrumented pass: when a list, every launch appends
+        # {family, bound, flops, bytes, e0, e1} with CUDA events recorded on the launching stream
+        self.profile = None
+
+    def _timed(self, family, bound, flops, nbytes, fn):
+        if self.profile is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        self.profile.append(dict(family=family, bound=bound, flops=float(flops), bytes=float(nbytes), e0=e0, e1=e1))
+        return r
 
     # ------------------------------------------------------------------------------------------ packing
     def _named(self):
@@ -157,7 +170,23 @@ class Engine:
                 out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=x.device, dtype=BF16)
             else:
                 out = torch.empty(B, H, W, pk.cout, device=x.device, dtype=BF16)
-        return L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act, subsample=subsample, **kw)
+        if self.profile is None:
+            return L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act, subsample=subsample,
+                              **kw)
+        cin = x.shape[3]
+        flops = 2.0 * B * H * W * pk.cout * cin * pk.ks * pk.ks           # algorithmic (stride-1 grid)
+        if subsample == 2:
+            flops /= 4.0
+        nbytes = x.numel() * 2 + out.numel() * out.element_size() + pk.w.numel() * 2
+        for t in (kw.get("resid"), kw.get("y"), kw.get("gb_s")):
+            if t is not None:
+                nbytes += t.numel() * 2
+        epi_name = {L.EPI_STORE: "store", L.EPI_STATS: "stats", L.EPI_SEAN: "sean", L.EPI_SHUFFLE2: "shuffle",
+                    L.EPI_NCHW_F32: "nchw"}[epi]
+        family = "conv%dx%d_%dto%d_%s" % (pk.ks, pk.ks, cin, pk.cout, epi_name)
+        return self._timed(family, "tensor", flops, nbytes,
+                           lambda: L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act,
+                                              subsample=subsample, **kw))
 
     def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, vec):
         """actv and gb_s of one SEAN instance (they depend on the network inputs only, not on x)."""
@@ -167,17 +196,23 @@ class Engine:
         K, lat = sean.label_nc, sean.len_latent
         s = L.stream_ptr()
         actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
-        L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias),
-                                  L.ptr(actv), B, H, W, nf2, s))
+        self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
+                    lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight),
+                                                      L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
         stp = torch.empty(1, 1, B * K, lat, device=depth.device, dtype=BF16)
-        L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias), L.ptr(stp), B, K,
-                                   lat, s))
+        self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp.numel() * 2,
+                    lambda: L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias),
+                                                       L.ptr(stp), B, K, lat, s)))
         pk = self._packed[n + ".table"]
         table = torch.empty(1, 1, B * K, 9 * nf2, device=depth.device, dtype=BF16)
-        L.conv_fwd(stp, pk.w, self._zero_bias, table, Cout=9 * nf2, ks=1)
+        self._timed("style_table_gemm", "tensor", 2.0 * B * K * lat * 9 * nf2,
+                    stp.numel() * 2 + table.numel() * 2 + pk.w.numel() * 2,
+                    lambda: L.conv_fwd(stp, pk.w, self._zero_bias, table, Cout=9 * nf2, ks=1))
         gb_s = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
-        L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W,
-                                     nf2, s))
+        # K-DYN algorithmic bytes: write gb_s + read labels (u8) + read the table
+        self._timed("dynconv", "hbm", 0, gb_s.numel() * 2 + B * H * W + table.numel() * 2,
+                    lambda: L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag),
+                                                         L.ptr(gb_s), B, K, H, W, nf2, s)))
         return actv, gb_s
 
     def _dgb(self, p: str, blk, x, depth, labels, masks, flag, vec):

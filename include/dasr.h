@@ -38,6 +38,8 @@ const char* dasr_last_error(void);
 int dasr_version(void);
 /* 0 if the current device is a B200-class (sm_100) part, DASR_ERR_ARCH otherwise */
 int dasr_check_device(void);
+/* number of kernels this library has launched in the calling process so far (bench.py's gpu_launches) */
+int64_t dasr_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (tcgen05 / TMEM / TMA), stride 1, square kernel ks in {1,3,9}, zero padding

@@ -4,13 +4,16 @@ import numpy as np
 import pytest
 import torch
 
-from common import CASES, case_tensors, load_golden, oracle
+from common import CASES, INIT_CASES, case_tensors, load_golden, oracle
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", INIT_CASES + CASES)
 def test_oracle_forward_matches_reference(name):
     z, meta = load_golden(name)
     sd, (lq, depth, masks, gt) = case_tensors(meta)
+    chk = np.array([sum(v.double().sum().item() for v in sd.values()),
+                    sum(v.double().abs().sum().item() for v in sd.values())])
+    np.testing.assert_allclose(chk, z["sd_checksum"], rtol=1e-12)      # identical weights as the reference had
     cap = {}
     with torch.no_grad():
         sr = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"], cap=cap)
