@@ -12,12 +12,13 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdasr_b200.so")
+# DASR_LIB_PATH: developer override (tools/prof_stalls.py loads the -DDASR_PROFILE build)
+LIB_PATH = os.environ.get("DASR_LIB_PATH") or os.path.join(_HERE, "libdasr_b200.so")
 
 # --- enums (include/dasr.h)
 EPI_STORE, EPI_STATS, EPI_SEAN, EPI_SHUFFLE2, EPI_NCHW_F32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-PACK_CONV, PACK_CONVT, PACK_STYLE = 0, 1, 2
+PACK_CONV, PACK_CONVT, PACK_STYLE, PACK_ROWTAPS = 0, 1, 2, 3
 
 
 class ConvDesc(C.Structure):
@@ -26,7 +27,8 @@ class ConvDesc(C.Structure):
 
 
 class ConvArgs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s")]
+    _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s", "resid_f32",
+                                          "out_aux_f32")]
 
 
 class PackDesc(C.Structure):
@@ -55,16 +57,18 @@ def load() -> C.CDLL:
     sigs = {
         "dasr_check_device": [],
         "dasr_conv_fwd": [C.POINTER(ConvDesc), C.POINTER(ConvArgs), vp],
+        "dasr_conv_out9": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_pack_weights": [C.POINTER(PackDesc), i32, vp, vp],
         "dasr_conv_first": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_zero_insert2": [vp, vp, i32, i32, i32, i32, vp],
-        "dasr_add": [vp, vp, vp, i64, vp],
+        "dasr_add": [vp, vp, vp, vp, i64, vp],
+        "dasr_conv_stats_slots": [C.POINTER(ConvDesc)],
         "dasr_region_pool_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "dasr_mask_labels": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_actv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
-        "dasr_instats_finalize": [vp, vp, i32, i32, i32, vp],
+        "dasr_instats_finalize": [vp, vp, i32, i32, i32, i32, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -74,7 +78,7 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_pack_weights",
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_out9", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize"]
 
@@ -107,14 +111,23 @@ def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
 # ------------------------------------------------------------------------------------------------ wrappers
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, *, Cout: int, ks: int,
              epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
-             resid=None, stats=None, y=None, norm=None, gb_s=None) -> torch.Tensor:
+             resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None) -> torch.Tensor:
     """x: NHWC bf16 [B,H,W,Cin]."""
     B, H, W, Cin = x.shape
     d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, 0)
     a = ConvArgs(ptr(x, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
-                 ptr(stats), ptr(y), ptr(norm), ptr(gb_s))
+                 ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(resid_f32, torch.float32),
+                 ptr(out_aux_f32, torch.float32))
     check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
     return out
+
+
+def conv_stats_slots(B, H, W, Cin, Cout, ks=3) -> int:
+    d = ConvDesc(B, H, W, Cin, Cout, ks, EPI_STATS, 0, 1, 0, 0, 0)
+    n = load().dasr_conv_stats_slots(C.byref(d))
+    if n <= 0:
+        check(n)
+    return n
 
 
 def pack_weights(descs: Sequence[PackDesc], scratch: torch.Tensor) -> None:

@@ -27,9 +27,24 @@
 
 namespace dasr {
 
+// Optional in-kernel stall accounting (build with -DDASR_PROFILE; tools/prof_stalls.py reads it back).
+// slots: 0 mma:wait acc_empty  1 mma:wait a_full  2 mma:wait b_full  3 mma:issue  4 epi:wait acc_full
+//        5 epi:work            6 a-producer:wait a_empty  7 b-producer:wait b_empty  8 kernel total (CTA 0..)
+#ifdef DASR_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_DECL long long prof_t = clock64(); long long prof_acc[4] = {0, 0, 0, 0}
+#define PROF_LAP(i) do { long long n_ = clock64(); prof_acc[i] += n_ - prof_t; prof_t = n_; } while (0)
+#define PROF_FLUSH(base, n) do { for (int i_ = 0; i_ < (n); i_++) atomicAdd(&g_prof[(base) + i_], (unsigned long long)prof_acc[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_LAP(i)
+#define PROF_FLUSH(base, n)
+#endif
+
 constexpr int kMaxBStages = 96;
 constexpr int kMaxAStages = 4;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // 4 role warps + 8 epilogue warps
+constexpr int kMaxBias = 1152;
 
 struct ConvK {
     // geometry
@@ -51,6 +66,10 @@ struct ConvK {
     const __nv_bfloat16* y;
     const float* norm;
     const __nv_bfloat16* gb_s;
+    const float* resid_f32;        // SEAN: fp32 residual stream (takes precedence over resid)
+    float* out_aux_f32;            // SEAN: fp32 copy of the output (the residual stream of the next block)
+    int nslots;                    // STATS: partial-sum slots per image
+    int n_bias;                    // padded Cout (bias entries staged in shared memory)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -120,6 +139,112 @@ __device__ __forceinline__ void warp_colsum16(float* v, int lane) {
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// Fused SEAN epilogue of one tile for one thread (accumulator row m of every M block, the 16-column chunks of
+// its warp half):  out = act( relu?( IN(IN(y)) * (1 + gamma) + beta ) + resid ),  gamma/beta = acc + bias + gb_s.
+// The HBM operands of step i+1 are requested before step i is computed (register double buffering), so
+// their latency hides behind the TMEM load and the arithmetic of the previous step.
+struct SeanOps {
+    uint4 y0, y1, g0, g1, b0, b1, r0, r1;
+    float4 rf[4];
+    bool valid;
+    size_t pix;
+};
+
+template <int N_TILE, int NB>
+__device__ __forceinline__ void sean_load(const ConvK& p, SeanOps& o, int img, int q0, int w0, int m, int blk, int c0) {
+    constexpr int NF = N_TILE / 2;
+    const int q = q0 + blk * 128 + m;
+    const int h = q / p.Wp;
+    const int wl = q - h * p.Wp;
+    const int w = w0 + wl;
+    o.valid = (h < p.H) && (wl < p.Wt) && (w < p.W);
+    o.pix = ((size_t)img * p.H + h) * p.W + w;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    o.y0 = o.y1 = o.g0 = o.g1 = o.b0 = o.b1 = o.r0 = o.r1 = z4;
+    if (!o.valid) return;
+    const uint4* yp = reinterpret_cast<const uint4*>(p.y + o.pix * NF + c0);
+    o.y0 = __ldg(yp);
+    o.y1 = __ldg(yp + 1);
+    if (p.gb_s) {
+        const uint4* sp = reinterpret_cast<const uint4*>(p.gb_s + o.pix * N_TILE + c0);
+        o.g0 = __ldg(sp);
+        o.g1 = __ldg(sp + 1);
+        o.b0 = __ldg(sp + NF / 8);
+        o.b1 = __ldg(sp + NF / 8 + 1);
+    }
+    if (p.resid_f32) {
+        const float4* rp = reinterpret_cast<const float4*>(p.resid_f32 + o.pix * NF + c0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) o.rf[j] = __ldg(rp + j);
+    } else if (p.resid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + o.pix * NF + c0);
+        o.r0 = __ldg(rp);
+        o.r1 = __ldg(rp + 1);
+    }
+}
+
+template <int N_TILE, int NB>
+__device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, const float* bias_t, const float* norm_s,
+                                              int img, int q0, int w0, int m, int half) {
+    constexpr int NF = N_TILE / 2;
+    constexpr int CH = (NF + 31) / 32;     // 16-column chunks per warp half and M block
+    constexpr int STEPS = NB * CH;
+    if (half * 16 >= NF) return;
+    SeanOps ops[2];
+    sean_load<N_TILE, NB>(p, ops[0], img, q0, w0, m, 0, half * 16);
+#pragma unroll
+    for (int it = 0; it < STEPS; it++) {
+        const int blk = it / CH, c0 = half * 16 + (it % CH) * 32;
+        if (it + 1 < STEPS)
+            sean_load<N_TILE, NB>(p, ops[(it + 1) & 1], img, q0, w0, m, (it + 1) / CH, half * 16 + ((it + 1) % CH) * 32);
+        const SeanOps& o = ops[it & 1];
+        uint32_t vg[16], vb[16];
+        tmem_ld16(t_acc + blk * N_TILE + c0, vg);
+        tmem_ld16(t_acc + blk * N_TILE + NF + c0, vb);
+        tmem_ld_wait();
+        if (!o.valid) continue;
+        float yv[16], gs[16], bs[16], f[16];
+        unpack8(o.y0, yv);
+        unpack8(o.y1, yv + 8);
+        unpack8(o.g0, gs);
+        unpack8(o.g1, gs + 8);
+        unpack8(o.b0, bs);
+        unpack8(o.b1, bs + 8);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float g = __uint_as_float(vg[j]) + bias_t[c0 + j] + gs[j];
+            const float b = __uint_as_float(vb[j]) + bias_t[NF + c0 + j] + bs[j];
+            const float n = (yv[j] - norm_s[2 * (c0 + j)]) * norm_s[2 * (c0 + j) + 1];
+            float t = fmaf(n, 1.f + g, b);
+            if (p.inner_relu) t = fmaxf(t, 0.f);
+            f[j] = t;
+        }
+        if (p.resid_f32) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                f[4 * j] += o.rf[j].x;
+                f[4 * j + 1] += o.rf[j].y;
+                f[4 * j + 2] += o.rf[j].z;
+                f[4 * j + 3] += o.rf[j].w;
+            }
+        } else if (p.resid) {
+            float rr[16];
+            unpack8(o.r0, rr);
+            unpack8(o.r1, rr + 8);
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] += rr[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
+        store16(p.out + o.pix * NF + c0, f);
+        if (p.out_aux_f32) {
+            float4* op32 = reinterpret_cast<float4*>(p.out_aux_f32 + o.pix * NF + c0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) op32[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+    }
+}
+
 template <int SWZ, int N_TILE, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -136,6 +261,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __shared__ uint64_t acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float norm_s[2 * 128];
+    __shared__ float bias_s[kMaxBias];
+    __shared__ uint32_t tap_lo_s[81];     // descriptor-low-word offset of tap (t,u): ((t*Wp + u) * SWZ) >> 4
 
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -156,7 +283,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_empty[i], 8);
         }
         fence_mbar_init();
     }
@@ -165,6 +292,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tma_prefetch_desc(&mapB);
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_s);
+    for (int i = threadIdx.x; i < p.n_bias; i += kThreads) bias_s[i] = __ldg(p.bias + i);
+    if (threadIdx.x < p.taps) {
+        const int t = threadIdx.x / p.ks, u = threadIdx.x - t * p.ks;
+        tap_lo_s[threadIdx.x] = (uint32_t)((t * p.Wp + u) * SWZ) >> 4;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -174,8 +306,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (warp == 0) {
         // ===================================================== A producer: one halo box per K chunk
-        if (lane == 0) {
+        // (elect.sync under a warp-uniform branch: ptxas then issues TMA/MMA straight from uniform registers;
+        //  a `lane == 0` test costs a 72-cycle waterfall loop per tcgen05.mma -- tools/rate_probe.cu)
+        if (elect_one()) {
             uint32_t a_it = 0;
+            PROF_DECL;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 int r = tile - img * tiles_per_img;
@@ -188,19 +323,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (int c = 0; c < p.nch; c++) {
                     const int sa = a_it % p.SA;
                     const uint32_t ph = (a_it / p.SA) & 1;
+                    PROF_LAP(1);
                     mbar_wait(&a_empty[sa], ph ^ 1);
+                    PROF_LAP(0);
                     mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
                     tma_load_4d(a_smem + (size_t)sa * p.a_stage_bytes, &mapA, &a_full[sa], c * KC,
                                 w0 - p.pad, r0 - p.pad, img);
                     a_it++;
                 }
             }
+            PROF_FLUSH(6, 1);
         }
     } else if (warp == 3) {
         // ===================================================== B producer: weight tiles (tap, chunk)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t b_it = 0;
             bool first = true;
+            PROF_DECL;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.ntn;
                 if (p.b_resident && !first) continue;
@@ -212,7 +351,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         } else {
                             sb = b_it % p.SB;
                             const uint32_t ph = (b_it / p.SB) & 1;
+                            PROF_LAP(1);
                             mbar_wait(&b_empty[sb], ph ^ 1);
+                            PROF_LAP(0);
                             b_it++;
                         }
                         mbar_expect_tx(&b_full[sb], p.b_tx_bytes);
@@ -222,14 +363,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 }
                 first = false;
             }
+            PROF_FLUSH(7, 1);
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (single thread)
-        if (lane == 0) {
+        // ===================================================== MMA issuer (single elected thread)
+        if (elect_one()) {
+            // Descriptor low words are additive in the smem address: lo(addr + x) = lo(addr) + (x >> 4).  All
+            // per-tap / per-block / per-k offsets are precomputed (tap_lo_s) or immediates, so the loop body is a
+            // handful of 32-bit adds per tcgen05.mma (the tensor pipe, not this thread, must be the limiter).
             const uint32_t idesc = make_idesc_bf16(128, N_TILE);
-            const uint64_t desc_hi = make_smem_desc<SWZ>(0, 0) & ~0x3FFFull;
+            const uint64_t desc0 = make_smem_desc<SWZ>(0, 0);
+            const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
+            const uint32_t lo_flags = (uint32_t)desc0 & ~0x3FFFu;
+            const uint32_t a_lo0 = lo_flags | ((smem_u32(a_smem) & 0x3FFFFu) >> 4);
+            const uint32_t b_lo0 = lo_flags | ((smem_u32(b_smem) & 0x3FFFFu) >> 4);
+            const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_stage_lo = p.b_stage_bytes >> 4;
+            constexpr uint32_t BLK_LO = (128u * SWZ) >> 4;
             uint32_t a_it = 0, b_it = 0, acc_it = 0;
             bool first = true;
+            PROF_DECL;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 int r = tile % tiles_per_img;
                 r %= (p.tiles_per_strip * p.ntn);
@@ -238,37 +390,52 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int soff = q0 - (q0 / p.Wp) * p.Wp;  // first output row inside the smem patch
                 const int buf = acc_it % NACC;
                 const uint32_t aph = (acc_it / NACC) & 1;
+                PROF_LAP(3);
                 mbar_wait(&acc_empty[buf], aph ^ 1);
+                PROF_LAP(0);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
                 for (int c = 0; c < p.nch; c++) {
                     const int sa = a_it % p.SA;
+                    PROF_LAP(3);
                     mbar_wait(&a_full[sa], (a_it / p.SA) & 1);
+                    PROF_LAP(1);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_smem + (size_t)sa * p.a_stage_bytes);
-                    for (int tap = 0; tap < p.taps; tap++) {
-                        int sb;
-                        if (p.b_resident) {
-                            sb = c * p.taps + tap;
-                            if (first) mbar_wait(&b_full[sb], 0);
-                        } else {
-                            sb = b_it % p.SB;
-                            mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
+                    const uint32_t a_lo_tile = a_lo0 + sa * a_stage_lo + (uint32_t)soff * (SWZ >> 4);
+                    if (p.b_resident) {
+                        if (first) {
+                            for (int tap = 0; tap < p.taps; tap++) mbar_wait(&b_full[c * p.taps + tap], 0);
+                            tc_fence_after();
                         }
-                        tc_fence_after();
-                        const uint32_t b_base = smem_u32(b_smem + (size_t)sb * p.b_stage_bytes);
-                        const int t = tap / p.ks, u = tap - t * p.ks;
-                        const uint32_t a_tap = a_base + (uint32_t)(soff + t * p.Wp + u) * SWZ;
+                        uint32_t b_lo = b_lo0 + (uint32_t)(c * p.taps) * b_stage_lo;
+#pragma unroll 1
+                        for (int tap = 0; tap < p.taps; tap++, b_lo += b_stage_lo) {
+                            const uint32_t a_lo = a_lo_tile + tap_lo_s[tap];
 #pragma unroll
-                        for (int blk = 0; blk < NB; blk++) {
+                            for (int blk = 0; blk < NB; blk++) {
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; k++) {
-                                const uint64_t da = desc_hi | (((a_tap + blk * 128 * SWZ + k * 32) & 0x3FFFFu) >> 4);
-                                const uint64_t db = desc_hi | (((b_base + k * 32) & 0x3FFFFu) >> 4);
-                                umma_bf16(d_tmem + blk * N_TILE, da, db, idesc, (c | tap | k) != 0);
+                                for (int k = 0; k < KSTEPS; k++)
+                                    umma_bf16_lohi(d_tmem + blk * N_TILE, a_lo + blk * BLK_LO + k * 2, b_lo + k * 2,
+                                                   desc_hi, idesc, (c | tap | k) != 0);
                             }
                         }
-                        if (!p.b_resident) {
+                    } else {
+#pragma unroll 1
+                        for (int tap = 0; tap < p.taps; tap++) {
+                            const int sb = b_it % p.SB;
+                            PROF_LAP(3);
+                            mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
+                            PROF_LAP(2);
+                            tc_fence_after();
+                            const uint32_t a_lo = a_lo_tile + tap_lo_s[tap];
+                            const uint32_t b_lo = b_lo0 + sb * b_stage_lo;
+#pragma unroll
+                            for (int blk = 0; blk < NB; blk++) {
+#pragma unroll
+                                for (int k = 0; k < KSTEPS; k++)
+                                    umma_bf16_lohi(d_tmem + blk * N_TILE, a_lo + blk * BLK_LO + k * 2, b_lo + k * 2,
+                                                   desc_hi, idesc, (c | tap | k) != 0);
+                            }
                             umma_commit(&b_empty[sb]);
                             b_it++;
                         }
@@ -280,13 +447,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 acc_it++;
                 first = false;
             }
+            PROF_LAP(3);
+            PROF_FLUSH(0, 4);
         }
     } else if (warp >= 4) {
-        // ===================================================== epilogue warps
+        // ===================================================== epilogue warps (8: 2 per TMEM lane quadrant)
+        // warp w may only read TMEM lanes 32*(w%4)..+31; the two warps of a quadrant take the even / odd
+        // 16-column chunks.  Operands that live in HBM (residual, y, gb_s) are requested BEFORE the TMEM load
+        // so that their latency overlaps it; bias / norm come from shared memory.
         const int ew = warp & 3;              // TMEM lane group
+        const int half = (warp - 4) >> 2;     // 0: even chunks, 1: odd chunks
         const int m = ew * 32 + lane;         // accumulator row inside an M block
-        const int et = threadIdx.x - 128;     // 0..127
+        const int et = threadIdx.x - 128;     // 0..255
         uint32_t acc_it = 0;
+        PROF_DECL;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int img = tile / tiles_per_img;
             int r = tile - img * tiles_per_img;
@@ -298,18 +472,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int w0 = strip * p.Wt;
             const int buf = acc_it % NACC;
             const uint32_t aph = (acc_it / NACC) & 1;
+            const float* bias_t = bias_s + nt * N_TILE;
 
             if (p.epi == DASR_EPI_SEAN) {
                 // (mean, scale) of this image for the nf = N_TILE/2 normalised channels
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 if (et < N_TILE) norm_s[et] = __ldg(p.norm + (size_t)img * N_TILE + et);
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
             }
 
+            PROF_LAP(1);
             mbar_wait(&acc_full[buf], aph);
+            PROF_LAP(0);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
 
+            if (p.epi == DASR_EPI_SEAN) {
+                sean_epilogue<N_TILE, NB>(p, t_acc, bias_t, norm_s, img, q0, w0, m, half);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                acc_it++;
+                continue;
+            }
 #pragma unroll 1
             for (int blk = 0; blk < NB; blk++) {
                 const int q = q0 + blk * 128 + m;
@@ -329,19 +514,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
                     __nv_bfloat16* op = p.out + pix * p.Cout + nt * N_TILE;
                     const __nv_bfloat16* rp = p.resid ? p.resid + pix * p.Cout + nt * N_TILE : nullptr;
+                    const int slot = ((strip * p.tiles_per_strip + tps) * NB + blk) * 4 + ew;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                    for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
+                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+                        if (rp && valid) {
+                            r0 = __ldg(reinterpret_cast<const uint4*>(rp + c0));
+                            r1 = __ldg(reinterpret_cast<const uint4*>(rp + c0) + 1);
+                        }
                         uint32_t v[16];
                         tmem_ld16(t_blk + c0, v);
                         tmem_ld_wait();
                         float f[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j++)
-                            f[j] = __uint_as_float(v[j]) + __ldg(p.bias + nt * N_TILE + c0 + j);
+                        for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_t[c0 + j];
                         if (p.epi == DASR_EPI_STORE) {
-                            if (rp && valid) {
+                            if (rp) {
                                 float rr[16];
-                                load16(rp + c0, rr);
+                                unpack8(r0, rr);
+                                unpack8(r1, rr + 8);
 #pragma unroll
                                 for (int j = 0; j < 16; j++) f[j] += rr[j];
                             }
@@ -349,11 +540,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
                             if (valid) store16(op + c0, f);
                         } else {
-                            if (valid) store16(op + c0, f);
+                            // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
+                            uint4 o0 = pack8(f), o1 = pack8(f + 8);
+                            if (valid) {
+                                reinterpret_cast<uint4*>(op + c0)[0] = o0;
+                                reinterpret_cast<uint4*>(op + c0)[1] = o1;
+                            }
                             float s1[16], s2[16];
+                            unpack8(o0, s1);
+                            unpack8(o1, s1 + 8);
 #pragma unroll
                             for (int j = 0; j < 16; j++) {
-                                float x = valid ? f[j] : 0.f;
+                                const float x = valid ? s1[j] : 0.f;
                                 s1[j] = x;
                                 s2[j] = x * x;
                             }
@@ -362,60 +560,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             if (!(lane & 1)) {
                                 const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
                                                 ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                                float* sp = p.stats + ((size_t)img * p.Cout + nt * N_TILE + c0 + col) * 2;
-                                atomicAdd(sp, s1[0]);
-                                atomicAdd(sp + 1, s2[0]);
+                                // one writer per (image, slot, channel): deterministic, no atomics
+                                float* sp = p.stats + (((size_t)img * p.nslots + slot) * p.Cout + nt * N_TILE + c0 + col) * 2;
+                                sp[0] = s1[0];
+                                sp[1] = s2[0];
                             }
-                        }
-                    }
-                } else if (p.epi == DASR_EPI_SEAN) {
-                    constexpr int NF = N_TILE / 2;
-                    const size_t pix = ((size_t)img * p.H + h) * p.W + w;
-                    const __nv_bfloat16* yp = p.y + pix * NF;
-                    const __nv_bfloat16* sp = p.gb_s ? p.gb_s + pix * N_TILE : nullptr;
-                    const __nv_bfloat16* rp = p.resid ? p.resid + pix * NF : nullptr;
-                    __nv_bfloat16* op = p.out + pix * NF;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < NF; c0 += 16) {
-                        uint32_t vg[16], vb[16];
-                        tmem_ld16(t_blk + c0, vg);
-                        tmem_ld16(t_blk + NF + c0, vb);
-                        tmem_ld_wait();
-                        if (valid) {
-                            float yv[16], o[16];
-                            load16(yp + c0, yv);
-                            float gs[16], bs[16];
-                            if (sp) {
-                                load16(sp + c0, gs);
-                                load16(sp + NF + c0, bs);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; j++) gs[j] = bs[j] = 0.f;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const float g = __uint_as_float(vg[j]) + __ldg(p.bias + c0 + j) + gs[j];
-                                const float b = __uint_as_float(vb[j]) + __ldg(p.bias + NF + c0 + j) + bs[j];
-                                const float n = (yv[j] - norm_s[2 * (c0 + j)]) * norm_s[2 * (c0 + j) + 1];
-                                float t = fmaf(n, 1.f + g, b);
-                                if (p.inner_relu) t = fmaxf(t, 0.f);
-                                o[j] = t;
-                            }
-                            if (rp) {
-                                float rr[16];
-                                load16(rp + c0, rr);
-#pragma unroll
-                                for (int j = 0; j < 16; j++) o[j] += rr[j];
-                            }
-#pragma unroll
-                            for (int j = 0; j < 16; j++) o[j] = apply_act(o[j], p.act);
-                            store16(op + c0, o);
                         }
                     }
                 } else if (p.epi == DASR_EPI_SHUFFLE2) {
                     const int Cq = p.Cout >> 2;  // channels after the shuffle
 #pragma unroll 1
-                    for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                    for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
                         uint32_t v[16];
                         tmem_ld16(t_blk + c0, v);
                         tmem_ld_wait();
@@ -426,13 +581,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             float f[16];
 #pragma unroll
                             for (int j = 0; j < 16; j++)
-                                f[j] = apply_act(__uint_as_float(v[j]) + __ldg(p.bias + n0 + j), p.act);
+                                f[j] = apply_act(__uint_as_float(v[j]) + bias_t[c0 + j], p.act);
                             store16(p.out + pix * Cq + c, f);
                         }
                     }
                 } else {  // DASR_EPI_NCHW_F32
 #pragma unroll 1
-                    for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                    for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
                         uint32_t v[16];
                         tmem_ld16(t_blk + c0, v);
                         tmem_ld_wait();
@@ -441,7 +596,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             for (int j = 0; j < 16; j++) {
                                 const int co = nt * N_TILE + c0 + j;
                                 if (co < p.Cout) {
-                                    float f = apply_act(__uint_as_float(v[j]) + __ldg(p.bias + co), p.act);
+                                    float f = apply_act(__uint_as_float(v[j]) + bias_t[c0 + j], p.act);
                                     if (p.clamp01) f = fminf(fmaxf(f, 0.f), 1.f);
                                     p.out_f32[(((size_t)img * p.Cout + co) * p.H + h) * p.W + w] = f;
                                 }
@@ -455,6 +610,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             acc_it++;
         }
+        PROF_LAP(1);
+#ifdef DASR_PROFILE
+        if (threadIdx.x == 128) PROF_FLUSH(4, 2);
+#endif
     }
 
     tc_fence_before();
@@ -471,7 +630,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, 
     int dev = 0;
     DASR_CUDA_OK(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
-        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
         configured[dev & 63] = true;
     }
     int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
@@ -495,6 +654,30 @@ static int dispatch_n(int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, 
 }  // namespace dasr
 
 using namespace dasr;
+
+#ifdef DASR_PROFILE
+extern "C" int dasr_prof_read(unsigned long long* host_out, int reset) {
+    DASR_CUDA_OK(cudaDeviceSynchronize());
+    DASR_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        DASR_CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof z));
+    }
+    return DASR_OK;
+}
+#endif
+
+extern "C" int dasr_conv_stats_slots(const dasr_conv_desc* d) {
+    DASR_REQUIRE(d && d->W > 0 && d->H > 0 && (d->ks == 1 || d->ks == 3 || d->ks == 9), "bad descriptor");
+    const int NB = 2, max_wt = 128;
+    const int n_strips = (d->W + max_wt - 1) / max_wt;
+    const int Wt = (d->W + n_strips - 1) / n_strips;
+    const int Wp = Wt + d->ks - 1;
+    const int span = (d->H - 1) * Wp + Wt;
+    const int blocks = (span + 127) / 128;
+    const int tiles_per_strip = (blocks + NB - 1) / NB;
+    return n_strips * tiles_per_strip * NB * 4;
+}
 
 extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -533,6 +716,8 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         DASR_REQUIRE(a->y && a->norm, "SEAN epilogue needs y and norm");
     }
     if (d->epi == DASR_EPI_STATS) DASR_REQUIRE(a->stats, "STATS epilogue needs a stats buffer");
+    k.n_bias = k.ntn * n_tile;
+    DASR_REQUIRE(k.n_bias <= kMaxBias, "Cout %d too large (max %d)", d->Cout, kMaxBias);
     if (d->epi == DASR_EPI_SHUFFLE2) DASR_REQUIRE(d->Cout % 64 == 0, "shuffle needs Cout multiple of 64");
 
     // strips / tiles
@@ -553,7 +738,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.b_tx_bytes = (uint32_t)n_tile * SWZ;
     k.b_stage_bytes = (k.b_tx_bytes + 1023u) & ~1023u;
 
-    const size_t budget = 220 * 1024;
+    const size_t budget = 217 * 1024;   // + 1 KB alignment slack + ~7 KB static = 227 KB
     const size_t all_b = (size_t)k.nch * k.taps * k.b_stage_bytes;
     k.SA = 2;
     if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
@@ -590,6 +775,9 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.y = (const __nv_bfloat16*)a->y;
     k.norm = a->norm;
     k.gb_s = (const __nv_bfloat16*)a->gb_s;
+    k.resid_f32 = a->resid_f32;
+    k.out_aux_f32 = a->out_aux_f32;
+    k.nslots = k.n_strips * k.tiles_per_strip * NB * 4;
 
     // tensor maps
     CUtensorMap mA, mB;

@@ -96,10 +96,17 @@ __global__ void zero_insert2_kernel(const uint4* __restrict__ x, uint4* __restri
     }
 }
 
-__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, size_t n8) {
+__global__ void add_kernel(const uint4* __restrict__ a, const float4* __restrict__ a32, const uint4* __restrict__ b,
+                           uint4* __restrict__ out, size_t n8) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         float fa[8], fb[8];
-        unpack8f(__ldg(a + i), fa);
+        if (a32) {
+            const float4 lo = __ldg(a32 + 2 * i), hi = __ldg(a32 + 2 * i + 1);
+            fa[0] = lo.x; fa[1] = lo.y; fa[2] = lo.z; fa[3] = lo.w;
+            fa[4] = hi.x; fa[5] = hi.y; fa[6] = hi.z; fa[7] = hi.w;
+        } else {
+            unpack8f(__ldg(a + i), fa);
+        }
         unpack8f(__ldg(b + i), fb);
 #pragma unroll
         for (int j = 0; j < 8; j++) fa[j] += fb[j];
@@ -191,46 +198,45 @@ __global__ void mask_labels_kernel(const float* __restrict__ masks, uint8_t* __r
 }
 
 // ------------------------------------------------------------------------------------ actv
-// thread = (pixel, 8-channel group); out NHWC bf16.  Weights transposed to smem [9][C].
+// Store-bandwidth kernel (2*C bytes per pixel out, 4 bytes in).  Thread = (8-channel group g, pixel slot): its
+// 72 weights + 8 biases live in REGISTERS for the whole block (re-reading them from shared memory per pixel made
+// v1 LDS-bound at 480 GB/s); lanes 0..G-1 of a pixel write one contiguous 2*C-byte row.
+template <int G>
 __global__ void __launch_bounds__(256) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
-                                                   const float* __restrict__ bias, uint4* __restrict__ out, int B,
-                                                   int H, int W, int C) {
-    extern __shared__ float sm[];
-    float* ws = sm;          // [9][C]
-    float* bs = sm + 9 * C;  // [C]
-    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
-        const int c = i / 9, t = i - c * 9;
-        ws[t * C + c] = w[i];
+                                                   const float* __restrict__ bias, uint4* __restrict__ out, int H,
+                                                   int W, int pix_per_block) {
+    constexpr int C = G * 8;
+    constexpr int SLOTS = 256 / G;
+    const int g = threadIdx.x % G, slot = threadIdx.x / G;
+    float wr[9][8], br[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        br[j] = __ldg(bias + g * 8 + j);
+#pragma unroll
+        for (int t = 0; t < 9; t++) wr[t][j] = __ldg(w + (g * 8 + j) * 9 + t);
     }
-    for (int i = threadIdx.x; i < C; i += blockDim.x) bs[i] = bias[i];
-    __syncthreads();
-    const int G = C / 8;
-    const size_t total = (size_t)B * H * W * G;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int gch = i % G;
-        const size_t pix = i / G;
-        const int x = pix % W;
-        const int y = (pix / W) % H;
-        const int b = pix / ((size_t)W * H);
-        const float* dp = depth + (size_t)b * H * W;
-        float d[9];
+    const int HW = H * W;
+    const float* dp = depth + (size_t)blockIdx.y * HW;
+    uint4* op = out + (size_t)blockIdx.y * HW * G;
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(p0 + pix_per_block, HW);
+    for (int pix = p0 + slot; pix < p1; pix += SLOTS) {
+        const int y = pix / W, x = pix - y * W;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = br[j];
 #pragma unroll
         for (int t = 0; t < 3; t++)
 #pragma unroll
             for (int u = 0; u < 3; u++) {
                 const int yy = y + t - 1, xx = x + u - 1;
-                d[t * 3 + u] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dp + (size_t)yy * W + xx) : 0.f;
+                const float d = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dp + yy * W + xx) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(d, wr[t * 3 + u][j], acc[j]);
             }
-        float acc[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = bs[gch * 8 + j];
-#pragma unroll
-        for (int t = 0; t < 9; t++)
-#pragma unroll
-            for (int j = 0; j < 8; j++) acc[j] = fmaf(d[t], ws[t * C + gch * 8 + j], acc[j]);
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
-        out[i] = pack8f(acc);
+        op[(size_t)pix * G + g] = pack8f(acc);
     }
 }
 
@@ -359,18 +365,27 @@ __global__ void dynconv_masks_kernel(const __nv_bfloat16* __restrict__ table, co
 }
 
 // ------------------------------------------------------------------------------------ IN statistics
-__global__ void instats_finalize_kernel(const float* __restrict__ stats, float* __restrict__ norm, int n, float inv_hw) {
+__global__ void instats_finalize_kernel(const float* __restrict__ stats, float* __restrict__ norm, int n, int C,
+                                        int nslots, float inv_hw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float mean = stats[2 * i] * inv_hw;
-    float var = stats[2 * i + 1] * inv_hw - mean * mean;
+    const int b = i / C, c = i - b * C;
+    const float2* sp = reinterpret_cast<const float2*>(stats) + (size_t)b * nslots * C + c;
+    float s1 = 0.f, s2 = 0.f;
+    for (int s = 0; s < nslots; s++) {   // fixed order: bit-reproducible
+        const float2 v = __ldg(sp + (size_t)s * C);
+        s1 += v.x;
+        s2 += v.y;
+    }
+    const float mean = s1 * inv_hw;
+    float var = s2 * inv_hw - mean * mean;
     var = fmaxf(var, 0.f);
     const float eps = 1e-5f;
     // IN(IN(y)) = (y - mean) * (var+eps)^-1/2 * (var/(var+eps) + eps)^-1/2
-    const float s1 = rsqrtf(var + eps);
-    const float s2 = rsqrtf(var * s1 * s1 + eps);
+    const float r1 = rsqrtf(var + eps);
+    const float r2 = rsqrtf(var * r1 * r1 + eps);
     norm[2 * i] = mean;
-    norm[2 * i + 1] = s1 * s2;
+    norm[2 * i + 1] = r1 * r2;
 }
 
 static inline int grid_for(size_t n, int block, int cap = 148 * 16) {
@@ -401,9 +416,9 @@ extern "C" int dasr_zero_insert2(const void* x, void* out, int B, int H, int W, 
     return DASR_OK;
 }
 
-extern "C" int dasr_add(const void* a, const void* b, void* out, int64_t n, void* stream) {
-    DASR_REQUIRE(a && b && out && n % 8 == 0, "bad arguments (n must be a multiple of 8)");
-    add_kernel<<<grid_for((size_t)n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, (size_t)n / 8);
+extern "C" int dasr_add(const void* a, const float* a32, const void* b, void* out, int64_t n, void* stream) {
+    DASR_REQUIRE((a || a32) && b && out && n % 8 == 0, "bad arguments (n must be a multiple of 8)");
+    add_kernel<<<grid_for((size_t)n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const float4*)a32, (const uint4*)b, (uint4*)out, (size_t)n / 8);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -428,8 +443,19 @@ extern "C" int dasr_mask_labels(const float* masks, uint8_t* labels, int32_t* fl
 extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bias, void* out, int B, int H, int W,
                              int C, void* stream) {
     DASR_REQUIRE(depth && w && bias && out && C % 8 == 0, "bad arguments");
-    const size_t total = (size_t)B * H * W * (C / 8);
-    actv_kernel<<<grid_for(total, 256), 256, 10 * C * sizeof(float), (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, B, H, W, C);
+    DASR_REQUIRE(C == 128 || C == 64, "actv: C (= 2*nf) must be 64 or 128 (got %d)", C);
+    DASR_REQUIRE((size_t)H * W < 0x7fffffffull, "frame too large");
+    // enough blocks to fill the GPU, few enough that the per-thread weight preload (80 floats) is amortised
+    const int HW = H * W;
+    int per_img = (2 * num_sms() + B - 1) / B;
+    if (per_img < 1) per_img = 1;
+    int ppb = (HW + per_img - 1) / per_img;
+    if (ppb < 256) ppb = 256;
+    const int gx = (HW + ppb - 1) / ppb;
+    if (C == 128)
+        actv_kernel<16><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, ppb);
+    else
+        actv_kernel<8><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, ppb);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -467,10 +493,10 @@ extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const 
     return DASR_OK;
 }
 
-extern "C" int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, void* stream) {
-    DASR_REQUIRE(stats && norm && HW > 0, "bad arguments");
+extern "C" int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, int nslots, void* stream) {
+    DASR_REQUIRE(stats && norm && HW > 0 && nslots > 0, "bad arguments");
     const int n = B * C;
-    instats_finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, norm, n, 1.f / (float)HW);
+    instats_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, norm, n, C, nslots, 1.f / (float)HW);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -72,6 +72,13 @@ __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ 
             dst[(size_t)row * I + c] = __float2bfloat16(w);
             continue;
         }
+        if (d.mode == DASR_PACK_ROWTAPS) {
+            // K-OUT9 operand: one [32][I] matrix per vertical tap t, row = u*O + o (horizontal taps folded into N)
+            w = d.v[(((size_t)o * I + c) * ks + t) * ks + u] * sc[o];
+            dst[((size_t)t * 32 + u * O + o) * I + c] = __float2bfloat16(w);
+            if (kk == 0 && d.dst_bias) d.dst_bias[o] = d.bias ? d.bias[o] : 0.f;
+            continue;
+        }
         if (d.mode == DASR_PACK_CONV) {
             w = d.v[(((size_t)o * I + c) * ks + t) * ks + u] * sc[o];
         } else {  // ConvTranspose2d weight [I][O][ks][ks] as an ordinary conv: flip taps, swap in/out

@@ -116,6 +116,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with the descriptors given as (low word, shared high word): the low word is additive in the operand
+// address (addr >> 4), so the issue loop only does 32-bit adds.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has retired.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile(

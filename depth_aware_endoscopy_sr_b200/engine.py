@@ -136,7 +136,12 @@ class Engine:
             add_wn("upscale2.0", shuffle_r=2)
             add_wn("upscale2.3")
         add_wn("upscale3.0", shuffle_r=2)
-        add("conv_output", P("conv_output.weight"), None, P("conv_output.bias"), rows_pad=16)
+        wq = torch.zeros(9 * 32, 32, device=device, dtype=BF16)
+        bq = torch.zeros(3, device=device, dtype=torch.float32)
+        self._descs.append(L.pack_desc(P("conv_output.weight"), wq, bias=P("conv_output.bias"), dst_bias=bq,
+                                       mode=L.PACK_ROWTAPS))
+        rows_total += 3
+        self._packed["conv_output"] = _Packed(wq, bq, 3, 32, 9)
         self._scratch = torch.zeros(rows_total, device=device, dtype=torch.float32)
         self._zero_bias = torch.zeros(9 * 2 * 64, device=device, dtype=torch.float32)
         self._device = device
@@ -215,25 +220,31 @@ class Engine:
                                                          L.ptr(gb_s), B, K, H, W, nf2, s)))
         return actv, gb_s
 
-    def _dgb(self, p: str, blk, x, depth, labels, masks, flag, vec):
-        """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834)."""
+    def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, vec):
+        """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834).  ``x`` is the bf16 copy of the block input
+        (GEMM operand), ``x32`` its fp32 residual stream (None for the first block: the bf16 tensor is exact).
+        Returns (bf16 output, fp32 output)."""
         lib = L.load()
         B, H, W, nf = x.shape
         s = L.stream_ptr()
-        stats = torch.zeros(2, B, nf, 2, device=x.device, dtype=torch.float32)
+        nslots = L.conv_stats_slots(B, H, W, nf, nf)
+        stats = torch.empty(B, nslots, nf, 2, device=x.device, dtype=torch.float32)
         norm = torch.empty(2, B, nf, 2, device=x.device, dtype=torch.float32)
         cur = x
+        out32 = torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32)
         for j, sean in ((1, blk.norm1), (2, blk.norm2)):
             n = "%s.norm%d" % (p, j)
             actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, vec)
-            y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats[j - 1])
-            L.check(lib.dasr_instats_finalize(L.ptr(stats[j - 1]), L.ptr(norm[j - 1]), B, nf, H * W, s))
+            y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats)
+            self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
+                        lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), B, nf, H * W,
+                                                                  nslots, s)))
             if j == 1:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
             else:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm[1], gb_s=gb_s,
-                                 resid=x)
-        return cur
+                                 resid=x if x32 is None else None, resid_f32=x32, out_aux_f32=out32)
+        return cur, out32
 
     def _classic(self, p: str, x):
         """Classic_Residual_Block.forward (sftmd_arch.py:147-151)."""
@@ -292,42 +303,48 @@ class Engine:
 
         # ---- head + trunk (sftmd_arch.py:920-931)
         fea_bef = self._conv(self._conv(f0, "head.0", act=L.ACT_LRELU), "head.2", act=L.ACT_LRELU)
-        x = fea_bef
+        x, x32 = fea_bef, None      # x32: fp32 residual stream of the trunk (bf16 copies feed the GEMMs)
         order = net.block_order()
 
-        def run_block(i, x):
+        def run_block(i, x, x32):
             if i in net.which_ResBlk_depth:
                 if x.shape[1] != h or x.shape[2] != w:
                     raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
                                               "%d at x%d) are not implemented yet" % (i, net.scale))
-                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, depth, labels, masks, flag, vec)
-            return self._classic("classic-residual%d" % (i + 1), x)
+                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, labels, masks, flag, vec)
+            return self._classic("classic-residual%d" % (i + 1), x), None
 
         for i, pos in order:
             if pos == "trunk":
-                x = run_block(i, x)
+                x, x32 = run_block(i, x, x32)
                 if cap is not None:
                     cap["block%d.out" % (i + 1)] = x
         if cap is not None:
             cap["fea_bef"] = fea_bef
         add = torch.empty_like(x)
-        L.check(lib.dasr_add(L.ptr(x), L.ptr(fea_bef), L.ptr(add), x.numel(), s))
+        self._timed("add", "hbm", 0, x.numel() * (2 + 2 + (4 if x32 is not None else 2)),
+                    lambda: L.check(lib.dasr_add(L.ptr(x), L.ptr(x32), L.ptr(fea_bef), L.ptr(add), x.numel(), s)))
         x = add
 
         # ---- tail (sftmd_arch.py:932-950)
         if net.scale == 8:
             x = self._conv(x, "upscale1.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
             x = self._conv(x, "upscale1.3", act=L.ACT_LRELU)
-        x = run_block(order[-2][0], x)
+        x, _ = run_block(order[-2][0], x, None)
         if net.scale >= 4:
             x = self._conv(x, "upscale2.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
             x = self._conv(x, "upscale2.3", act=L.ACT_LRELU)
-        x = run_block(order[-1][0], x)
+        x, _ = run_block(order[-1][0], x, None)
         x = self._conv(x, "upscale3.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
         out = torch.empty(B, 3, x.shape[1], x.shape[2], device=dev, dtype=torch.float32)
         if net.min != 0.0 or net.max != 1.0:
             raise NotImplementedError("the fused output epilogue clamps to [0,1] (the only range define_G builds)")
         if cap is not None:
             cap["feat_up3"] = x
-        self._conv(x, "conv_output", epi=L.EPI_NCHW_F32, clamp01=1 if clamp else 0, out=out)
+        pk = self._packed["conv_output"]
+        Bo, Ho, Wo, _ = x.shape
+        # algorithmic bytes: read feat_up3 once + write the fp32 frames
+        self._timed("conv_out9", "tensor", 2.0 * Bo * Ho * Wo * 3 * 32 * 81, x.numel() * 2 + out.numel() * 4,
+                    lambda: L.check(lib.dasr_conv_out9(L.ptr(x), L.ptr(pk.w), L.ptr(pk.bias), L.ptr(out), Bo, Ho, Wo, 3,
+                                                       1 if clamp else 0, s)))
         return out

@@ -50,7 +50,8 @@ int64_t dasr_launch_count(void);
  * ------------------------------------------------------------------------------------------------ */
 enum {
     DASR_EPI_STORE = 0,      /* out_bf16 NHWC = act(acc + bias [+ resid])                          */
-    DASR_EPI_STATS = 1,      /* out_bf16 NHWC = acc + bias ; stats[b][c][0..1] += sum, sum of squares */
+    DASR_EPI_STATS = 1,      /* out_bf16 NHWC = acc + bias ; stats[b][slot][c][0..1] = partial sum, sum of
+                                squares of the stored values (one writer per entry: deterministic)    */
     DASR_EPI_SEAN = 2,       /* acc = [gamma_o | beta_o]; fused SEAN modulate (normalization.py:87-89) */
     DASR_EPI_SHUFFLE2 = 3,   /* PixelShuffle(2) + act folded into the store (sftmd_arch.py:893-908)  */
     DASR_EPI_NCHW_F32 = 4    /* out_f32 NCHW [B,Cout,H,W] = clamp?(acc + bias)  (sftmd_arch.py:948-950) */
@@ -74,13 +75,26 @@ typedef struct {
     const float* bias;    /* [Npad]                                                                 */
     void* out;            /* bf16 NHWC (or fp32 NCHW for DASR_EPI_NCHW_F32)                          */
     const void* resid;    /* optional NHWC bf16 residual, same shape as out                         */
-    float* stats;         /* DASR_EPI_STATS: [B][Cout][2] accumulators (caller zeroes them)         */
+    float* stats;         /* DASR_EPI_STATS: [B][dasr_conv_stats_slots()][Cout][2] partial sums (every
+                             entry is written; no zeroing needed)                                   */
     const void* y;        /* DASR_EPI_SEAN: conv output to normalise, NHWC bf16 [B,H,W,Cout/2]      */
     const float* norm;    /* DASR_EPI_SEAN: [B][Cout/2][2] = (mean, scale) from dasr_instats_finalize */
     const void* gb_s;     /* DASR_EPI_SEAN: dynamic-conv term NHWC bf16 [B,H,W,Cout] (or NULL)       */
+    const float* resid_f32; /* DASR_EPI_SEAN: fp32 NHWC residual (the trunk's fp32 residual stream); used
+                               instead of `resid` when not NULL                                     */
+    float* out_aux_f32;   /* DASR_EPI_SEAN: optional fp32 NHWC copy of the output                    */
 } dasr_conv_args;
 
 int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream);
+/* number of partial-statistics slots per image the DASR_EPI_STATS epilogue writes for this shape (> 0),
+ * or a negative dasr_status                                                                         */
+int dasr_conv_stats_slots(const dasr_conv_desc* d);
+
+/* conv_output + clamp (sftmd_arch.py:910,948-950): 9x9, Cin = 32 -> Cout = 3, zero padding 4.
+ * x NHWC bf16 [B,H,W,32]; wq packed by DASR_PACK_ROWTAPS ([9][32][32] bf16); bias fp32 [3];
+ * out NCHW fp32 [B,3,H,W] = clamp01 ? clamp(conv + bias, 0, 1) : conv + bias                          */
+int dasr_conv_out9(const void* x, const void* wq, const float* bias, float* out, int B, int H, int W,
+                   int Cout, int clamp01, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight preparation: weight-norm (w = g*v/||v||, sftmd_arch.py:740,851), alpha folding and repacking
@@ -89,8 +103,10 @@ int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream
 enum {
     DASR_PACK_CONV = 0,        /* rows = O, K = (tap, I)                                             */
     DASR_PACK_CONVT = 1,       /* source is ConvTranspose2d [I][O][ks][ks]; rows = O, taps flipped   */
-    DASR_PACK_STYLE = 2        /* source [O][I][ks][ks]; dst [taps*rows_per_tap][I], row = tap*rows_per_tap
+    DASR_PACK_STYLE = 2,       /* source [O][I][ks][ks]; dst [taps*rows_per_tap][I], row = tap*rows_per_tap
                                   + row_offset + o, K = I  (style-table GEMM B operand)             */
+    DASR_PACK_ROWTAPS = 3      /* source [O][I][ks][ks], ks*O <= 32; dst [ks][32][I], row = t*32 + u*O + o
+                                  (dasr_conv_out9 operand; caller zero-fills dst once)              */
 };
 typedef struct {
     const float* v;       /* weight or weight_v                                                      */
@@ -120,8 +136,9 @@ int dasr_conv_first(const float* x_nchw, const float* v, const float* g, const f
                     void* out_nhwc, int B, int H, int W, void* stream);
 /* zero-insertion upsample for the transposed conv (sftmd_arch.py:748): [B,H,W,C] -> [B,2H-1,2W-1,C]   */
 int dasr_zero_insert2(const void* x, void* out, int B, int H, int W, int C, void* stream);
-/* out = a + b (bf16 NHWC, n elements)  -- feat_add1 (sftmd_arch.py:931)                              */
-int dasr_add(const void* a, const void* b, void* out, int64_t n, void* stream);
+/* out = a + b (bf16 NHWC, n elements)  -- feat_add1 (sftmd_arch.py:931); a32 (fp32) replaces a when
+ * not NULL (the trunk's fp32 residual stream)                                                        */
+int dasr_add(const void* a, const float* a32, const void* b, void* out, int64_t n, void* stream);
 
 /* RegionWiseAvgPooling (sftmd_arch.py:714-733): e5 NHWC bf16 [B,hf,wf,C], masks NCHW fp32 [B,K,H,W]
  * -> depthVec fp32 [B,K,C]                                                                          */
@@ -156,8 +173,9 @@ int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* mask
                      void* out, int B, int K, int H, int W, int nf2, void* stream);
 
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
- * stats [B][C][2] (sum, sumsq over H*W) -> norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)  */
-int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, void* stream);
+ * stats [B][nslots][C][2] (partial sum, sumsq over H*W; summed here in slot order) ->
+ * norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)                                          */
+int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, int nslots, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,11 @@ TOL_PIX_STRESS = 5e-2
 TOL_PSNR = 0.01     # dB
 
 
+def stress_tol(pre_clamp_absmax):
+    """Stress cases: bf16 error is relative to the magnitude of the pre-clamp output (x2 reaches |9|)."""
+    return TOL_PIX_STRESS * max(1.0, float(pre_clamp_absmax) / 2.0)
+
+
 def _build(meta, sd):
     import depth_aware_endoscopy_sr_b200 as dasr
     net = dasr.DepthNet(which_ResBlk_depth=list(meta["which"]), in_nc=3, out_nc=3, nf=64, nb=16, scale=meta["scale"],
@@ -38,7 +43,7 @@ def _nchw(t):
 @pytest.mark.parametrize("name", INIT_CASES + CASES)
 def test_forward_matches_reference_golden(name):
     z, meta = load_golden(name)
-    tol = TOL_PIX if meta["init"] == "default" else TOL_PIX_STRESS
+    tol = TOL_PIX if meta["init"] == "default" else stress_tol(np.abs(z["pre_clamp"]).max())
     sd, (lq, depth, masks, gt) = case_tensors(meta)
     net = _build(meta, sd)
     cap = {}
@@ -49,8 +54,7 @@ def test_forward_matches_reference_golden(name):
     torch.cuda.synchronize()
     assert sr.dtype == torch.float32 and tuple(sr.shape) == (meta["B"], 3, meta["scale"] * meta["h"],
                                                              meta["scale"] * meta["w"])
-    # fp32 atomics accumulate the InstanceNorm statistics: run-to-run differences are round-off only
-    assert (sr - sr2).abs().max().item() <= 1e-3
+    assert torch.equal(sr, sr2)      # no atomics anywhere on the path: runs are bit-reproducible
     st = meta["stride"]
     sr_c, pre_c = sr.cpu(), pre.cpu()
     # intermediates (looser: trunk activations are O(10), bf16 has 8 bits of mantissa)
@@ -71,7 +75,7 @@ def test_forward_matches_reference_golden(name):
 def test_forward_matches_oracle_full_frame(name):
     """Full-resolution comparison + PSNR delta against the CPU oracle (itself pinned to the goldens)."""
     _z, meta = load_golden(name)
-    tol = TOL_PIX if meta["init"] == "default" else TOL_PIX_STRESS
+    tol = TOL_PIX if meta["init"] == "default" else stress_tol(np.abs(_z["pre_clamp"]).max())
     sd, (lq, depth, masks, gt) = case_tensors(meta)
     with torch.no_grad():
         ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"])
@@ -111,7 +115,8 @@ def test_images_are_independent():
         full = net(lq, depth, masks)
         for b in (0, 3, 7):
             one = net(lq[b:b + 1], depth[b:b + 1], masks[b:b + 1])
-            assert (one[0] - full[b]).abs().max().item() <= 2e-3   # atomics order in the IN statistics
+            # statistics are per-image partial sums in a fixed slot order: bit-exact regardless of the batch
+            assert torch.equal(one[0], full[b])
 
 
 def test_non_onehot_masks_take_the_general_path():

@@ -80,15 +80,16 @@ w = torch.randn(Cn, Cn, 3, 3, device=dev) / 24
 b = torch.randn(Cn, device=dev)
 wp, bp = pack(w, bias=b)
 y = torch.empty(B, H, W, Cn, device=dev, dtype=torch.bfloat16)
-stats = torch.zeros(B, Cn, 2, device=dev)
+nslots = L.conv_stats_slots(B, H, W, Cn, Cn)
+stats = torch.full((B, nslots, Cn, 2), float("nan"), device=dev)
 L.conv_fwd(nhwc(x).to(torch.bfloat16), wp, bp, y, Cout=Cn, ks=3, epi=L.EPI_STATS, stats=stats)
 torch.cuda.synchronize()
 ref = F.conv2d(bf(x), bf(w), b, padding=1)
 allok &= report("stats: y", nchw(y), ref, 1.5e-2)
-allok &= report("stats: sum", stats[..., 0], ref.sum(dim=(2, 3)), 2e-3)
-allok &= report("stats: sumsq", stats[..., 1], (ref * ref).sum(dim=(2, 3)), 2e-3)
+allok &= report("stats: sum", stats[..., 0].sum(1), ref.sum(dim=(2, 3)), 2e-3)
+allok &= report("stats: sumsq", stats[..., 1].sum(1), (ref * ref).sum(dim=(2, 3)), 2e-3)
 norm = torch.empty(B, Cn, 2, device=dev)
-L.check(L.load().dasr_instats_finalize(stats.data_ptr(), norm.data_ptr(), B, Cn, H * W, L.stream_ptr()))
+L.check(L.load().dasr_instats_finalize(stats.data_ptr(), norm.data_ptr(), B, Cn, H * W, nslots, L.stream_ptr()))
 mu = ref.mean(dim=(2, 3))
 var = ref.var(dim=(2, 3), unbiased=False)
 sc = (var + 1e-5).rsqrt() * (var / (var + 1e-5) + 1e-5).rsqrt()
@@ -102,19 +103,24 @@ bgb = torch.randn(128, device=dev) * 0.1
 wp2, bp2 = pack(wgb, bias=bgb)
 gbs = (torch.randn(B, H, W, 128, device=dev) * 0.3).to(torch.bfloat16)
 resid = torch.randn(B, H, W, Cn, device=dev).to(torch.bfloat16)
-for inner, use_res in ((1, False), (0, True)):
+resid32 = torch.randn(B, H, W, Cn, device=dev)
+for inner, use_res in ((1, 0), (0, 1), (0, 2)):
     out = torch.empty(B, H, W, Cn, device=dev, dtype=torch.bfloat16)
+    out32 = torch.empty(B, H, W, Cn, device=dev) if use_res == 2 else None
     L.conv_fwd(nhwc(actv).to(torch.bfloat16), wp2, bp2, out, Cout=128, ks=3, epi=L.EPI_SEAN,
                act=L.ACT_RELU if use_res else L.ACT_NONE, inner_relu=inner, y=y, norm=norm, gb_s=gbs,
-               resid=resid if use_res else None)
+               resid=resid if use_res == 1 else None, resid_f32=resid32 if use_res == 2 else None, out_aux_f32=out32)
     torch.cuda.synchronize()
     gb = F.conv2d(bf(actv), bf(wgb), bgb, padding=1) + nchw(gbs).float()
     n = (nchw(y).float() - norm[..., 0][:, :, None, None]) * norm[..., 1][:, :, None, None]
     r = n * (1 + gb[:, :64]) + gb[:, 64:]
     if inner:
         r = F.relu(r)
-    if use_res:
+    if use_res == 1:
         r = F.relu(r + nchw(resid).float())
+    if use_res == 2:
+        r = F.relu(r + nchw(resid32))
+        allok &= report("sean epilogue fp32 aux out", nchw(out32), r, 2e-3)
     allok &= report("sean epilogue inner=%d resid=%d" % (inner, use_res), nchw(out), r, 2e-2)
 
 # --- pixel shuffle epilogue
@@ -137,17 +143,26 @@ torch.cuda.synchronize()
 ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(bf(x), bf(w), b, padding=1), 2), 0.2)
 allok &= report("shuffle2 64->256", nchw(out), ref, 1.5e-2)
 
-# --- 9x9 output conv, NCHW fp32 + clamp
-for (hh, ww) in ((96, 96), (64, 200)):
-    x = torch.rand(1, 32, hh, ww, device=dev)
+# --- 9x9 output conv, NCHW fp32 + clamp (K-OUT9)
+def pack9(w, b):
+    wq = torch.zeros(9 * 32, 32, device=dev, dtype=torch.bfloat16)
+    bq = torch.zeros(3, device=dev)
+    L.pack_weights([L.pack_desc(w, wq, bias=b, dst_bias=bq, mode=L.PACK_ROWTAPS)], torch.zeros(64, device=dev))
+    return wq, bq
+
+for (bb, hh, ww, cl) in ((1, 96, 96, 1), (2, 64, 200, 0), (1, 37, 61, 1), (3, 128, 128, 0)):
+    x = torch.rand(bb, 32, hh, ww, device=dev)
     w = torch.randn(3, 32, 9, 9, device=dev) / 51
     b = torch.randn(3, device=dev) * 0.1 + 0.3
-    wp, bp = pack(w, rows_pad=16, bias=b)
-    out = torch.empty(1, 3, hh, ww, device=dev)
-    L.conv_fwd(nhwc(x).to(torch.bfloat16), wp, bp, out, Cout=3, ks=9, epi=L.EPI_NCHW_F32, clamp01=1)
+    wq, bq = pack9(w, b)
+    out = torch.full((bb, 3, hh, ww), float("nan"), device=dev)
+    L.check(L.load().dasr_conv_out9(nhwc(x).to(torch.bfloat16).data_ptr(), wq.data_ptr(), bq.data_ptr(), out.data_ptr(),
+                                    bb, hh, ww, 3, cl, L.stream_ptr()))
     torch.cuda.synchronize()
-    ref = F.conv2d(bf(x), bf(w), b, padding=4).clamp(0, 1)
-    allok &= report("conv_output 9x9 %dx%d" % (hh, ww), out, ref, 1e-2)
+    ref = F.conv2d(bf(x), bf(w), b, padding=4)
+    if cl:
+        ref = ref.clamp(0, 1)
+    allok &= report("conv_out9 B%d %dx%d clamp=%d" % (bb, hh, ww, cl), out, ref, 2e-3)
 
 # --- stride 2 via subsample
 for hh in (64, 31):
@@ -207,12 +222,12 @@ for (Cin, Cout, hh, name) in ((64, 64, 64, "trunk 64->64"), (128, 128, 64, "gamm
     ms2 = timeit(lambda: F.conv2d(xt, wt, None, padding=1))
     print("     cudnn bf16 channels_last            %.3f ms  %.1f TFLOP/s" % (ms2, fl / ms2 / 1e9), flush=True)
 
-x = torch.rand(16, 512, 512, 32, device=dev).to(torch.bfloat16)
+x = torch.rand(64, 512, 512, 32, device=dev).to(torch.bfloat16)
 w = torch.randn(3, 32, 9, 9, device=dev) / 51
 b = torch.zeros(3, device=dev)
-wp, bp = pack(w, rows_pad=16, bias=b)
-out = torch.empty(16, 3, 512, 512, device=dev)
-ms = timeit(lambda: L.conv_fwd(x, wp, bp, out, Cout=3, ks=9, epi=L.EPI_NCHW_F32, clamp01=1), n=5)
-print("time conv_output 9x9 B16@512: %.3f ms (%.1f real TFLOP/s)" % (ms, 2.0 * 16 * 512 * 512 * 3 * 32 * 81 / ms / 1e9))
+wq, bq = pack9(w, b)
+out = torch.empty(64, 3, 512, 512, device=dev)
+ms = timeit(lambda: L.check(L.load().dasr_conv_out9(x.data_ptr(), wq.data_ptr(), bq.data_ptr(), out.data_ptr(), 64, 512, 512, 3, 1, L.stream_ptr())), n=5)
+print("time conv_out9 B64@512: %.3f ms (%.1f real TFLOP/s, %.0f GB/s algorithmic)" % (ms, 2.0 * 64 * 512 * 512 * 3 * 32 * 81 / ms / 1e9, (x.numel() * 2 + out.numel() * 4) / ms / 1e6))
 
 print("ALL PASS" if allok else "SOME FAILED")
