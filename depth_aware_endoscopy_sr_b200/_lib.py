@@ -31,6 +31,10 @@ class ConvArgs(C.Structure):
                                           "out_aux_f32")]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "Cout", "Cin", "kh", "kw", "reserved")]
+
+
 class PackDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("v", "g", "alpha", "bias", "bias2", "dst", "dst_bias")] + \
                [(n, C.c_int32) for n in ("dim0", "dim1", "ks", "mode", "alpha_mode", "shuffle_r", "row_offset",
@@ -58,6 +62,7 @@ def load() -> C.CDLL:
         "dasr_check_device": [],
         "dasr_conv_fwd": [C.POINTER(ConvDesc), C.POINTER(ConvArgs), vp],
         "dasr_conv_out9": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dasr_conv_wgrad": [C.POINTER(WgradDesc), vp, vp, vp, vp],
         "dasr_pack_weights": [C.POINTER(PackDesc), i32, vp, vp],
         "dasr_conv_first": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_zero_insert2": [vp, vp, i32, i32, i32, i32, vp],
@@ -78,7 +83,7 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_out9", "dasr_pack_weights",
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize"]
 
@@ -120,6 +125,16 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Te
                  ptr(out_aux_f32, torch.float32))
     check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
     return out
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int = 3, kw: int = 3) -> torch.Tensor:
+    """dw[Cout][kh*kw*Cin] (fp32, zeroed by the caller) += weight gradient; dy / x NHWC bf16."""
+    B, H, W, Cout = dy.shape
+    Cin = x.shape[3]
+    d = WgradDesc(B, H, W, Cout, Cin, kh, kw, 0)
+    check(load().dasr_conv_wgrad(C.byref(d), ptr(dy, torch.bfloat16), ptr(x, torch.bfloat16), ptr(dw, torch.float32),
+                                 stream_ptr()))
+    return dw
 
 
 def conv_stats_slots(B, H, W, Cin, Cout, ks=3) -> int:

@@ -1,0 +1,312 @@
+// K-CONV-WGRAD: weight gradient of a stride-1 "same" convolution on the 5th-gen tensor cores.
+//
+//   dWp[o][tap*Cin + i] += sum_{b,h,w} dY[b,h,w,o] * X[b, h+t-pad_h, w+u-pad_w, i]        (bf16 x bf16 -> fp32)
+//
+// (the packed GEMM-B layout of conv_igemm.cu, so dasr_unpack_grads can undo weight-norm / alpha folding /
+// PixelShuffle permutation row by row).  It is the backward of every nn.Conv2d call site cited in conv_igemm.cu
+// (autograd's conv2d weight gradient in the reference, codes/models/F_model_depthCond.py:191).
+//
+// Both GEMM operands have the reduction (pixel) dimension OUTERMOST in memory ([pixel][channel], channels
+// contiguous), i.e. they are MN-major.  tcgen05 consumes MN-major operands directly (instruction-descriptor
+// bits 15/16, canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -- verified on B200 with
+// tools/umma_probe.cu test 6, including arbitrary row shifts of the start address), so NO transposition pass
+// exists anywhere: a TMA box of [rows = pixels][64 channels] IS the operand tile, the 64-channel blocks of a
+// wider operand sit LBO bytes apart, and the tap (t,u) of the B operand is the same X patch viewed
+// (t*Wp + u) rows further down -- the halo-reuse trick of the forward kernel applied to the K dimension.
+//
+// Work split: grid.x = split-K over (image, row-tile, strip) tiles; grid.y = (tap-group, Cin chunk) column
+// slices of at most 512 fp32 TMEM columns; grid.z = blocks of 128 (64) output channels.  Each CTA keeps its
+// [M x cols] slice in TMEM across ALL its K tiles and flushes once with fp32 red.global.add.
+// Warp roles: w0 TMA producer (multi-stage ring), w1 MMA issuer (one elected thread), w2 TMEM allocator,
+// w4..7 final flush.
+#include "dasr_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace dasr {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgMaxStages = 4;
+
+struct WgK {
+    int B, H, W, Cout, Cin;
+    int kh, kw, pad_h, pad_w;
+    int TR, Wt, Wp, PR;                 // rows per K tile, strip width, patch width / rows
+    int n_strips, n_rowtiles, ktiles_total;
+    int taps_per_slice, n_tapgroups, n_cchunks, Nc;
+    int Mb, m_valid_last;               // MMA M (64 / 128); grid.z blocks
+    int swz_a, swz_b, cb_a, cb_b;       // swizzle bytes and channels per smem block of dY / X
+    int a_blocks, b_blocks;             // TMA loads per stage
+    uint32_t a_blk_bytes, b_blk_bytes, stage_bytes, a_lbo, b_lbo;
+    uint32_t a_tx, b_tx;                // bytes one TMA box really transfers (blocks are padded to 1 KB)
+    int stages;
+    float* dw;
+    int ldw;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, const WgK p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full[kWgMaxStages], empty[kWgMaxStages], acc_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(&acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapX);
+    }
+    if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // this CTA's slice
+    const int tapgroup = blockIdx.y / p.n_cchunks;
+    const int cchunk = blockIdx.y - tapgroup * p.n_cchunks;
+    const int tap0 = tapgroup * p.taps_per_slice;
+    const int ntaps = min(p.taps_per_slice, p.kh * p.kw - tap0);
+    const int t_first = tap0 / p.kw;
+    const int mblk = blockIdx.z;
+    const int ca0 = mblk * p.Mb;             // first dY channel of this M block
+    const int cb0 = cchunk * p.Nc;           // first X channel of this column slice
+    const int tiles_per_img = p.n_rowtiles * p.n_strips;
+    const uint32_t a_bytes_stage = p.a_blocks * p.a_blk_bytes;
+    const int n_my = (p.ktiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int kt = blockIdx.x; kt < p.ktiles_total; kt += gridDim.x, it++) {
+                const int img = kt / tiles_per_img;
+                const int r = kt - img * tiles_per_img;
+                const int rt = r / p.n_strips, strip = r - rt * p.n_strips;
+                const int s = it % p.stages;
+                mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+                mbar_expect_tx(&full[s], p.a_blocks * p.a_tx + p.b_blocks * p.b_tx);
+                uint8_t* sa = smem + (size_t)s * p.stage_bytes;
+                uint8_t* sb = sa + a_bytes_stage;
+                for (int j = 0; j < p.a_blocks; j++)
+                    tma_load_4d(sa + (size_t)j * p.a_blk_bytes, &mapY, &full[s], ca0 + j * p.cb_a, strip * p.Wt, rt * p.TR, img);
+                for (int j = 0; j < p.b_blocks; j++)
+                    tma_load_4d(sb + (size_t)j * p.b_blk_bytes, &mapX, &full[s], cb0 + j * p.cb_b, strip * p.Wt - p.pad_w,
+                                rt * p.TR + t_first - p.pad_h, img);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // MN-major operands: idesc bits 15 (A) and 16 (B); descriptor = addr>>4 | LBO>>4 <<16 | SBO>>4 <<32 | ...
+            const uint32_t idesc = make_idesc_bf16(p.Mb, p.Nc) | (1u << 15) | (1u << 16);
+            const uint32_t hi_a = ((8u * p.swz_a) >> 4) | (1u << 14) | ((p.swz_a == 128 ? 2u : 4u) << 29);
+            const uint32_t hi_b = ((8u * p.swz_b) >> 4) | (1u << 14) | ((p.swz_b == 128 ? 2u : 4u) << 29);
+            const uint32_t lo_a_flags = ((p.a_lbo >> 4) & 0x3FFFu) << 16;
+            const uint32_t lo_b_flags = ((p.b_lbo >> 4) & 0x3FFFu) << 16;
+            const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+            const int ksteps = p.Wt >> 4;
+            const uint32_t a_kstep = (16u * p.swz_a) >> 4, b_kstep = (16u * p.swz_b) >> 4;
+            uint32_t it = 0;
+            for (int kt = blockIdx.x; kt < p.ktiles_total; kt += gridDim.x, it++) {
+                const int s = it % p.stages;
+                mbar_wait(&full[s], (it / p.stages) & 1);
+                tc_fence_after();
+                const uint32_t sa_lo = smem_lo + ((uint32_t)s * p.stage_bytes >> 4);
+                const uint32_t sb_lo = sa_lo + (a_bytes_stage >> 4);
+#pragma unroll 1
+                for (int r = 0; r < p.TR; r++) {
+                    const uint32_t a_row = sa_lo + (((uint32_t)(r * p.Wt) * p.swz_a) >> 4);
+#pragma unroll 1
+                    for (int tp = 0; tp < ntaps; tp++) {
+                        const int tap = tap0 + tp;
+                        const int t = tap / p.kw, u = tap - t * p.kw;
+                        const uint32_t b_row = sb_lo + (((uint32_t)((r + t - t_first) * p.Wp + u) * p.swz_b) >> 4);
+                        const uint32_t d = tmem_base + tp * p.Nc;
+                        const uint32_t acc0 = (it | r) != 0;
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            // umma_bf16_lohi with distinct high words for A and B
+                            const uint32_t a_lo = (a_row + ks * a_kstep) | lo_a_flags;
+                            const uint32_t b_lo = (b_row + ks * b_kstep) | lo_b_flags;
+                            const uint32_t accum = acc0 | (ks != 0);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                                "setp.ne.b32 p, %6, 0;\n\t"
+                                "mov.b64 da, {%1, %3};\n\t"
+                                "mov.b64 db, {%2, %4};\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d),
+                                "r"(a_lo), "r"(b_lo), "r"(hi_a), "r"(hi_b), "r"(idesc), "r"(accum)
+                                : "memory");
+                        }
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(&acc_full);
+        }
+    } else if (warp >= 4) {
+        // ===================================================== flush: TMEM -> red.global.add.f32
+        if (n_my > 0) {
+            mbar_wait(&acc_full, 0);
+            tc_fence_after();
+            const int ew = warp & 3;
+            // accumulator row of this lane: M = 128 -> lane index; M = 64 -> lanes 0..15 of each 32-lane quadrant
+            int m;
+            bool row_ok;
+            if (p.Mb == 128) {
+                m = ew * 32 + lane;
+                row_ok = true;
+            } else {
+                m = ew * 16 + lane;
+                row_ok = lane < 16;
+            }
+            const int o = ca0 + m;
+            row_ok = row_ok && (o < p.Cout);
+            const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16);
+            for (int tp = 0; tp < ntaps; tp++) {
+                float* dst = p.dw + (size_t)o * p.ldw + (size_t)(tap0 + tp) * p.Cin + cb0;
+                for (int c0 = 0; c0 < p.Nc; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_row + tp * p.Nc + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DASR_REQUIRE(d && dy && x && dw, "null argument");
+    DASR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "bad shape");
+    DASR_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= 81, "bad kernel size");
+    DASR_REQUIRE(d->Cin % 32 == 0 && d->Cout % 32 == 0, "channels must be multiples of 32 (Cout %d, Cin %d)", d->Cout, d->Cin);
+
+    WgK k;
+    memset(&k, 0, sizeof k);
+    k.B = d->B; k.H = d->H; k.W = d->W; k.Cout = d->Cout; k.Cin = d->Cin;
+    k.kh = d->kh; k.kw = d->kw; k.pad_h = d->kh / 2; k.pad_w = d->kw / 2;
+    k.dw = dw;
+    k.ldw = d->kh * d->kw * d->Cin;
+
+    // operand blocks
+    k.swz_a = (d->Cout % 64 == 0) ? 128 : 64;
+    k.swz_b = (d->Cin % 64 == 0) ? 128 : 64;
+    k.cb_a = k.swz_a / 2;
+    k.cb_b = k.swz_b / 2;
+    // M blocks of dY channels
+    k.Mb = d->Cout >= 128 ? 128 : 64;
+    const int n_mblocks = (d->Cout + k.Mb - 1) / k.Mb;
+    DASR_REQUIRE(d->Cout % k.Mb == 0 || d->Cout < k.Mb, "Cout %d not supported", d->Cout);
+    const int m_rows = d->Cout < k.Mb ? d->Cout : k.Mb;   // valid dY channels per M block
+    k.a_blocks = m_rows / k.cb_a;
+    // column slices: Nc X-channels per MMA, taps_per_slice taps per CTA, <= 512 TMEM columns
+    k.Nc = d->Cin > 128 ? 128 : d->Cin;
+    DASR_REQUIRE(d->Cin % k.Nc == 0, "Cin %d not supported", d->Cin);
+    k.n_cchunks = d->Cin / k.Nc;
+    k.b_blocks = k.Nc / k.cb_b;
+    k.taps_per_slice = d->kw;                               // one kernel row per slice
+    if (k.taps_per_slice * k.Nc > 512) k.taps_per_slice = 512 / k.Nc;
+    if (d->kw == 1) {                                        // vertical-only kernels: all taps in one slice if they fit
+        k.taps_per_slice = d->kh;
+        if (k.taps_per_slice * k.Nc > 512) k.taps_per_slice = 512 / k.Nc;
+    }
+    DASR_REQUIRE(k.taps_per_slice >= 1, "slice does not fit TMEM");
+    if (d->kw > 1) DASR_REQUIRE(k.taps_per_slice == d->kw, "kernel row does not fit one TMEM slice (kw %d, Cin chunk %d)", d->kw, k.Nc);
+    k.n_tapgroups = (d->kh * d->kw + k.taps_per_slice - 1) / k.taps_per_slice;
+    const int dt = (d->kw > 1) ? 0 : (k.taps_per_slice - 1);   // extra patch rows spanned by one slice
+
+    // K tiles
+    const int max_wt = 128;
+    k.n_strips = (d->W + max_wt - 1) / max_wt;
+    k.Wt = (((d->W + k.n_strips - 1) / k.n_strips) + 15) & ~15;
+    k.n_strips = (d->W + k.Wt - 1) / k.Wt;
+    k.Wp = k.Wt + d->kw - 1;
+    DASR_REQUIRE(k.Wp <= 256, "strip too wide");
+    const size_t budget = 200 * 1024;
+    int TR = 8;
+    for (;; TR >>= 1) {
+        k.TR = TR;
+        k.PR = TR + dt;
+        k.a_blk_bytes = (uint32_t)TR * k.Wt * k.swz_a;
+        k.b_blk_bytes = (uint32_t)k.PR * k.Wp * k.swz_b;
+        const uint32_t a_al = (k.a_blocks * k.a_blk_bytes + 1023u) & ~1023u;
+        k.stage_bytes = a_al + ((k.b_blocks * k.b_blk_bytes + 1023u) & ~1023u);
+        if (2 * (size_t)k.stage_bytes <= budget || TR == 1) break;
+    }
+    DASR_REQUIRE(2 * (size_t)k.stage_bytes <= budget && k.PR <= 256, "K tile does not fit in shared memory");
+    // blocks inside one operand must each start 1024-byte aligned for the swizzle pattern to match TMA's
+    k.a_blk_bytes = (k.a_blk_bytes + 1023u) & ~1023u;
+    k.b_blk_bytes = (k.b_blk_bytes + 1023u) & ~1023u;
+    {
+        const uint32_t a_al = k.a_blocks * k.a_blk_bytes;
+        k.stage_bytes = a_al + k.b_blocks * k.b_blk_bytes;
+    }
+    DASR_REQUIRE(2 * (size_t)k.stage_bytes <= budget + 16 * 1024, "K tile does not fit in shared memory");
+    k.stages = (int)(budget / k.stage_bytes);
+    if (k.stages > kWgMaxStages) k.stages = kWgMaxStages;
+    if (k.stages < 2) k.stages = 2;
+    // LBO: distance between channel blocks; a lone / duplicated block (Cout = 32 with M = 64) uses LBO = 0
+    k.a_lbo = (k.a_blocks * k.cb_a >= k.Mb) ? k.a_blk_bytes : 0;
+    k.b_lbo = k.b_blk_bytes;
+    k.n_rowtiles = (d->H + k.TR - 1) / k.TR;
+    k.ktiles_total = d->B * k.n_rowtiles * k.n_strips;
+
+    const int slices = k.n_tapgroups * k.n_cchunks * n_mblocks;
+    int ksplit = (2 * num_sms()) / slices;      // a CTA owns all 512 TMEM columns -> one CTA per SM; 2 waves
+    if (ksplit > num_sms() / slices && slices <= num_sms()) ksplit = num_sms() / slices;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > k.ktiles_total) ksplit = k.ktiles_total;
+
+    CUtensorMap mY, mX;
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->W * d->Cout * 2, (uint64_t)d->H * d->W * d->Cout * 2};
+        uint32_t box[4] = {(uint32_t)k.cb_a, (uint32_t)k.Wt, (uint32_t)k.TR, 1};
+        int rc = encode_tmap_bf16(&mY, dy, 4, dims, str, box, k.swz_a);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        uint32_t box[4] = {(uint32_t)k.cb_b, (uint32_t)k.Wp, (uint32_t)k.PR, 1};
+        int rc = encode_tmap_bf16(&mX, x, 4, dims, str, box, k.swz_b);
+        if (rc) return rc;
+    }
+    k.a_tx = (uint32_t)k.TR * k.Wt * k.swz_a;
+    k.b_tx = (uint32_t)k.PR * k.Wp * k.swz_b;
+    static bool configured[64] = {false};
+    int dev = 0;
+    DASR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        DASR_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured[dev & 63] = true;
+    }
+    const size_t smem_bytes = (size_t)k.stages * k.stage_bytes + 1024;
+    DASR_REQUIRE(smem_bytes <= 220 * 1024, "shared memory budget exceeded (%zu)", smem_bytes);
+    dim3 grid(ksplit, k.n_tapgroups * k.n_cchunks, n_mblocks);
+    conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(mY, mX, k);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}

@@ -90,6 +90,16 @@ int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream
  * or a negative dasr_status                                                                         */
 int dasr_conv_stats_slots(const dasr_conv_desc* d);
 
+/* Weight gradient of a stride-1 "same" convolution with a kh x kw kernel (autograd of the nn.Conv2d call sites
+ * above; reference codes/models/F_model_depthCond.py:191):
+ *   dw[o][(t*kw+u)*Cin + i] += sum_{b,h,w} dy[b,h,w,o] * x[b,h+t-kh/2,w+u-kw/2,i]
+ * dy NHWC bf16 [B,H,W,Cout], x NHWC bf16 [B,H,W,Cin], dw fp32 [Cout][kh*kw*Cin] in the packed GEMM-B layout
+ * of dasr_pack_weights (accumulated with fp32 atomics: the caller zeroes it).  Channels multiples of 32.     */
+typedef struct {
+    int32_t B, H, W, Cout, Cin, kh, kw, reserved;
+} dasr_wgrad_desc;
+int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, void* stream);
+
 /* conv_output + clamp (sftmd_arch.py:910,948-950): 9x9, Cin = 32 -> Cout = 3, zero padding 4.
  * x NHWC bf16 [B,H,W,32]; wq packed by DASR_PACK_ROWTAPS ([9][32][32] bf16); bias fp32 [3];
  * out NCHW fp32 [B,3,H,W] = clamp01 ? clamp(conv + bias, 0, 1) : conv + bias                          */

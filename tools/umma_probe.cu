@@ -143,6 +143,69 @@ __global__ void probe_tma4d(const __grid_constant__ CUtensorMap map, int c0, int
     for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
 }
 
+// ------------------------------------------------------------------ MN-major probe (wgrad operands)
+// dY: [R][CM] bf16, X: [R + 80][CN] bf16 (pixel rows, channels contiguous).  D[m][n] = sum_r dY[r][m] * X[r+shift][n]
+// Both operands are MN-major: smem block j = channels [j*CB, (j+1)*CB) of all rows, CB = SWZ/2; blocks LBO apart.
+template <int SWZ>
+__global__ void __launch_bounds__(128, 1)
+probe_mnmajor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int R, int M, int N,
+              int shift, float* D) {
+    constexpr int CB = SWZ / 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int RB = R + 80;
+    const uint32_t blkA = (uint32_t)R * SWZ, blkB = (uint32_t)RB * SWZ;   // bytes per 64(32)-channel block
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (((M / CB) * blkA + 1023) & ~1023u);
+    __shared__ uint64_t bar_full, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_full, 1);
+        mbar_init(&bar_mma, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (warp == 1) {
+        if (elect_one()) {
+            mbar_expect_tx(&bar_full, (M / CB) * blkA + (N / CB) * blkB);
+            for (int j = 0; j < M / CB; j++) tma_load_2d(sA + j * blkA, &mapA, &bar_full, j * CB, 0);
+            for (int j = 0; j < N / CB; j++) tma_load_2d(sB + j * blkB, &mapB, &bar_full, j * CB, 0);
+            if (!mbar_wait_bounded(&bar_full, 0)) { D[0] = -12345.f; }
+            tc_fence_after();
+            // instruction descriptor: bf16 x bf16 -> f32, A and B MN-major (bits 15, 16)
+            const uint32_t idesc = make_idesc_bf16(M, N) | (1u << 15) | (1u << 16);
+            constexpr uint64_t layout = (SWZ == 128) ? 2ull : 4ull;
+            constexpr uint64_t sbo = (8ull * SWZ) >> 4;     // next 8-row (K) group
+            for (int k0 = 0; k0 < R; k0 += 16) {
+                const uint32_t a_addr = smem_u32(sA) + k0 * SWZ;
+                const uint32_t b_addr = smem_u32(sB) + (k0 + shift) * SWZ;
+                const uint64_t da = uint64_t((a_addr & 0x3FFFFu) >> 4) | (uint64_t(blkA >> 4) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+                const uint64_t db = uint64_t((b_addr & 0x3FFFFu) >> 4) | (uint64_t(blkB >> 4) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+                umma_bf16(tmem, da, db, idesc, k0 > 0);
+            }
+            umma_commit(&bar_mma);
+        }
+    }
+    __syncwarp();
+    if (!mbar_wait_bounded(&bar_mma, 0)) { if (threadIdx.x == 0) printf("TIMEOUT waiting for MMA commit\n"); }
+    tc_fence_after();
+    const int row = threadIdx.x;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + (uint32_t(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; j++) D[row * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 static float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 static std::vector<__nv_bfloat16> rand_bf16(size_t n, unsigned seed) {
@@ -225,6 +288,60 @@ static int run_gemm(int N, int r, int bo_mode, const char* tag, bool dump) {
     cudaFree(dB);
     cudaFree(dD);
     return bad;
+}
+
+template <int SWZ>
+static void run_mnmajor(int R, int M, int N, int shift) {
+    const int CB = SWZ / 2;
+    const int RB = R + 80;
+    auto hA = rand_bf16((size_t)R * M, 5 + shift);
+    auto hB = rand_bf16((size_t)RB * N, 9 + N);
+    __nv_bfloat16 *dA, *dB;
+    float* dD;
+    CK(cudaMalloc(&dA, hA.size() * 2));
+    CK(cudaMalloc(&dB, hB.size() * 2));
+    CK(cudaMalloc(&dD, 128 * N * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xFF, 128 * N * 4));
+    uint64_t dimsA[2] = {(uint64_t)M, (uint64_t)R}, strA[1] = {(uint64_t)M * 2};
+    uint32_t boxA[2] = {(uint32_t)CB, (uint32_t)R};
+    uint64_t dimsB[2] = {(uint64_t)N, (uint64_t)RB}, strB[1] = {(uint64_t)N * 2};
+    uint32_t boxB[2] = {(uint32_t)CB, (uint32_t)RB};
+    CUtensorMapSwizzle sw = SWZ == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap mA = make_map(dA, 2, dimsA, strA, boxA, nullptr, sw);
+    CUtensorMap mB = make_map(dB, 2, dimsB, strB, boxB, nullptr, sw);
+    size_t smem = (size_t)(M / CB) * R * SWZ + (size_t)(N / CB) * RB * SWZ + 4096;
+    CK(cudaFuncSetAttribute(probe_mnmajor<SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    probe_mnmajor<SWZ><<<1, 128, smem>>>(mA, mB, R, M, N, shift, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("mnmajor SWZ=%d M=%d N=%d shift=%d : CUDA ERROR %s\n", SWZ, M, N, shift, cudaGetErrorString(e));
+        exit(3);
+    }
+    std::vector<float> hD(128 * N);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    // hypotheses for the TMEM lane of accumulator row m: 0: lane = m ; 1 (M=64): lane = (m/16)*32 + m%16 ; 2: lane = m*2
+    for (int hyp = 0; hyp < (M == 64 ? 3 : 1); hyp++) {
+        int bad = 0;
+        double maxerr = 0;
+        for (int m = 0; m < M; m++) {
+            const int lane = hyp == 0 ? m : hyp == 1 ? (m / 16) * 32 + (m % 16) : m * 2;
+            for (int n = 0; n < N; n++) {
+                float ref = 0;
+                for (int r = 0; r < R; r++) ref += bf2f(hA[(size_t)r * M + m]) * bf2f(hB[(size_t)(r + shift) * N + n]);
+                float d = fabsf(ref - hD[lane * N + n]);
+                if (!(d <= 1e-3f)) bad++;
+                if (d > maxerr) maxerr = d;
+            }
+        }
+        printf("mnmajor SWZ=%d R=%d M=%d N=%d shift=%d lane-hyp=%d : %s (bad=%d/%d maxerr=%g)\n", SWZ, R, M, N, shift, hyp,
+               bad ? "FAIL" : "PASS", bad, M * N, maxerr);
+        if (!bad) break;
+    }
+    cudaFree(dA);
+    cudaFree(dB);
+    cudaFree(dD);
 }
 
 static void run_tma4d(bool strided) {
@@ -313,6 +430,16 @@ int main(int argc, char** argv) {
         run_gemm<32>(64, 0, 0, "sw32", true);
         for (int bo = 0; bo < 2; bo++)
             for (int r = 1; r <= 3; r++) run_gemm<32>(64, r, bo, "sw32shift", false);
+    }
+    else if (test == 6) {
+        for (int shift : {0, 1, 3, 8, 67}) run_mnmajor<128>(64, 128, 128, shift);
+        run_mnmajor<128>(128, 128, 64, 5);
+        run_mnmajor<128>(64, 64, 64, 0);
+        run_mnmajor<128>(64, 64, 128, 2);
+        run_mnmajor<128>(32, 128, 256, 66);
+        for (int shift : {0, 1, 5, 66}) run_mnmajor<64>(64, 128, 32, shift);
+        run_mnmajor<64>(64, 32, 32, 3);
+        run_mnmajor<64>(64, 64, 128, 1);
     }
     return 0;
 }
