@@ -18,17 +18,25 @@ LIB_PATH = os.environ.get("DASR_LIB_PATH") or os.path.join(_HERE, "libdasr_b200.
 # --- enums (include/dasr.h)
 EPI_STORE, EPI_STATS, EPI_SEAN, EPI_SHUFFLE2, EPI_NCHW_F32 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-PACK_CONV, PACK_CONVT, PACK_STYLE, PACK_ROWTAPS = 0, 1, 2, 3
+PACK_CONV, PACK_CONVT, PACK_STYLE, PACK_ROWTAPS, PACK_DGRAD, PACK_DGRAD_CONVT, PACK_OUT9_DGRAD = 0, 1, 2, 3, 4, 5, 6
 
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
-                ("B", "H", "W", "Cin", "Cout", "ks", "epi", "act", "subsample", "clamp01", "inner_relu", "reserved")]
+                ("B", "H", "W", "Cin", "Cout", "ks", "epi", "act", "subsample", "clamp01", "inner_relu", "kw")] + \
+               [("mask_slope", C.c_float)]
 
 
 class ConvArgs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s", "resid_f32",
-                                          "out_aux_f32")]
+    _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s", "actmask",
+                                          "gamma_out", "resid_f32", "out_aux_f32")]
+
+
+class UnpackDesc(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dwp", "dbias_p", "v", "g", "alpha", "bias", "bias2", "dv", "dg", "dbias",
+                                          "dbias2", "dalpha")] + \
+               [(n, C.c_int32) for n in ("dim0", "dim1", "ks", "mode", "alpha_mode", "shuffle_r", "row_offset",
+                                         "rows_per_tap", "ipack", "reserved")]
 
 
 class WgradDesc(C.Structure):
@@ -68,12 +76,28 @@ def load() -> C.CDLL:
         "dasr_zero_insert2": [vp, vp, i32, i32, i32, i32, vp],
         "dasr_add": [vp, vp, vp, vp, i64, vp],
         "dasr_conv_stats_slots": [C.POINTER(ConvDesc)],
-        "dasr_region_pool_fwd": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "dasr_region_pool_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "dasr_unpack_grads": [C.POINTER(UnpackDesc), i32, vp],
+        "dasr_sean_bwd_slots": [i32],
+        "dasr_sean_bwd1": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_sean_bwd_finalize": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_sean_bwd2": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_colsum": [vp, vp, i64, i32, vp],
+        "dasr_dynconv_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dasr_table_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_style_mix_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_region_pool_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_actv_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_unshuffle_actgrad": [vp, vp, vp, i32, i32, i32, i32, C.c_float, vp],
+        "dasr_out9_bwd_prep": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_nchw3_to_nhwc32": [vp, vp, i32, i32, i32, vp],
+        "dasr_actgrad": [vp, vp, vp, i64, C.c_float, vp],
+        "dasr_zero_insert2_to": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "dasr_mask_labels": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_actv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
-        "dasr_instats_finalize": [vp, vp, i32, i32, i32, i32, vp],
+        "dasr_instats_finalize": [vp, vp, vp, i32, i32, i32, i32, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -85,7 +109,11 @@ def load() -> C.CDLL:
 
 EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
-            "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize"]
+            "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize", "dasr_unpack_grads",
+            "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd_finalize", "dasr_sean_bwd2", "dasr_colsum",
+            "dasr_dynconv_bwd", "dasr_table_bwd", "dasr_style_mix_bwd", "dasr_region_pool_bwd", "dasr_actv_bwd",
+            "dasr_unshuffle_actgrad", "dasr_out9_bwd_prep", "dasr_nchw3_to_nhwc32", "dasr_actgrad",
+            "dasr_zero_insert2_to"]
 
 
 def launch_count() -> int:
@@ -116,13 +144,14 @@ def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
 # ------------------------------------------------------------------------------------------------ wrappers
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, *, Cout: int, ks: int,
              epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
-             resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None) -> torch.Tensor:
+             resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None, kw: int = 0,
+             actmask=None, mask_slope: float = 0.0, gamma_out=None) -> torch.Tensor:
     """x: NHWC bf16 [B,H,W,Cin]."""
     B, H, W, Cin = x.shape
-    d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, 0)
+    d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, kw, mask_slope)
     a = ConvArgs(ptr(x, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
-                 ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(resid_f32, torch.float32),
-                 ptr(out_aux_f32, torch.float32))
+                 ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(actmask, torch.bfloat16),
+                 ptr(gamma_out, torch.bfloat16), ptr(resid_f32, torch.float32), ptr(out_aux_f32, torch.float32))
     check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
     return out
 
@@ -138,7 +167,7 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int = 3,
 
 
 def conv_stats_slots(B, H, W, Cin, Cout, ks=3) -> int:
-    d = ConvDesc(B, H, W, Cin, Cout, ks, EPI_STATS, 0, 1, 0, 0, 0)
+    d = ConvDesc(B, H, W, Cin, Cout, ks, EPI_STATS, 0, 1, 0, 0, 0, 0.0)
     n = load().dasr_conv_stats_slots(C.byref(d))
     if n <= 0:
         check(n)

@@ -1,0 +1,409 @@
+"""Training path of DepthNet on libdasr_b200.so: forward with saved activations + hand-written backward.
+
+``depthnet_apply`` is what ``DepthNet.forward`` calls when gradients are enabled.  It is ONE
+``torch.autograd.Function`` over (LQ, depth, masks, *parameters): the forward runs the same kernel schedule as
+``Engine.infer`` while recording a tape of backward closures; the backward replays the tape in reverse and
+returns one gradient per parameter (``None`` for parameters the reference never touches either, e.g.
+``depth-residual14.*`` -- SURVEY.md headline fact 5).  It restates autograd of the reference graph
+(``total_loss.backward()``, codes/models/F_model_depthCond.py:191) with these kernels:
+
+    data gradients     dasr_conv_fwd over DASR_PACK_DGRAD weights (flipped / transposed), with the ReLU /
+                       LeakyReLU mask and the residual accumulation fused into the epilogue
+    weight gradients   dasr_conv_wgrad (tcgen05, MN-major operands) into one flat fp32 buffer in the packed
+                       layout, then dasr_unpack_grads (weight-norm backward, SEAN alpha blend, index maps)
+    SEAN / IN          dasr_sean_bwd1 / _finalize / _bwd2;   K-DYN  dasr_dynconv_bwd + dasr_table_bwd +
+                       dasr_style_mix_bwd;   pooling  dasr_region_pool_bwd;   mlp_mask  dasr_actv_bwd
+    tail               dasr_unshuffle_actgrad (PixelShuffle + LeakyReLU), dasr_out9_bwd_prep (clamp + im2row)
+
+All parameter gradients of one backward live in ONE flat fp32 buffer (``Engine.last_flat_grad``), which is what
+the data-parallel wrapper all-reduces (parallel.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+class _T:
+    """Activation on the tape: NHWC bf16 tensor + how its producer's activation is undone in the backward."""
+    __slots__ = ("data", "act", "pending", "grad", "masked")
+
+    def __init__(self, data, act="none"):
+        self.data = data
+        self.act = act          # 'none' | 'relu' | 'lrelu' : mask applied lazily by the producer's backward
+        self.pending = 0        # consumers that have not back-propagated yet
+        self.grad = None
+        self.masked = False     # the accumulated grad already includes the activation mask
+
+    @property
+    def slope(self):
+        return 0.0 if self.act == "relu" else 0.2
+
+
+class Tape:
+    def __init__(self, eng):
+        self.eng = eng
+        self.lib = L.load()
+        self.ops = []
+        self.s = L.stream_ptr()
+
+    # ------------------------------------------------------------------ gradient bookkeeping
+    def use(self, t: _T) -> _T:
+        t.pending += 1
+        return t
+
+    def accum(self, t: _T, g: torch.Tensor):
+        """Add a contribution (already a finished tensor) to t.grad."""
+        t.pending -= 1
+        if t.grad is None:
+            t.grad = g
+        else:
+            out = torch.empty_like(g)
+            L.check(self.lib.dasr_add(L.ptr(t.grad), None, L.ptr(g), L.ptr(out), g.numel(), self.s))
+            t.grad = out
+
+    def take(self, t: _T) -> torch.Tensor:
+        """Final gradient w.r.t. the PRE-activation value of t (applies the lazy activation mask)."""
+        g = t.grad
+        if g is None:
+            raise RuntimeError("tape: tensor without gradient")
+        t.grad = None
+        if t.act in ("relu", "lrelu") and not t.masked:
+            out = torch.empty_like(g)
+            L.check(self.lib.dasr_actgrad(L.ptr(g), L.ptr(t.data), L.ptr(out), g.numel(), t.slope, self.s))
+            g = out
+        return g
+
+    def dgrad_into(self, t: _T, dy: torch.Tensor, wname: str, *, ks=3, kw=0, subsample=1):
+        """t.grad (+)= conv(dy, dgrad-packed weights).  Fuses the accumulation and -- when this is the last
+        contribution -- the activation mask of t into the convolution epilogue."""
+        eng = self.eng
+        pk = eng._packed[wname]
+        t.pending -= 1
+        last = t.pending == 0
+        B, H, W, _ = dy.shape
+        if subsample == 2:
+            out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=dy.device, dtype=BF16)
+        else:
+            out = torch.empty(B, H, W, pk.cout, device=dy.device, dtype=BF16)
+        mask = None
+        slope = 0.0
+        if last and t.act in ("relu", "lrelu") and not t.masked:
+            mask, slope = t.data, t.slope
+            t.masked = True
+        L.conv_fwd(dy, pk.w, eng._zero_bias, out, Cout=pk.cout, ks=ks, kw=kw, subsample=subsample, resid=t.grad,
+                   actmask=mask, mask_slope=slope)
+        t.grad = out
+
+    # ------------------------------------------------------------------ weight-gradient helpers
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, kh=3, kw=3):
+        dw = self.eng._dw_view(wname)
+        L.conv_wgrad(dy, x, dw, kh, kw)
+
+    def bias_grad(self, dy: torch.Tensor, wname: str):
+        db = self.eng._db_view(wname)
+        C_ = dy.shape[-1]
+        L.check(self.lib.dasr_colsum(L.ptr(dy), L.ptr(db), dy.numel() // C_, C_, self.s))
+
+
+def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=False, convt_src: Optional[_T] = None,
+                need_dgrad=True, bias_grad=True) -> _T:
+    """Generic convolution of the trunk / tail / encoder with its backward closure.
+    x is the tensor the kernel reads (for the transposed conv: the zero-stuffed tensor; convt_src is then the
+    tensor that receives the data gradient, through the subsampling epilogue)."""
+    eng = tp.eng
+    lib = tp.lib
+    acts = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU}
+    if shuffle:
+        out = eng._conv(x.data, name, epi=L.EPI_SHUFFLE2, act=acts[act])
+        o = _T(out, "handled")
+    else:
+        out = eng._conv(x.data, name, act=acts[act], subsample=subsample)
+        o = _T(out, act)
+    target = convt_src if convt_src is not None else x
+    if need_dgrad:
+        tp.use(target)
+
+    def backward():
+        s = tp.s
+        g = o.grad
+        if shuffle:
+            o.grad = None
+            B, H2, W2, Cq = o.data.shape
+            dy = torch.empty(B, H2 // 2, W2 // 2, 4 * Cq, device=g.device, dtype=BF16)
+            L.check(lib.dasr_unshuffle_actgrad(L.ptr(g), L.ptr(o.data), L.ptr(dy), B, H2 // 2, W2 // 2, Cq, 0.2, s))
+        else:
+            dy = tp.take(o)
+        if subsample == 2:      # gradient on the stride-1 grid of the forward kernel
+            B, Ho, Wo, Co = dy.shape
+            H, W = x.data.shape[1], x.data.shape[2]
+            full = torch.empty(B, H, W, Co, device=dy.device, dtype=BF16)
+            L.check(lib.dasr_zero_insert2_to(L.ptr(dy), L.ptr(full), B, Ho, Wo, Co, H, W, s))
+            dy = full
+        tp.wgrad(dy, x.data, name)
+        if bias_grad:
+            tp.bias_grad(dy, name)
+        if need_dgrad:
+            if convt_src is not None:
+                tp.dgrad_into(convt_src, dy, name + ".dg", subsample=2)
+            else:
+                tp.dgrad_into(x, dy, name + ".dg")
+
+    tp.ops.append(backward)
+    return o
+
+
+def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, *, first: bool,
+                resid: Optional[_T]) -> _T:
+    """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
+    eng, lib, s = tp.eng, tp.lib, tp.s
+    x = cur.data
+    B, H, W, nf = x.shape
+    nf2 = 2 * nf
+    K, lat = sean.label_nc, sean.len_latent
+    dev = x.device
+    # ---- forward (same kernels as Engine._dgb, plus the tensors the backward needs)
+    actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+    L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B,
+                              H, W, nf2, s))
+    stp = torch.empty(1, 1, B * K, lat, device=dev, dtype=BF16)
+    L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias), L.ptr(stp), B, K, lat, s))
+    pkt = eng._packed[n + ".table"]
+    table = torch.empty(1, 1, B * K, 9 * nf2, device=dev, dtype=BF16)
+    L.conv_fwd(stp, pkt.w, eng._zero_bias, table, Cout=9 * nf2, ks=1)
+    gb_s = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+    L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W, nf2, s))
+    nslots = L.conv_stats_slots(B, H, W, nf, nf)
+    stats = torch.empty(B, nslots, nf, 2, device=dev, dtype=torch.float32)
+    norm = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
+    normk = torch.empty(B, nf, device=dev, dtype=torch.float32)
+    y = eng._conv(x, conv_name, epi=L.EPI_STATS, stats=stats)
+    L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm), L.ptr(normk), B, nf, H * W, nslots, s))
+    gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
+    if first:
+        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm, gb_s=gb_s, gamma_out=gamma)
+    else:
+        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm, gb_s=gb_s, resid=resid.data,
+                        gamma_out=gamma)
+    del gb_s, table, stats
+    o = _T(out, "handled")
+    tp.use(cur)
+    if resid is not None:
+        tp.use(resid)
+
+    def backward():
+        HW = H * W
+        dout = o.grad
+        o.grad = None
+        slots = lib.dasr_sean_bwd_slots(HW)
+        dgb = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+        dn = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
+        dskip = torch.empty(B, H, W, nf, device=dev, dtype=BF16) if resid is not None else None
+        part = torch.empty(B, slots, nf, 2, device=dev, dtype=torch.float32)
+        L.check(lib.dasr_sean_bwd1(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(norm), L.ptr(gamma), L.ptr(dgb), L.ptr(dn),
+                                   L.ptr(dskip), L.ptr(part), B, HW, nf, s))
+        if resid is not None:
+            tp.accum(resid, dskip)
+        coef = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
+        L.check(lib.dasr_sean_bwd_finalize(L.ptr(part), L.ptr(norm), L.ptr(normk), L.ptr(coef), B, nf, HW, s))
+        dy = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
+        L.check(lib.dasr_sean_bwd2(L.ptr(dn), L.ptr(y), L.ptr(norm), L.ptr(coef), L.ptr(dy), B, HW, nf, s))
+        # ---- gamma_o / beta_o convolution and mlp_mask
+        tp.wgrad(dgb, actv, n + ".gb_o")
+        tp.bias_grad(dgb, n + ".gb_o")
+        pkd = eng._packed[n + ".gb_o.dg"]
+        dA = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+        L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)
+        gw, gb = eng._grad_view(n + ".mlp_mask.0.weight"), eng._grad_view(n + ".mlp_mask.0.bias")
+        L.check(lib.dasr_actv_bwd(L.ptr(dA), L.ptr(depth), L.ptr(gw), L.ptr(gb), B, H, W, nf2, s))
+        # ---- style branch: K-DYN backward -> table GEMM backward -> A_i_j backward
+        dT = torch.zeros(B * K, 9 * nf2, device=dev, dtype=torch.float32)
+        L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+        dWs = eng._dw_view(n + ".table")
+        dstp = torch.empty(B * K, lat, device=dev, dtype=torch.float32)
+        L.check(lib.dasr_table_bwd(L.ptr(dT), L.ptr(stp), L.ptr(pkt.w), L.ptr(dWs), L.ptr(dstp), B * K, 9 * nf2, lat, s))
+        L.check(lib.dasr_style_mix_bwd(L.ptr(dstp), L.ptr(vec), L.ptr(sean.A_i_j.weight),
+                                       L.ptr(eng._grad_view(n + ".A_i_j.weight")),
+                                       L.ptr(eng._grad_view(n + ".A_i_j.bias")), L.ptr(dvec), B, K, lat, s))
+        # ---- the block convolution in front of the norm (its bias gradient is exactly zero: IN removes the mean)
+        tp.wgrad(dy, x, conv_name)
+        tp.dgrad_into(cur, dy, conv_name + ".dg")
+
+    tp.ops.append(backward)
+    return o
+
+
+def _forward_train(eng, lq, depth, masks):
+    net = eng.net
+    lib = L.load()
+    tp = Tape(eng)
+    s = tp.s
+    B, _, h, w = lq.shape
+    K = masks.shape[1]
+    dev = lq.device
+    enc = net.encoder
+
+    # ---- encoder
+    f0d = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
+    L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g), L.ptr(enc.layer1.bias),
+                                L.ptr(f0d), B, h, w, s))
+    f0 = _T(f0d, "lrelu")
+
+    def bwd_first():
+        dy = tp.take(f0)
+        lq32 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
+        L.check(lib.dasr_nchw3_to_nhwc32(L.ptr(lq), L.ptr(lq32), B, h, w, s))
+        tp.wgrad(dy, lq32, "encoder.layer1")
+        tp.bias_grad(dy, "encoder.layer1")
+
+    tp.ops.append(bwd_first)
+
+    vec = labels = flag = dvec = None
+    if not net.isBaseline:
+        e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
+        e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
+        h3, w3 = e3.data.shape[1], e3.data.shape[2]
+        zd = torch.empty(B, 2 * h3 - 1, 2 * w3 - 1, 128, device=dev, dtype=BF16)
+        L.check(lib.dasr_zero_insert2(L.ptr(e3.data), L.ptr(zd), B, h3, w3, 128, s))
+        z = _T(zd, "none")
+        e4 = _conv_train(tp, z, "encoder.layer4", act="lrelu", convt_src=e3)
+        e5 = _conv_train(tp, e4, "encoder.layer5", subsample=2)
+        lat = e5.data.shape[3]
+        P = e5.data.shape[1] * e5.data.shape[2]
+        vec = torch.empty(B, K, lat, device=dev, dtype=torch.float32)
+        msel = torch.empty(B, K, P, device=dev, dtype=torch.float32)
+        cnt = torch.empty(B, K, device=dev, dtype=torch.float32)
+        L.check(lib.dasr_region_pool_fwd(L.ptr(e5.data), L.ptr(masks), L.ptr(vec), L.ptr(msel), L.ptr(cnt), B,
+                                         e5.data.shape[1], e5.data.shape[2], lat, K, h, w, s))
+        dvec = torch.zeros(B, K, lat, device=dev, dtype=torch.float32)
+        tp.use(e5)
+
+        def bwd_pool():
+            de5 = torch.empty_like(e5.data)
+            L.check(lib.dasr_region_pool_bwd(L.ptr(dvec), L.ptr(msel), L.ptr(cnt), L.ptr(de5), B, P, lat, K, s))
+            tp.accum(e5, de5)
+
+        tp.ops.append(bwd_pool)
+        labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
+        flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
+
+    # ---- head + trunk
+    h1 = _conv_train(tp, f0, "head.0", act="lrelu")
+    fea_bef = _conv_train(tp, h1, "head.2", act="lrelu")
+    order = net.block_order()
+
+    def run_block(i, x):
+        if i in net.which_ResBlk_depth:
+            if x.data.shape[1] != h or x.data.shape[2] != w:
+                raise NotImplementedError("depth-guided blocks above LR resolution are not implemented")
+            p = "depth-residual%d" % (i + 1)
+            blk = net.block(i)
+            a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec,
+                            first=True, resid=None)
+            return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec,
+                               first=False, resid=x)
+        p = "classic-residual%d" % (i + 1)
+        f = _conv_train(tp, x, p + ".block.0", act="relu")
+        # relu(x + conv(f)): the residual add is the conv epilogue; its backward = lazy ReLU mask, then both paths
+        pk = eng._packed[p + ".block.2"]
+        outd = eng._conv(f.data, p + ".block.2", act=L.ACT_RELU, resid=x.data)
+        o = _T(outd, "relu")
+        tp.use(f)
+        tp.use(x)
+
+        def bwd_res():
+            dy = tp.take(o)
+            tp.wgrad(dy, f.data, p + ".block.2")
+            tp.bias_grad(dy, p + ".block.2")
+            tp.accum(x, dy)
+            tp.dgrad_into(f, dy, p + ".block.2.dg")
+
+        tp.ops.append(bwd_res)
+        return o
+
+    x = fea_bef
+    for i, pos in order:
+        if pos == "trunk":
+            x = run_block(i, x)
+    addd = torch.empty_like(x.data)
+    L.check(lib.dasr_add(L.ptr(x.data), None, L.ptr(fea_bef.data), L.ptr(addd), addd.numel(), s))
+    add = _T(addd, "none")
+    xa, xb = tp.use(x), tp.use(fea_bef)
+
+    def bwd_add():
+        g = tp.take(add)
+        tp.accum(xa, g)
+        tp.accum(xb, g)
+
+    tp.ops.append(bwd_add)
+    x = add
+
+    # ---- tail
+    if net.scale == 8:
+        x = _conv_train(tp, x, "upscale1.0", act="lrelu", shuffle=True)
+        x = _conv_train(tp, x, "upscale1.3", act="lrelu")
+    x = run_block(order[-2][0], x)
+    if net.scale >= 4:
+        x = _conv_train(tp, x, "upscale2.0", act="lrelu", shuffle=True)
+        x = _conv_train(tp, x, "upscale2.3", act="lrelu")
+    x = run_block(order[-1][0], x)
+    u3 = _conv_train(tp, x, "upscale3.0", act="lrelu", shuffle=True)
+    Bo, Ho, Wo, _ = u3.data.shape
+    sr = torch.empty(B, 3, Ho, Wo, device=dev, dtype=torch.float32)
+    pk = eng._packed["conv_output"]
+    L.check(lib.dasr_conv_out9(L.ptr(u3.data), L.ptr(pk.w), L.ptr(pk.bias), L.ptr(sr), Bo, Ho, Wo, 3, 1, s))
+    tp.use(u3)
+
+    def bwd_out(dsr):
+        ap = torch.empty(Bo, Ho, Wo, 32, device=dev, dtype=BF16)
+        L.check(lib.dasr_out9_bwd_prep(L.ptr(dsr), L.ptr(sr), L.ptr(ap), L.ptr(eng._grad_view("conv_output.bias")), Bo,
+                                       Ho, Wo, s))
+        tp.wgrad(ap, u3.data, "conv_output", kh=9, kw=1)
+        tp.dgrad_into(u3, ap, "conv_output.dg", ks=9, kw=1)
+
+    tp.bwd_out = bwd_out
+    return sr, tp
+
+
+class _DepthNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, lq, depth, masks, *params):
+        if not lq.is_cuda:
+            raise RuntimeError("DepthNet (B200) needs CUDA tensors; there is no CPU fallback")
+        lq = lq.detach().contiguous().float()
+        depth = depth.detach().contiguous().float()
+        masks = masks.detach().contiguous().float()
+        eng.pack(training=True)
+        sr, tp = _forward_train(eng, lq, depth, masks)
+        ctx.eng = eng
+        ctx.tape = tp
+        ctx.n_params = len(params)
+        return sr
+
+    @staticmethod
+    def backward(ctx, dsr):
+        eng, tp = ctx.eng, ctx.tape
+        if tp is None:
+            raise RuntimeError("DepthNet backward called twice (activations are released after the first pass)")
+        ctx.tape = None
+        tp.s = L.stream_ptr()
+        dsr = dsr.contiguous().float()
+        eng._begin_backward(dsr.device)
+        tp.bwd_out(dsr)
+        for op in reversed(tp.ops):
+            op()
+        grads = eng._finish_backward()
+        tp.ops = None
+        return (None, None, None, None) + tuple(grads)
+
+
+def depthnet_apply(eng, lq, depth, masks):
+    params = list(eng.net.parameters())
+    return _DepthNetFn.apply(eng, lq, depth, masks, *params)

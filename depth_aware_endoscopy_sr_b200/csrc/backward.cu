@@ -1,0 +1,623 @@
+// Memory-bound kernels of the DepthNet BACKWARD pass (autograd of the reference graph, reached through
+// total_loss.backward() at codes/models/F_model_depthCond.py:191).  All activations NHWC bf16, all
+// reductions fp32 with a fixed summation order per block (cross-block sums use fp32 atomics where noted).
+//
+//   sean_bwd1 / sean_bwd_finalize / sean_bwd2   SEAN modulate + double InstanceNorm backward
+//                                               (normalization.py:56,87-89; sftmd_arch.py:813,820,828,832-833)
+//   colsum            bias gradients (sum over pixels of a gradient tensor)
+//   dynconv_bwd       K-DYN backward: per-image table gradient dT (normalization.py:81-85 restated)
+//   table_bwd_w/_s    style-table GEMM backward (dW_s, d st')
+//   style_mix_bwd     A_i_j backward (normalization.py:27,80) + accumulation of d depthVec
+//   region_pool_bwd   RegionWiseAvgPooling backward (sftmd_arch.py:714-733)
+//   actv_bwd          mlp_mask (1 -> 2nf conv) weight / bias gradient (normalization.py:37-40)
+//   unshuffle_actgrad PixelShuffle(2) + LeakyReLU backward as one gather (sftmd_arch.py:893-908)
+//   out9_bwd_prep     clamp backward + im2row of the output gradient for the 9x9 conv (sftmd_arch.py:948-950)
+//   nchw3_to_nhwc32   LR image as a 32-channel NHWC bf16 tensor (operand of encoder.layer1's weight gradient)
+#include "dasr_internal.h"
+
+namespace dasr {
+
+__device__ __forceinline__ uint4 bpack8(const float* f) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ void bunpack8(const uint4& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t = __bfloat1622float2(h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------ SEAN backward, pass 1
+// block = (image b, pixel chunk); thread = (8-channel group g, pixel lane).  G = nf / 8.
+//   dz = dout * [act_out > 0]      (ReLU after the modulation / after the residual add)
+//   n  = (y - mean) * scale ;  dgamma = dz * n ; dbeta = dz ; dn = dz * (1 + gamma)
+//   part[b][slot][c] = (sum dn, sum dn * n) over the block's pixels
+template <int G>
+__global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ act_out,
+                                                        const uint4* __restrict__ y, const float* __restrict__ norm,
+                                                        const uint4* __restrict__ gamma, uint4* __restrict__ dgb,
+                                                        uint4* __restrict__ dn_out, uint4* __restrict__ dskip,
+                                                        float* __restrict__ part, int HW, int pix_per_block, int nslots) {
+    constexpr int NF = G * 8;
+    constexpr int LANES = 256 / G;
+    const int b = blockIdx.y, slot = blockIdx.x;
+    const int g = threadIdx.x % G, pl = threadIdx.x / G;
+    float mean[8], scale[8], s1[8], t2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        mean[j] = __ldg(norm + ((size_t)b * NF + g * 8 + j) * 2);
+        scale[j] = __ldg(norm + ((size_t)b * NF + g * 8 + j) * 2 + 1);
+        s1[j] = t2[j] = 0.f;
+    }
+    const int p0 = slot * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+    for (int pix = p0 + pl; pix < p1; pix += LANES) {
+        const size_t i = ((size_t)b * HW + pix) * G + g;
+        float d[8], a[8], yv[8], gm[8], dg[8], dnv[8];
+        bunpack8(__ldg(dout + i), d);
+        bunpack8(__ldg(act_out + i), a);
+        bunpack8(__ldg(y + i), yv);
+        bunpack8(__ldg(gamma + i), gm);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float dz = a[j] > 0.f ? d[j] : 0.f;
+            const float n = (yv[j] - mean[j]) * scale[j];
+            d[j] = dz;
+            dg[j] = dz * n;
+            dnv[j] = dz * (1.f + gm[j]);
+            s1[j] += dnv[j];
+            t2[j] += dnv[j] * n;
+        }
+        const size_t o = ((size_t)b * HW + pix) * (2 * G);
+        dgb[o + g] = bpack8(dg);
+        dgb[o + G + g] = bpack8(d);
+        dn_out[i] = bpack8(dnv);
+        if (dskip) dskip[i] = bpack8(d);
+    }
+    __shared__ float red[2][LANES][NF + 1];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        red[0][pl][g * 8 + j] = s1[j];
+        red[1][pl][g * 8 + j] = t2[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * NF) {
+        const int which = threadIdx.x / NF, c = threadIdx.x - which * NF;
+        float s = 0.f;
+        for (int l = 0; l < LANES; l++) s += red[which][l][c];
+        part[(((size_t)b * nslots + slot) * NF + c) * 2 + which] = s;
+    }
+}
+
+// coef[b][c] = (c1, c2):  dy = scale * (dn - c1) + c2 * n,  c1 = S1 / N,  c2 = -k * T2 / (N * scale)
+// with k = 1/a + eps/(a^2 r), a = var + eps, r = var/a + eps   (norm[b][c] = (mean, scale); normk[b][c] = k)
+__global__ void sean_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ norm,
+                                         const float* __restrict__ normk, float* __restrict__ coef, int n, int C,
+                                         int nslots, float inv_hw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = i / C, c = i - b * C;
+    const float2* sp = reinterpret_cast<const float2*>(part) + (size_t)b * nslots * C + c;
+    float s1 = 0.f, t2 = 0.f;
+    for (int s = 0; s < nslots; s++) {
+        const float2 v = __ldg(sp + (size_t)s * C);
+        s1 += v.x;
+        t2 += v.y;
+    }
+    const float scale = norm[2 * i + 1], k = normk[i];
+    coef[2 * i] = s1 * inv_hw;
+    coef[2 * i + 1] = -k * t2 * inv_hw / scale;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) sean_bwd2_kernel(const uint4* __restrict__ dn, const uint4* __restrict__ y,
+                                                        const float* __restrict__ norm, const float* __restrict__ coef,
+                                                        uint4* __restrict__ dy, int HW, int pix_per_block) {
+    constexpr int NF = G * 8;
+    constexpr int LANES = 256 / G;
+    const int b = blockIdx.y;
+    const int g = threadIdx.x % G, pl = threadIdx.x / G;
+    float mean[8], scale[8], c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const size_t k = (size_t)b * NF + g * 8 + j;
+        mean[j] = __ldg(norm + k * 2);
+        scale[j] = __ldg(norm + k * 2 + 1);
+        c1[j] = __ldg(coef + k * 2);
+        c2[j] = __ldg(coef + k * 2 + 1);
+    }
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+    for (int pix = p0 + pl; pix < p1; pix += LANES) {
+        const size_t i = ((size_t)b * HW + pix) * G + g;
+        float d[8], yv[8];
+        bunpack8(__ldg(dn + i), d);
+        bunpack8(__ldg(y + i), yv);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float n = (yv[j] - mean[j]) * scale[j];
+            d[j] = scale[j] * (d[j] - c1[j]) + c2[j] * n;
+        }
+        dy[i] = bpack8(d);
+    }
+}
+
+// ------------------------------------------------------------------------------------ column sums
+// out[c] += sum_rows x[row][c]   (x bf16 [rows][C], C multiple of 8, C <= 2048); fp32 atomics across blocks
+__global__ void __launch_bounds__(256) colsum_kernel(const uint4* __restrict__ x, float* __restrict__ out, size_t rows,
+                                                     int G, size_t rows_per_block) {
+    const int LANES = 256 / G;
+    const int g = threadIdx.x % G, pl = threadIdx.x / G;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t r0 = blockIdx.x * rows_per_block;
+    const size_t r1 = min(r0 + rows_per_block, rows);
+    if (pl < LANES)
+        for (size_t r = r0 + pl; r < r1; r += LANES) {
+            float f[8];
+            bunpack8(__ldg(x + r * G + g), f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) s[j] += f[j];
+        }
+    extern __shared__ float red[];   // [LANES][G*8 + 1]
+    const int ld = G * 8 + 1;
+    if (pl < LANES)
+#pragma unroll
+        for (int j = 0; j < 8; j++) red[pl * ld + g * 8 + j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < G * 8; c += blockDim.x) {
+        float t = 0.f;
+        for (int l = 0; l < LANES; l++) t += red[l * ld + c];
+        atomicAdd(out + c, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------ K-DYN backward
+// dT[b][k][tap][c] += sum_p dgb[b,p,c] * [label(p + tap - 1) == k]      (one-hot masks)
+//                  += sum_p dgb[b,p,c] * mask[b,k,p + tap - 1]           (general masks)
+// block = (image, band of rows); thread c owns column c of a shared [K*9][C2] fp32 accumulator (no atomics
+// inside the block); bands are combined with fp32 atomics.
+__global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* __restrict__ dgb,
+                                                          const uint8_t* __restrict__ labels,
+                                                          const float* __restrict__ masks, const int* __restrict__ flag,
+                                                          float* __restrict__ dT, int K, int H, int W, int C2,
+                                                          int rows_per_block) {
+    extern __shared__ float acc[];   // [K*9][C2]
+    const int bands = (H + rows_per_block - 1) / rows_per_block;
+    const int b = blockIdx.x / bands, band = blockIdx.x % bands;
+    const int h0 = band * rows_per_block, h1 = min(h0 + rows_per_block, H);
+    const int c = threadIdx.x;
+    if (c >= C2) return;
+    for (int i = 0; i < K * 9; i++) acc[i * C2 + c] = 0.f;
+    const bool general = (labels == nullptr) || (flag != nullptr && *flag != 0);
+    for (int y = h0; y < h1; y++)
+        for (int x = 0; x < W; x++) {
+            const float v = __bfloat162float(dgb[(((size_t)b * H + y) * W + x) * C2 + c]);
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int yy = y + t - 1, xx = x + u - 1;
+                    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                    if (!general) {
+                        const int lab = labels[((size_t)b * H + yy) * W + xx];
+                        if (lab != 255) acc[(lab * 9 + t * 3 + u) * C2 + c] += v;
+                    } else {
+                        for (int k = 0; k < K; k++) {
+                            const float m = __ldg(masks + (((size_t)b * K + k) * H + yy) * W + xx);
+                            if (m != 0.f) acc[(k * 9 + t * 3 + u) * C2 + c] += m * v;
+                        }
+                    }
+                }
+        }
+    float* dst = dT + (size_t)b * K * 9 * C2;
+    for (int i = 0; i < K * 9; i++) atomicAdd(dst + (size_t)i * C2 + c, acc[i * C2 + c]);
+}
+
+// ------------------------------------------------------------------------------------ style-table GEMM backward
+// T[bk][n] = sum_c stp[bk][c] * Ws[n][c]  (n = tap*C2 + o2)
+// dWs[n][c] = sum_bk dT[bk][n] * stp[bk][c]     thread = (n, c)
+__global__ void table_bwd_w_kernel(const float* __restrict__ dT, const __nv_bfloat16* __restrict__ stp,
+                                   float* __restrict__ dWs, int BK, int N, int L) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (c >= L) return;
+    float s = 0.f;
+    for (int bk = 0; bk < BK; bk++) s = fmaf(__ldg(dT + (size_t)bk * N + n), __bfloat162float(stp[(size_t)bk * L + c]), s);
+    dWs[(size_t)n * L + c] = s;
+}
+// dstp[bk][c] = sum_n dT[bk][n] * Ws[n][c]       thread = (bk, c)
+__global__ void table_bwd_s_kernel(const float* __restrict__ dT, const __nv_bfloat16* __restrict__ Ws,
+                                   float* __restrict__ dstp, int BK, int N, int L) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bk = blockIdx.y;
+    if (c >= L) return;
+    float s = 0.f;
+    for (int n = 0; n < N; n++) s = fmaf(__ldg(dT + (size_t)bk * N + n), __bfloat162float(Ws[(size_t)n * L + c]), s);
+    dstp[(size_t)bk * L + c] = s;
+}
+
+// ------------------------------------------------------------------------------------ style mix backward
+// stp[b][j][c] = sum_i A[j][i] vec[b][i][c] + a[j]
+//   dA[j][i] += sum_{b,c} dstp[b][j][c] vec[b][i][c] ; da[j] += sum_{b,c} dstp[b][j][c]     block = (j, i)
+//   dvec[b][i][c] += sum_j A[j][i] dstp[b][j][c]                                             (second kernel)
+__global__ void __launch_bounds__(256) style_mix_bwd_a_kernel(const float* __restrict__ dstp, const float* __restrict__ vec,
+                                                              float* __restrict__ dA, float* __restrict__ da, int B, int K,
+                                                              int L) {
+    const int j = blockIdx.x / K, i = blockIdx.x % K;
+    float s = 0.f, sa = 0.f;
+    for (int idx = threadIdx.x; idx < B * L; idx += blockDim.x) {
+        const int b = idx / L, c = idx - b * L;
+        const float d = dstp[((size_t)b * K + j) * L + c];
+        s = fmaf(d, vec[((size_t)b * K + i) * L + c], s);
+        sa += d;
+    }
+    __shared__ float r0[256], r1[256];
+    r0[threadIdx.x] = s;
+    r1[threadIdx.x] = sa;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off) {
+            r0[threadIdx.x] += r0[threadIdx.x + off];
+            r1[threadIdx.x] += r1[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        dA[j * K + i] += r0[0];
+        if (i == 0) da[j] += r1[0];
+    }
+}
+__global__ void style_mix_bwd_v_kernel(const float* __restrict__ dstp, const float* __restrict__ A,
+                                       float* __restrict__ dvec, int B, int K, int L) {
+    const size_t total = (size_t)B * K * L;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % L;
+        const int i = (idx / L) % K;
+        const int b = idx / ((size_t)L * K);
+        float s = 0.f;
+        for (int j = 0; j < K; j++) s = fmaf(A[j * K + i], dstp[((size_t)b * K + j) * L + c], s);
+        dvec[idx] += s;
+    }
+}
+
+// ------------------------------------------------------------------------------------ region pooling backward
+// de5[b][p][c] = sum_k msel[b][k][p] * dvec[b][k][c] / (cnt[b][k] + 1e-10)      (msel, cnt saved by the forward)
+__global__ void region_pool_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ msel,
+                                       const float* __restrict__ cnt, __nv_bfloat16* __restrict__ de5, int B, int P, int C,
+                                       int K) {
+    const size_t total = (size_t)B * P * C;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % C;
+        const int p = (idx / C) % P;
+        const int b = idx / ((size_t)C * P);
+        float s = 0.f;
+        for (int k = 0; k < K; k++) {
+            const float m = msel[((size_t)b * K + k) * P + p];
+            if (m != 0.f) s += m * dvec[((size_t)b * K + k) * C + c] / (cnt[b * K + k] + 1e-10f);
+        }
+        de5[idx] = __float2bfloat16(s);
+    }
+}
+
+// ------------------------------------------------------------------------------------ actv (mlp_mask) backward
+// dW[c][tap] += sum_{b,p} dA[b,p,c] * depth[b, p + tap - 1] ;  db[c] += sum dA        (dA already ReLU-masked)
+__global__ void __launch_bounds__(128) actv_bwd_kernel(const __nv_bfloat16* __restrict__ dA, const float* __restrict__ depth,
+                                                       float* __restrict__ dW, float* __restrict__ db, int H, int W, int C,
+                                                       int rows_per_block) {
+    const int bands = (H + rows_per_block - 1) / rows_per_block;
+    const int b = blockIdx.x / bands, band = blockIdx.x % bands;
+    const int h0 = band * rows_per_block, h1 = min(h0 + rows_per_block, H);
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    const float* dp = depth + (size_t)b * H * W;
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ab = 0.f;
+    for (int y = h0; y < h1; y++)
+        for (int x = 0; x < W; x++) {
+            const float v = __bfloat162float(dA[(((size_t)b * H + y) * W + x) * C + c]);
+            ab += v;
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int yy = y + t - 1, xx = x + u - 1;
+                    const float d = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dp + yy * W + xx) : 0.f;
+                    acc[t * 3 + u] = fmaf(v, d, acc[t * 3 + u]);
+                }
+        }
+#pragma unroll
+    for (int t = 0; t < 9; t++) atomicAdd(dW + c * 9 + t, acc[t]);
+    atomicAdd(db + c, ab);
+}
+
+// ------------------------------------------------------------------------------------ PixelShuffle + LeakyReLU backward
+// dconv[b,h,w,s*Cq + c] = dps[b,2h+i,2w+j,c] * (ps_out[b,2h+i,2w+j,c] > 0 ? 1 : slope),  s = 2i + j
+__global__ void unshuffle_actgrad_kernel(const uint4* __restrict__ dps, const uint4* __restrict__ ps_out,
+                                         uint4* __restrict__ dconv, int B, int H, int W, int Gq, float slope) {
+    const size_t total = (size_t)B * H * W * 4 * Gq;   // uint4 items of the output
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % Gq;
+        const int s = (idx / Gq) % 4;
+        const size_t pix = idx / ((size_t)Gq * 4);
+        const int w = pix % W;
+        const int h = (pix / W) % H;
+        const int b = pix / ((size_t)W * H);
+        const size_t src = ((((size_t)b * 2 * H + 2 * h + (s >> 1)) * 2 * W) + 2 * w + (s & 1)) * Gq + g;
+        float d[8], o[8];
+        bunpack8(__ldg(dps + src), d);
+        bunpack8(__ldg(ps_out + src), o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j] *= (o[j] > 0.f ? 1.f : slope);
+        dconv[idx] = bpack8(d);
+    }
+}
+
+// ------------------------------------------------------------------------------------ output conv backward prep
+// g = dout * [0 < sr < 1]  (clamp backward);  A'[b,h,w,u*3 + co] = g[b,co,h,w - (u - 4)]  (zero outside), 27 of 32
+// channels used;  dbias[co] += sum g
+__global__ void __launch_bounds__(256) out9_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ sr,
+                                                            __nv_bfloat16* __restrict__ aprime, float* __restrict__ dbias,
+                                                            int B, int H, int W) {
+    const size_t plane = (size_t)H * W;
+    const size_t total = (size_t)B * plane;
+    float sb[3] = {0.f, 0.f, 0.f};
+    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+        const int w = pix % W;
+        const size_t bh = pix / W;          // b*H + h
+        const size_t b = bh / H;
+        const size_t row = b * 3 * plane + (bh - b * H) * W;
+        float out[32];
+#pragma unroll
+        for (int i = 27; i < 32; i++) out[i] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 9; u++) {
+            const int ww = w - (u - 4);
+            const bool in = ww >= 0 && ww < W;
+#pragma unroll
+            for (int co = 0; co < 3; co++) {
+                float gv = 0.f;
+                if (in) {
+                    const size_t k = row + co * plane + ww;
+                    const float s = __ldg(sr + k);
+                    gv = (s > 0.f && s < 1.f) ? __ldg(dout + k) : 0.f;
+                }
+                out[u * 3 + co] = gv;
+                if (u == 4) sb[co] += gv;
+            }
+        }
+        uint4* op = reinterpret_cast<uint4*>(aprime + pix * 32);
+#pragma unroll
+        for (int q = 0; q < 4; q++) op[q] = bpack8(out + 8 * q);
+    }
+    __shared__ float red[3][256];
+    for (int co = 0; co < 3; co++) red[co][threadIdx.x] = sb[co];
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off)
+            for (int co = 0; co < 3; co++) red[co][threadIdx.x] += red[co][threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) atomicAdd(dbias + threadIdx.x, red[threadIdx.x][0]);
+}
+
+// x NCHW fp32 [B,3,H,W] -> NHWC bf16 [B,H,W,32] (channels 3..31 zero)
+__global__ void nchw3_to_nhwc32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+    const size_t plane = (size_t)H * W;
+    const size_t total = (size_t)B * plane;
+    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = pix / plane, p = pix - b * plane;
+        float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 3; c++) f[c] = __ldg(x + (b * 3 + c) * plane + p);
+        uint4* op = reinterpret_cast<uint4*>(out + pix * 32);
+        op[0] = bpack8(f);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        op[1] = z;
+        op[2] = z;
+        op[3] = z;
+    }
+}
+
+// out = d * (act_out > 0 ? 1 : slope)      (ReLU / LeakyReLU backward, out of place)
+__global__ void actgrad_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act_out, uint4* __restrict__ out,
+                               size_t n8, float slope) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float g[8], a[8];
+        bunpack8(__ldg(d + i), g);
+        bunpack8(__ldg(act_out + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; j++) g[j] *= (a[j] > 0.f ? 1.f : slope);
+        out[i] = bpack8(g);
+    }
+}
+
+// zero-stuffed copy with an explicit output size: out[b,ho,wo,:] = x[b,ho/2,wo/2,:] when ho, wo are even and inside
+// the source, else 0  (gradient of a stride-2 convolution on the stride-1 grid)
+__global__ void zero_insert2_to_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int C8,
+                                       int Ho, int Wo) {
+    const size_t total = (size_t)B * Ho * Wo * C8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % C8;
+        size_t pix = i / C8;
+        const int wo = pix % Wo;
+        const int ho = (pix / Wo) % Ho;
+        const int b = pix / ((size_t)Wo * Ho);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (!(ho & 1) && !(wo & 1) && (ho >> 1) < H && (wo >> 1) < W)
+            v = __ldg(x + (((size_t)b * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c);
+        out[i] = v;
+    }
+}
+
+static inline int grid_for(size_t n, int block, int cap = 148 * 16) {
+    size_t g = (n + block - 1) / block;
+    if (g > (size_t)cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace dasr
+
+using namespace dasr;
+
+extern "C" int dasr_sean_bwd_slots(int HW) {
+    // pixels per block chosen so that an image gives ~16 blocks (>= 256 pixels each)
+    int ppb = (HW + 15) / 16;
+    if (ppb < 256) ppb = 256;
+    return (HW + ppb - 1) / ppb;
+}
+static int sean_ppb(int HW) {
+    int ppb = (HW + 15) / 16;
+    if (ppb < 256) ppb = 256;
+    return ppb;
+}
+
+extern "C" int dasr_sean_bwd1(const void* dout, const void* act_out, const void* y, const float* norm, const void* gamma,
+                              void* dgb, void* dn, void* dskip, float* part, int B, int HW, int nf, void* stream) {
+    DASR_REQUIRE(dout && act_out && y && norm && gamma && dgb && dn && part, "null pointer");
+    DASR_REQUIRE(nf == 64 || nf == 32, "nf must be 32 or 64 (got %d)", nf);
+    const int ppb = sean_ppb(HW), slots = (HW + ppb - 1) / ppb;
+    dim3 grid(slots, B);
+    if (nf == 64)
+        sean_bwd1_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint4*)act_out, (const uint4*)y, norm, (const uint4*)gamma, (uint4*)dgb, (uint4*)dn, (uint4*)dskip, part, HW, ppb, slots);
+    else
+        sean_bwd1_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint4*)act_out, (const uint4*)y, norm, (const uint4*)gamma, (uint4*)dgb, (uint4*)dn, (uint4*)dskip, part, HW, ppb, slots);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_sean_bwd_finalize(const float* part, const float* norm, const float* normk, float* coef, int B,
+                                      int nf, int HW, void* stream) {
+    DASR_REQUIRE(part && norm && normk && coef, "null pointer");
+    const int n = B * nf, slots = dasr_sean_bwd_slots(HW);
+    sean_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, norm, normk, coef, n, nf, slots, 1.f / (float)HW);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, const float* coef, void* dy, int B,
+                              int HW, int nf, void* stream) {
+    DASR_REQUIRE(dn && y && norm && coef && dy, "null pointer");
+    DASR_REQUIRE(nf == 64 || nf == 32, "nf must be 32 or 64 (got %d)", nf);
+    const int ppb = sean_ppb(HW), slots = (HW + ppb - 1) / ppb;
+    dim3 grid(slots, B);
+    if (nf == 64)
+        sean_bwd2_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, coef, (uint4*)dy, HW, ppb);
+    else
+        sean_bwd2_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, coef, (uint4*)dy, HW, ppb);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_colsum(const void* x, float* out, int64_t rows, int C, void* stream) {
+    DASR_REQUIRE(x && out && rows > 0, "bad arguments");
+    DASR_REQUIRE(C % 8 == 0 && C >= 8 && 256 % (C / 8) == 0, "colsum: unsupported C %d", C);
+    const int G = C / 8;
+    const int lanes = 256 / G;
+    size_t rpb = ((size_t)rows + 2 * 148 - 1) / (2 * 148);
+    if (rpb < (size_t)lanes * 4) rpb = (size_t)lanes * 4;
+    const int grid = (int)(((size_t)rows + rpb - 1) / rpb);
+    colsum_kernel<<<grid, 256, (size_t)lanes * (C + 1) * sizeof(float), (cudaStream_t)stream>>>((const uint4*)x, out, (size_t)rows, G, rpb);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const float* masks, const int32_t* flag,
+                                float* dT, int B, int K, int H, int W, int nf2, void* stream) {
+    DASR_REQUIRE(dgb && dT && (labels || masks), "null pointer");
+    DASR_REQUIRE(nf2 <= 128, "2*nf must be <= 128");
+    const int rows = 8;
+    const size_t smem = (size_t)K * 9 * nf2 * sizeof(float);
+    static bool configured[64] = {false};
+    int dev = 0;
+    DASR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        DASR_CUDA_OK(cudaFuncSetAttribute(dynconv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured[dev & 63] = true;
+    }
+    DASR_REQUIRE(smem <= 100 * 1024, "table too large");
+    const int bands = (H + rows - 1) / rows;
+    dynconv_bwd_kernel<<<B * bands, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dgb, labels, masks, flag, dT, K, H, W, nf2, rows);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N,
+                              int L, void* stream) {
+    DASR_REQUIRE(dT && stp && Ws && dWs && dstp, "null pointer");
+    const int bx = L < 128 ? L : 128;
+    table_bwd_w_kernel<<<dim3((L + bx - 1) / bx, N), bx, 0, (cudaStream_t)stream>>>(dT, (const __nv_bfloat16*)stp, dWs, BK, N, L);
+    DASR_LAUNCH_OK();
+    table_bwd_s_kernel<<<dim3((L + bx - 1) / bx, BK), bx, 0, (cudaStream_t)stream>>>(dT, (const __nv_bfloat16*)Ws, dstp, BK, N, L);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_style_mix_bwd(const float* dstp, const float* vec, const float* A, float* dA, float* da, float* dvec,
+                                  int B, int K, int L, void* stream) {
+    DASR_REQUIRE(dstp && vec && A && dA && da && dvec, "null pointer");
+    style_mix_bwd_a_kernel<<<K * K, 256, 0, (cudaStream_t)stream>>>(dstp, vec, dA, da, B, K, L);
+    DASR_LAUNCH_OK();
+    style_mix_bwd_v_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(dstp, A, dvec, B, K, L);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_region_pool_bwd(const float* dvec, const float* msel, const float* cnt, void* de5, int B, int P, int C,
+                                    int K, void* stream) {
+    DASR_REQUIRE(dvec && msel && cnt && de5, "null pointer");
+    region_pool_bwd_kernel<<<grid_for((size_t)B * P * C, 256), 256, 0, (cudaStream_t)stream>>>(dvec, msel, cnt, (__nv_bfloat16*)de5, B, P, C, K);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_actv_bwd(const void* dA, const float* depth, float* dW, float* db, int B, int H, int W, int C,
+                             void* stream) {
+    DASR_REQUIRE(dA && depth && dW && db && C <= 128, "bad arguments");
+    const int rows = 8;
+    const int bands = (H + rows - 1) / rows;
+    actv_bwd_kernel<<<B * bands, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dA, depth, dW, db, H, W, C, rows);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_unshuffle_actgrad(const void* dps, const void* ps_out, void* dconv, int B, int H, int W, int Cq,
+                                      float slope, void* stream) {
+    DASR_REQUIRE(dps && ps_out && dconv && Cq % 8 == 0, "bad arguments");
+    const size_t total = (size_t)B * H * W * 4 * (Cq / 8);
+    unshuffle_actgrad_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)dps, (const uint4*)ps_out, (uint4*)dconv, B, H, W, Cq / 8, slope);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_out9_bwd_prep(const float* dout, const float* sr, void* aprime, float* dbias, int B, int H, int W,
+                                  void* stream) {
+    DASR_REQUIRE(dout && sr && aprime && dbias, "null pointer");
+    out9_bwd_prep_kernel<<<grid_for((size_t)B * H * W, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(dout, sr, (__nv_bfloat16*)aprime, dbias, B, H, W);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_actgrad(const void* d, const void* act_out, void* out, int64_t n, float slope, void* stream) {
+    DASR_REQUIRE(d && act_out && out && n % 8 == 0, "bad arguments");
+    actgrad_kernel<<<grid_for((size_t)n / 8, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)d, (const uint4*)act_out, (uint4*)out, (size_t)n / 8, slope);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_zero_insert2_to(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
+    DASR_REQUIRE(x && out && C % 8 == 0, "bad arguments");
+    zero_insert2_to_kernel<<<grid_for((size_t)B * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, B, H, W, C / 8, Ho, Wo);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_nchw3_to_nhwc32(const float* x, void* out, int B, int H, int W, void* stream) {
+    DASR_REQUIRE(x && out, "null pointer");
+    nchw3_to_nhwc32_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, B, H, W);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}

@@ -49,7 +49,7 @@ constexpr int kMaxBias = 1152;
 struct ConvK {
     // geometry
     int B, H, W, Cin, Cout;
-    int ks, pad, taps;
+    int kh, kw, pad_h, pad_w, taps;
     int Wt, Wp, RB;
     int n_strips, tiles_per_strip, ntn, total_tiles;
     int nch;                       // Cin / KC
@@ -66,6 +66,9 @@ struct ConvK {
     const __nv_bfloat16* y;
     const float* norm;
     const __nv_bfloat16* gb_s;
+    const __nv_bfloat16* actmask;  // STORE: multiply by (actmask > 0 ? 1 : mask_slope) -- activation backward
+    float mask_slope;
+    __nv_bfloat16* gamma_out;      // SEAN: optional copy of gamma (bf16 [B,H,W,nf]) for the backward pass
     const float* resid_f32;        // SEAN: fp32 residual stream (takes precedence over resid)
     float* out_aux_f32;            // SEAN: fp32 copy of the output (the residual stream of the next block)
     int nslots;                    // STATS: partial-sum slots per image
@@ -218,7 +221,9 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
             float t = fmaf(n, 1.f + g, b);
             if (p.inner_relu) t = fmaxf(t, 0.f);
             f[j] = t;
+            gs[j] = g;
         }
+        if (p.gamma_out) store16(p.gamma_out + o.pix * NF + c0, gs);
         if (p.resid_f32) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -294,7 +299,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_s);
     for (int i = threadIdx.x; i < p.n_bias; i += kThreads) bias_s[i] = __ldg(p.bias + i);
     if (threadIdx.x < p.taps) {
-        const int t = threadIdx.x / p.ks, u = threadIdx.x - t * p.ks;
+        const int t = threadIdx.x / p.kw, u = threadIdx.x - t * p.kw;
         tap_lo_s[threadIdx.x] = (uint32_t)((t * p.Wp + u) * SWZ) >> 4;
     }
     tc_fence_before();
@@ -328,7 +333,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     PROF_LAP(0);
                     mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
                     tma_load_4d(a_smem + (size_t)sa * p.a_stage_bytes, &mapA, &a_full[sa], c * KC,
-                                w0 - p.pad, r0 - p.pad, img);
+                                w0 - p.pad_w, r0 - p.pad_h, img);
                     a_it++;
                 }
             }
@@ -514,13 +519,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
                     __nv_bfloat16* op = p.out + pix * p.Cout + nt * N_TILE;
                     const __nv_bfloat16* rp = p.resid ? p.resid + pix * p.Cout + nt * N_TILE : nullptr;
+                    const __nv_bfloat16* mp = p.actmask ? p.actmask + pix * p.Cout + nt * N_TILE : nullptr;
                     const int slot = ((strip * p.tiles_per_strip + tps) * NB + blk) * 4 + ew;
 #pragma unroll 1
                     for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
-                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+                        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, m0 = r0, m1 = r0;
                         if (rp && valid) {
                             r0 = __ldg(reinterpret_cast<const uint4*>(rp + c0));
                             r1 = __ldg(reinterpret_cast<const uint4*>(rp + c0) + 1);
+                        }
+                        if (mp && valid) {
+                            m0 = __ldg(reinterpret_cast<const uint4*>(mp + c0));
+                            m1 = __ldg(reinterpret_cast<const uint4*>(mp + c0) + 1);
                         }
                         uint32_t v[16];
                         tmem_ld16(t_blk + c0, v);
@@ -538,6 +548,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             }
 #pragma unroll
                             for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
+                            if (mp) {
+                                float mm[16];
+                                unpack8(m0, mm);
+                                unpack8(m1, mm + 8);
+#pragma unroll
+                                for (int j = 0; j < 16; j++) f[j] *= (mm[j] > 0.f ? 1.f : p.mask_slope);
+                            }
                             if (valid) store16(op + c0, f);
                         } else {
                             // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
@@ -672,7 +689,7 @@ extern "C" int dasr_conv_stats_slots(const dasr_conv_desc* d) {
     const int NB = 2, max_wt = 128;
     const int n_strips = (d->W + max_wt - 1) / max_wt;
     const int Wt = (d->W + n_strips - 1) / n_strips;
-    const int Wp = Wt + d->ks - 1;
+    const int Wp = Wt + (d->kw > 0 ? d->kw : d->ks) - 1;
     const int span = (d->H - 1) * Wp + Wt;
     const int blocks = (span + 127) / 128;
     const int tiles_per_strip = (blocks + NB - 1) / NB;
@@ -690,7 +707,9 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     ConvK k;
     memset(&k, 0, sizeof k);
     k.B = d->B; k.H = d->H; k.W = d->W; k.Cin = d->Cin; k.Cout = d->Cout;
-    k.ks = d->ks; k.pad = d->ks / 2; k.taps = d->ks * d->ks;
+    k.kh = d->ks; k.kw = d->kw > 0 ? d->kw : d->ks;
+    k.pad_h = k.kh / 2; k.pad_w = k.kw / 2; k.taps = k.kh * k.kw;
+    DASR_REQUIRE(k.kw == 1 || k.kw == 3 || k.kw == 9, "kw must be 1, 3 or 9 (got %d)", k.kw);
     k.epi = d->epi; k.act = d->act; k.subsample = d->subsample ? d->subsample : 1;
     k.clamp01 = d->clamp01; k.inner_relu = d->inner_relu;
 
@@ -725,12 +744,12 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     const int max_wt = 128;
     k.n_strips = (d->W + max_wt - 1) / max_wt;
     k.Wt = (d->W + k.n_strips - 1) / k.n_strips;
-    k.Wp = k.Wt + d->ks - 1;
+    k.Wp = k.Wt + k.kw - 1;
     const int span = (d->H - 1) * k.Wp + k.Wt;  // padded-flat positions that contain valid outputs
     const int blocks = (span + 127) / 128;
     k.tiles_per_strip = (blocks + NB - 1) / NB;
     k.total_tiles = d->B * k.n_strips * k.tiles_per_strip * k.ntn;
-    k.RB = (k.Wp - 1 + NB * 128 + (d->ks - 1) * (k.Wp + 1) + k.Wp - 1) / k.Wp;
+    k.RB = (k.Wp - 1 + NB * 128 + (k.kh - 1) * k.Wp + (k.kw - 1) + k.Wp - 1) / k.Wp;
     DASR_REQUIRE(k.RB <= 256 && k.Wp <= 256, "TMA box too large");
 
     k.a_tx_bytes = (uint32_t)k.RB * k.Wp * SWZ;
@@ -775,6 +794,9 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.y = (const __nv_bfloat16*)a->y;
     k.norm = a->norm;
     k.gb_s = (const __nv_bfloat16*)a->gb_s;
+    k.actmask = (const __nv_bfloat16*)a->actmask;
+    k.mask_slope = d->mask_slope;
+    k.gamma_out = (__nv_bfloat16*)a->gamma_out;
     k.resid_f32 = a->resid_f32;
     k.out_aux_f32 = a->out_aux_f32;
     k.nslots = k.n_strips * k.tiles_per_strip * NB * 4;

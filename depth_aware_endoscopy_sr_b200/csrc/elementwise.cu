@@ -119,6 +119,7 @@ __global__ void add_kernel(const uint4* __restrict__ a, const float4* __restrict
 constexpr int kPoolMaxPos = 8192;
 __global__ void __launch_bounds__(256) region_pool_kernel(const __nv_bfloat16* __restrict__ e5,
                                                           const float* __restrict__ masks, float* __restrict__ vec,
+                                                          float* __restrict__ msel_out, float* __restrict__ cnt_out,
                                                           int hf, int wf, int C, int K, int H, int W) {
     __shared__ float msel[kPoolMaxPos];
     __shared__ float cnt_s;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(256) region_pool_kernel(const __nv_bfloat16* _
             m = (val >= 0.5f) ? 1.f : 0.f;
         }
         msel[p] = m;
+        if (msel_out) msel_out[(size_t)blockIdx.x * P + p] = m;   // saved for the backward pass
         local += m;
     }
     __shared__ float red[8];
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256) region_pool_kernel(const __nv_bfloat16* _
         float t = 0.f;
         for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
         cnt_s = t;
+        if (cnt_out) cnt_out[blockIdx.x] = t;
     }
     __syncthreads();
     const float inv = 1.f / (cnt_s + 1e-10f);
@@ -365,8 +368,8 @@ __global__ void dynconv_masks_kernel(const __nv_bfloat16* __restrict__ table, co
 }
 
 // ------------------------------------------------------------------------------------ IN statistics
-__global__ void instats_finalize_kernel(const float* __restrict__ stats, float* __restrict__ norm, int n, int C,
-                                        int nslots, float inv_hw) {
+__global__ void instats_finalize_kernel(const float* __restrict__ stats, float* __restrict__ norm,
+                                        float* __restrict__ normk, int n, int C, int nslots, float inv_hw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int b = i / C, c = i - b * C;
@@ -386,6 +389,10 @@ __global__ void instats_finalize_kernel(const float* __restrict__ stats, float* 
     const float r2 = rsqrtf(var * r1 * r1 + eps);
     norm[2 * i] = mean;
     norm[2 * i + 1] = r1 * r2;
+    if (normk) {   // backward: k = -2 s'(v) / s = 1/a + eps / (a^2 r), a = v + eps, r = v/a + eps
+        const float a = var + eps, r = var / a + eps;
+        normk[i] = 1.f / a + eps / (a * a * r);
+    }
 }
 
 static inline int grid_for(size_t n, int block, int cap = 148 * 16) {
@@ -423,11 +430,11 @@ extern "C" int dasr_add(const void* a, const float* a32, const void* b, void* ou
     return DASR_OK;
 }
 
-extern "C" int dasr_region_pool_fwd(const void* e5, const float* masks, float* depth_vec, int B, int hf, int wf, int C,
-                                    int K, int H, int W, void* stream) {
+extern "C" int dasr_region_pool_fwd(const void* e5, const float* masks, float* depth_vec, float* msel, float* cnt,
+                                    int B, int hf, int wf, int C, int K, int H, int W, void* stream) {
     DASR_REQUIRE(e5 && masks && depth_vec, "null pointer");
     DASR_REQUIRE(hf * wf <= kPoolMaxPos, "feature map %dx%d too large for region pooling (max %d positions)", hf, wf, kPoolMaxPos);
-    region_pool_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)e5, masks, depth_vec, hf, wf, C, K, H, W);
+    region_pool_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)e5, masks, depth_vec, msel, cnt, hf, wf, C, K, H, W);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -493,10 +500,11 @@ extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const 
     return DASR_OK;
 }
 
-extern "C" int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, int nslots, void* stream) {
+extern "C" int dasr_instats_finalize(const float* stats, float* norm, float* normk, int B, int C, int HW, int nslots,
+                                     void* stream) {
     DASR_REQUIRE(stats && norm && HW > 0 && nslots > 0, "bad arguments");
     const int n = B * C;
-    instats_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, norm, n, C, nslots, 1.f / (float)HW);
+    instats_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, norm, normk, n, C, nslots, 1.f / (float)HW);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -54,6 +54,33 @@ __global__ void pack_scale_kernel(const PackBatch pb, float* __restrict__ scratc
 __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ scratch) {
     const dasr_pack_desc& d = pb.d[blockIdx.y];
     const int ks = d.ks, taps = ks * ks;
+    if (d.mode >= DASR_PACK_DGRAD) {
+        // data-gradient layouts: walk the SOURCE linearly (coalesced reads), scatter to dst
+        const float* scd = scratch + pb.scale_off[blockIdx.y];
+        __nv_bfloat16* dstd = (__nv_bfloat16*)d.dst;
+        const int n = d.dim0 * d.dim1 * taps;
+        for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+            const int a = idx / (d.dim1 * taps);
+            const int rem = idx - a * (d.dim1 * taps);
+            const int b = rem / taps, tap = rem - b * taps;
+            const float w = d.v[idx] * scd[a];
+            if (d.mode == DASR_PACK_DGRAD) {            // a = o, b = i
+                const int Ot = d.rows_per_tap > 0 ? d.rows_per_tap : d.dim0;
+                int no = a;
+                if (d.shuffle_r > 1) {
+                    const int r2 = d.shuffle_r * d.shuffle_r;
+                    no = (a % r2) * (d.dim0 / r2) + a / r2;
+                }
+                dstd[(size_t)b * (taps * Ot) + (size_t)(taps - 1 - tap) * Ot + d.row_offset + no] = __float2bfloat16(w);
+            } else if (d.mode == DASR_PACK_DGRAD_CONVT) {   // a = i, b = o
+                dstd[(size_t)a * (taps * d.dim1) + (size_t)tap * d.dim1 + b] = __float2bfloat16(w);
+            } else {                                     // OUT9_DGRAD: a = o (3), b = i (32), tap = t*9 + u
+                const int t = tap / ks, u = tap - t * ks;
+                dstd[(size_t)b * (ks * 32) + (size_t)(ks - 1 - t) * 32 + u * d.dim0 + a] = __float2bfloat16(w);
+            }
+        }
+        return;
+    }
     const int O = d.mode != DASR_PACK_CONVT ? d.dim0 : d.dim1;
     const int I = d.mode != DASR_PACK_CONVT ? d.dim1 : d.dim0;
     const int K = taps * I;
@@ -102,9 +129,128 @@ __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------ gradient unpacking
+// Inverse of the packing above for GRADIENTS: the weight-gradient kernels produce d(packed weight) in fp32; this
+// kernel gathers it back into the parameter's own layout and applies the chain rule of
+//   w_eff[a] = f * (g[a] / ||v[a]||) * v[a]      (f = alpha | 1 - alpha | 1; g absent for plain convs)
+// i.e. weight-norm backward (sftmd_arch.py:740,851 -> torch._weight_norm backward) and the SEAN blend
+// (normalization.py:87-88).  One block per (descriptor, dim0 index a).
+constexpr int kUnpackBatch = 16;
+struct UnpackBatch {
+    dasr_unpack_desc d[kUnpackBatch];
+    int n;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += red[i];
+    return t;
+}
+
+__device__ __forceinline__ size_t packed_index(const dasr_unpack_desc& d, int a, int b, int tap) {
+    const int ks = d.ks, taps = ks * ks;
+    const int ipk = d.ipack > 0 ? d.ipack : d.dim1;
+    switch (d.mode) {
+        case DASR_PACK_CONV: {
+            int row = a;
+            if (d.shuffle_r > 1) {
+                const int r2 = d.shuffle_r * d.shuffle_r;
+                row = (a % r2) * (d.dim0 / r2) + a / r2;
+            }
+            return (size_t)(row + d.row_offset) * (taps * ipk) + (size_t)tap * ipk + b;
+        }
+        case DASR_PACK_CONVT:   // a = i, b = o ; forward packed w'[o][(flip tap, i)]
+            return (size_t)b * (taps * d.dim0) + (size_t)(taps - 1 - tap) * d.dim0 + a;
+        case DASR_PACK_STYLE:
+            return (size_t)(tap * d.rows_per_tap + d.row_offset + a) * d.dim1 + b;
+        default: {              // DASR_PACK_ROWTAPS: gradient laid out [u*O + o][t*32 + c]
+            const int t = tap / ks, u = tap - t * ks;
+            return (size_t)(u * d.dim0 + a) * (ks * 32) + (size_t)t * 32 + b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) unpack_grads_kernel(const UnpackBatch ub) {
+    int a = blockIdx.x, di = 0;
+    while (di < ub.n && a >= ub.d[di].dim0) {
+        a -= ub.d[di].dim0;
+        di++;
+    }
+    if (di >= ub.n) return;
+    const dasr_unpack_desc& d = ub.d[di];
+    __shared__ float red[8];
+    const int taps = d.ks * d.ks;
+    const int inner = d.dim1 * taps;
+    const float* vp = d.v + (size_t)a * inner;
+    // pass 1: <DW, v> and ||v||^2
+    float dot = 0.f, vv = 0.f;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+        const int b = i / taps, tap = i - b * taps;
+        const float w = vp[i];
+        dot = fmaf(d.dwp[packed_index(d, a, b, tap)], w, dot);
+        vv = fmaf(w, w, vv);
+    }
+    dot = block_sum(dot, red);
+    vv = block_sum(vv, red);
+    float f = 1.f;
+    if (d.alpha_mode == 1) f = *d.alpha;
+    if (d.alpha_mode == 2) f = 1.f - *d.alpha;
+    const float nrm = sqrtf(vv);
+    const float s = d.g ? d.g[a] / nrm : 1.f;           // w_raw = s * v
+    // pass 2: dv
+    const float k = d.g ? dot / vv : 0.f;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+        const int b = i / taps, tap = i - b * taps;
+        const float dw = d.dwp[packed_index(d, a, b, tap)];
+        d.dv[(size_t)a * inner + i] = f * s * (dw - k * vp[i]);
+    }
+    if (threadIdx.x == 0) {
+        if (d.g) d.dg[a] = f * dot / nrm;
+        float dal = 0.f;
+        if (d.alpha_mode) dal = (d.alpha_mode == 1 ? 1.f : -1.f) * s * dot;   // <DW, w_raw>
+        if (d.dbias_p) {
+            int row = a;
+            if (d.mode == DASR_PACK_CONV && d.shuffle_r > 1) {
+                const int r2 = d.shuffle_r * d.shuffle_r;
+                row = (a % r2) * (d.dim0 / r2) + a / r2;
+            }
+            const float db = d.dbias_p[row + d.row_offset];
+            if (d.dbias) d.dbias[a] = (d.alpha_mode ? f : 1.f) * db;
+            if (d.dbias2) d.dbias2[a] = (1.f - f) * db;
+            if (d.alpha_mode == 2 && d.bias && d.bias2) dal += db * (d.bias2[a] - d.bias[a]);
+        }
+        if (d.alpha_mode && d.dalpha) atomicAdd(d.dalpha, dal);
+    }
+}
+
 }  // namespace dasr
 
 using namespace dasr;
+
+extern "C" int dasr_unpack_grads(const dasr_unpack_desc* descs, int n, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DASR_REQUIRE(descs && n > 0, "bad arguments");
+    for (int start = 0; start < n; start += kUnpackBatch) {
+        UnpackBatch ub;
+        ub.n = (n - start) < kUnpackBatch ? (n - start) : kUnpackBatch;
+        int rows = 0;
+        for (int i = 0; i < ub.n; i++) {
+            ub.d[i] = descs[start + i];
+            const dasr_unpack_desc& d = ub.d[i];
+            DASR_REQUIRE(d.dwp && d.v && d.dv && d.dim0 > 0 && d.dim1 > 0 && d.ks > 0, "bad unpack descriptor %d", start + i);
+            DASR_REQUIRE(!d.g || d.dg, "descriptor %d: weight_g without a gradient buffer", start + i);
+            DASR_REQUIRE(d.alpha_mode == 0 || d.alpha, "descriptor %d: alpha_mode without alpha", start + i);
+            rows += d.dim0;
+        }
+        unpack_grads_kernel<<<rows, 128, 0, stream>>>(ub);
+        DASR_LAUNCH_OK();
+    }
+    return DASR_OK;
+}
 
 extern "C" int dasr_pack_weights(const dasr_pack_desc* descs, int n, float* scratch, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -40,6 +40,8 @@ class Engine:
     def __init__(self, net):
         self.net = net
         self._key = None
+        self._key_bwd = None
+        self.last_flat_grad = None
         self._packed: Dict[str, _Packed] = {}
         self._descs: List[L.PackDesc] = []
         self._scratch = None
@@ -73,8 +75,32 @@ class Engine:
 
         self._packed = {}
         self._descs = []
-        self._keep = []   # tensors referenced by raw pointers in the descriptors
+        self._descs_bwd = []      # data-gradient (flipped / transposed) copies, packed only when training
+        self._wg = {}             # name -> (offset, rows, K) into the flat fp32 weight-gradient buffer
+        self._bg = {}             # name -> (offset, rows) into the flat fp32 packed-bias-gradient buffer
+        self._unpack_specs = []   # recipes for dasr_unpack_grads (built lazily, see _build_unpack)
+        self._wg_total = 0
+        self._bg_total = 0
+        self._used_params = set()
         rows_total = 0
+        rows_bwd = 0
+
+        def reserve(name, rows, kdim):
+            self._wg[name] = (self._wg_total, rows, kdim)
+            self._wg_total += rows * kdim
+            self._bg[name] = (self._bg_total, rows)
+            self._bg_total += rows
+
+        def add_dgrad(name, v, g, *, mode=L.PACK_DGRAD, shuffle_r=0):
+            nonlocal rows_bwd
+            if mode == L.PACK_DGRAD:
+                rows, kdim, co = v.shape[1], v.shape[2] * v.shape[3] * v.shape[0], v.shape[1]
+            else:   # PACK_DGRAD_CONVT: [I][O][k][k] -> rows = I
+                rows, kdim, co = v.shape[0], v.shape[2] * v.shape[3] * v.shape[1], v.shape[0]
+            dst = torch.zeros(rows, kdim, device=device, dtype=BF16)
+            self._descs_bwd.append(L.pack_desc(v, dst, g=g, mode=mode, shuffle_r=shuffle_r))
+            rows_bwd += v.shape[0]
+            self._packed[name + ".dg"] = _Packed(dst, None, co, kdim // (v.shape[2] * v.shape[3]), v.shape[2])
 
         def add(name, v, g, bias, *, mode=L.PACK_CONV, shuffle_r=0, rows_pad=None):
             nonlocal rows_total
@@ -87,9 +113,22 @@ class Engine:
             self._descs.append(L.pack_desc(v, dst, g=g, bias=bias, dst_bias=dbias, mode=mode, shuffle_r=shuffle_r))
             rows_total += v.shape[0]
             self._packed[name] = _Packed(dst, dbias, cout, cin, ks)
+            reserve(name, rows, ks * ks * cin)
 
-        def add_wn(name, **kw):
+        def add_wn(name, dgrad=True, **kw):
             add(name, P(name + ".weight_v"), P(name + ".weight_g"), P(name + ".bias"), **kw)
+            mode = kw.get("mode", L.PACK_CONV)
+            if dgrad:
+                add_dgrad(name, P(name + ".weight_v"), P(name + ".weight_g"),
+                          mode=L.PACK_DGRAD_CONVT if mode == L.PACK_CONVT else L.PACK_DGRAD,
+                          shuffle_r=kw.get("shuffle_r", 0))
+            self._unpack_specs.append(dict(kind="wn", name=name, mode=mode, shuffle_r=kw.get("shuffle_r", 0)))
+            self._used_params.update([name + ".weight_v", name + ".weight_g", name + ".bias"])
+
+        # encoder.layer1 runs in its own kernel; only its weight gradient goes through the generic path
+        reserve("encoder.layer1", 32, 9 * 32)
+        self._unpack_specs.append(dict(kind="wn", name="encoder.layer1", mode=L.PACK_CONV, shuffle_r=0, ipack=32))
+        self._used_params.update(["encoder.layer1.weight_v", "encoder.layer1.weight_g", "encoder.layer1.bias"])
 
         if not net.isBaseline:
             add_wn("encoder.layer2")
@@ -104,7 +143,11 @@ class Engine:
                 p = "depth-residual%d" % (i + 1)
                 nf = blk.nf
                 for j in (1, 2):
-                    add("%s.conv%d.0" % (p, j), P("%s.conv%d.0.weight" % (p, j)), None, P("%s.conv%d.0.bias" % (p, j)))
+                    cn = "%s.conv%d.0" % (p, j)
+                    add(cn, P(cn + ".weight"), None, P(cn + ".bias"))
+                    add_dgrad(cn, P(cn + ".weight"), None)
+                    self._unpack_specs.append(dict(kind="plain", name=cn))
+                    self._used_params.update([cn + ".weight", cn + ".bias"])
                     n = "%s.norm%d" % (p, j)
                     ag, ab = P(n + ".alpha_gamma"), P(n + ".alpha_beta")
                     lat = blk.norm1.len_latent
@@ -118,6 +161,20 @@ class Engine:
                                                        row_offset=off))
                         rows_total += nf
                     self._packed[n + ".gb_o"] = _Packed(wo, bo, 2 * nf, 2 * nf, 3)
+                    reserve(n + ".gb_o", 2 * nf, 9 * 2 * nf)
+                    wod = torch.zeros(2 * nf, 9 * 2 * nf, device=device, dtype=BF16)
+                    for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
+                        self._descs_bwd.append(L.pack_desc(P("%s.mlp_%s_o.weight" % (n, x)), wod, alpha=al, alpha_mode=2,
+                                                           mode=L.PACK_DGRAD, row_offset=off, rows_per_tap=2 * nf))
+                        rows_bwd += nf
+                    self._packed[n + ".gb_o.dg"] = _Packed(wod, None, 2 * nf, 2 * nf, 3)
+                    self._unpack_specs.append(dict(kind="sean", name=n, nf=nf, lat=lat))
+                    for x in ("gamma", "beta"):
+                        self._used_params.update(["%s.mlp_%s_o.weight" % (n, x), "%s.mlp_%s_o.bias" % (n, x),
+                                                  "%s.mlp_%s_s.weight" % (n, x), "%s.mlp_%s_s.bias" % (n, x),
+                                                  "%s.alpha_%s" % (n, x)])
+                    self._used_params.update([n + ".mlp_mask.0.weight", n + ".mlp_mask.0.bias", n + ".A_i_j.weight",
+                                              n + ".A_i_j.bias"])
                     # style-table GEMM operand: rows = tap * 2nf + [gamma | beta], K = latent, scaled by alpha
                     ws = torch.zeros(9 * 2 * nf, lat, device=device, dtype=BF16)
                     for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
@@ -125,6 +182,8 @@ class Engine:
                                                        mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf))
                         rows_total += nf
                     self._packed[n + ".table"] = _Packed(ws, None, 9 * 2 * nf, lat, 1)
+                    self._wg[n + ".table"] = (self._wg_total, 9 * 2 * nf, lat)
+                    self._wg_total += 9 * 2 * nf * lat
             else:
                 p = "classic-residual%d" % (i + 1)
                 add_wn(p + ".block.0")
@@ -142,25 +201,128 @@ class Engine:
                                        mode=L.PACK_ROWTAPS))
         rows_total += 3
         self._packed["conv_output"] = _Packed(wq, bq, 3, 32, 9)
-        self._scratch = torch.zeros(rows_total, device=device, dtype=torch.float32)
+        self._wg["conv_output"] = (self._wg_total, 32, 9 * 32)      # gradient laid out [u*3+co][t*32+ci]
+        self._wg_total += 32 * 9 * 32
+        wqd = torch.zeros(32, 9 * 32, device=device, dtype=BF16)
+        self._descs_bwd.append(L.pack_desc(P("conv_output.weight"), wqd, mode=L.PACK_OUT9_DGRAD))
+        rows_bwd += 3
+        self._packed["conv_output.dg"] = _Packed(wqd, None, 32, 32, 9)
+        self._unpack_specs.append(dict(kind="out9"))
+        self._used_params.update(["conv_output.weight", "conv_output.bias"])
+        self._scratch = torch.zeros(max(rows_total, rows_bwd), device=device, dtype=torch.float32)
+        self._dw_flat = None          # allocated on the first backward
+        self._unpack_descs = None
         self._zero_bias = torch.zeros(9 * 2 * 64, device=device, dtype=torch.float32)
         self._device = device
 
     def _state_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.net.parameters())
 
-    def pack(self, force: bool = False):
-        """(Re)pack the weights when any parameter changed (optimizer step, load_state_dict, .to())."""
+    def pack(self, force: bool = False, training: bool = False):
+        """(Re)pack the weights when any parameter changed (optimizer step, load_state_dict, .to()).
+        ``training`` also packs the data-gradient (flipped / transposed) copies."""
         key = self._state_key()
-        if not force and key == self._key:
+        if force:
+            self._key = self._key_bwd = None
+        if key == self._key and (not training or self._key_bwd == key):
             return
         device = next(self.net.parameters()).device
         ptrs = tuple(k[0] for k in key)
         if self._device != device or getattr(self, "_ptrs", None) != ptrs:
             self._build_pack_plan(device)
             self._ptrs = ptrs
-        L.pack_weights(self._descs, self._scratch)
-        self._key = key
+            self._key = self._key_bwd = None
+        if key != self._key:
+            L.pack_weights(self._descs, self._scratch)
+            self._key = key
+        if training and key != self._key_bwd:
+            L.pack_weights(self._descs_bwd, self._scratch)
+            self._key_bwd = key
+
+    # ------------------------------------------------------------------------------------------ backward support
+    def _dw_view(self, name):
+        off, rows, kdim = self._wg[name]
+        return self._dw_flat[off:off + rows * kdim].view(rows, kdim)
+
+    def _db_view(self, name):
+        off, rows = self._bg[name]
+        return self._db_flat[off:off + rows]
+
+    def _grad_view(self, pname):
+        off, shape, n = self._goff[pname]
+        return self._g_flat[off:off + n].view(shape)
+
+    def _begin_backward(self, device):
+        """Zero the flat buffers the backward kernels accumulate into (one memset each)."""
+        if self._dw_flat is None:
+            self._dw_flat = torch.empty(self._wg_total, device=device, dtype=torch.float32)
+            self._db_flat = torch.empty(self._bg_total, device=device, dtype=torch.float32)
+            self._goff = {}
+            off = 0
+            for name, p in self.net.named_parameters():
+                self._goff[name] = (off, tuple(p.shape), p.numel())
+                off += p.numel()
+            self._g_flat = torch.empty(off, device=device, dtype=torch.float32)
+            self._build_unpack()
+        self._dw_flat.zero_()
+        self._db_flat.zero_()
+        self._g_flat.zero_()
+
+    def _build_unpack(self):
+        params, bufs = self._named()
+
+        def P(name):
+            return params[name] if name in params else bufs[name]
+
+        def G(name):
+            return self._grad_view(name) if name in params else None
+
+        descs = []
+
+        def U(dwp, v, dv, *, dbias_p=None, g=None, alpha=None, bias=None, bias2=None, dg=None, dbias=None, dbias2=None,
+              dalpha=None, mode=L.PACK_CONV, alpha_mode=0, shuffle_r=0, row_offset=0, rows_per_tap=0, ipack=0):
+            descs.append(L.UnpackDesc(L.ptr(dwp), L.ptr(dbias_p), L.ptr(v), L.ptr(g), L.ptr(alpha), L.ptr(bias),
+                                      L.ptr(bias2), L.ptr(dv), L.ptr(dg), L.ptr(dbias), L.ptr(dbias2), L.ptr(dalpha),
+                                      v.shape[0], v.shape[1], v.shape[2], mode, alpha_mode, shuffle_r, row_offset,
+                                      rows_per_tap, ipack, 0))
+
+        for sp in self._unpack_specs:
+            if sp["kind"] == "wn":
+                n = sp["name"]
+                U(self._dw_view(n), P(n + ".weight_v"), G(n + ".weight_v"), dbias_p=self._db_view(n),
+                  g=P(n + ".weight_g"), dg=G(n + ".weight_g"), dbias=G(n + ".bias"), mode=sp["mode"],
+                  shuffle_r=sp["shuffle_r"], ipack=sp.get("ipack", 0))
+            elif sp["kind"] == "plain":
+                n = sp["name"]    # bias in front of an InstanceNorm: gradient exactly zero (stays zero-filled)
+                U(self._dw_view(n), P(n + ".weight"), G(n + ".weight"))
+            elif sp["kind"] == "sean":
+                n, nf = sp["name"], sp["nf"]
+                for off, x in ((0, "gamma"), (nf, "beta")):
+                    al, dal = P("%s.alpha_%s" % (n, x)), G("%s.alpha_%s" % (n, x))
+                    U(self._dw_view(n + ".gb_o"), P("%s.mlp_%s_o.weight" % (n, x)), G("%s.mlp_%s_o.weight" % (n, x)),
+                      dbias_p=self._db_view(n + ".gb_o"), alpha=al, alpha_mode=2, bias=P("%s.mlp_%s_o.bias" % (n, x)),
+                      bias2=P("%s.mlp_%s_s.bias" % (n, x)), dbias=G("%s.mlp_%s_o.bias" % (n, x)),
+                      dbias2=G("%s.mlp_%s_s.bias" % (n, x)), dalpha=dal, row_offset=off)
+                    U(self._dw_view(n + ".table"), P("%s.mlp_%s_s.weight" % (n, x)), G("%s.mlp_%s_s.weight" % (n, x)),
+                      alpha=al, alpha_mode=1, dalpha=dal, mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf)
+            elif sp["kind"] == "out9":
+                U(self._dw_view("conv_output"), P("conv_output.weight"), G("conv_output.weight"), mode=L.PACK_ROWTAPS)
+        self._unpack_descs = (L.UnpackDesc * len(descs))(*descs)
+
+    def _finish_backward(self):
+        """Packed-layout gradients -> parameter gradients; returns one tensor (or None) per parameter, all of them
+        views of ONE flat fp32 buffer (kept as ``last_flat_grad`` for the data-parallel all-reduce)."""
+        L.check(L.load().dasr_unpack_grads(self._unpack_descs, len(self._unpack_descs), L.stream_ptr()))
+        flat = self._g_flat.clone()
+        self.last_flat_grad = flat
+        out = []
+        for name, p in self.net.named_parameters():
+            if name in self._used_params and p.requires_grad:
+                off, shape, n = self._goff[name]
+                out.append(flat[off:off + n].view(shape))
+            else:
+                out.append(None)
+        return out
 
     # ------------------------------------------------------------------------------------------ helpers
     def _conv(self, x, name, *, epi=L.EPI_STORE, act=L.ACT_NONE, subsample=1, out=None, **kw):
@@ -237,8 +399,8 @@ class Engine:
             actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, vec)
             y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats)
             self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
-                        lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), B, nf, H * W,
-                                                                  nslots, s)))
+                        lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), None, B, nf,
+                                                                  H * W, nslots, s)))
             if j == 1:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
             else:
@@ -293,8 +455,8 @@ class Engine:
             e5 = self._conv(e4, "encoder.layer5", subsample=2)
             lat = e5.shape[3]
             vec = torch.empty(B, K, lat, device=dev, dtype=torch.float32)
-            L.check(lib.dasr_region_pool_fwd(L.ptr(e5), L.ptr(masks), L.ptr(vec), B, e5.shape[1], e5.shape[2], lat, K,
-                                             h, w, s))
+            L.check(lib.dasr_region_pool_fwd(L.ptr(e5), L.ptr(masks), L.ptr(vec), None, None, B, e5.shape[1],
+                                             e5.shape[2], lat, K, h, w, s))
             labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
             flag = torch.zeros(1, device=dev, dtype=torch.int32)
             L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))

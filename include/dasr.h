@@ -60,13 +60,14 @@ enum { DASR_ACT_NONE = 0, DASR_ACT_RELU = 1, DASR_ACT_LRELU = 2 };
 
 typedef struct {
     int32_t B, H, W, Cin, Cout;   /* Cout = real output channels                                   */
-    int32_t ks;                   /* 1, 3 or 9                                                     */
+    int32_t ks;                   /* kernel height (and width when kw == 0): 1, 3 or 9             */
     int32_t epi;                  /* DASR_EPI_*                                                    */
     int32_t act;                  /* DASR_ACT_* applied last                                       */
     int32_t subsample;            /* 1, or 2: keep even (h,w) only -> stride-2 conv output          */
     int32_t clamp01;              /* DASR_EPI_NCHW_F32: clamp to [0,1]                              */
     int32_t inner_relu;           /* DASR_EPI_SEAN: relu before the residual add (norm1 path)       */
-    int32_t reserved;
+    int32_t kw;                   /* kernel width; 0 = ks (square)                                  */
+    float mask_slope;             /* DASR_EPI_STORE with actmask: factor where actmask <= 0         */
 } dasr_conv_desc;
 
 typedef struct {
@@ -80,6 +81,10 @@ typedef struct {
     const void* y;        /* DASR_EPI_SEAN: conv output to normalise, NHWC bf16 [B,H,W,Cout/2]      */
     const float* norm;    /* DASR_EPI_SEAN: [B][Cout/2][2] = (mean, scale) from dasr_instats_finalize */
     const void* gb_s;     /* DASR_EPI_SEAN: dynamic-conv term NHWC bf16 [B,H,W,Cout] (or NULL)       */
+    const void* actmask;  /* DASR_EPI_STORE: optional NHWC bf16 tensor shaped like out; the result is multiplied
+                             by (actmask > 0 ? 1 : mask_slope) last -- ReLU / LeakyReLU backward fused into a
+                             data-gradient convolution                                               */
+    void* gamma_out;      /* DASR_EPI_SEAN: optional NHWC bf16 [B,H,W,Cout/2] copy of gamma (saved for backward) */
     const float* resid_f32; /* DASR_EPI_SEAN: fp32 NHWC residual (the trunk's fp32 residual stream); used
                                instead of `resid` when not NULL                                     */
     float* out_aux_f32;   /* DASR_EPI_SEAN: optional fp32 NHWC copy of the output                    */
@@ -115,8 +120,15 @@ enum {
     DASR_PACK_CONVT = 1,       /* source is ConvTranspose2d [I][O][ks][ks]; rows = O, taps flipped   */
     DASR_PACK_STYLE = 2,       /* source [O][I][ks][ks]; dst [taps*rows_per_tap][I], row = tap*rows_per_tap
                                   + row_offset + o, K = I  (style-table GEMM B operand)             */
-    DASR_PACK_ROWTAPS = 3      /* source [O][I][ks][ks], ks*O <= 32; dst [ks][32][I], row = t*32 + u*O + o
+    DASR_PACK_ROWTAPS = 3,     /* source [O][I][ks][ks], ks*O <= 32; dst [ks][32][I], row = t*32 + u*O + o
                                   (dasr_conv_out9 operand; caller zero-fills dst once)              */
+    DASR_PACK_DGRAD = 4,       /* data-gradient operand of a Conv2d [O][I][ks][ks]: dst [I][ks*ks*Ot],
+                                  dst[i][tap'*Ot + row_offset + n(o)] = w[o][i][flipped tap'], Ot = rows_per_tap
+                                  (0 = O), n(o) = the PixelShuffle permutation when shuffle_r > 1      */
+    DASR_PACK_DGRAD_CONVT = 5, /* data-gradient operand of the ConvTranspose2d-as-conv [I][O][ks][ks]:
+                                  dst[i][tap*O + o] = w[i][o][tap] (weight-norm scale of row i)        */
+    DASR_PACK_OUT9_DGRAD = 6   /* conv_output [3][32][9][9] -> dst [32][9*32], dst[i][t'*32 + u*3 + o] =
+                                  w[o][i][8-t'][u]  (vertical 9x1 conv over the im2row gradient)       */
 };
 typedef struct {
     const float* v;       /* weight or weight_v                                                      */
@@ -136,6 +148,68 @@ typedef struct {
 /* descs: HOST array of n descriptors; scratch: device fp32 [sum of dim0] for the weight-norm scales */
 int dasr_pack_weights(const dasr_pack_desc* descs, int n, float* scratch, void* stream);
 
+/* Gradient unpacking: d(packed weight) fp32 -> parameter gradients (weight-norm backward, SEAN alpha blend,
+ * PixelShuffle / ConvTranspose index maps).  Mirrors dasr_pack_desc; see pack.cu.                        */
+typedef struct {
+    const float* dwp;     /* gradient in the packed layout of `mode` (fp32)                              */
+    const float* dbias_p; /* packed bias gradient [rows] or NULL                                         */
+    const float* v;       /* weight / weight_v (forward value)                                           */
+    const float* g;       /* weight_g or NULL                                                            */
+    const float* alpha;   /* device scalar or NULL                                                       */
+    const float* bias;    /* alpha_mode 2: own bias (b_o)  -- for d alpha                                */
+    const float* bias2;   /* alpha_mode 2: the style bias (b_s)                                          */
+    float* dv;            /* out: gradient of weight / weight_v, parameter layout                        */
+    float* dg;            /* out: gradient of weight_g or NULL                                           */
+    float* dbias;         /* out: gradient of bias or NULL                                               */
+    float* dbias2;        /* out: gradient of the style bias (alpha_mode 2) or NULL                      */
+    float* dalpha;        /* accumulated (atomicAdd): gradient of alpha or NULL                          */
+    int32_t dim0, dim1, ks, mode, alpha_mode, shuffle_r, row_offset, rows_per_tap;
+    int32_t ipack;        /* packed input channels when padded (encoder.layer1: 32), else 0              */
+    int32_t reserved;
+} dasr_unpack_desc;
+int dasr_unpack_grads(const dasr_unpack_desc* descs, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backward, memory-bound kernels (backward.cu)
+ * ------------------------------------------------------------------------------------------------ */
+/* SEAN modulate + double-InstanceNorm backward (normalization.py:56,87-89; sftmd_arch.py:813,820,828,832-833).
+ * pass 1: dz = dout * [act_out > 0]; n = (y-mean)*scale; dgb = [dz*n | dz]; dn = dz*(1+gamma);
+ *         part[b][slot][c] = (sum dn, sum dn*n); dskip = dz (optional).  All NHWC bf16 [B,HW,nf] but dgb [B,HW,2nf].
+ * finalize: coef[b][c] = (S1/N, -k*T2/(N*scale)).   pass 2: dy = scale*(dn - c1) + c2*n.                  */
+int dasr_sean_bwd_slots(int HW);
+int dasr_sean_bwd1(const void* dout, const void* act_out, const void* y, const float* norm, const void* gamma,
+                   void* dgb, void* dn, void* dskip, float* part, int B, int HW, int nf, void* stream);
+int dasr_sean_bwd_finalize(const float* part, const float* norm, const float* normk, float* coef, int B, int nf,
+                           int HW, void* stream);
+int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, const float* coef, void* dy, int B, int HW,
+                   int nf, void* stream);
+/* out[c] += sum over rows of x[row][c] (x bf16 [rows][C]) -- bias gradients                               */
+int dasr_colsum(const void* x, float* out, int64_t rows, int C, void* stream);
+/* K-DYN backward: dT[b][k][tap][c] += sum_p dgb[b,p,c] * mask[b,k,p+tap-1] (labels fast path like the forward) */
+int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const float* masks, const int32_t* flag, float* dT,
+                     int B, int K, int H, int W, int nf2, void* stream);
+/* style-table GEMM backward: dWs[n][c] = sum_bk dT[bk][n] stp[bk][c];  dstp[bk][c] = sum_n dT[bk][n] Ws[n][c]    */
+int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N, int L,
+                   void* stream);
+/* A_i_j backward: dA += , da += , dvec += (accumulating over the SEAN instances)                        */
+int dasr_style_mix_bwd(const float* dstp, const float* vec, const float* A, float* dA, float* da, float* dvec, int B,
+                       int K, int L, void* stream);
+int dasr_region_pool_bwd(const float* dvec, const float* msel, const float* cnt, void* de5, int B, int P, int C, int K,
+                         void* stream);
+/* mlp_mask backward: dW[c][9] += , db[c] += from dA (NHWC bf16 [B,H,W,C], ReLU mask already applied)      */
+int dasr_actv_bwd(const void* dA, const float* depth, float* dW, float* db, int B, int H, int W, int C, void* stream);
+/* PixelShuffle(2) + LeakyReLU backward: dps/ps_out NHWC bf16 [B,2H,2W,Cq] -> dconv NHWC bf16 [B,H,W,4Cq]     */
+int dasr_unshuffle_actgrad(const void* dps, const void* ps_out, void* dconv, int B, int H, int W, int Cq, float slope,
+                           void* stream);
+/* clamp backward + horizontal im2row of d(sr): dout, sr NCHW fp32 [B,3,H,W] -> aprime NHWC bf16 [B,H,W,32];
+ * dbias[3] += sum of the masked gradient                                                                 */
+int dasr_out9_bwd_prep(const float* dout, const float* sr, void* aprime, float* dbias, int B, int H, int W, void* stream);
+int dasr_nchw3_to_nhwc32(const float* x, void* out, int B, int H, int W, void* stream);
+/* out = d * (act_out > 0 ? 1 : slope)  (ReLU / LeakyReLU backward; n bf16 elements)                       */
+int dasr_actgrad(const void* d, const void* act_out, void* out, int64_t n, float slope, void* stream);
+/* zero-stuffed copy onto an [Ho,Wo] grid (gradient of a stride-2 conv on the stride-1 grid)               */
+int dasr_zero_insert2_to(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Layout / small ops
  * ------------------------------------------------------------------------------------------------ */
@@ -152,8 +226,9 @@ int dasr_add(const void* a, const float* a32, const void* b, void* out, int64_t 
 
 /* RegionWiseAvgPooling (sftmd_arch.py:714-733): e5 NHWC bf16 [B,hf,wf,C], masks NCHW fp32 [B,K,H,W]
  * -> depthVec fp32 [B,K,C]                                                                          */
-int dasr_region_pool_fwd(const void* e5, const float* masks, float* depth_vec, int B, int hf, int wf,
-                         int C, int K, int H, int W, void* stream);
+int dasr_region_pool_fwd(const void* e5, const float* masks, float* depth_vec, float* msel, float* cnt, int B,
+                         int hf, int wf, int C, int K, int H, int W, void* stream);
+/* msel [B,K,hf*wf] / cnt [B,K]: optional (NULL) copies of the thresholded masks and their sums for the backward */
 
 /* masks NCHW fp32 [B,K,H,W] -> labels u8 [B,H,W] (k if one-hot at k, 255 if all zero); *flag_not_onehot
  * (device int, caller zeroes) is set when some pixel is neither                                      */
@@ -185,7 +260,9 @@ int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* mask
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
  * stats [B][nslots][C][2] (partial sum, sumsq over H*W; summed here in slot order) ->
  * norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)                                          */
-int dasr_instats_finalize(const float* stats, float* norm, int B, int C, int HW, int nslots, void* stream);
+int dasr_instats_finalize(const float* stats, float* norm, float* normk, int B, int C, int HW, int nslots,
+                          void* stream);
+/* normk [B][C] (optional, NULL): k = 1/a + eps/(a^2 r) with a = v+eps, r = v/a+eps, used by dasr_sean_bwd_finalize */
 
 #ifdef __cplusplus
 }

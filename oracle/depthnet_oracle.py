@@ -24,6 +24,46 @@ import torch.nn.functional as F
 EPS_IN = 1e-5  # nn.InstanceNorm2d default eps (models/modules/sftmd_arch.py:813, normalization.py:17)
 
 
+# --------------------------------------------------------------------------------------------- bf16 emulation
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 in the forward, identity in the backward (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class bf16_operands:
+    """Context manager: every convolution of this module rounds its two operands (activation, weight) to bf16
+    and accumulates in fp32 -- the arithmetic contract of a bf16 tensor-core implementation (what
+    ``torch.autocast(bfloat16)`` does to the reference).  DepthNet's gradients are ill-conditioned (26
+    normalisation layers): this 2^-9 operand perturbation alone moves early-layer gradients of the REFERENCE by
+    30-40 % (tests/test_gpu_backward.py), so gradient parity of a bf16 implementation is defined against this
+    oracle variant; the fp32 oracle remains the checker for outputs."""
+
+    def __enter__(self):
+        self._orig = F.conv2d
+        self._orig_t = F.conv_transpose2d
+        orig, orig_t = self._orig, self._orig_t
+
+        def conv2d(x, w, b=None, stride=1, padding=0):
+            return orig(_RoundBF16.apply(x), _RoundBF16.apply(w), b, stride=stride, padding=padding)
+
+        def conv_t(x, w, b=None, stride=1, padding=0):
+            return orig_t(_RoundBF16.apply(x), _RoundBF16.apply(w), b, stride=stride, padding=padding)
+
+        F.conv2d, F.conv_transpose2d = conv2d, conv_t
+        return self
+
+    def __exit__(self, *exc):
+        F.conv2d, F.conv_transpose2d = self._orig, self._orig_t
+        return False
+
+
 # --------------------------------------------------------------------------------------------- helpers
 def weight_norm(g: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     """torch.nn.utils.weight_norm(dim=0): w = g * v / ||v||, norm over all dims but 0

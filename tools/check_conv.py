@@ -89,7 +89,7 @@ allok &= report("stats: y", nchw(y), ref, 1.5e-2)
 allok &= report("stats: sum", stats[..., 0].sum(1), ref.sum(dim=(2, 3)), 2e-3)
 allok &= report("stats: sumsq", stats[..., 1].sum(1), (ref * ref).sum(dim=(2, 3)), 2e-3)
 norm = torch.empty(B, Cn, 2, device=dev)
-L.check(L.load().dasr_instats_finalize(stats.data_ptr(), norm.data_ptr(), B, Cn, H * W, nslots, L.stream_ptr()))
+L.check(L.load().dasr_instats_finalize(stats.data_ptr(), norm.data_ptr(), None, B, Cn, H * W, nslots, L.stream_ptr()))
 mu = ref.mean(dim=(2, 3))
 var = ref.var(dim=(2, 3), unbiased=False)
 sc = (var + 1e-5).rsqrt() * (var / (var + 1e-5) + 1e-5).rsqrt()
