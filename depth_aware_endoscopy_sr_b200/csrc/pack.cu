@@ -212,7 +212,11 @@ __global__ void __launch_bounds__(128) unpack_grads_kernel(const UnpackBatch ub)
         if (d.g) d.dg[a] = f * dot / nrm;
         float dal = 0.f;
         if (d.alpha_mode) dal = (d.alpha_mode == 1 ? 1.f : -1.f) * s * dot;   // <DW, w_raw>
-        if (d.dbias_p) {
+        if (d.dbias_p && d.mode == DASR_PACK_CONVT) {
+            // ConvTranspose2d: dim0 is Cin, the bias has dim1 = Cout entries and no weight-norm / alpha factor
+            if (a == 0 && d.dbias)
+                for (int o = 0; o < d.dim1; o++) d.dbias[o] = d.dbias_p[o];
+        } else if (d.dbias_p) {
             int row = a;
             if (d.mode == DASR_PACK_CONV && d.shuffle_r > 1) {
                 const int r2 = d.shuffle_r * d.shuffle_r;

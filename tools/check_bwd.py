@@ -8,6 +8,7 @@ from depth_aware_endoscopy_sr_b200 import _lib as L
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 allok = True
+failures = []
 
 
 def report(name, got, ref, tol):
@@ -16,6 +17,8 @@ def report(name, got, ref, tol):
     scale = ref.float().abs().max().item()
     ok = err <= tol * max(scale, 1e-6)
     allok &= ok
+    if not ok:
+        failures.append(name)
     print("%-52s max|err|=%.4g (ref max %.3g) %s" % (name, err, scale, "PASS" if ok else "FAIL"), flush=True)
 
 
@@ -136,7 +139,7 @@ def dyn_bwd_case(B=2, K=10, H=16, W=16, nf2=128, L_=256):
     T = torch.zeros(B, nf2, K, 3, 3, device=dev, requires_grad=True)
     outs = torch.cat([F.conv2d(masks[b:b + 1], T[b], None, padding=1) for b in range(B)], 0)   # [B,nf2,H,W]
     (outs * dgb.float().permute(0, 3, 1, 2)).sum().backward()
-    ref = T.grad.permute(0, 2, 3, 4, 1).reshape(B * K, 9 * nf2)       # [b][k][tap][c]
+    ref = T.grad.permute(0, 2, 3, 4, 1).reshape(B * K, 9 * nf2).contiguous()       # [b][k][tap][c]
     for use_labels in (True, False):
         dT = torch.zeros(B * K, 9 * nf2, device=dev)
         L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), L.ptr(labels) if use_labels else None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
@@ -147,7 +150,7 @@ def dyn_bwd_case(B=2, K=10, H=16, W=16, nf2=128, L_=256):
     Ws = (torch.randn(9 * nf2, L_, device=dev) / 16).to(torch.bfloat16)
     dWs = torch.empty(9 * nf2, L_, device=dev)
     dstp = torch.empty(B * K, L_, device=dev)
-    L.check(lib.dasr_table_bwd(L.ptr(ref.contiguous()), L.ptr(stp), L.ptr(Ws), L.ptr(dWs), L.ptr(dstp), B * K, 9 * nf2, L_, s))
+    L.check(lib.dasr_table_bwd(L.ptr(ref), L.ptr(stp), L.ptr(Ws), L.ptr(dWs), L.ptr(dstp), B * K, 9 * nf2, L_, s))
     torch.cuda.synchronize()
     report("table_bwd dWs", dWs, ref.t() @ stp.float(), 1e-4)
     report("table_bwd dstp", dstp, ref @ Ws.float(), 1e-4)
@@ -160,7 +163,8 @@ def dyn_bwd_case(B=2, K=10, H=16, W=16, nf2=128, L_=256):
     dst = torch.randn(B, K, L_, device=dev)
     (stp_r * dst).sum().backward()
     dA = torch.zeros(K, K, device=dev); da = torch.zeros(K, device=dev); dvec = torch.zeros(B, K, L_, device=dev)
-    L.check(lib.dasr_style_mix_bwd(L.ptr(dst), L.ptr(vec), L.ptr(A.detach()), L.ptr(dA), L.ptr(da), L.ptr(dvec), B, K, L_, s))
+    A_d = A.detach().contiguous()
+    L.check(lib.dasr_style_mix_bwd(L.ptr(dst), L.ptr(vec), L.ptr(A_d), L.ptr(dA), L.ptr(da), L.ptr(dvec), B, K, L_, s))
     torch.cuda.synchronize()
     report("style_mix_bwd dA", dA, A.grad, 1e-4)
     report("style_mix_bwd da", da, a.grad, 1e-4)
@@ -195,7 +199,8 @@ def misc_bwd_case():
     dps = torch.randn_like(ps)
     ps.backward(dps)
     dconv = torch.empty(B, H, W, 4 * Cq, device=dev, dtype=torch.bfloat16)
-    L.check(lib.dasr_unshuffle_actgrad(L.ptr(nhwc(dps).to(torch.bfloat16)), L.ptr(nhwc(ps.detach()).to(torch.bfloat16)), L.ptr(dconv), B, H, W, Cq, 0.2, s))
+    dps_a, ps_a = nhwc(dps).to(torch.bfloat16), nhwc(ps.detach()).to(torch.bfloat16)   # keep the operands alive
+    L.check(lib.dasr_unshuffle_actgrad(L.ptr(dps_a), L.ptr(ps_a), L.ptr(dconv), B, H, W, Cq, 0.2, s))
     torch.cuda.synchronize()
     # our channel order is s*Cq + c (packed / permuted), torch's is c*4 + s
     ref = conv.grad.reshape(B, Cq, 4, H, W).permute(0, 3, 4, 2, 1).reshape(B, H, W, 4 * Cq)
