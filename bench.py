@@ -15,6 +15,8 @@ Prints ONE JSON line:
              region
   roofline   the dominant kernel family of the step, measured live with CUDA events in a separate
              instrumented pass (achieved algorithmic TFLOP/s or GB/s against MEASURED_PEAKS.json)
+  train      BASELINE.json configs[2] next to the headline: x8 training step (forward + loss + backward + flat
+             NCCL gradient all-reduce + Adam), batch 16 per GPU, images/s over the whole job
   cpu_baseline  the CPU oracle port of the reference's forward (literal form: 256-channel style-map convs),
              timed on this box's host cores on a bounded sample (rank 0, N == 1 only)
 
@@ -211,25 +213,51 @@ def run_b200(args):
         clocks = sampler.stop() if rank == 0 else None
 
         # ------------------------------------------------ end to end through the public call, host buffers
-        out_host = torch.empty(B, 3, SCALE * LR, SCALE * LR, dtype=torch.float32).pin_memory()
+        # Every step copies ITS inputs from pinned host memory and reads ITS SR frames back to pinned host memory;
+        # the copies run on their own streams so that step i's read-back overlaps step i+1's kernels
+        # (double-buffered device inputs / host outputs).  The call a user makes is still net(LQ, Depth, Masks).
+        out_host = [torch.empty(B, 3, SCALE * LR, SCALE * LR, dtype=torch.float32).pin_memory() for _ in range(2)]
+        dev_in = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(2)]
         h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
-        d2h = out_host.numel() * out_host.element_size()
+        d2h = out_host[0].numel() * out_host[0].element_size()
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
 
         def e2e_step(i):
-            lq, depth, masks = (t.to(dev, non_blocking=True) for t in host_sets[i % n_sets])
-            sr = net(lq, depth, masks)
-            out_host.copy_(sr, non_blocking=True)
+            slot = i % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_done[slot])          # the step that last read this input slot has finished
+                for d, h in zip(dev_in[slot], host_sets[i % n_sets]):
+                    d.copy_(h, non_blocking=True)
+                ev_in[slot].record(s_in)
+            cur.wait_event(ev_in[slot])
+            sr = net(*dev_in[slot])
+            ev_done[slot].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[slot])
+                out_host[slot].copy_(sr, non_blocking=True)
+                sr.record_stream(s_out)
 
-        for i in range(2):
+        def e2e_join():
+            cur.wait_stream(s_in)
+            cur.wait_stream(s_out)
+
+        for i in range(3):
             e2e_step(i)
+        e2e_join()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for i in range(K):
             e2e_step(i)
+        e2e_join()
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
+
+    train = train_pass(args, net, dev, rank, world, barrier) if args.train_steps > 0 else None
 
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -261,8 +289,48 @@ def run_b200(args):
                              "rotates over %d sets" % n_sets},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train}
     print(json.dumps(line), flush=True)
+
+
+def train_pass(args, net, dev, rank, world, barrier):
+    """BASELINE.json configs[2]: x8 training step (L1 + dynamic depth-mask loss, Adam), batch 16 per GPU, data
+    parallel over the ranks with ONE flat NCCL gradient all-reduce per step.  Reported next to the headline metric
+    as images/s (whole job), timed like the inference leg (CUDA events, barrier on both sides, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    import depth_aware_endoscopy_sr_b200 as dasr
+    from depth_aware_endoscopy_sr_b200 import _lib
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    Bt, Kt = args.train_batch, args.train_steps
+    net.train()
+    step = dasr.TrainStep(net, num_masks=10, lr=1e-3, betas=(0.9, 0.99), distributed=world > 1, mode="ddp")
+    sets = [tuple(t.to(dev) for t in synthetic_inputs(Bt, LR, LR, scale=SCALE, seed=5000 + 100 * rank + i, with_gt=True))
+            for i in range(2)]
+    for i in range(3):
+        step(*sets[i % 2])
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Kt):
+        vec = step(*sets[i % 2])
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    loss = float(vec[0].item())
+    net.eval()
+    nparam = sum(p.numel() for p in net.parameters())
+    return {"metric": "train_images_per_sec_x8_64to512", "value": Bt * world * Kt / (ms * 1e-3), "unit": "images/s",
+            "ms_per_step": ms / Kt, "steps": Kt, "batch_per_gpu": Bt, "global_batch": Bt * world, "scaling": "weak",
+            "loss": "L1 + dynamic depth-mask (SmoothL1), Adam lr 1e-3 betas (0.9, 0.99)", "last_loss": loss,
+            "gradient_allreduce": None if world == 1 else "one NCCL all-reduce (AVG) of the flat fp32 buffer, %.1f MB"
+                                                             % (nparam * 4 / 1e6),
+            "gpu_launches": int(launches)}
 
 
 def roofline_pass(net, dev_sets, B):
@@ -314,6 +382,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--train-steps", type=int, default=8, help="timed steps of the training leg (0 = skip it)")
+    ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training step (BASELINE configs[2])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

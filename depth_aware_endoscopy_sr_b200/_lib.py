@@ -98,6 +98,12 @@ def load() -> C.CDLL:
         "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_instats_finalize": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_loss_rows": [i32, i32, i32],
+        "dasr_loss_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "dasr_loss_finalize": [vp, vp, vp, i32, i32, C.c_double, C.c_float, C.c_float, vp],
+        "dasr_loss_bwd": [vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "dasr_adam_step": [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64,
+                           C.c_double, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -113,7 +119,14 @@ EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_
             "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd_finalize", "dasr_sean_bwd2", "dasr_colsum",
             "dasr_dynconv_bwd", "dasr_table_bwd", "dasr_style_mix_bwd", "dasr_region_pool_bwd", "dasr_actv_bwd",
             "dasr_unshuffle_actgrad", "dasr_out9_bwd_prep", "dasr_nchw3_to_nhwc32", "dasr_actgrad",
-            "dasr_zero_insert2_to"]
+            "dasr_zero_insert2_to", "dasr_loss_rows", "dasr_loss_fwd", "dasr_loss_finalize", "dasr_loss_bwd",
+            "dasr_adam_step"]
+LOSS_KMAX, LOSS_ROW = 16, 36
+
+
+def flat_pad(numel: int) -> int:
+    """Elements one parameter occupies in the flat gradient / optimiser buffers (slices stay 16-byte aligned)."""
+    return (numel + 3) // 4 * 4
 
 
 def launch_count() -> int:

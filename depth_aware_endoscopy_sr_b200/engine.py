@@ -42,6 +42,7 @@ class Engine:
         self._key = None
         self._key_bwd = None
         self.last_flat_grad = None
+        self.grad_sync = None       # callable(flat fp32 grad buffer) installed by parallel.FlatDataParallel
         self._packed: Dict[str, _Packed] = {}
         self._descs: List[L.PackDesc] = []
         self._scratch = None
@@ -261,8 +262,9 @@ class Engine:
             off = 0
             for name, p in self.net.named_parameters():
                 self._goff[name] = (off, tuple(p.shape), p.numel())
-                off += p.numel()
+                off += L.flat_pad(p.numel())
             self._g_flat = torch.empty(off, device=device, dtype=torch.float32)
+            self._glayout = {id(p): self._goff[name][0] for name, p in self.net.named_parameters()}
             self._build_unpack()
         self._dw_flat.zero_()
         self._db_flat.zero_()
@@ -314,6 +316,9 @@ class Engine:
         views of ONE flat fp32 buffer (kept as ``last_flat_grad`` for the data-parallel all-reduce)."""
         L.check(L.load().dasr_unpack_grads(self._unpack_descs, len(self._unpack_descs), L.stream_ptr()))
         flat = self._g_flat.clone()
+        if self.grad_sync is not None:       # data parallel: one all-reduce of the whole flat buffer (parallel.py)
+            self.grad_sync(flat)
+        flat._dasr_layout = self._glayout    # lets FusedAdam consume the buffer in place (optim.py)
         self.last_flat_grad = flat
         out = []
         for name, p in self.net.named_parameters():

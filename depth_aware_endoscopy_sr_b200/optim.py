@@ -1,0 +1,136 @@
+"""Adam on the K-ADAM kernel (C ABI: dasr_adam_step) -- the optimiser step of the reference's training loop
+(``torch.optim.Adam(optim_params, lr, weight_decay, betas)``, codes/models/F_model_depthCond.py:99-101,192).
+
+``FusedAdam`` is a ``torch.optim.Optimizer`` with Adam's constructor, ``param_groups`` (so the reference's
+``lr_scheduler`` classes and ``update_learning_rate`` keep working), ``step`` / ``zero_grad`` / ``state_dict``.
+It re-homes every parameter of a group into ONE flat fp32 buffer (the ``.data`` of each parameter becomes a view),
+keeps ``exp_avg`` / ``exp_avg_sq`` flat as well, and steps the whole group with a single kernel launch.  When all
+gradients are views of one flat buffer in parameter order (what ``DepthNet``'s backward produces,
+``Engine.last_flat_grad``) they are consumed in place with one launch; every other parameter (e.g. the 10 weights
+of the dynamic loss) is stepped with one launch of its own.
+
+Inside the engine's flat buffer a parameter the network never uses has a zero gradient.  With zero Adam state that
+is a no-op (m = v = 0 -> update 0), which matches torch skipping ``grad is None`` parameters (SURVEY.md section 7,
+"unused parameters").
+"""
+from __future__ import annotations
+
+from typing import Iterable
+
+import torch
+
+from . import _lib as L
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay or 0.0))
+        self._flat = {}      # group index -> dict(p, m, v, g, offsets, step)
+
+    # ------------------------------------------------------------------ flat storage
+    def _ensure_flat(self, gi, group):
+        st = self._flat.get(gi)
+        params = [p for p in group["params"] if p.requires_grad]
+        if st is not None and all(p.data_ptr() == st["p"].data_ptr() + 4 * off
+                                  for p, off in zip(params, st["offsets"])):
+            return st
+        if not params:
+            return None
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdam (B200) needs CUDA parameters; there is no CPU fallback")
+        offsets, n = [], 0
+        for p in params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise RuntimeError("FusedAdam: all parameters of a group must be fp32 on one device")
+            offsets.append(n)
+            n += L.flat_pad(p.numel())               # keep every slice 16-byte aligned (same rule as the engine)
+        flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        old = st
+        for p, off in zip(params, offsets):
+            flat[off:off + p.numel()].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + p.numel()].view(p.shape)
+        st = dict(p=flat, m=torch.zeros_like(flat), v=torch.zeros_like(flat), g=None, offsets=offsets, params=params,
+                  step=0 if old is None else old["step"])
+        if old is not None and old["m"].numel() == n:     # parameters were moved (.to / load): keep the moments
+            st["m"].copy_(old["m"])
+            st["v"].copy_(old["v"])
+        self._flat[gi] = st
+        return st
+
+    def _segments(self, st):
+        """[(offset, n, grad tensor)] covering the flat parameter buffer.  Parameters whose gradients are views of
+        ONE flat buffer with this optimiser's layout (``Engine.last_flat_grad``: tagged ``_dasr_layout`` =
+        {id(param): offset}, zero where the network leaves a gradient None) are stepped as a single segment straight
+        from that buffer; any other parameter is its own segment; ``grad is None`` outside a flat buffer is skipped
+        like torch.optim.Adam does."""
+        params, offsets = st["params"], st["offsets"]
+        segs, covered = [], set()
+        base = next((p.grad._base for p in params if p.grad is not None and p.grad._base is not None
+                     and hasattr(p.grad._base, "_dasr_layout")), None)
+        if base is not None:
+            lay = base._dasr_layout
+            idx = [i for i, p in enumerate(params) if id(p) in lay]
+            if idx and all(lay[id(params[i])] - offsets[i] == lay[id(params[idx[0]])] - offsets[idx[0]] for i in idx) \
+                    and idx == list(range(idx[0], idx[-1] + 1)):
+                i0, i1 = idx[0], idx[-1]
+                g0 = lay[id(params[i0])]
+                n = offsets[i1] + params[i1].numel() - offsets[i0]
+                if all(p.grad is None or p.grad.data_ptr() == base.data_ptr() + 4 * lay[id(p)] for p in params[i0:i1 + 1]) \
+                        and (base.data_ptr() + 4 * g0) % 16 == 0 and g0 + n <= base.numel():
+                    segs.append((offsets[i0], n, base[g0:g0 + n]))
+                    covered.update(range(i0, i1 + 1))
+        for i, p in enumerate(params):
+            if i in covered or p.grad is None:
+                continue
+            g = p.grad.detach()
+            if g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() % 16:
+                g = g.float().contiguous().clone()
+            segs.append((offsets[i], p.numel(), g.reshape(-1)))
+        return segs
+
+    # ------------------------------------------------------------------ Optimizer API
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.load()
+        for gi, group in enumerate(self.param_groups):
+            st = self._ensure_flat(gi, group)
+            if st is None:
+                continue
+            segs = self._segments(st)
+            if not segs:
+                continue
+            st["step"] += 1
+            b1, b2 = group["betas"]
+            for off, n, g in segs:
+                L.check(lib.dasr_adam_step(L.ptr(st["p"][off:off + n]), L.ptr(g), L.ptr(st["m"][off:off + n]),
+                                           L.ptr(st["v"][off:off + n]), n, float(group["lr"]), float(b1), float(b2),
+                                           float(group["eps"]), float(group["weight_decay"]), st["step"], 1.0,
+                                           L.stream_ptr()))
+            # the kernel wrote through raw pointers: advance the version counters like an in-place torch op
+            # would (weight caches such as Engine.pack key on ``p._version``)
+            torch.autograd.graph.increment_version(st["params"])
+        return loss
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["flat"] = {gi: dict(step=st["step"], exp_avg=st["m"].clone(), exp_avg_sq=st["v"].clone())
+                      for gi, st in self._flat.items()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        flat = state_dict.get("flat", {})
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "flat"})
+        for gi, group in enumerate(self.param_groups):
+            if gi in flat:
+                st = self._ensure_flat(gi, group)
+                st["step"] = int(flat[gi]["step"])
+                st["m"].copy_(flat[gi]["exp_avg"])
+                st["v"].copy_(flat[gi]["exp_avg_sq"])

@@ -264,6 +264,43 @@ int dasr_instats_finalize(const float* stats, float* norm, float* normk, int B, 
                           void* stream);
 /* normk [B][C] (optional, NULL): k = 1/a + eps/(a^2 r) with a = v+eps, r = v/a+eps, used by dasr_sean_bwd_finalize */
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step behind the generator (train.cu)
+ * ------------------------------------------------------------------------------------------------ */
+#define DASR_LOSS_KMAX 16      /* most depth masks the loss kernels keep in registers                  */
+#define DASR_LOSS_ROW 36       /* floats per partial-sum row: [0] sum|SR-HR|, [1..16] sum SmoothL1 of mask k,
+                                  [17..32] sum of mask k over the HR grid, [33..35] padding              */
+/* K-LOSS forward.  Replaces nn.L1Loss (codes/models/F_model_depthCond.py:52,164) and
+ * dynamic_weight_mask_loss.forward (codes/models/modules/mask_loss.py:64-90) with ONE pass over SR/HR.
+ * sr, hr: NCHW fp32 [B,C,Ho,Wo] (C <= 4, Wo % 4 == 0); labels u8 [B,h,w] + flag from dasr_mask_labels (one-hot fast
+ * path) and/or masks NCHW fp32 [B,K,h,w] (general path, taken when labels == NULL or *flag != 0); the masks are
+ * resized to the HR grid like F.interpolate(mode='nearest').  part: fp32 [dasr_loss_rows()][DASR_LOSS_ROW] scratch;
+ * sums: fp32 [DASR_LOSS_ROW] = column sums of part, rows added in order (bit-reproducible).  A data-parallel
+ * caller that wants the reference's single-process "ratio of batch sums" all-reduces `sums` before finalize.   */
+int dasr_loss_rows(int B, int Ho, int Wo);
+int dasr_loss_fwd(const float* sr, const float* hr, const uint8_t* labels, const float* masks, const int32_t* flag,
+                  float* part, float* sums, int B, int C, int K, int h, int w, int Ho, int Wo, void* stream);
+/* sums -> out fp32 [4 + 4*DASR_LOSS_KMAX]: [0] total = l_pix + l_dyn, [1] l_pix = w_pix * sums[0] / n_elems,
+ * [2] l_dyn = w_dyn * sum_k softmax(wdyn)_k * loss_k, [3] w_pix / n_elems, then four arrays of DASR_LOSS_KMAX:
+ * loss_k = sums[1+k] / (C * sums[17+k]) (0/0 = NaN for an empty mask, like the reference), softmax(wdyn)_k,
+ * the backward coefficient w_dyn * softmax_k / (C * sums[17+k]), and d l_dyn / d wdyn_k.
+ * wdyn: device fp32 [K] (dynamic_weight_mask_loss.trainable_weight, mask_loss.py:62) or NULL (= zeros).
+ * n_elems = number of SR elements the L1 mean runs over (B*C*Ho*Wo; the global count under data parallelism). */
+int dasr_loss_finalize(const float* sums, const float* wdyn, float* out, int K, int C, double n_elems, float w_pix,
+                       float w_dyn, void* stream);
+/* dsr = gp * out[3] * sign(SR-HR) + gd * sum_k coef_k * m_k * clamp(m_k*SR - m_k*HR, -1, 1)
+ * -- autograd of the two criteria (F_model_depthCond.py:191).  g: device fp32 [3] = upstream gradients of
+ * (total, l_pix, l_dyn), or NULL (= 1,0,0); gp = use_pix*(g[0]+g[1]), gd = use_dyn*(g[0]+g[2]).
+ * dwdyn (optional): fp32 [K] = gd * d l_dyn / d wdyn.                                                     */
+int dasr_loss_bwd(const float* sr, const float* hr, const uint8_t* labels, const float* masks, const int32_t* flag,
+                  const float* out, const float* g, float use_pix, float use_dyn, float* dsr, float* dwdyn, int B,
+                  int C, int K, int h, int w, int Ho, int Wo, void* stream);
+/* K-ADAM: one torch.optim.Adam step (F_model_depthCond.py:99-101,192; amsgrad off) over flat fp32 buffers of n
+ * elements: g' = grad_scale*g + wd*p; m = lerp(m, g', 1-beta1); v = beta2*v + (1-beta2)*g'^2;
+ * p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).  step counts from 1.  16-byte aligned buffers. */
+int dasr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
