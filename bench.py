@@ -304,10 +304,11 @@ def train_pass(args, net, dev, rank, world, barrier):
     from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
     Bt, Kt = args.train_batch, args.train_steps
     net.train()
-    step = dasr.TrainStep(net, num_masks=10, lr=1e-3, betas=(0.9, 0.99), distributed=world > 1, mode="ddp")
+    step = dasr.TrainStep(net, num_masks=10, lr=1e-3, betas=(0.9, 0.99), distributed=world > 1, mode="ddp",
+                          graph=not args.no_graph)
     sets = [tuple(t.to(dev) for t in synthetic_inputs(Bt, LR, LR, scale=SCALE, seed=5000 + 100 * rank + i, with_gt=True))
             for i in range(2)]
-    for i in range(3):
+    for i in range(4):
         step(*sets[i % 2])
     barrier()
     n0 = _lib.launch_count()
@@ -330,7 +331,8 @@ def train_pass(args, net, dev, rank, world, barrier):
             "loss": "L1 + dynamic depth-mask (SmoothL1), Adam lr 1e-3 betas (0.9, 0.99)", "last_loss": loss,
             "gradient_allreduce": None if world == 1 else "one NCCL all-reduce (AVG) of the flat fp32 buffer, %.1f MB"
                                                              % (nparam * 4 / 1e6),
-            "gpu_launches": int(launches)}
+            "cuda_graph": not args.no_graph,
+            "gpu_launches": int(launches) if args.no_graph else int(step.launches_per_step) * Kt}
 
 
 def roofline_pass(net, dev_sets, B):
@@ -383,6 +385,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--train-steps", type=int, default=8, help="timed steps of the training leg (0 = skip it)")
+    ap.add_argument("--no-graph", action="store_true", help="issue the training step kernel by kernel (no CUDA graph)")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training step (BASELINE configs[2])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

@@ -98,12 +98,15 @@ def load() -> C.CDLL:
         "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_instats_finalize": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_build_aux": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_dynconv_bwd_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dasr_actv_bwd_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_loss_rows": [i32, i32, i32],
         "dasr_loss_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "dasr_loss_finalize": [vp, vp, vp, i32, i32, C.c_double, C.c_float, C.c_float, vp],
         "dasr_loss_bwd": [vp, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "dasr_adam_step": [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i64,
-                           C.c_double, vp],
+                           C.c_double, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -120,8 +123,25 @@ EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_
             "dasr_dynconv_bwd", "dasr_table_bwd", "dasr_style_mix_bwd", "dasr_region_pool_bwd", "dasr_actv_bwd",
             "dasr_unshuffle_actgrad", "dasr_out9_bwd_prep", "dasr_nchw3_to_nhwc32", "dasr_actgrad",
             "dasr_zero_insert2_to", "dasr_loss_rows", "dasr_loss_fwd", "dasr_loss_finalize", "dasr_loss_bwd",
-            "dasr_adam_step"]
+            "dasr_adam_step", "dasr_build_aux", "dasr_dynconv_bwd_tc", "dasr_actv_bwd_tc"]
+AUX_CH = 32
 LOSS_KMAX, LOSS_ROW = 16, 36
+
+
+# Flat gradient buffers produced by Engine._finish_backward: (weakref to the fp32 buffer, {id(param): offset}).
+# autograd hands the views to ``.grad`` without copying, so FusedAdam can recognise them by address and step the
+# whole network with one launch straight from the buffer.
+_FLAT_GRADS = []
+
+
+def register_flat_grad(flat: torch.Tensor, layout: dict) -> None:
+    import weakref
+    _FLAT_GRADS[:] = [(r, l) for r, l in _FLAT_GRADS if r() is not None][-7:]
+    _FLAT_GRADS.append((weakref.ref(flat), layout))
+
+
+def flat_grads():
+    return [(r(), l) for r, l in _FLAT_GRADS if r() is not None]
 
 
 def flat_pad(numel: int) -> int:

@@ -159,8 +159,8 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
     return o
 
 
-def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, *, first: bool,
-                resid: Optional[_T]) -> _T:
+def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, *,
+                first: bool, resid: Optional[_T]) -> _T:
     """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
     eng, lib, s = tp.eng, tp.lib, tp.s
     x = cur.data
@@ -221,10 +221,14 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         dA = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
         L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)
         gw, gb = eng._grad_view(n + ".mlp_mask.0.weight"), eng._grad_view(n + ".mlp_mask.0.bias")
-        L.check(lib.dasr_actv_bwd(L.ptr(dA), L.ptr(depth), L.ptr(gw), L.ptr(gb), B, H, W, nf2, s))
+        scr = torch.zeros(nf2, 9 * L.AUX_CH, device=dev, dtype=torch.float32)
+        L.check(lib.dasr_actv_bwd_tc(L.ptr(dA), L.ptr(aux), L.ptr(scr), L.ptr(gw), L.ptr(gb), B, H, W, nf2, s))
         # ---- style branch: K-DYN backward -> table GEMM backward -> A_i_j backward
         dT = torch.zeros(B * K, 9 * nf2, device=dev, dtype=torch.float32)
-        L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+        # one-hot masks: tensor-core kernel; otherwise (device flag) the exact general-mask kernel -- each is a
+        # no-op in the other's case, so no host synchronisation is needed to choose
+        L.check(lib.dasr_dynconv_bwd_tc(L.ptr(dgb), L.ptr(aux), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+        L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
         dWs = eng._dw_view(n + ".table")
         dstp = torch.empty(B * K, lat, device=dev, dtype=torch.float32)
         L.check(lib.dasr_table_bwd(L.ptr(dT), L.ptr(stp), L.ptr(pkt.w), L.ptr(dWs), L.ptr(dstp), B * K, 9 * nf2, lat, s))
@@ -264,7 +268,7 @@ def _forward_train(eng, lq, depth, masks):
 
     tp.ops.append(bwd_first)
 
-    vec = labels = flag = dvec = None
+    vec = labels = flag = dvec = aux = None
     if not net.isBaseline:
         e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
         e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
@@ -293,6 +297,8 @@ def _forward_train(eng, lq, depth, masks):
         labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
         flag = torch.zeros(1, device=dev, dtype=torch.int32)
         L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
+        aux = torch.empty(B, h, w, L.AUX_CH, device=dev, dtype=BF16)
+        L.check(lib.dasr_build_aux(L.ptr(labels), L.ptr(depth), L.ptr(aux), B, K, h, w, s))
 
     # ---- head + trunk
     h1 = _conv_train(tp, f0, "head.0", act="lrelu")
@@ -305,9 +311,9 @@ def _forward_train(eng, lq, depth, masks):
                 raise NotImplementedError("depth-guided blocks above LR resolution are not implemented")
             p = "depth-residual%d" % (i + 1)
             blk = net.block(i)
-            a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec,
+            a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec, aux,
                             first=True, resid=None)
-            return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec,
+            return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec, aux,
                                first=False, resid=x)
         p = "classic-residual%d" % (i + 1)
         f = _conv_train(tp, x, p + ".block.0", act="relu")
@@ -380,7 +386,7 @@ class _DepthNetFn(torch.autograd.Function):
         lq = lq.detach().contiguous().float()
         depth = depth.detach().contiguous().float()
         masks = masks.detach().contiguous().float()
-        eng.pack(training=True)
+        eng.pack(training=True, force=eng.always_pack)
         sr, tp = _forward_train(eng, lq, depth, masks)
         ctx.eng = eng
         ctx.tape = tp

@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* _
     const int h0 = band * rows_per_block, h1 = min(h0 + rows_per_block, H);
     const int c = threadIdx.x;
     if (c >= C2) return;
+    // fallback role (labels == NULL, flag given): dasr_dynconv_bwd_tc already handled one-hot masks
+    if (labels == nullptr && flag != nullptr && *flag == 0) return;
     for (int i = 0; i < K * 9; i++) acc[i * C2 + c] = 0.f;
     const bool general = (labels == nullptr) || (flag != nullptr && *flag != 0);
     for (int y = h0; y < h1; y++)
@@ -220,25 +222,66 @@ __global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* _
 
 // ------------------------------------------------------------------------------------ style-table GEMM backward
 // T[bk][n] = sum_c stp[bk][c] * Ws[n][c]  (n = tap*C2 + o2)
-// dWs[n][c] = sum_bk dT[bk][n] * stp[bk][c]     thread = (n, c)
-__global__ void table_bwd_w_kernel(const float* __restrict__ dT, const __nv_bfloat16* __restrict__ stp,
-                                   float* __restrict__ dWs, int BK, int N, int L) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = blockIdx.y;
-    if (c >= L) return;
-    float s = 0.f;
-    for (int bk = 0; bk < BK; bk++) s = fmaf(__ldg(dT + (size_t)bk * N + n), __bfloat162float(stp[(size_t)bk * L + c]), s);
-    dWs[(size_t)n * L + c] = s;
-}
-// dstp[bk][c] = sum_n dT[bk][n] * Ws[n][c]       thread = (bk, c)
-__global__ void table_bwd_s_kernel(const float* __restrict__ dT, const __nv_bfloat16* __restrict__ Ws,
-                                   float* __restrict__ dstp, int BK, int N, int L) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int bk = blockIdx.y;
-    if (c >= L) return;
-    float s = 0.f;
-    for (int n = 0; n < N; n++) s = fmaf(__ldg(dT + (size_t)bk * N + n), __bfloat162float(Ws[(size_t)n * L + c]), s);
-    dstp[(size_t)bk * L + c] = s;
+//   dWs[n][c]   = sum_bk dT[bk][n] * stp[bk][c]      (A = dT read transposed, B = stp)
+//   dstp[bk][c] = sum_n  dT[bk][n] * Ws[n][c]        (A = dT, B = Ws; split-K with fp32 atomics)
+// Both are small fp32 x bf16 GEMMs (94 MFLOP at B = 16): one shared-memory tiled kernel, 64x64x16 tiles, 4x4
+// outputs per thread.  C[m][n] (+)= sum_k A(m,k) * B[k][n];  A(m,k) = AT ? A[k*lda + m] : A[m*lda + k].
+template <bool AT>
+__global__ void __launch_bounds__(256) gemm_f32_bf16_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Bm,
+                                                            float* __restrict__ C, int M, int N, int K, int lda, int ldb,
+                                                            int ldc, int k_per_split, int atomic) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = threadIdx.x + i * 256;
+            int r, kk;
+            if (AT) { kk = idx >> 6; r = idx & 63; } else { r = idx >> 4; kk = idx & 15; }
+            const int m = m0 + r, k = k0 + kk;
+            float v = 0.f;
+            if (m < M && k < kend) v = AT ? __ldg(A + (size_t)k * lda + m) : __ldg(A + (size_t)m * lda + k);
+            As[kk][r] = v;
+            const int kb = idx >> 6, c = idx & 63;
+            const int kq = k0 + kb, n = n0 + c;
+            Bs[kb][c] = (kq < kend && n < N) ? __bfloat162float(Bm[(size_t)kq * ldb + n]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            if (atomic) atomicAdd(C + (size_t)m * ldc + n, acc[i][j]);
+            else C[(size_t)m * ldc + n] = acc[i][j];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------ style mix backward
@@ -548,10 +591,21 @@ extern "C" int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const fl
 extern "C" int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N,
                               int L, void* stream) {
     DASR_REQUIRE(dT && stp && Ws && dWs && dstp, "null pointer");
-    const int bx = L < 128 ? L : 128;
-    table_bwd_w_kernel<<<dim3((L + bx - 1) / bx, N), bx, 0, (cudaStream_t)stream>>>(dT, (const __nv_bfloat16*)stp, dWs, BK, N, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    // dWs [N][L] = dT^T [N][BK] * stp [BK][L]
+    gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, 1), 256, 0, st>>>(
+        dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0);
     DASR_LAUNCH_OK();
-    table_bwd_s_kernel<<<dim3((L + bx - 1) / bx, BK), bx, 0, (cudaStream_t)stream>>>(dT, (const __nv_bfloat16*)Ws, dstp, BK, N, L);
+    // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles -> split the reduction over N
+    const int tiles = ((L + 63) / 64) * ((BK + 63) / 64);
+    int splits = (num_sms() + tiles - 1) / tiles;
+    if (splits > (N + 63) / 64) splits = (N + 63) / 64;
+    if (splits < 1) splits = 1;
+    const int kps = (((N + splits - 1) / splits) + 15) / 16 * 16;
+    splits = (N + kps - 1) / kps;
+    DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)BK * L * sizeof(float), st));
+    gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, splits), 256, 0, st>>>(
+        dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -41,6 +41,12 @@ struct WgK {
     int stages;
     float* dw;
     int ldw;
+    // per-image mode (K-DYN backward): grid.x = B * ksplit_i, every CTA reduces over the pixels of ONE image and
+    // flushes columns c < n_valid of tap tp to  dw[img*dw_img_stride + (c*taps + tap)*Cout + o]  ("bin-major":
+    // the [k][tap][channel] layout of the style table)
+    int per_image, ksplit_i, n_valid;
+    long long dw_img_stride;
+    const int* skip_flag;               // optional device int: the whole kernel is a no-op when *skip_flag != 0
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -83,12 +89,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
     const int cb0 = cchunk * p.Nc;           // first X channel of this column slice
     const int tiles_per_img = p.n_rowtiles * p.n_strips;
     const uint32_t a_bytes_stage = p.a_blocks * p.a_blk_bytes;
-    const int n_my = (p.ktiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    int kt_begin = blockIdx.x, kt_end = p.ktiles_total, kt_step = gridDim.x, my_img = 0;
+    if (p.per_image) {
+        my_img = blockIdx.x / p.ksplit_i;
+        kt_begin = my_img * tiles_per_img + (int)(blockIdx.x % p.ksplit_i);
+        kt_end = (my_img + 1) * tiles_per_img;
+        kt_step = p.ksplit_i;
+    }
+    if (p.skip_flag && *p.skip_flag != 0) kt_end = kt_begin;     // uniform over the grid: nothing to do
+    const int n_my = kt_end > kt_begin ? (kt_end - kt_begin + kt_step - 1) / kt_step : 0;
 
     if (warp == 0) {
         if (elect_one()) {
             uint32_t it = 0;
-            for (int kt = blockIdx.x; kt < p.ktiles_total; kt += gridDim.x, it++) {
+            for (int kt = kt_begin; kt < kt_end; kt += kt_step, it++) {
                 const int img = kt / tiles_per_img;
                 const int r = kt - img * tiles_per_img;
                 const int rt = r / p.n_strips, strip = r - rt * p.n_strips;
@@ -116,7 +130,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
             const int ksteps = p.Wt >> 4;
             const uint32_t a_kstep = (16u * p.swz_a) >> 4, b_kstep = (16u * p.swz_b) >> 4;
             uint32_t it = 0;
-            for (int kt = blockIdx.x; kt < p.ktiles_total; kt += gridDim.x, it++) {
+            for (int kt = kt_begin; kt < kt_end; kt += kt_step, it++) {
                 const int s = it % p.stages;
                 mbar_wait(&full[s], (it / p.stages) & 1);
                 tc_fence_after();
@@ -151,7 +165,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                 }
                 umma_commit(&empty[s]);
             }
-            umma_commit(&acc_full);
+            if (n_my > 0) umma_commit(&acc_full);
         }
     } else if (warp >= 4) {
         // ===================================================== flush: TMEM -> red.global.add.f32
@@ -174,13 +188,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
             const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16);
             for (int tp = 0; tp < ntaps; tp++) {
                 float* dst = p.dw + (size_t)o * p.ldw + (size_t)(tap0 + tp) * p.Cin + cb0;
-                for (int c0 = 0; c0 < p.Nc; c0 += 16) {
+                float* dst_img = p.dw + (size_t)my_img * p.dw_img_stride + (size_t)(tap0 + tp) * p.Cout + o;
+                const int ncols = p.per_image ? min(p.Nc, p.n_valid - cb0) : p.Nc;
+                for (int c0 = 0; c0 < ncols; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(t_row + tp * p.Nc + c0, v);
                     tmem_ld_wait();
                     if (row_ok) {
+                        if (p.per_image) {
+                            const int taps = p.kh * p.kw;
 #pragma unroll
-                        for (int j = 0; j < 16; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+                            for (int j = 0; j < 16; j++)
+                                if (cb0 + c0 + j < p.n_valid)
+                                    atomicAdd(dst_img + (size_t)(cb0 + c0 + j) * taps * p.Cout, __uint_as_float(v[j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -196,7 +220,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
 
 using namespace dasr;
 
-extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, void* stream_) {
+struct WgOpts {
+    int per_image = 0, n_valid = 0;
+    long long dw_img_stride = 0;
+    const int* skip_flag = nullptr;
+};
+
+static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, const WgOpts& o,
+                        void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DASR_REQUIRE(d && dy && x && dw, "null argument");
     DASR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "bad shape");
@@ -278,6 +309,18 @@ extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const v
     if (ksplit > num_sms() / slices && slices <= num_sms()) ksplit = num_sms() / slices;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > k.ktiles_total) ksplit = k.ktiles_total;
+    k.skip_flag = o.skip_flag;
+    if (o.per_image) {
+        const int tiles_per_img = k.n_rowtiles * k.n_strips;
+        int ks_i = num_sms() / (slices * d->B);
+        if (ks_i < 1) ks_i = 1;
+        if (ks_i > tiles_per_img) ks_i = tiles_per_img;
+        k.per_image = 1;
+        k.ksplit_i = ks_i;
+        k.n_valid = o.n_valid;
+        k.dw_img_stride = o.dw_img_stride;
+        ksplit = d->B * ks_i;
+    }
 
     CUtensorMap mY, mX;
     {
@@ -307,6 +350,56 @@ extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const v
     DASR_REQUIRE(smem_bytes <= 220 * 1024, "shared memory budget exceeded (%zu)", smem_bytes);
     dim3 grid(ksplit, k.n_tapgroups * k.n_cchunks, n_mblocks);
     conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(mY, mX, k);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, void* stream) {
+    return wgrad_launch(d, dy, x, dw, WgOpts(), stream);
+}
+
+// K-DYN backward on the tensor cores: per image, dT[b][k][tap][c] += sum_p dgb[b,p,c] * onehot[b, p+tap-1, k]
+// -- the weight gradient of the dynamic 3x3 convolution of the one-hot depth-mask image (channels 0..K-1 of the
+// auxiliary tensor built by dasr_build_aux) with the per-image filters.  No-op when *flag != 0 (masks not one-hot:
+// dasr_dynconv_bwd's exact path runs instead).
+extern "C" int dasr_dynconv_bwd_tc(const void* dgb, const void* aux, const int32_t* flag, float* dT, int B, int K, int H,
+                                   int W, int nf2, void* stream) {
+    DASR_REQUIRE(dgb && aux && dT, "null pointer");
+    DASR_REQUIRE(K >= 1 && K <= 16, "K-DYN backward: at most 16 depth masks (got %d)", K);
+    dasr_wgrad_desc d;
+    d.B = B; d.H = H; d.W = W; d.Cout = nf2; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.reserved = 0;
+    WgOpts o;
+    o.per_image = 1;
+    o.n_valid = K;
+    o.dw_img_stride = (long long)K * 9 * nf2;
+    o.skip_flag = flag;
+    return wgrad_launch(&d, dgb, aux, dT, o, stream);
+}
+
+// mlp_mask (1 -> 2nf, 3x3) weight / bias gradient on the tensor cores: dasr_conv_wgrad of dA against the auxiliary
+// tensor, whose channels DASR_AUX_DEPTH_HI / _LO hold the depth split into two bf16 parts (hi + lo carries 16
+// mantissa bits) and DASR_AUX_ONE is 1 (its centre tap is the bias gradient).  scratch: fp32 [C][9*DASR_AUX_CH],
+// zeroed by the caller.  dW[c][tap] += , db[c] += .
+namespace dasr {
+__global__ void actv_bwd_gather_kernel(const float* __restrict__ scr, float* __restrict__ dW, float* __restrict__ db,
+                                       int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * 9) return;
+    const int c = i / 9, tap = i - c * 9;
+    const float* row = scr + (size_t)c * 9 * DASR_AUX_CH + tap * DASR_AUX_CH;
+    dW[i] += row[DASR_AUX_DEPTH_HI] + (row[DASR_AUX_DEPTH_LO] + row[DASR_AUX_DEPTH_LO2]);
+    if (tap == 4) db[c] += row[DASR_AUX_ONE];
+}
+}  // namespace dasr
+
+extern "C" int dasr_actv_bwd_tc(const void* dA, const void* aux, float* scratch, float* dW, float* db, int B, int H,
+                                int W, int C, void* stream) {
+    DASR_REQUIRE(dA && aux && scratch && dW && db, "null pointer");
+    dasr_wgrad_desc d;
+    d.B = B; d.H = H; d.W = W; d.Cout = C; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.reserved = 0;
+    int rc = wgrad_launch(&d, dA, aux, scratch, WgOpts(), stream);
+    if (rc) return rc;
+    actv_bwd_gather_kernel<<<(C * 9 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, dW, db, C);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -200,6 +200,31 @@ __global__ void mask_labels_kernel(const float* __restrict__ masks, uint8_t* __r
     }
 }
 
+// ------------------------------------------------------------------------------------ auxiliary input tensor
+// aux NHWC bf16 [B,H,W,32]: ch 0..K-1 one-hot depth mask (from the label map), ch 16/17 depth split into two bf16
+// parts (hi + lo), ch 18 = 1, others 0.  It is the X operand of the tensor-core weight-gradient kernels that
+// differentiate the two input-driven convolutions of SEAN (K-DYN and mlp_mask); built once per forward.
+__global__ void build_aux_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ depth,
+                                 uint4* __restrict__ aux, size_t npix) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const int lab = labels[i];
+        const float d = __ldg(depth + i);
+        const __nv_bfloat16 hi = __float2bfloat16(d);
+        const __nv_bfloat16 lo = __float2bfloat16(d - __bfloat162float(hi));
+        const __nv_bfloat16 lo2 = __float2bfloat16((d - __bfloat162float(hi)) - __bfloat162float(lo));
+        __align__(16) __nv_bfloat16 v[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) v[c] = __float2bfloat16(c == lab ? 1.f : 0.f);
+        v[DASR_AUX_DEPTH_HI] = hi;
+        v[DASR_AUX_DEPTH_LO] = lo;
+        v[DASR_AUX_DEPTH_LO2] = lo2;
+        v[DASR_AUX_ONE] = __float2bfloat16(1.f);
+        const uint4* src = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) aux[i * 4 + j] = src[j];
+    }
+}
+
 // ------------------------------------------------------------------------------------ actv
 // Store-bandwidth kernel (2*C bytes per pixel out, 4 bytes in).  Thread = (8-channel group g, pixel slot): its
 // 72 weights + 8 biases live in REGISTERS for the whole block (re-reading them from shared memory per pixel made
@@ -443,6 +468,16 @@ extern "C" int dasr_mask_labels(const float* masks, uint8_t* labels, int32_t* fl
                                 void* stream) {
     DASR_REQUIRE(masks && labels && flag, "null pointer");
     mask_labels_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(masks, labels, flag, B, K, H * W);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_build_aux(const uint8_t* labels, const float* depth, void* aux, int B, int K, int H, int W,
+                              void* stream) {
+    DASR_REQUIRE(labels && depth && aux, "null pointer");
+    DASR_REQUIRE(K >= 1 && K <= 16, "aux tensor: at most 16 depth masks (got %d)", K);
+    const size_t npix = (size_t)B * H * W;
+    build_aux_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(labels, depth, (uint4*)aux, npix);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -266,7 +266,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
                                                    float* __restrict__ pt, const float* __restrict__ gt,
                                                    float* __restrict__ mt, float* __restrict__ vt, int tail, float omb1,
                                                    float b2, float omb2, float eps, float wd, float step_size,
-                                                   float sqrt_bc2, float gscale) {
+                                                   float sqrt_bc2, float gscale, const float* __restrict__ dev_scal) {
+    if (dev_scal) {      // CUDA-graph replays: the step-dependent scalars live in device memory
+        step_size = dev_scal[0];
+        sqrt_bc2 = dev_scal[1];
+    }
     auto upd = [&](float& pp, float gg, float& mm, float& vv) {
         gg = gg * gscale;
         if (wd != 0.f) gg = fmaf(wd, pp, gg);
@@ -348,8 +352,9 @@ extern "C" int dasr_loss_bwd(const float* sr, const float* hr, const uint8_t* la
 
 extern "C" int dasr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
                               double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
-                              void* stream) {
-    DASR_REQUIRE(p && g && m && v && n > 0 && step >= 1, "bad arguments");
+                              const float* dev_scalars, void* stream) {
+    DASR_REQUIRE(p && g && m && v && n > 0 && (step >= 1 || dev_scalars), "bad arguments");
+    if (step < 1) step = 1;
     DASR_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
                  "adam: buffers must be 16-byte aligned");
     const double bc1 = 1.0 - pow(beta1, (double)step);
@@ -366,7 +371,7 @@ extern "C" int dasr_adam_step(float* p, const float* g, float* m, float* v, int6
                                                              p + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, tail,
                                                              (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                                              (float)eps, (float)weight_decay, step_size, sqrt_bc2,
-                                                             (float)grad_scale);
+                                                             (float)grad_scale, dev_scalars);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

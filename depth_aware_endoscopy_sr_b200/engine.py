@@ -42,6 +42,7 @@ class Engine:
         self._key = None
         self._key_bwd = None
         self.last_flat_grad = None
+        self.always_pack = False    # CUDA-graph capture of a training step: repack inside every forward
         self.grad_sync = None       # callable(flat fp32 grad buffer) installed by parallel.FlatDataParallel
         self._packed: Dict[str, _Packed] = {}
         self._descs: List[L.PackDesc] = []
@@ -318,7 +319,7 @@ class Engine:
         flat = self._g_flat.clone()
         if self.grad_sync is not None:       # data parallel: one all-reduce of the whole flat buffer (parallel.py)
             self.grad_sync(flat)
-        flat._dasr_layout = self._glayout    # lets FusedAdam consume the buffer in place (optim.py)
+        L.register_flat_grad(flat, self._glayout)    # lets FusedAdam consume the buffer in place (optim.py)
         self.last_flat_grad = flat
         out = []
         for name, p in self.net.named_parameters():

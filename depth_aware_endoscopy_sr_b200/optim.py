@@ -24,11 +24,14 @@ from . import _lib as L
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0):
+                 weight_decay: float = 0.0, capturable: bool = False):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay or 0.0))
         self._flat = {}      # group index -> dict(p, m, v, g, offsets, step)
+        # capturable: the step-dependent scalars (lr / bias corrections) are read from device memory, so step()
+        # can be recorded once in a CUDA graph; call advance() before every step() / graph replay
+        self.capturable = capturable
 
     # ------------------------------------------------------------------ flat storage
     def _ensure_flat(self, gi, group):
@@ -54,7 +57,8 @@ class FusedAdam(torch.optim.Optimizer):
             flat[off:off + p.numel()].copy_(p.data.reshape(-1))
             p.data = flat[off:off + p.numel()].view(p.shape)
         st = dict(p=flat, m=torch.zeros_like(flat), v=torch.zeros_like(flat), g=None, offsets=offsets, params=params,
-                  step=0 if old is None else old["step"])
+                  step=0 if old is None else old["step"],
+                  pstep=[0] * len(params) if old is None or len(old["pstep"]) != len(params) else old["pstep"])
         if old is not None and old["m"].numel() == n:     # parameters were moved (.to / load): keep the moments
             st["m"].copy_(old["m"])
             st["v"].copy_(old["v"])
@@ -63,34 +67,49 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _segments(self, st):
         """[(offset, n, grad tensor)] covering the flat parameter buffer.  Parameters whose gradients are views of
-        ONE flat buffer with this optimiser's layout (``Engine.last_flat_grad``: tagged ``_dasr_layout`` =
-        {id(param): offset}, zero where the network leaves a gradient None) are stepped as a single segment straight
+        ONE flat buffer with this optimiser's layout (``Engine.last_flat_grad``, registered with its layout
+        {id(param): offset} in ``_lib.flat_grads()``; zero where the network leaves a gradient None) are stepped as a single segment straight
         from that buffer; any other parameter is its own segment; ``grad is None`` outside a flat buffer is skipped
         like torch.optim.Adam does."""
         params, offsets = st["params"], st["offsets"]
         segs, covered = [], set()
-        base = next((p.grad._base for p in params if p.grad is not None and p.grad._base is not None
-                     and hasattr(p.grad._base, "_dasr_layout")), None)
-        if base is not None:
-            lay = base._dasr_layout
-            idx = [i for i, p in enumerate(params) if id(p) in lay]
-            if idx and all(lay[id(params[i])] - offsets[i] == lay[id(params[idx[0]])] - offsets[idx[0]] for i in idx) \
-                    and idx == list(range(idx[0], idx[-1] + 1)):
-                i0, i1 = idx[0], idx[-1]
-                g0 = lay[id(params[i0])]
-                n = offsets[i1] + params[i1].numel() - offsets[i0]
-                if all(p.grad is None or p.grad.data_ptr() == base.data_ptr() + 4 * lay[id(p)] for p in params[i0:i1 + 1]) \
-                        and (base.data_ptr() + 4 * g0) % 16 == 0 and g0 + n <= base.numel():
-                    segs.append((offsets[i0], n, base[g0:g0 + n]))
-                    covered.update(range(i0, i1 + 1))
+        for base, lay in L.flat_grads():
+            idx = [i for i, p in enumerate(params) if id(p) in lay and i not in covered]
+            if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+                continue
+            i0, i1 = idx[0], idx[-1]
+            g0 = lay[id(params[i0])]
+            n = offsets[i1] + params[i1].numel() - offsets[i0]
+            same_layout = all(lay[id(params[i])] - offsets[i] == g0 - offsets[i0] for i in idx)
+            in_place = all(p.grad is None or p.grad.data_ptr() == base.data_ptr() + 4 * lay[id(p)]
+                           for p in params[i0:i1 + 1])
+            if same_layout and in_place and any(p.grad is not None for p in params[i0:i1 + 1]) \
+                    and (base.data_ptr() + 4 * g0) % 16 == 0 and g0 + n <= base.numel() and base.device == st["p"].device:
+                segs.append((offsets[i0], n, base[g0:g0 + n], list(range(i0, i1 + 1))))
+                covered.update(range(i0, i1 + 1))
         for i, p in enumerate(params):
             if i in covered or p.grad is None:
                 continue
             g = p.grad.detach()
             if g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() % 16:
                 g = g.float().contiguous().clone()
-            segs.append((offsets[i], p.numel(), g.reshape(-1)))
+            segs.append((offsets[i], p.numel(), g.reshape(-1), [i]))
         return segs
+
+    def advance(self):
+        """Host half of a step in capturable mode: bump the step counter and upload {lr/(1-b1^t), sqrt(1-b2^t)}."""
+        for gi, group in enumerate(self.param_groups):
+            st = self._ensure_flat(gi, group)
+            if st is None:
+                continue
+            st["step"] += 1
+            st["pstep"] = [st["step"]] * len(st["params"])
+            b1, b2 = group["betas"]
+            t = st["step"]
+            host = torch.tensor([group["lr"] / (1.0 - b1 ** t), (1.0 - b2 ** t) ** 0.5], dtype=torch.float32)
+            if "scal" not in st:
+                st["scal"] = torch.empty(2, device=st["p"].device, dtype=torch.float32)
+            st["scal"].copy_(host, non_blocking=True)
 
     # ------------------------------------------------------------------ Optimizer API
     @torch.no_grad()
@@ -107,13 +126,25 @@ class FusedAdam(torch.optim.Optimizer):
             segs = self._segments(st)
             if not segs:
                 continue
-            st["step"] += 1
             b1, b2 = group["betas"]
-            for off, n, g in segs:
+            pstep = st["pstep"]
+            scal = None
+            if self.capturable:
+                if "scal" not in st:
+                    raise RuntimeError("FusedAdam(capturable=True): call advance() before step()")
+                scal = st["scal"]
+            else:
+                st["step"] += 1
+            for off, n, g, members in segs:
+                # torch keeps one step counter per parameter (a parameter without gradient does not advance);
+                # the members of a flat segment always step together
+                if not self.capturable:
+                    for i in members:
+                        pstep[i] += 1
                 L.check(lib.dasr_adam_step(L.ptr(st["p"][off:off + n]), L.ptr(g), L.ptr(st["m"][off:off + n]),
                                            L.ptr(st["v"][off:off + n]), n, float(group["lr"]), float(b1), float(b2),
-                                           float(group["eps"]), float(group["weight_decay"]), st["step"], 1.0,
-                                           L.stream_ptr()))
+                                           float(group["eps"]), float(group["weight_decay"]), pstep[members[0]], 1.0,
+                                           L.ptr(scal), L.stream_ptr()))
             # the kernel wrote through raw pointers: advance the version counters like an in-place torch op
             # would (weight caches such as Engine.pack key on ``p._version``)
             torch.autograd.graph.increment_version(st["params"])
@@ -121,7 +152,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     def state_dict(self):
         sd = super().state_dict()
-        sd["flat"] = {gi: dict(step=st["step"], exp_avg=st["m"].clone(), exp_avg_sq=st["v"].clone())
+        sd["flat"] = {gi: dict(step=st["step"], pstep=list(st["pstep"]), exp_avg=st["m"].clone(),
+                               exp_avg_sq=st["v"].clone())
                       for gi, st in self._flat.items()}
         return sd
 
@@ -132,5 +164,6 @@ class FusedAdam(torch.optim.Optimizer):
             if gi in flat:
                 st = self._ensure_flat(gi, group)
                 st["step"] = int(flat[gi]["step"])
+                st["pstep"] = list(flat[gi].get("pstep", [st["step"]] * len(st["params"])))
                 st["m"].copy_(flat[gi]["exp_avg"])
                 st["v"].copy_(flat[gi]["exp_avg_sq"])

@@ -188,6 +188,23 @@ int dasr_colsum(const void* x, float* out, int64_t rows, int C, void* stream);
 /* K-DYN backward: dT[b][k][tap][c] += sum_p dgb[b,p,c] * mask[b,k,p+tap-1] (labels fast path like the forward) */
 int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const float* masks, const int32_t* flag, float* dT,
                      int B, int K, int H, int W, int nf2, void* stream);
+/* Auxiliary input tensor aux NHWC bf16 [B,H,W,DASR_AUX_CH]: channels 0..K-1 = one-hot depth mask (from the label
+ * map of dasr_mask_labels), DASR_AUX_DEPTH_HI/LO = the depth split into two bf16 parts (hi + lo = 16 mantissa
+ * bits), DASR_AUX_ONE = 1, others 0.  X operand of the two tensor-core kernels below; built once per forward.   */
+#define DASR_AUX_CH 32
+#define DASR_AUX_DEPTH_HI 16
+#define DASR_AUX_DEPTH_LO 17
+#define DASR_AUX_ONE 18
+#define DASR_AUX_DEPTH_LO2 19   /* third bf16 part: hi + lo + lo2 reproduces the fp32 depth exactly */
+int dasr_build_aux(const uint8_t* labels, const float* depth, void* aux, int B, int K, int H, int W, void* stream);
+/* K-DYN backward on tcgen05 (one-hot masks): same result as dasr_dynconv_bwd, computed as the per-image weight
+ * gradient of a 3x3 convolution over the one-hot channels of aux.  No-op when *flag != 0; the caller then also
+ * issues dasr_dynconv_bwd(labels = NULL, masks, flag), which is a no-op when *flag == 0.                        */
+int dasr_dynconv_bwd_tc(const void* dgb, const void* aux, const int32_t* flag, float* dT, int B, int K, int H, int W,
+                        int nf2, void* stream);
+/* mlp_mask backward on tcgen05: same result as dasr_actv_bwd; scratch fp32 [C][9*DASR_AUX_CH] zeroed by the caller */
+int dasr_actv_bwd_tc(const void* dA, const void* aux, float* scratch, float* dW, float* db, int B, int H, int W, int C,
+                     void* stream);
 /* style-table GEMM backward: dWs[n][c] = sum_bk dT[bk][n] stp[bk][c];  dstp[bk][c] = sum_n dT[bk][n] Ws[n][c]    */
 int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N, int L,
                    void* stream);
@@ -297,9 +314,12 @@ int dasr_loss_bwd(const float* sr, const float* hr, const uint8_t* labels, const
                   int C, int K, int h, int w, int Ho, int Wo, void* stream);
 /* K-ADAM: one torch.optim.Adam step (F_model_depthCond.py:99-101,192; amsgrad off) over flat fp32 buffers of n
  * elements: g' = grad_scale*g + wd*p; m = lerp(m, g', 1-beta1); v = beta2*v + (1-beta2)*g'^2;
- * p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).  step counts from 1.  16-byte aligned buffers. */
+ * p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps).  step counts from 1.  16-byte aligned buffers.
+ * dev_scalars (optional): device fp32 [2] = { lr/(1-beta1^step), sqrt(1-beta2^step) } read by the kernel instead of
+ * the values derived from lr/step -- lets a captured CUDA graph of the training step be replayed for every step. */
 int dasr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
-                   double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
+                   double eps, double weight_decay, int64_t step, double grad_scale, const float* dev_scalars,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ def test_sean_instance_norm_backward_kernels(kb):
 def test_dynamic_conv_and_style_backward_kernels(kb):
     kb.failures.clear()
     kb.dyn_bwd_case()
+    kb.dyn_bwd_case(B=3, H=24, W=40)
+    kb.dyn_bwd_case(B=4, H=64, W=64)
     assert not kb.failures, kb.failures
 
 

@@ -142,9 +142,37 @@ def dyn_bwd_case(B=2, K=10, H=16, W=16, nf2=128, L_=256):
     ref = T.grad.permute(0, 2, 3, 4, 1).reshape(B * K, 9 * nf2).contiguous()       # [b][k][tap][c]
     for use_labels in (True, False):
         dT = torch.zeros(B * K, 9 * nf2, device=dev)
-        L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), L.ptr(labels) if use_labels else None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+        L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), L.ptr(labels) if use_labels else None, L.ptr(masks), L.ptr(flag) if use_labels else None, L.ptr(dT), B, K, H, W, nf2, s))
         torch.cuda.synchronize()
         report("dynconv_bwd labels=%d" % use_labels, dT, ref, 1e-4)
+    # tensor-core path (one-hot channels of the aux tensor) + the flag protocol between the two kernels
+    depth = torch.rand(B, 1, H, W, device=dev) * 9.99 + 0.01
+    aux = torch.empty(B, H, W, L.AUX_CH, device=dev, dtype=torch.bfloat16)
+    L.check(lib.dasr_build_aux(L.ptr(labels), L.ptr(depth), L.ptr(aux), B, K, H, W, s))
+    dT = torch.zeros(B * K, 9 * nf2, device=dev)
+    L.check(lib.dasr_dynconv_bwd_tc(L.ptr(dgb), L.ptr(aux), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+    L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+    torch.cuda.synchronize()
+    report("dynconv_bwd_tc (flag 0: tc runs, fallback idle)", dT, ref, 1e-4)
+    one = torch.ones(1, device=dev, dtype=torch.int32)
+    dT = torch.zeros(B * K, 9 * nf2, device=dev)
+    L.check(lib.dasr_dynconv_bwd_tc(L.ptr(dgb), L.ptr(aux), L.ptr(one), L.ptr(dT), B, K, H, W, nf2, s))
+    torch.cuda.synchronize()
+    report("dynconv_bwd_tc (flag 1: idle)", dT, torch.zeros_like(dT), 1e-9)
+    L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), None, L.ptr(masks), L.ptr(one), L.ptr(dT), B, K, H, W, nf2, s))
+    torch.cuda.synchronize()
+    report("dynconv_bwd fallback (flag 1)", dT, ref, 1e-4)
+    # mlp_mask backward on the tensor cores against autograd of conv3x3(depth, 1 -> nf2)
+    dA = torch.randn(B, H, W, nf2, device=dev).to(torch.bfloat16)
+    wm = torch.zeros(nf2, 1, 3, 3, device=dev, requires_grad=True)
+    bm = torch.zeros(nf2, device=dev, requires_grad=True)
+    (F.conv2d(depth, wm, bm, padding=1) * dA.float().permute(0, 3, 1, 2)).sum().backward()
+    scr = torch.zeros(nf2, 9 * L.AUX_CH, device=dev)
+    gW = torch.zeros(nf2, 9, device=dev); gb = torch.zeros(nf2, device=dev)
+    L.check(lib.dasr_actv_bwd_tc(L.ptr(dA), L.ptr(aux), L.ptr(scr), L.ptr(gW), L.ptr(gb), B, H, W, nf2, s))
+    torch.cuda.synchronize()
+    report("actv_bwd_tc dW", gW, wm.grad.reshape(nf2, 9), 2e-4)
+    report("actv_bwd_tc db", gb, bm.grad, 2e-4)
     # table backward
     stp = torch.randn(B * K, L_, device=dev).to(torch.bfloat16)
     Ws = (torch.randn(9 * nf2, L_, device=dev) / 16).to(torch.bfloat16)
