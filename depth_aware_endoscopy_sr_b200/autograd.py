@@ -169,9 +169,6 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     K, lat = sean.label_nc, sean.len_latent
     dev = x.device
     # ---- forward (same kernels as Engine._dgb, plus the tensors the backward needs)
-    actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
-    L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B,
-                              H, W, nf2, s))
     stp = torch.empty(1, 1, B * K, lat, device=dev, dtype=BF16)
     L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias), L.ptr(stp), B, K, lat, s))
     pkt = eng._packed[n + ".table"]
@@ -185,6 +182,9 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     normk = torch.empty(B, nf, device=dev, dtype=torch.float32)
     y = eng._conv(x, conv_name, epi=L.EPI_STATS, stats=stats)
     L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm), L.ptr(normk), B, nf, H * W, nslots, s))
+    actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+    L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B,
+                              H, W, nf2, s))
     gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
     if first:
         out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm, gb_s=gb_s, gamma_out=gamma)

@@ -97,16 +97,34 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return u;
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  The epilogues touch 32-byte pieces of 64..256-byte pixel
+// rows, one row per lane, so every warp-level access spans 32 cache lines: halving the instruction count halves the
+// LSU wavefronts, which is what bounds the fused epilogues (ncu: lg_throttle).  Addresses are 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg256f(float* p, const float* f) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(f[0])),
+                 "r"(__float_as_uint(f[1])), "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])),
+                 "r"(__float_as_uint(f[4])), "r"(__float_as_uint(f[5])), "r"(__float_as_uint(f[6])),
+                 "r"(__float_as_uint(f[7]))
+                 : "memory");
+}
 __device__ __forceinline__ void load16(const __nv_bfloat16* p, float* f) {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
+    uint4 a, b;
+    ldg256(p, a, b);
     unpack8(a, f);
     unpack8(b, f + 8);
 }
 __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = pack8(f);
-    q[1] = pack8(f + 8);
+    stg256(p, pack8(f), pack8(f + 8));
 }
 
 // Reduce 16 per-thread values over the 32 lanes of a warp (recursive halving).  On return lane L holds in
@@ -165,24 +183,23 @@ __device__ __forceinline__ void sean_load(const ConvK& p, SeanOps& o, int img, i
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     o.y0 = o.y1 = o.g0 = o.g1 = o.b0 = o.b1 = o.r0 = o.r1 = z4;
     if (!o.valid) return;
-    const uint4* yp = reinterpret_cast<const uint4*>(p.y + o.pix * NF + c0);
-    o.y0 = __ldg(yp);
-    o.y1 = __ldg(yp + 1);
+    ldg256(p.y + o.pix * NF + c0, o.y0, o.y1);
     if (p.gb_s) {
-        const uint4* sp = reinterpret_cast<const uint4*>(p.gb_s + o.pix * N_TILE + c0);
-        o.g0 = __ldg(sp);
-        o.g1 = __ldg(sp + 1);
-        o.b0 = __ldg(sp + NF / 8);
-        o.b1 = __ldg(sp + NF / 8 + 1);
+        const __nv_bfloat16* sp = p.gb_s + o.pix * N_TILE + c0;
+        ldg256(sp, o.g0, o.g1);
+        ldg256(sp + NF, o.b0, o.b1);
     }
     if (p.resid_f32) {
-        const float4* rp = reinterpret_cast<const float4*>(p.resid_f32 + o.pix * NF + c0);
-#pragma unroll
-        for (int j = 0; j < 4; j++) o.rf[j] = __ldg(rp + j);
+        const float* rp = p.resid_f32 + o.pix * NF + c0;
+        uint4 a, b, c, d;
+        ldg256(rp, a, b);
+        ldg256(rp + 8, c, d);
+        o.rf[0] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+        o.rf[1] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
+        o.rf[2] = make_float4(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), __uint_as_float(c.w));
+        o.rf[3] = make_float4(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z), __uint_as_float(d.w));
     } else if (p.resid) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.resid + o.pix * NF + c0);
-        o.r0 = __ldg(rp);
-        o.r1 = __ldg(rp + 1);
+        ldg256(p.resid + o.pix * NF + c0, o.r0, o.r1);
     }
 }
 
@@ -243,9 +260,8 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
         for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
         store16(p.out + o.pix * NF + c0, f);
         if (p.out_aux_f32) {
-            float4* op32 = reinterpret_cast<float4*>(p.out_aux_f32 + o.pix * NF + c0);
-#pragma unroll
-            for (int j = 0; j < 4; j++) op32[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            stg256f(p.out_aux_f32 + o.pix * NF + c0, f);
+            stg256f(p.out_aux_f32 + o.pix * NF + c0 + 8, f + 8);
         }
     }
 }
@@ -524,14 +540,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
                     for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
                         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, m0 = r0, m1 = r0;
-                        if (rp && valid) {
-                            r0 = __ldg(reinterpret_cast<const uint4*>(rp + c0));
-                            r1 = __ldg(reinterpret_cast<const uint4*>(rp + c0) + 1);
-                        }
-                        if (mp && valid) {
-                            m0 = __ldg(reinterpret_cast<const uint4*>(mp + c0));
-                            m1 = __ldg(reinterpret_cast<const uint4*>(mp + c0) + 1);
-                        }
+                        if (rp && valid) ldg256(rp + c0, r0, r1);
+                        if (mp && valid) ldg256(mp + c0, m0, m1);
                         uint32_t v[16];
                         tmem_ld16(t_blk + c0, v);
                         tmem_ld_wait();
@@ -559,10 +569,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         } else {
                             // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
                             uint4 o0 = pack8(f), o1 = pack8(f + 8);
-                            if (valid) {
-                                reinterpret_cast<uint4*>(op + c0)[0] = o0;
-                                reinterpret_cast<uint4*>(op + c0)[1] = o1;
-                            }
+                            if (valid) stg256(op + c0, o0, o1);
                             float s1[16], s2[16];
                             unpack8(o0, s1);
                             unpack8(o1, s1 + 8);

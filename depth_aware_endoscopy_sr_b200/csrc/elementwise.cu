@@ -226,45 +226,84 @@ __global__ void build_aux_kernel(const uint8_t* __restrict__ labels, const float
 }
 
 // ------------------------------------------------------------------------------------ actv
-// Store-bandwidth kernel (2*C bytes per pixel out, 4 bytes in).  Thread = (8-channel group g, pixel slot): its
-// 72 weights + 8 biases live in REGISTERS for the whole block (re-reading them from shared memory per pixel made
-// v1 LDS-bound at 480 GB/s); lanes 0..G-1 of a pixel write one contiguous 2*C-byte row.
+// Store-bandwidth kernel (2*C bytes per pixel out, 4 bytes in).  Block = (image, band of kActvRows rows): the
+// zero-padded depth halo of the band sits in shared memory (no bounds checks in the loop).  Thread = (8-channel
+// group g, pixel slot): its 72 weights + 8 biases live in REGISTERS as float2 pairs and every tap is 4 packed
+// FFMA2 (fma.rn.f32x2, two fp32 FMAs per instruction on sm_100); a slot walks a run of consecutive pixels of one
+// row with a sliding 3x3 window (3 shared-memory loads per pixel).  Lanes 0..G-1 of a pixel write one contiguous
+// 2*C-byte row.  v1 -> v2: 242 -> ~75 instructions per (pixel, 8 channels), grid sized to whole waves.
+constexpr int kActvRows = 2;
 template <int G>
 __global__ void __launch_bounds__(256) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
                                                    const float* __restrict__ bias, uint4* __restrict__ out, int H,
-                                                   int W, int pix_per_block) {
-    constexpr int C = G * 8;
+                                                   int W, int n_items) {
     constexpr int SLOTS = 256 / G;
+    extern __shared__ float dsm[];                 // (rows + 2) x (W + 2), zero padded
+    const int bands = (H + kActvRows - 1) / kActvRows;
+    const int LW = W + 2;
     const int g = threadIdx.x % G, slot = threadIdx.x / G;
-    float wr[9][8], br[8];
+    float2 wr[9][4], br[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        br[j] = __ldg(bias + g * 8 + j);
+    for (int j = 0; j < 4; j++) {
+        br[j] = make_float2(__ldg(bias + g * 8 + 2 * j), __ldg(bias + g * 8 + 2 * j + 1));
 #pragma unroll
-        for (int t = 0; t < 9; t++) wr[t][j] = __ldg(w + (g * 8 + j) * 9 + t);
+        for (int t = 0; t < 9; t++)
+            wr[t][j] = make_float2(__ldg(w + (g * 8 + 2 * j) * 9 + t), __ldg(w + (g * 8 + 2 * j + 1) * 9 + t));
     }
-    const int HW = H * W;
-    const float* dp = depth + (size_t)blockIdx.y * HW;
-    uint4* op = out + (size_t)blockIdx.y * HW * G;
-    const int p0 = blockIdx.x * pix_per_block;
-    const int p1 = min(p0 + pix_per_block, HW);
-    for (int pix = p0 + slot; pix < p1; pix += SLOTS) {
-        const int y = pix / W, x = pix - y * W;
-        float acc[8];
+    // persistent over (image, band) items: the weights (identical for every image) are loaded once per block
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / bands, band = item - b * bands;
+    const int h0 = band * kActvRows;
+    const int rows = min(kActvRows, H - h0);
+    const float* dp = depth + (size_t)b * H * W;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (rows + 2) * LW; i += 256) {
+        const int r = i / LW, c = i - r * LW;
+        const int hh = h0 + r - 1, ww = c - 1;
+        dsm[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(dp + hh * W + ww) : 0.f;
+    }
+    __syncthreads();
+    // runs: each row is cut into segments of `seg` pixels; slot s takes run s, s + SLOTS, ...
+    const int seg = 8;
+    const int segs_per_row = (W + seg - 1) / seg;
+    const int nruns = rows * segs_per_row;
+    uint4* op = out + ((size_t)b * H + h0) * W * G;
+    for (int run = slot; run < nruns; run += SLOTS) {
+        const int r = run / segs_per_row;
+        const int x0 = (run - r * segs_per_row) * seg;
+        const int x1 = min(x0 + seg, W);
+        const float* d0 = dsm + r * LW + x0;       // window row 0, column x-1 (padded coordinates)
+        float win[3][3];
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = br[j];
+        for (int t = 0; t < 3; t++) {
+            win[t][1] = d0[t * LW];
+            win[t][2] = d0[t * LW + 1];
+        }
+        for (int x = x0; x < x1; x++) {
 #pragma unroll
-        for (int t = 0; t < 3; t++)
-#pragma unroll
-            for (int u = 0; u < 3; u++) {
-                const int yy = y + t - 1, xx = x + u - 1;
-                const float d = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dp + yy * W + xx) : 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; j++) acc[j] = fmaf(d, wr[t * 3 + u][j], acc[j]);
+            for (int t = 0; t < 3; t++) {
+                win[t][0] = win[t][1];
+                win[t][1] = win[t][2];
+                win[t][2] = d0[t * LW + (x - x0) + 2];
             }
+            float2 acc[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
-        op[(size_t)pix * G + g] = pack8f(acc);
+            for (int j = 0; j < 4; j++) acc[j] = br[j];
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const float2 d2 = make_float2(win[t][u], win[t][u]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[j] = __ffma2_rn(d2, wr[t * 3 + u][j], acc[j]);
+                }
+            uint4 o;
+            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; j++) oh[j] = __floats2bfloat162_rn(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
+            op[((size_t)r * W + x) * G + g] = o;
+        }
+    }
     }
 }
 
@@ -284,33 +323,57 @@ __global__ void style_mix_kernel(const float* __restrict__ st, const float* __re
 }
 
 // ------------------------------------------------------------------------------------ K-DYN apply
-// Block = one (image, 8-row band); table T[b] ([K][9][C2] bf16) and the label halo are staged in smem.
-// thread item = (pixel, 8-channel group): 9 label lookups + 9 16-byte smem reads + one 16-byte store.
+// Block = one (image, band of rows); table T[b] ([K][9][C2] bf16, plus one all-zero row for pixels in no mask) and
+// the label halo are staged in smem.  thread item = (pixel, 8-channel group): 9 label lookups + 9 16-byte smem
+// reads + one 16-byte store; the bf16 table entries are accumulated in fp32 with the mixed-precision add of sm_100
+// (add.rn.f32.bf16 -> FHADD.BF16 with a free .H0/.H1 operand select: no unpacking instructions).
+__device__ __forceinline__ void acc_bf16x8(float* acc, const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        unsigned short lo, hi;
+        asm("mov.b32 {%0, %1}, %2;" : "=h"(lo), "=h"(hi) : "r"(w[j]));
+        asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(acc[2 * j]) : "h"(lo));
+        asm("add.rn.f32.bf16 %0, %1, %0;" : "+f"(acc[2 * j + 1]) : "h"(hi));
+    }
+}
+
 __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16* __restrict__ table,
                                                              const uint8_t* __restrict__ labels,
                                                              const float* __restrict__ masks, const int* __restrict__ flag,
                                                              uint4* __restrict__ out, int K, int H, int W, int C2,
-                                                             int rows_per_block) {
+                                                             int rows_per_block, int n_items) {
     extern __shared__ __align__(16) uint8_t smraw[];
-    uint4* ts = reinterpret_cast<uint4*>(smraw);  // K*9*C2/8 uint4
+    uint4* ts = reinterpret_cast<uint4*>(smraw);  // (K + 1)*9*C2/8 uint4; row K is all zero
     const int G = C2 / 8;
     const int tsz = K * 9 * G;
-    uint8_t* ls = smraw + (size_t)tsz * 16;  // (rows+2) x (W+2) labels
+    uint8_t* ls = smraw + (size_t)(tsz + 9 * G) * 16;  // (rows+2) x (W+2) labels
     const int bands = (H + rows_per_block - 1) / rows_per_block;
-    const int b = blockIdx.x / bands, band = blockIdx.x % bands;
+    // persistent over a CONTIGUOUS range of (image, band) items: the table is restaged only when the image changes
+    const int item0 = (int)((long long)blockIdx.x * n_items / gridDim.x);
+    const int item1 = (int)((long long)(blockIdx.x + 1) * n_items / gridDim.x);
+    const bool general = (flag != nullptr) && (*flag != 0) && (masks != nullptr);
+    int staged_img = -1;
+    for (int item = item0; item < item1; item++) {
+    const int b = item / bands, band = item - b * bands;
     const int h0 = band * rows_per_block;
     const int rows = min(rows_per_block, H - h0);
-    const uint4* tg = reinterpret_cast<const uint4*>(table + (size_t)b * K * 9 * C2);
-    for (int i = threadIdx.x; i < tsz; i += blockDim.x) ts[i] = __ldg(tg + i);
+    __syncthreads();
+    if (b != staged_img) {
+        const uint4* tg = reinterpret_cast<const uint4*>(table + (size_t)b * K * 9 * C2);
+        for (int i = threadIdx.x; i < tsz; i += blockDim.x) ts[i] = __ldg(tg + i);
+        for (int i = threadIdx.x; i < 9 * G; i += blockDim.x) ts[tsz + i] = make_uint4(0, 0, 0, 0);
+        staged_img = b;
+    }
     const int LW = W + 2;
     for (int i = threadIdx.x; i < (rows + 2) * LW; i += blockDim.x) {
         const int r = i / LW, c = i - r * LW;
         const int hh = h0 + r - 1, ww = c - 1;
-        ls[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? labels[((size_t)b * H + hh) * W + ww] : (uint8_t)255;
+        int lab = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? labels[((size_t)b * H + hh) * W + ww] : K;
+        ls[i] = (uint8_t)(lab < K ? lab : K);      // 255 (pixel in no mask) and the zero padding -> the zero row
     }
     __syncthreads();
     const int items = rows * W * G;
-    const bool general = (flag != nullptr) && (*flag != 0) && (masks != nullptr);
     if (general) {
         // masks are not one-hot: exact linear form  sum_{k,tap} mask * T  (slow path, same smem table)
         for (int it = threadIdx.x; it < items; it += blockDim.x) {
@@ -335,12 +398,43 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
                     }
             out[(((size_t)b * H + h0 + r) * W + c) * G + gch] = pack8f(acc);
         }
-        return;
+        continue;
     }
+    // one-hot fast path.  A thread keeps its channel group and walks pixels with a fixed stride (no divisions in
+    // the loop); the tap offsets into the table are compile-time multiples of G.
+    if (G == 16) {
+        const int gch = threadIdx.x & 15;
+        const uint4* tp = ts + gch;
+        const int npix = rows * W;
+        int pl = threadIdx.x >> 4;
+        int r = pl / W, c = pl - r * W;
+        const int step = blockDim.x >> 4;          // pixels advanced per iteration (< W is not required)
+        uint4* op = out + ((size_t)b * H + h0) * W * 16 + gch;
+        for (; pl < npix; pl += step) {
+            const uint8_t* lp = ls + r * LW + c;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int lab = lp[t * LW + u];
+                    acc_bf16x8(acc, tp[lab * (9 * 16) + (t * 3 + u) * 16]);
+                }
+            op[(size_t)pl * 16] = pack8f(acc);
+            c += step;
+            while (c >= W) { c -= W; r++; }
+        }
+        continue;
+    }
+    const int G9 = 9 * G;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int gch = it % G;
         const int pl = it / G;
         const int r = pl / W, c = pl - r * W;
+        const uint8_t* lp = ls + r * LW + c;
+        const uint4* tp = ts + gch;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[j] = 0.f;
@@ -348,15 +442,11 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
         for (int t = 0; t < 3; t++)
 #pragma unroll
             for (int u = 0; u < 3; u++) {
-                const int lab = ls[(r + t) * LW + c + u];
-                if (lab != 255) {
-                    float f[8];
-                    unpack8f(ts[(lab * 9 + t * 3 + u) * G + gch], f);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) acc[j] += f[j];
-                }
+                const int lab = lp[t * LW + u];
+                acc_bf16x8(acc, tp[lab * G9 + (t * 3 + u) * G]);
             }
         out[(((size_t)b * H + h0 + r) * W + c) * G + gch] = pack8f(acc);
+    }
     }
 }
 
@@ -487,17 +577,15 @@ extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bi
     DASR_REQUIRE(depth && w && bias && out && C % 8 == 0, "bad arguments");
     DASR_REQUIRE(C == 128 || C == 64, "actv: C (= 2*nf) must be 64 or 128 (got %d)", C);
     DASR_REQUIRE((size_t)H * W < 0x7fffffffull, "frame too large");
-    // enough blocks to fill the GPU, few enough that the per-thread weight preload (80 floats) is amortised
-    const int HW = H * W;
-    int per_img = (2 * num_sms() + B - 1) / B;
-    if (per_img < 1) per_img = 1;
-    int ppb = (HW + per_img - 1) / per_img;
-    if (ppb < 256) ppb = 256;
-    const int gx = (HW + ppb - 1) / ppb;
+    const int bands = (H + kActvRows - 1) / kActvRows;
+    const size_t smem = (size_t)(kActvRows + 2) * (W + 2) * sizeof(float);
+    DASR_REQUIRE(smem <= 48 * 1024, "actv: frame too wide (%d)", W);
+    const int n_items = B * bands;
+    const int grid = n_items < 2 * num_sms() ? n_items : 2 * num_sms();     // 2 resident blocks per SM (114 registers)
     if (C == 128)
-        actv_kernel<16><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, ppb);
+        actv_kernel<16><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, n_items);
     else
-        actv_kernel<8><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, ppb);
+        actv_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, n_items);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -515,8 +603,8 @@ extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const 
     DASR_REQUIRE(table && out && (labels || masks), "null pointer");
     DASR_REQUIRE(nf2 % 8 == 0, "2*nf must be a multiple of 8");
     if (labels) {
-        const int rows = 8;
-        const size_t smem = (size_t)K * 9 * nf2 * 2 + (size_t)(rows + 2) * (W + 2);
+        const int rows = 2;
+        const size_t smem = (size_t)(K + 1) * 9 * nf2 * 2 + (size_t)(rows + 2) * (W + 2);
         DASR_REQUIRE(smem <= 200 * 1024, "image too wide for the label tile");
         static bool configured[64] = {false};
         int dev = 0;
@@ -526,7 +614,9 @@ extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const 
             configured[dev & 63] = true;
         }
         const int bands = (H + rows - 1) / rows;
-        dynconv_labels_kernel<<<B * bands, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, labels, masks, flag, (uint4*)out, K, H, W, nf2, rows);
+        const int n_items = B * bands;
+        const int grid = n_items < 4 * num_sms() ? n_items : 4 * num_sms();      // 4 resident blocks per SM
+        dynconv_labels_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, labels, masks, flag, (uint4*)out, K, H, W, nf2, rows, n_items);
     } else {
         const size_t total = (size_t)B * H * W * (nf2 / 8);
         dynconv_masks_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, masks, (uint4*)out, B, K, H, W, nf2);

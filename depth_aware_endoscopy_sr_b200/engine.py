@@ -368,10 +368,6 @@ class Engine:
         nf2 = 2 * sean.norm_nc
         K, lat = sean.label_nc, sean.len_latent
         s = L.stream_ptr()
-        actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
-        self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
-                    lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight),
-                                                      L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
         stp = torch.empty(1, 1, B * K, lat, device=depth.device, dtype=BF16)
         self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp.numel() * 2,
                     lambda: L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias),
@@ -386,6 +382,11 @@ class Engine:
         self._timed("dynconv", "hbm", 0, gb_s.numel() * 2 + B * H * W + table.numel() * 2,
                     lambda: L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag),
                                                          L.ptr(gb_s), B, K, H, W, nf2, s)))
+        # actv last: it is the operand the SEAN convolution reads first, so it is still L2-resident (126 MB L2)
+        actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
+        self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
+                    lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight),
+                                                      L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
         return actv, gb_s
 
     def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, vec):
@@ -402,11 +403,11 @@ class Engine:
         out32 = torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32)
         for j, sean in ((1, blk.norm1), (2, blk.norm2)):
             n = "%s.norm%d" % (p, j)
-            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, vec)
             y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats)
             self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
                         lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), None, B, nf,
                                                                   H * W, nslots, s)))
+            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, vec)
             if j == 1:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
             else:

@@ -2,6 +2,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+torch.backends.cudnn.allow_tf32 = False          # references must be true fp32 (cuDNN defaults to TF32 convs)
+torch.backends.cuda.matmul.allow_tf32 = False
 import torch.nn.functional as F
 from depth_aware_endoscopy_sr_b200 import _lib as L
 
