@@ -159,7 +159,7 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
     return o
 
 
-def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, *,
+def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, tables, *,
                 first: bool, resid: Optional[_T]) -> _T:
     """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
     eng, lib, s = tp.eng, tp.lib, tp.s
@@ -169,11 +169,9 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     K, lat = sean.label_nc, sean.len_latent
     dev = x.device
     # ---- forward (same kernels as Engine._dgb, plus the tensors the backward needs)
-    stp = torch.empty(1, 1, B * K, lat, device=dev, dtype=BF16)
-    L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias), L.ptr(stp), B, K, lat, s))
+    sidx = eng._sean_index[n]
+    stp, table = tables[0][sidx], tables[1][sidx]        # all instances were computed in two launches
     pkt = eng._packed[n + ".table"]
-    table = torch.empty(1, 1, B * K, 9 * nf2, device=dev, dtype=BF16)
-    L.conv_fwd(stp, pkt.w, eng._zero_bias, table, Cout=9 * nf2, ks=1)
     gb_s = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
     L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W, nf2, s))
     nslots = L.conv_stats_slots(B, H, W, nf, nf)
@@ -268,7 +266,7 @@ def _forward_train(eng, lq, depth, masks):
 
     tp.ops.append(bwd_first)
 
-    vec = labels = flag = dvec = aux = None
+    vec = labels = flag = dvec = aux = tables = None
     if not net.isBaseline:
         e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
         e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
@@ -297,6 +295,7 @@ def _forward_train(eng, lq, depth, masks):
         labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
         flag = torch.zeros(1, device=dev, dtype=torch.int32)
         L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
+        tables = eng.style_tables(vec)
         aux = torch.empty(B, h, w, L.AUX_CH, device=dev, dtype=BF16)
         L.check(lib.dasr_build_aux(L.ptr(labels), L.ptr(depth), L.ptr(aux), B, K, h, w, s))
 
@@ -312,9 +311,9 @@ def _forward_train(eng, lq, depth, masks):
             p = "depth-residual%d" % (i + 1)
             blk = net.block(i)
             a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec, aux,
-                            first=True, resid=None)
+                            tables, first=True, resid=None)
             return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec, aux,
-                               first=False, resid=x)
+                               tables, first=False, resid=x)
         p = "classic-residual%d" % (i + 1)
         f = _conv_train(tp, x, p + ".block.0", act="relu")
         # relu(x + conv(f)): the residual add is the conv epilogue; its backward = lazy ReLU mask, then both paths

@@ -73,6 +73,7 @@ struct ConvK {
     float* out_aux_f32;            // SEAN: fp32 copy of the output (the residual stream of the next block)
     int nslots;                    // STATS: partial-sum slots per image
     int n_bias;                    // padded Cout (bias entries staged in shared memory)
+    int w_img_rows;                // > 0: per-image weights, image b uses rows [b*w_img_rows, +Cout) of the B matrix
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -281,7 +282,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __shared__ uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
     __shared__ uint64_t acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float norm_s[2 * 128];
+    __shared__ float norm_s[512];         // SEAN: (mean, scale) of the image; STATS: scratch of the fused finalize
     __shared__ float bias_s[kMaxBias];
     __shared__ uint32_t tap_lo_s[81];     // descriptor-low-word offset of tap (t,u): ((t*Wp + u) * SWZ) >> 4
 
@@ -363,6 +364,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             PROF_DECL;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.ntn;
+                const int wrow0 = p.w_img_rows ? (tile / tiles_per_img) * p.w_img_rows : 0;
                 if (p.b_resident && !first) continue;
                 for (int c = 0; c < p.nch; c++) {
                     for (int tap = 0; tap < p.taps; tap++) {
@@ -379,7 +381,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         }
                         mbar_expect_tx(&b_full[sb], p.b_tx_bytes);
                         tma_load_2d(b_smem + (size_t)sb * p.b_stage_bytes, &mapB, &b_full[sb],
-                                    tap * p.Cin + c * KC, nt * N_TILE);
+                                    tap * p.Cin + c * KC, wrow0 + nt * N_TILE);
                     }
                 }
                 first = false;
@@ -536,7 +538,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     __nv_bfloat16* op = p.out + pix * p.Cout + nt * N_TILE;
                     const __nv_bfloat16* rp = p.resid ? p.resid + pix * p.Cout + nt * N_TILE : nullptr;
                     const __nv_bfloat16* mp = p.actmask ? p.actmask + pix * p.Cout + nt * N_TILE : nullptr;
-                    const int slot = ((strip * p.tiles_per_strip + tps) * NB + blk) * 4 + ew;
 #pragma unroll 1
                     for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
                         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, m0 = r0, m1 = r0;
@@ -584,10 +585,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             if (!(lane & 1)) {
                                 const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
                                                 ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                                // one writer per (image, slot, channel): deterministic, no atomics
-                                float* sp = p.stats + (((size_t)img * p.nslots + slot) * p.Cout + nt * N_TILE + c0 + col) * 2;
-                                sp[0] = s1[0];
-                                sp[1] = s2[0];
+                                // per-tile partials of this warp's row quadrant in shared memory: (ew, column) has
+                                // exactly one owner lane, the M blocks are added in order -> deterministic
+                                float* rp2 = norm_s + (ew * N_TILE + c0 + col) * 2;
+                                if (blk == 0) {
+                                    rp2[0] = s1[0];
+                                    rp2[1] = s2[0];
+                                } else {
+                                    rp2[0] += s1[0];
+                                    rp2[1] += s2[0];
+                                }
                             }
                         }
                     }
@@ -633,6 +640,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             acc_it++;
+            if (p.epi == DASR_EPI_STATS) {
+                // one statistics slot per (image, tile): the four row quadrants are added in a fixed order
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                if (et < N_TILE) {
+                    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        a1 += norm_s[(q * N_TILE + et) * 2];
+                        a2 += norm_s[(q * N_TILE + et) * 2 + 1];
+                    }
+                    const int slot = strip * p.tiles_per_strip + tps;
+                    float2* sp = reinterpret_cast<float2*>(p.stats) + ((size_t)img * p.nslots + slot) * p.Cout + nt * N_TILE + et;
+                    *sp = make_float2(a1, a2);
+                }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            }
         }
         PROF_LAP(1);
 #ifdef DASR_PROFILE
@@ -654,7 +677,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, 
     int dev = 0;
     DASR_CUDA_OK(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
-        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
+        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 10 * 1024));
         configured[dev & 63] = true;
     }
     int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
@@ -700,7 +723,7 @@ extern "C" int dasr_conv_stats_slots(const dasr_conv_desc* d) {
     const int span = (d->H - 1) * Wp + Wt;
     const int blocks = (span + 127) / 128;
     const int tiles_per_strip = (blocks + NB - 1) / NB;
-    return n_strips * tiles_per_strip * NB * 4;
+    return n_strips * tiles_per_strip;
 }
 
 extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream_) {
@@ -764,17 +787,18 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.b_tx_bytes = (uint32_t)n_tile * SWZ;
     k.b_stage_bytes = (k.b_tx_bytes + 1023u) & ~1023u;
 
-    const size_t budget = 217 * 1024;   // + 1 KB alignment slack + ~7 KB static = 227 KB
+    const size_t budget = 216 * 1024;   // + 1 KB alignment slack + ~9.5 KB static <= 227 KB
     const size_t all_b = (size_t)k.nch * k.taps * k.b_stage_bytes;
     k.SA = 2;
     if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
     DASR_REQUIRE((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes <= budget,
                  "A tile (%u bytes) does not fit in shared memory", k.a_stage_bytes);
-    if (k.ntn == 1 && k.nch * k.taps <= kMaxBStages &&
+    const bool may_reside = (k.ntn == 1) && (d->w_img_rows == 0);    // per-image weights always stream
+    if (may_reside && k.nch * k.taps <= kMaxBStages &&
         (size_t)k.SA * k.a_stage_bytes + all_b <= budget) {
         k.b_resident = 1;
         k.SB = k.nch * k.taps;
-    } else if (k.ntn == 1 && k.nch * k.taps <= kMaxBStages && (size_t)k.a_stage_bytes + all_b <= budget) {
+    } else if (may_reside && k.nch * k.taps <= kMaxBStages && (size_t)k.a_stage_bytes + all_b <= budget) {
         k.b_resident = 1;
         k.SA = 1;
         k.SB = k.nch * k.taps;
@@ -806,7 +830,10 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.gamma_out = (__nv_bfloat16*)a->gamma_out;
     k.resid_f32 = a->resid_f32;
     k.out_aux_f32 = a->out_aux_f32;
-    k.nslots = k.n_strips * k.tiles_per_strip * NB * 4;
+    k.nslots = k.n_strips * k.tiles_per_strip;
+    if (d->epi == DASR_EPI_STATS)
+        DASR_REQUIRE(n_tile <= 64, "STATS epilogue supports Cout tiles up to 64 (shared-memory partials)");
+    k.w_img_rows = d->w_img_rows;
 
     // tensor maps
     CUtensorMap mA, mB;
@@ -819,7 +846,8 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     }
     {
         const uint64_t ktot = (uint64_t)k.taps * d->Cin;
-        const uint64_t rows = (uint64_t)k.ntn * n_tile;
+        const uint64_t rows = (uint64_t)k.ntn * n_tile * (d->w_img_rows ? d->B : 1);
+        if (d->w_img_rows) DASR_REQUIRE(d->w_img_rows == k.ntn * n_tile, "per-image weights: w_img_rows must equal the padded Cout");
         uint64_t dims[2] = {ktot, rows};
         uint64_t str[1] = {ktot * 2};
         uint32_t box[2] = {(uint32_t)KC, (uint32_t)n_tile};

@@ -322,6 +322,25 @@ __global__ void style_mix_kernel(const float* __restrict__ st, const float* __re
     }
 }
 
+// all SEAN instances of the network in one launch: stp[s][b][j][c] with per-instance A_i_j weights (pointer tables)
+__global__ void style_mix_batched_kernel(const float* __restrict__ st, const float* const* __restrict__ A_ptrs,
+                                         const float* const* __restrict__ a_ptrs, __nv_bfloat16* __restrict__ stp,
+                                         int B, int K, int L) {
+    const int sidx = blockIdx.y;
+    const float* A = A_ptrs[sidx];
+    const float* a = a_ptrs[sidx];
+    const size_t total = (size_t)B * K * L;
+    __nv_bfloat16* dst = stp + (size_t)sidx * total;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = i % L;
+        const int j = (i / L) % K;
+        const int b = i / ((size_t)L * K);
+        float s = __ldg(a + j);
+        for (int q = 0; q < K; q++) s = fmaf(__ldg(A + j * K + q), st[((size_t)b * K + q) * L + c], s);
+        dst[i] = __float2bfloat16(s);
+    }
+}
+
 // ------------------------------------------------------------------------------------ K-DYN apply
 // Block = one (image, band of rows); table T[b] ([K][9][C2] bf16, plus one all-zero row for pixels in no mask) and
 // the label halo are staged in smem.  thread item = (pixel, 8-channel group): 9 label lookups + 9 16-byte smem
@@ -594,6 +613,16 @@ extern "C" int dasr_style_mix(const float* depth_vec, const float* A, const floa
                               void* stream) {
     DASR_REQUIRE(depth_vec && A && a && stp, "null pointer");
     style_mix_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(depth_vec, A, a, (__nv_bfloat16*)stp, B, K, L);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs, const void* a_ptrs, void* stp, int nS,
+                                      int B, int K, int L, void* stream) {
+    DASR_REQUIRE(depth_vec && A_ptrs && a_ptrs && stp && nS > 0, "bad arguments");
+    const int gx = grid_for((size_t)B * K * L, 256, 64);
+    style_mix_batched_kernel<<<dim3(gx, nS), 256, 0, (cudaStream_t)stream>>>(
+        depth_vec, (const float* const*)A_ptrs, (const float* const*)a_ptrs, (__nv_bfloat16*)stp, B, K, L);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -86,6 +86,23 @@ class Engine:
         self._used_params = set()
         rows_total = 0
         rows_bwd = 0
+        # every active SEAN instance, in execution order: their style-table GEMM operands live in ONE buffer so that
+        # the 26 table GEMMs are a single launch with per-image weights (dasr_conv_desc.w_img_rows)
+        sean_names = []
+        for i, _pos in net.block_order():
+            if i in net.which_ResBlk_depth:
+                sean_names += ["depth-residual%d.norm%d" % (i + 1, j) for j in (1, 2)]
+        self._sean_names = sean_names
+        self._sean_index = {n: k for k, n in enumerate(sean_names)}
+        self._ws_all = None
+        if sean_names:
+            blk0 = net.block(next(i for i, _ in net.block_order() if i in net.which_ResBlk_depth))
+            nf0, lat0 = blk0.nf, blk0.norm1.len_latent
+            self._ws_rows = 9 * 2 * nf0
+            self._ws_all = torch.zeros(len(sean_names) * self._ws_rows, lat0, device=device, dtype=BF16)
+            seans = [getattr(net.block(int(n.split(".")[0][len("depth-residual"):]) - 1), n.split(".")[1]) for n in sean_names]
+            self._A_ptrs = torch.tensor([m.A_i_j.weight.data_ptr() for m in seans], dtype=torch.int64, device=device)
+            self._a_ptrs = torch.tensor([m.A_i_j.bias.data_ptr() for m in seans], dtype=torch.int64, device=device)
 
         def reserve(name, rows, kdim):
             self._wg[name] = (self._wg_total, rows, kdim)
@@ -178,7 +195,10 @@ class Engine:
                     self._used_params.update([n + ".mlp_mask.0.weight", n + ".mlp_mask.0.bias", n + ".A_i_j.weight",
                                               n + ".A_i_j.bias"])
                     # style-table GEMM operand: rows = tap * 2nf + [gamma | beta], K = latent, scaled by alpha
-                    ws = torch.zeros(9 * 2 * nf, lat, device=device, dtype=BF16)
+                    if 9 * 2 * nf != self._ws_rows or lat != self._ws_all.shape[1]:
+                        raise NotImplementedError("depth-guided blocks with different widths in one network")
+                    k0 = self._sean_index[n] * self._ws_rows
+                    ws = self._ws_all[k0:k0 + self._ws_rows]
                     for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
                         self._descs.append(L.pack_desc(P("%s.mlp_%s_s.weight" % (n, x)), ws, alpha=al, alpha_mode=1,
                                                        mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf))
@@ -361,22 +381,34 @@ class Engine:
                            lambda: L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act,
                                               subsample=subsample, **kw))
 
-    def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, vec):
+    def style_tables(self, vec):
+        """The per-image dynamic-filter tables of ALL SEAN instances in two launches:
+        stp[s] = A_i_j^(s)(depthVec) (dasr_style_mix_batched) and T[s] = alpha^(s) W_s^(s) . stp[s] (one 1x1
+        dasr_conv_fwd over the batch of instances with per-image weights).  Returns (stp_all [nS,1,B*K,L],
+        table_all [nS,1,B*K,9*2nf]); instance ``n`` uses index ``self._sean_index[n]``."""
+        lib = L.load()
+        nS = len(self._sean_names)
+        B, K, lat = vec.shape
+        s = L.stream_ptr()
+        stp_all = torch.empty(nS, 1, B * K, lat, device=vec.device, dtype=BF16)
+        self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp_all.numel() * 2,
+                    lambda: L.check(lib.dasr_style_mix_batched(L.ptr(vec), L.ptr(self._A_ptrs), L.ptr(self._a_ptrs),
+                                                               L.ptr(stp_all), nS, B, K, lat, s)))
+        table_all = torch.empty(nS, 1, B * K, self._ws_rows, device=vec.device, dtype=BF16)
+        self._timed("style_table_gemm", "tensor", 2.0 * nS * B * K * lat * self._ws_rows,
+                    stp_all.numel() * 2 + table_all.numel() * 2 + self._ws_all.numel() * 2,
+                    lambda: L.conv_fwd(stp_all, self._ws_all, self._zero_bias, table_all, Cout=self._ws_rows, ks=1,
+                                       w_img_rows=self._ws_rows))
+        return stp_all, table_all
+
+    def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, tables):
         """actv and gb_s of one SEAN instance (they depend on the network inputs only, not on x)."""
         lib = L.load()
         B, _, H, W = depth.shape
         nf2 = 2 * sean.norm_nc
         K, lat = sean.label_nc, sean.len_latent
         s = L.stream_ptr()
-        stp = torch.empty(1, 1, B * K, lat, device=depth.device, dtype=BF16)
-        self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp.numel() * 2,
-                    lambda: L.check(lib.dasr_style_mix(L.ptr(vec), L.ptr(sean.A_i_j.weight), L.ptr(sean.A_i_j.bias),
-                                                       L.ptr(stp), B, K, lat, s)))
-        pk = self._packed[n + ".table"]
-        table = torch.empty(1, 1, B * K, 9 * nf2, device=depth.device, dtype=BF16)
-        self._timed("style_table_gemm", "tensor", 2.0 * B * K * lat * 9 * nf2,
-                    stp.numel() * 2 + table.numel() * 2 + pk.w.numel() * 2,
-                    lambda: L.conv_fwd(stp, pk.w, self._zero_bias, table, Cout=9 * nf2, ks=1))
+        table = tables[1][self._sean_index[n]]
         gb_s = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
         # K-DYN algorithmic bytes (SURVEY.md 8(d)): write gb_s + read labels (u8) + read the table
         self._timed("dynconv", "hbm", 0, gb_s.numel() * 2 + B * H * W + table.numel() * 2,
@@ -389,7 +421,7 @@ class Engine:
                                                       L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
         return actv, gb_s
 
-    def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, vec):
+    def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, tables):
         """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834).  ``x`` is the bf16 copy of the block input
         (GEMM operand), ``x32`` its fp32 residual stream (None for the first block: the bf16 tensor is exact).
         Returns (bf16 output, fp32 output)."""
@@ -407,7 +439,7 @@ class Engine:
             self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
                         lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), None, B, nf,
                                                                   H * W, nslots, s)))
-            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, vec)
+            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, tables)
             if j == 1:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
             else:
@@ -451,7 +483,7 @@ class Engine:
         f0 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
         L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g),
                                     L.ptr(enc.layer1.bias), L.ptr(f0), B, h, w, s))
-        vec = labels = flag = None
+        vec = labels = flag = tables = None
         if not net.isBaseline:
             e2 = self._conv(f0, "encoder.layer2", subsample=2, act=L.ACT_LRELU)
             e3 = self._conv(e2, "encoder.layer3", subsample=2, act=L.ACT_LRELU)
@@ -467,6 +499,7 @@ class Engine:
             labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
             flag = torch.zeros(1, device=dev, dtype=torch.int32)
             L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
+            tables = self.style_tables(vec)
             if cap is not None:
                 cap.update(e5=e5, depthVec=vec, labels=labels, flag=flag)
 
@@ -480,7 +513,7 @@ class Engine:
                 if x.shape[1] != h or x.shape[2] != w:
                     raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
                                               "%d at x%d) are not implemented yet" % (i, net.scale))
-                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, labels, masks, flag, vec)
+                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, labels, masks, flag, tables)
             return self._classic("classic-residual%d" % (i + 1), x), None
 
         for i, pos in order:

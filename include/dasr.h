@@ -68,6 +68,8 @@ typedef struct {
     int32_t inner_relu;           /* DASR_EPI_SEAN: relu before the residual add (norm1 path)       */
     int32_t kw;                   /* kernel width; 0 = ks (square)                                  */
     float mask_slope;             /* DASR_EPI_STORE with actmask: factor where actmask <= 0         */
+    int32_t w_img_rows;           /* 0, or Cout: per-image weights -- image b uses rows [b*Cout, (b+1)*Cout) of w (a
+                                     batch of independent GEMMs in one launch: the 26 style-table GEMMs)  */
 } dasr_conv_desc;
 
 typedef struct {
@@ -264,6 +266,12 @@ int dasr_actv_fwd(const float* depth, const float* w, const float* bias, void* o
  * (rows = tap*2nf + o, gamma rows o in [0,nf), beta rows o in [nf,2nf)) -> T bf16 [B][K][9][2nf].     */
 int dasr_style_mix(const float* depth_vec, const float* A, const float* a, void* stp, int B, int K,
                    int L, void* stream);
+
+/* The same for ALL nS SEAN instances of the network in one launch: A_ptrs / a_ptrs are DEVICE arrays of nS device
+ * pointers (A_i_j.weight [K][K], A_i_j.bias [K]); stp bf16 [nS][B*K][L].  The nS style tables are then one
+ * dasr_conv_fwd with per-image weights (w_img_rows) over the "batch" of nS instances.                      */
+int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs, const void* a_ptrs, void* stp, int nS, int B,
+                           int K, int L, void* stream);
 
 /* K-DYN, the depth-guided dynamic convolution apply step:
  *   gb_s[b,p,:] = sum_tap T[b][label(p+tap)][tap][:]          (one-hot masks: labels given, *flag == 0)

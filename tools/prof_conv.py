@@ -28,7 +28,7 @@ def case(B, H, Cin, Cout, ks, epi, **kw):
         out = torch.empty(B, H, H, Cout, device=dev, dtype=torch.bfloat16)
     extra = {}
     if epi == L.EPI_STATS:
-        extra["stats"] = torch.zeros(B, Cout, 2, device=dev)
+        extra["stats"] = torch.zeros(B, L.conv_stats_slots(B, H, H, Cin, Cout), Cout, 2, device=dev)
     if epi == L.EPI_SEAN:
         extra["y"] = torch.randn(B, H, H, Cout // 2, device=dev).to(torch.bfloat16)
         extra["norm"] = torch.rand(B, Cout // 2, 2, device=dev)
