@@ -53,41 +53,58 @@ def _peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe): one
+    `nvidia-smi -lms 50` child process streams CSV rows while the benchmark runs; stop() ends exactly that PID."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._halt = threading.Event()
+        self.proc = None
+        self.thread = None
 
-    def run(self):
-        while not self._halt.is_set():
+    def _reader(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._reader, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def mark(self):
+        """Number of rows so far (rows before the mark belong to warm-up)."""
+        return len(self.rows)
+
+    def stop(self, since=0):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                self.proc.wait(timeout=5)
             except Exception:
-                pass
-            self._halt.wait(0.15)
-
-    def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+                self.proc.kill()
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+        rows = self.rows[since:] or self.rows
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
         reasons = []
         for i, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
-            if any(r[i].lower().startswith("active") for r in self.rows):
+            if any(r[i].lower().startswith("active") for r in rows):
                 reasons.append(name)
-        mx = max([float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()] or [0.0])
+        mx = max([float(r[1]) for r in rows if r[1].replace(".", "").isdigit()] or [0.0])
+        pw = max([float(r[2]) for r in rows if r[2].replace(".", "").isdigit()] or [0.0])
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(rows), "power_w_max": pw or None}
 
 
 def _make_state(seed=0):
@@ -106,6 +123,10 @@ def _make_state(seed=0):
 def cpu_reference_rate(seconds_budget=20.0, batch=1, warmup=1, min_iters=3):
     """frames/s of the CPU oracle port (the reference's algorithm, fp32, all host threads) on B=`batch` frames."""
     import torch
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     from oracle import depthnet_oracle as oracle     # the checker, allowed here as the cpu_baseline leg
     from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
     net = _make_state(0)
@@ -135,6 +156,11 @@ def run_reference(args):
     K, W = args.steps, args.warmup
     from oracle import depthnet_oracle as oracle
     from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core the box has
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     net = _make_state(0)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     sample_b = 2       # frames per step of the bounded sample (the workload is 64 frames per step)
@@ -195,12 +221,13 @@ def run_b200(args):
 
     with torch.no_grad():
         # ------------------------------------------------ device-resident throughput
-        for i in range(W):
-            net(*dev_sets[i % n_sets])
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for i in range(W):
+            net(*dev_sets[i % n_sets])
+        barrier()
+        clk_mark = sampler.mark()
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -210,7 +237,6 @@ def run_b200(args):
         barrier()
         launches = _lib.launch_count() - n0
         ms_total = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
 
         # ------------------------------------------------ end to end through the public call, host buffers
         # Every step copies ITS inputs from pinned host memory and reads ITS SR frames back to pinned host memory;
@@ -256,6 +282,7 @@ def run_b200(args):
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
+        clocks = sampler.stop(clk_mark) if rank == 0 else None      # samples span both timed regions
 
     train = train_pass(args, net, dev, rank, world, barrier) if args.train_steps > 0 else None
 
@@ -379,7 +406,7 @@ def roofline_pass(net, dev_sets, B):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")

@@ -282,6 +282,15 @@ int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs, const voi
 int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, const int32_t* flag,
                      void* out, int B, int K, int H, int W, int nf2, void* stream);
 
+/* K-DYN on tcgen05 (one-hot masks).  dasr_table_to_dynweights re-lays the n = (instances x images) tables
+ * [n][K][9][2nf] as GEMM-B weights wdyn bf16 [n][2nf][9*DASR_AUX_CH] (columns tap*32 + k, zero for k >= K);
+ * dasr_dynconv_fwd_tc is then dasr_conv_fwd over the aux tensor with per-image weights: out NHWC bf16 [B,H,W,2nf].
+ * For masks that are not one-hot the caller also issues dasr_dynconv_fwd(labels = NULL, masks, flag), which
+ * recomputes `out` with the exact general formula when *flag != 0 and is a no-op otherwise.                   */
+int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream);
+int dasr_dynconv_fwd_tc(const void* aux, const void* wdyn, const float* zero_bias, void* out, int B, int H, int W,
+                        int nf2, void* stream);
+
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
  * stats [B][nslots][C][2] (partial sum, sumsq over H*W; summed here in slot order) ->
  * norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)                                          */
@@ -328,6 +337,19 @@ int dasr_loss_bwd(const float* sr, const float* hr, const uint8_t* labels, const
 int dasr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                    double eps, double weight_decay, int64_t step, double grad_scale, const float* dev_scalars,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Input / output steps either side of the generator (io.cu)
+ * ------------------------------------------------------------------------------------------------ */
+/* getDepthMask (codes/data/LQGTker_Depth_dataset.py:204-226) on the device: depth NCHW fp32 [B,1,H,W] -> labels u8
+ * [B,H,W] (bin index, 255 = in no bin -- the pixel(s) at the image maximum, whose upper edge is exclusive) and,
+ * when masks != NULL, the reference's one-hot fp32 planes [B,K,H,W].  fixed_range = depthFixedRange (bins over
+ * [0,1]); otherwise per-image (min,max), written to range_out [B][2] when not NULL.  Same fp32 roundings as torch. */
+int dasr_depth_masks(const float* depth, uint8_t* labels, float* masks, float* range_out, int B, int K, int H, int W,
+                     int fixed_range, void* stream);
+/* tensor2img (codes/utils/util.py:566-590) per frame: sr NCHW fp32 [B,3,H,W] RGB -> img u8 [B,H,W,3] BGR,
+ * round_half_even((clamp(x, lo, hi) - lo) / (hi - lo) * 255)                                                     */
+int dasr_tensor2img(const float* sr, uint8_t* img, int B, int H, int W, float lo, float hi, void* stream);
 
 #ifdef __cplusplus
 }
