@@ -362,6 +362,24 @@ def train_pass(args, net, dev, rank, world, barrier):
             "gpu_launches": int(launches) if args.no_graph else int(step.launches_per_step) * Kt}
 
 
+def _ncu_traffic(kernel_family):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/r01_conv_ncu_full_v3_summary.csv), or None."""
+    col = {"conv3x3_128to128_sean": 2}.get(kernel_family)
+    path = os.path.join(ROOT, "profiles", "r01_conv_ncu_full_v3_summary.csv")
+    if col is None or not os.path.exists(path):
+        return None
+    import csv
+    rd = wr = None
+    with open(path) as f:
+        for row in csv.reader(f):
+            if row and row[0] == "dram__bytes_read.sum":
+                rd = float(row[1 + col]) * (1e6 if row[1] == "Mbyte" else 1.0)
+            if row and row[0] == "dram__bytes_write.sum":
+                wr = float(row[1 + col]) * (1e6 if row[1] == "Mbyte" else 1.0)
+    return None if rd is None or wr is None else rd + wr
+
+
 def roofline_pass(net, dev_sets, B):
     """Instrumented pass: CUDA events around every kernel launch of the engine (on the launching stream),
     grouped by kernel family; reports the family that takes the largest share of the step."""
@@ -399,7 +417,7 @@ def roofline_pass(net, dev_sets, B):
     else:
         ach, peak, unit = f["bytes"] / f["ms"] / 1e6, peaks["hbm"], "GB/s"
     return {"kernel": name, "bound": "tensor" if f["bound"] == "tensor" else "hbm", "achieved": ach, "peak": peak,
-            "unit": unit, "frac": ach / peak, "traffic": None, "peak_source": peaks["src"],
+            "unit": unit, "frac": ach / peak, "traffic": _ncu_traffic(name), "peak_source": peaks["src"],
             "ms_per_launch": f["ms"] / f["n"], "share_of_step": f["ms"] / total, "families": table}
 
 

@@ -173,8 +173,7 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     stp, table = tables[0][sidx], tables[1][sidx]        # all instances were computed in two launches
     pkt = eng._packed[n + ".table"]
     gb_s = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
-    L.check(lib.dasr_dynconv_fwd_tc(L.ptr(aux), L.ptr(tables[2][sidx]), L.ptr(eng._zero_bias), L.ptr(gb_s), B, H, W, nf2, s))
-    L.check(lib.dasr_dynconv_fwd(L.ptr(table), None, L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W, nf2, s))
+    L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W, nf2, s))
     nslots = L.conv_stats_slots(B, H, W, nf, nf)
     stats = torch.empty(B, nslots, nf, 2, device=dev, dtype=torch.float32)
     norm = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)

@@ -373,9 +373,6 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
     const int item0 = (int)((long long)blockIdx.x * n_items / gridDim.x);
     const int item1 = (int)((long long)(blockIdx.x + 1) * n_items / gridDim.x);
     const bool general = (flag != nullptr) && (*flag != 0) && (masks != nullptr);
-    // fallback role (labels == NULL): the tensor-core path (dasr_dynconv_fwd_tc) already wrote `out` for one-hot
-    // masks; only non-one-hot masks (device flag) are recomputed here with the exact general formula
-    if (labels == nullptr && !general) return;
     int staged_img = -1;
     for (int item = item0; item < item1; item++) {
     const int b = item / bands, band = item - b * bands;
@@ -392,7 +389,7 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
     for (int i = threadIdx.x; i < (rows + 2) * LW; i += blockDim.x) {
         const int r = i / LW, c = i - r * LW;
         const int hh = h0 + r - 1, ww = c - 1;
-        int lab = (labels != nullptr && hh >= 0 && hh < H && ww >= 0 && ww < W) ? labels[((size_t)b * H + hh) * W + ww] : K;
+        int lab = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? labels[((size_t)b * H + hh) * W + ww] : K;
         ls[i] = (uint8_t)(lab < K ? lab : K);      // 255 (pixel in no mask) and the zero padding -> the zero row
     }
     __syncthreads();
@@ -470,33 +467,6 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
             }
         out[(((size_t)b * H + h0 + r) * W + c) * G + gch] = pack8f(acc);
     }
-    }
-}
-
-// table T[n][k][tap][c] (bf16) -> GEMM-B weights of the dynamic convolution over the one-hot channels of the aux
-// tensor: wdyn[n][c][tap*32 + k] (k >= K zero), n = (SEAN instance, image).  One block per n.
-__global__ void __launch_bounds__(256) table_to_dynweights_kernel(const __nv_bfloat16* __restrict__ table,
-                                                                  __nv_bfloat16* __restrict__ wdyn, int K, int C2) {
-    extern __shared__ __align__(16) uint8_t smraw[];
-    __nv_bfloat16* ts = reinterpret_cast<__nv_bfloat16*>(smraw);       // [K][9][C2]
-    const size_t n = blockIdx.x;
-    const int tsz8 = K * 9 * C2 / 8;
-    const uint4* tg = reinterpret_cast<const uint4*>(table + n * (size_t)K * 9 * C2);
-    for (int i = threadIdx.x; i < tsz8; i += blockDim.x) reinterpret_cast<uint4*>(ts)[i] = __ldg(tg + i);
-    __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(wdyn + n * (size_t)C2 * 9 * DASR_AUX_CH);
-    const int items = C2 * 9 * (DASR_AUX_CH / 8);                      // 16-byte pieces: (c, tap, 8 k's)
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int kg = it % (DASR_AUX_CH / 8);
-        const int tap = (it / (DASR_AUX_CH / 8)) % 9;
-        const int c = it / ((DASR_AUX_CH / 8) * 9);
-        __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int k = kg * 8 + j;
-            v[j] = k < K ? ts[(k * 9 + tap) * C2 + c] : __float2bfloat16(0.f);
-        }
-        dst[it] = *reinterpret_cast<const uint4*>(v);
     }
 }
 
@@ -658,36 +628,11 @@ extern "C" int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs
     return DASR_OK;
 }
 
-extern "C" int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream) {
-    DASR_REQUIRE(table && wdyn && n > 0, "bad arguments");
-    DASR_REQUIRE(K >= 1 && K <= 16 && nf2 % 8 == 0, "dynamic-conv weights: K <= 16, 2*nf multiple of 8");
-    const size_t smem = (size_t)K * 9 * nf2 * 2;
-    DASR_REQUIRE(smem <= 48 * 1024, "table too large");
-    table_to_dynweights_kernel<<<n, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, (__nv_bfloat16*)wdyn, K, nf2);
-    DASR_LAUNCH_OK();
-    return DASR_OK;
-}
-
-// K-DYN apply on the tensor cores (one-hot masks): the dynamic 3x3 convolution of the one-hot channels of `aux`
-// with the per-image filters `wdyn` IS an implicit GEMM with per-image weights -- M = pixels, N = 2nf, K = 9*32.
-extern "C" int dasr_dynconv_fwd_tc(const void* aux, const void* wdyn, const float* zero_bias, void* out, int B, int H,
-                                   int W, int nf2, void* stream) {
-    DASR_REQUIRE(aux && wdyn && zero_bias && out, "null pointer");
-    dasr_conv_desc d;
-    memset(&d, 0, sizeof d);
-    d.B = B; d.H = H; d.W = W; d.Cin = DASR_AUX_CH; d.Cout = nf2; d.ks = 3;
-    d.epi = DASR_EPI_STORE; d.act = DASR_ACT_NONE; d.subsample = 1; d.w_img_rows = nf2;
-    dasr_conv_args a;
-    memset(&a, 0, sizeof a);
-    a.x = aux; a.w = wdyn; a.bias = zero_bias; a.out = out;
-    return dasr_conv_fwd(&d, &a, stream);
-}
-
 extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, const int32_t* flag,
                                 void* out, int B, int K, int H, int W, int nf2, void* stream) {
     DASR_REQUIRE(table && out && (labels || masks), "null pointer");
     DASR_REQUIRE(nf2 % 8 == 0, "2*nf must be a multiple of 8");
-    if (labels || flag) {       // labels == NULL with a flag: fallback role behind dasr_dynconv_fwd_tc
+    if (labels) {
         const int rows = 2;
         const size_t smem = (size_t)(K + 1) * 9 * nf2 * 2 + (size_t)(rows + 2) * (W + 2);
         DASR_REQUIRE(smem <= 200 * 1024, "image too wide for the label tile");

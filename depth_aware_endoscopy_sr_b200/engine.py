@@ -399,14 +399,9 @@ class Engine:
                     stp_all.numel() * 2 + table_all.numel() * 2 + self._ws_all.numel() * 2,
                     lambda: L.conv_fwd(stp_all, self._ws_all, self._zero_bias, table_all, Cout=self._ws_rows, ks=1,
                                        w_img_rows=self._ws_rows))
-        # GEMM-B form of every table for the tensor-core K-DYN apply: [nS][B*2nf][9*32]
-        nf2 = self._ws_rows // 9
-        wdyn_all = torch.empty(nS, B * nf2, 9 * L.AUX_CH, device=vec.device, dtype=BF16)
-        self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
-                    lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, s)))
-        return stp_all, table_all, wdyn_all
+        return stp_all, table_all
 
-    def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, tables, aux):
+    def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, tables):
         """actv and gb_s of one SEAN instance (they depend on the network inputs only, not on x)."""
         lib = L.load()
         B, _, H, W = depth.shape
@@ -414,14 +409,11 @@ class Engine:
         K, lat = sean.label_nc, sean.len_latent
         s = L.stream_ptr()
         table = tables[1][self._sean_index[n]]
-        wdyn = tables[2][self._sean_index[n]]
         gb_s = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
-        # K-DYN algorithmic bytes: write gb_s + read the one-hot mask (aux, 64 B/pixel) + weights
-        self._timed("dynconv", "hbm", 2.0 * B * H * W * nf2 * 9 * L.AUX_CH, gb_s.numel() * 2 + aux.numel() * 2 + wdyn.numel() * 2,
-                    lambda: L.check(lib.dasr_dynconv_fwd_tc(L.ptr(aux), L.ptr(wdyn), L.ptr(self._zero_bias), L.ptr(gb_s),
-                                                            B, H, W, nf2, s)))
-        # masks that are not one-hot (device flag): exact general formula overwrites gb_s; no-op otherwise
-        L.check(lib.dasr_dynconv_fwd(L.ptr(table), None, L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W, nf2, s))
+        # K-DYN algorithmic bytes: write gb_s + read labels (u8) + read the table
+        self._timed("dynconv", "hbm", 0, gb_s.numel() * 2 + B * H * W + table.numel() * 2,
+                    lambda: L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag),
+                                                         L.ptr(gb_s), B, K, H, W, nf2, s)))
         # actv last: it is the operand the SEAN convolution reads first, so it is still L2-resident (126 MB L2)
         actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
         self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
@@ -429,7 +421,7 @@ class Engine:
                                                       L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
         return actv, gb_s
 
-    def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, tables, aux):
+    def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, tables):
         """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834).  ``x`` is the bf16 copy of the block input
         (GEMM operand), ``x32`` its fp32 residual stream (None for the first block: the bf16 tensor is exact).
         Returns (bf16 output, fp32 output)."""
@@ -447,7 +439,7 @@ class Engine:
             self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
                         lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), None, B, nf,
                                                                   H * W, nslots, s)))
-            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, tables, aux)
+            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, tables)
             if j == 1:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
             else:
@@ -491,7 +483,7 @@ class Engine:
         f0 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
         L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g),
                                     L.ptr(enc.layer1.bias), L.ptr(f0), B, h, w, s))
-        vec = labels = flag = tables = aux = None
+        vec = labels = flag = tables = None
         if not net.isBaseline:
             e2 = self._conv(f0, "encoder.layer2", subsample=2, act=L.ACT_LRELU)
             e3 = self._conv(e2, "encoder.layer3", subsample=2, act=L.ACT_LRELU)
@@ -508,8 +500,6 @@ class Engine:
             flag = torch.zeros(1, device=dev, dtype=torch.int32)
             L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
             tables = self.style_tables(vec)
-            aux = torch.empty(B, h, w, L.AUX_CH, device=dev, dtype=BF16)
-            L.check(lib.dasr_build_aux(L.ptr(labels), L.ptr(depth), L.ptr(aux), B, K, h, w, s))
             if cap is not None:
                 cap.update(e5=e5, depthVec=vec, labels=labels, flag=flag)
 
@@ -523,7 +513,7 @@ class Engine:
                 if x.shape[1] != h or x.shape[2] != w:
                     raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
                                               "%d at x%d) are not implemented yet" % (i, net.scale))
-                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, labels, masks, flag, tables, aux)
+                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, labels, masks, flag, tables)
             return self._classic("classic-residual%d" % (i + 1), x), None
 
         for i, pos in order:

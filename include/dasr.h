@@ -282,15 +282,6 @@ int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs, const voi
 int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, const int32_t* flag,
                      void* out, int B, int K, int H, int W, int nf2, void* stream);
 
-/* K-DYN on tcgen05 (one-hot masks).  dasr_table_to_dynweights re-lays the n = (instances x images) tables
- * [n][K][9][2nf] as GEMM-B weights wdyn bf16 [n][2nf][9*DASR_AUX_CH] (columns tap*32 + k, zero for k >= K);
- * dasr_dynconv_fwd_tc is then dasr_conv_fwd over the aux tensor with per-image weights: out NHWC bf16 [B,H,W,2nf].
- * For masks that are not one-hot the caller also issues dasr_dynconv_fwd(labels = NULL, masks, flag), which
- * recomputes `out` with the exact general formula when *flag != 0 and is a no-op otherwise.                   */
-int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream);
-int dasr_dynconv_fwd_tc(const void* aux, const void* wdyn, const float* zero_bias, void* out, int B, int H, int W,
-                        int nf2, void* stream);
-
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
  * stats [B][nslots][C][2] (partial sum, sumsq over H*W; summed here in slot order) ->
  * norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)                                          */
