@@ -29,7 +29,7 @@ class ConvDesc(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s", "actmask",
-                                          "gamma_out", "resid_f32", "out_aux_f32")]
+                                          "gamma_out", "resid_f32", "out_aux_f32", "dyn_x", "dyn_w")]
 
 
 class UnpackDesc(C.Structure):
@@ -99,6 +99,8 @@ def load() -> C.CDLL:
         "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_instats_finalize": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_style_mix_batched": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_build_mask16": [vp, vp, i32, i32, i32, i32, vp],
+        "dasr_table_to_dynweights": [vp, vp, i32, i32, i32, vp],
         "dasr_build_aux": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_dynconv_bwd_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_actv_bwd_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
@@ -126,7 +128,7 @@ EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_
             "dasr_dynconv_bwd", "dasr_table_bwd", "dasr_style_mix_bwd", "dasr_region_pool_bwd", "dasr_actv_bwd",
             "dasr_unshuffle_actgrad", "dasr_out9_bwd_prep", "dasr_nchw3_to_nhwc32", "dasr_actgrad",
             "dasr_zero_insert2_to", "dasr_loss_rows", "dasr_loss_fwd", "dasr_loss_finalize", "dasr_loss_bwd",
-            "dasr_adam_step", "dasr_build_aux", "dasr_depth_masks", "dasr_tensor2img", "dasr_style_mix_batched", "dasr_dynconv_bwd_tc", "dasr_actv_bwd_tc"]
+            "dasr_adam_step", "dasr_build_aux", "dasr_build_mask16", "dasr_table_to_dynweights", "dasr_depth_masks", "dasr_tensor2img", "dasr_style_mix_batched", "dasr_dynconv_bwd_tc", "dasr_actv_bwd_tc"]
 AUX_CH = 32
 LOSS_KMAX, LOSS_ROW = 16, 36
 
@@ -181,13 +183,14 @@ def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, *, Cout: int, ks: int,
              epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
              resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None, kw: int = 0,
-             actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0) -> torch.Tensor:
+             actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0, dyn_x=None, dyn_w=None) -> torch.Tensor:
     """x: NHWC bf16 [B,H,W,Cin]."""
     B, H, W, Cin = x.shape
     d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, kw, mask_slope, w_img_rows)
     a = ConvArgs(ptr(x, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
                  ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(actmask, torch.bfloat16),
-                 ptr(gamma_out, torch.bfloat16), ptr(resid_f32, torch.float32), ptr(out_aux_f32, torch.float32))
+                 ptr(gamma_out, torch.bfloat16), ptr(resid_f32, torch.float32), ptr(out_aux_f32, torch.float32),
+                 ptr(dyn_x, torch.bfloat16), ptr(dyn_w, torch.bfloat16))
     check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
     return out
 

@@ -159,8 +159,8 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
     return o
 
 
-def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, tables, *,
-                first: bool, resid: Optional[_T]) -> _T:
+def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, tables,
+                mask16, *, first: bool, resid: Optional[_T]) -> _T:
     """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
     eng, lib, s = tp.eng, tp.lib, tp.s
     x = cur.data
@@ -172,8 +172,7 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     sidx = eng._sean_index[n]
     stp, table = tables[0][sidx], tables[1][sidx]        # all instances were computed in two launches
     pkt = eng._packed[n + ".table"]
-    gb_s = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
-    L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gb_s), B, K, H, W, nf2, s))
+    wdyn = tables[2][sidx]                                # K-DYN runs inside the SEAN GEMM as a K extension
     nslots = L.conv_stats_slots(B, H, W, nf, nf)
     stats = torch.empty(B, nslots, nf, 2, device=dev, dtype=torch.float32)
     norm = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
@@ -185,11 +184,12 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
                               H, W, nf2, s))
     gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
     if first:
-        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm, gb_s=gb_s, gamma_out=gamma)
-    else:
-        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm, gb_s=gb_s, resid=resid.data,
+        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm, dyn_x=mask16, dyn_w=wdyn,
                         gamma_out=gamma)
-    del gb_s, table, stats
+    else:
+        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm, dyn_x=mask16, dyn_w=wdyn,
+                        resid=resid.data, gamma_out=gamma)
+    del table, stats
     o = _T(out, "handled")
     tp.use(cur)
     if resid is not None:
@@ -266,7 +266,7 @@ def _forward_train(eng, lq, depth, masks):
 
     tp.ops.append(bwd_first)
 
-    vec = labels = flag = dvec = aux = tables = None
+    vec = labels = flag = dvec = aux = tables = mask16 = None
     if not net.isBaseline:
         e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
         e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
@@ -296,6 +296,8 @@ def _forward_train(eng, lq, depth, masks):
         flag = torch.zeros(1, device=dev, dtype=torch.int32)
         L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
         tables = eng.style_tables(vec)
+        mask16 = torch.empty(B, h, w, 16, device=dev, dtype=BF16)
+        L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(mask16), B, K, h, w, s))
         aux = torch.empty(B, h, w, L.AUX_CH, device=dev, dtype=BF16)
         L.check(lib.dasr_build_aux(L.ptr(labels), L.ptr(depth), L.ptr(aux), B, K, h, w, s))
 
@@ -311,9 +313,9 @@ def _forward_train(eng, lq, depth, masks):
             p = "depth-residual%d" % (i + 1)
             blk = net.block(i)
             a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec, aux,
-                            tables, first=True, resid=None)
+                            tables, mask16, first=True, resid=None)
             return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec, aux,
-                               tables, first=False, resid=x)
+                               tables, mask16, first=False, resid=x)
         p = "classic-residual%d" % (i + 1)
         f = _conv_train(tp, x, p + ".block.0", act="relu")
         # relu(x + conv(f)): the residual add is the conv epilogue; its backward = lazy ReLU mask, then both paths

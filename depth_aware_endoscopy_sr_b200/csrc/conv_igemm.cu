@@ -31,11 +31,16 @@ namespace dasr {
 // slots: 0 mma:wait acc_empty  1 mma:wait a_full  2 mma:wait b_full  3 mma:issue  4 epi:wait acc_full
 //        5 epi:work            6 a-producer:wait a_empty  7 b-producer:wait b_empty  8 kernel total (CTA 0..)
 #ifdef DASR_PROFILE
+// ablation knob of the profile build (tools/prof_stalls.py, DASR_DBG): bit 0 = the epilogues skip their global
+// loads, bit 1 = they skip their global stores (ConvK::dbg, set by dasr_prof_set)
+#define DBG(p, bit) ((p).dbg & (bit))
+static int g_host_dbg = 0;
 __device__ unsigned long long g_prof[16];
 #define PROF_DECL long long prof_t = clock64(); long long prof_acc[4] = {0, 0, 0, 0}
 #define PROF_LAP(i) do { long long n_ = clock64(); prof_acc[i] += n_ - prof_t; prof_t = n_; } while (0)
 #define PROF_FLUSH(base, n) do { for (int i_ = 0; i_ < (n); i_++) atomicAdd(&g_prof[(base) + i_], (unsigned long long)prof_acc[i_]); } while (0)
 #else
+#define DBG(p, bit) 0
 #define PROF_DECL
 #define PROF_LAP(i)
 #define PROF_FLUSH(base, n)
@@ -73,6 +78,12 @@ struct ConvK {
     float* out_aux_f32;            // SEAN: fp32 copy of the output (the residual stream of the next block)
     int nslots;                    // STATS: partial-sum slots per image
     int n_bias;                    // padded Cout (bias entries staged in shared memory)
+    int dbg;                       // profile build only (see DBG)
+    // K-DYN folded into the GEMM (SEAN epilogue only): after the main K loop, 9 more taps of K = 16 over the
+    // mask image `aux16` (NHWC bf16 [B,H,W,16], 32-byte swizzled rows) with the PER-IMAGE filters wdyn
+    // ([B*Cout][taps*16]) accumulate the dynamic convolution gb_s straight into the same TMEM accumulators.
+    int dyn;
+    uint32_t a2_tx_bytes, b2_tx_bytes, a2_off;
     int w_img_rows;                // > 0: per-image weights, image b uses rows [b*w_img_rows, +Cout) of the B matrix
 };
 
@@ -183,7 +194,7 @@ __device__ __forceinline__ void sean_load(const ConvK& p, SeanOps& o, int img, i
     o.pix = ((size_t)img * p.H + h) * p.W + w;
     const uint4 z4 = make_uint4(0, 0, 0, 0);
     o.y0 = o.y1 = o.g0 = o.g1 = o.b0 = o.b1 = o.r0 = o.r1 = z4;
-    if (!o.valid) return;
+    if (!o.valid || DBG(p, 1)) return;
     ldg256(p.y + o.pix * NF + c0, o.y0, o.y1);
     if (p.gb_s) {
         const __nv_bfloat16* sp = p.gb_s + o.pix * N_TILE + c0;
@@ -241,6 +252,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
             f[j] = t;
             gs[j] = g;
         }
+        if (DBG(p, 2)) continue;
         if (p.gamma_out) store16(p.gamma_out + o.pix * NF + c0, gs);
         if (p.resid_f32) {
 #pragma unroll
@@ -270,7 +282,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
 template <int SWZ, int N_TILE, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const ConvK p) {
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const ConvK p) {
     constexpr int KC = SWZ / 2;          // channels per K chunk (one swizzle span per pixel row)
     constexpr int KSTEPS = SWZ / 32;     // UMMA K = 16 bf16 = 32 bytes
     constexpr int ACC_COLS = NB * N_TILE;
@@ -281,6 +293,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __shared__ uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
     __shared__ uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
     __shared__ uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint64_t a2_full, a2_empty;
     __shared__ uint32_t tmem_base_s;
     __shared__ float norm_s[512];         // SEAN: (mean, scale) of the image; STATS: scratch of the fused finalize
     __shared__ float bias_s[kMaxBias];
@@ -290,6 +303,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* a_smem = smem;
     uint8_t* b_smem = smem + (size_t)p.SA * p.a_stage_bytes;
+    uint8_t* a2_smem = smem + p.a2_off;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -307,11 +321,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 8);
         }
+        mbar_init(&a2_full, 1);
+        mbar_init(&a2_empty, 1);
         fence_mbar_init();
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
+        if (p.dyn) {
+            tma_prefetch_desc(&mapA2);
+            tma_prefetch_desc(&mapB2);
+        }
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_s);
     for (int i = threadIdx.x; i < p.n_bias; i += kThreads) bias_s[i] = __ldg(p.bias + i);
@@ -331,7 +351,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // (elect.sync under a warp-uniform branch: ptxas then issues TMA/MMA straight from uniform registers;
         //  a `lane == 0` test costs a 72-cycle waterfall loop per tcgen05.mma -- tools/rate_probe.cu)
         if (elect_one()) {
-            uint32_t a_it = 0;
+            uint32_t a_it = 0, t_it = 0;
             PROF_DECL;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
@@ -353,6 +373,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 w0 - p.pad_w, r0 - p.pad_h, img);
                     a_it++;
                 }
+                if (p.dyn) {       // the mask patch of this tile (single buffer, released by the MMA issuer)
+                    mbar_wait(&a2_empty, (t_it & 1) ^ 1);
+                    mbar_expect_tx(&a2_full, p.a2_tx_bytes);
+                    tma_load_4d(a2_smem, &mapA2, &a2_full, 0, w0 - p.pad_w, r0 - p.pad_h, img);
+                }
+                t_it++;
             }
             PROF_FLUSH(6, 1);
         }
@@ -384,6 +410,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                     tap * p.Cin + c * KC, wrow0 + nt * N_TILE);
                     }
                 }
+                if (p.dyn) {       // this image's dynamic filters, one [Cout x 16] tile per tap through the same ring
+                    const int img = tile / tiles_per_img;
+                    for (int tap = 0; tap < p.taps; tap++) {
+                        const int sb = b_it % p.SB;
+                        const uint32_t ph = (b_it / p.SB) & 1;
+                        mbar_wait(&b_empty[sb], ph ^ 1);
+                        b_it++;
+                        mbar_expect_tx(&b_full[sb], p.b2_tx_bytes);
+                        tma_load_2d(b_smem + (size_t)sb * p.b_stage_bytes, &mapB2, &b_full[sb], tap * 16,
+                                    img * N_TILE);
+                    }
+                }
                 first = false;
             }
             PROF_FLUSH(7, 1);
@@ -402,7 +440,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t b_lo0 = lo_flags | ((smem_u32(b_smem) & 0x3FFFFu) >> 4);
             const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_stage_lo = p.b_stage_bytes >> 4;
             constexpr uint32_t BLK_LO = (128u * SWZ) >> 4;
-            uint32_t a_it = 0, b_it = 0, acc_it = 0;
+            uint32_t a_it = 0, b_it = 0, acc_it = 0, t_it = 0;
+            const uint32_t desc_hi32 = (uint32_t)(make_smem_desc<32>(0, 0) >> 32);
+            const uint32_t a2_lo0 = lo_flags | ((smem_u32(a2_smem) & 0x3FFFFu) >> 4);
             bool first = true;
             PROF_DECL;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -466,6 +506,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     umma_commit(&a_empty[sa]);
                     a_it++;
                 }
+                if (p.dyn) {
+                    // K extension: gb_s = sum_{tap,k} mask[p+tap][k] * T[img][k][tap][:]  (K = 16 per tap, 32-byte rows)
+                    PROF_LAP(3);
+                    mbar_wait(&a2_full, t_it & 1);
+                    PROF_LAP(1);
+                    tc_fence_after();
+                    const uint32_t a2_lo_tile = a2_lo0 + (uint32_t)soff * (32u >> 4);
+#pragma unroll 1
+                    for (int tap = 0; tap < p.taps; tap++) {
+                        const int sb = b_it % p.SB;
+                        PROF_LAP(3);
+                        mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
+                        PROF_LAP(2);
+                        tc_fence_after();
+                        const uint32_t a_lo = a2_lo_tile + (tap_lo_s[tap] * 32u) / SWZ;     // row offset at 32 B per row
+                        const uint32_t b_lo = b_lo0 + sb * b_stage_lo;
+#pragma unroll
+                        for (int blk = 0; blk < NB; blk++)
+                            umma_bf16_lohi(d_tmem + blk * N_TILE, a_lo + blk * ((128u * 32u) >> 4), b_lo, desc_hi32, idesc, 1);
+                        umma_commit(&b_empty[sb]);
+                        b_it++;
+                    }
+                    umma_commit(&a2_empty);
+                }
+                t_it++;
                 umma_commit(&acc_full[buf]);
                 acc_it++;
                 first = false;
@@ -541,8 +606,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
                     for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
                         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, m0 = r0, m1 = r0;
-                        if (rp && valid) ldg256(rp + c0, r0, r1);
-                        if (mp && valid) ldg256(mp + c0, m0, m1);
+                        if (rp && valid && !DBG(p, 1)) ldg256(rp + c0, r0, r1);
+                        if (mp && valid && !DBG(p, 1)) ldg256(mp + c0, m0, m1);
                         uint32_t v[16];
                         tmem_ld16(t_blk + c0, v);
                         tmem_ld_wait();
@@ -566,11 +631,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                                 for (int j = 0; j < 16; j++) f[j] *= (mm[j] > 0.f ? 1.f : p.mask_slope);
                             }
-                            if (valid) store16(op + c0, f);
+                            if (valid && !DBG(p, 2)) store16(op + c0, f);
                         } else {
                             // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
                             uint4 o0 = pack8(f), o1 = pack8(f + 8);
-                            if (valid) stg256(op + c0, o0, o1);
+                            if (valid && !DBG(p, 2)) stg256(op + c0, o0, o1);
                             float s1[16], s2[16];
                             unpack8(o0, s1);
                             unpack8(o1, s1 + 8);
@@ -613,7 +678,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 16; j++)
                                 f[j] = apply_act(__uint_as_float(v[j]) + bias_t[c0 + j], p.act);
-                            store16(p.out + pix * Cq + c, f);
+                            if (!DBG(p, 2)) store16(p.out + pix * Cq + c, f);
                         }
                     }
                 } else {  // DASR_EPI_NCHW_F32
@@ -670,8 +735,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
 // ------------------------------------------------------------------------------------------------ host
 template <int SWZ, int N_TILE, int NB>
-static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, size_t smem_bytes,
-                  cudaStream_t stream) {
+static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
+                  const ConvK& k, size_t smem_bytes, cudaStream_t stream) {
     auto fn = conv_halo_kernel<SWZ, N_TILE, NB>;
     static bool configured[64] = {false};
     int dev = 0;
@@ -681,19 +746,19 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, 
         configured[dev & 63] = true;
     }
     int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
-    fn<<<grid, kThreads, smem_bytes, stream>>>(mA, mB, k);
+    fn<<<grid, kThreads, smem_bytes, stream>>>(mA, mB, mA2, mB2, k);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
 
 template <int SWZ, int NB>
-static int dispatch_n(int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, const ConvK& k, size_t smem,
-                      cudaStream_t s) {
+static int dispatch_n(int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2,
+                      const CUtensorMap& mB2, const ConvK& k, size_t smem, cudaStream_t s) {
     switch (n_tile) {
-        case 16: return launch<SWZ, 16, NB>(mA, mB, k, smem, s);
-        case 32: return launch<SWZ, 32, NB>(mA, mB, k, smem, s);
-        case 64: return launch<SWZ, 64, NB>(mA, mB, k, smem, s);
-        case 128: return launch<SWZ, 128, NB>(mA, mB, k, smem, s);
+        case 16: return launch<SWZ, 16, NB>(mA, mB, mA2, mB2, k, smem, s);
+        case 32: return launch<SWZ, 32, NB>(mA, mB, mA2, mB2, k, smem, s);
+        case 64: return launch<SWZ, 64, NB>(mA, mB, mA2, mB2, k, smem, s);
+        case 128: return launch<SWZ, 128, NB>(mA, mB, mA2, mB2, k, smem, s);
     }
     return fail(DASR_ERR_BAD_ARG, "unsupported N tile %d", n_tile);
 }
@@ -703,6 +768,10 @@ static int dispatch_n(int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, 
 using namespace dasr;
 
 #ifdef DASR_PROFILE
+extern "C" int dasr_prof_set(int dbg) {
+    g_host_dbg = dbg;
+    return DASR_OK;
+}
 extern "C" int dasr_prof_read(unsigned long long* host_out, int reset) {
     DASR_CUDA_OK(cudaDeviceSynchronize());
     DASR_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_prof, sizeof(unsigned long long) * 16));
@@ -787,7 +856,17 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.b_tx_bytes = (uint32_t)n_tile * SWZ;
     k.b_stage_bytes = (k.b_tx_bytes + 1023u) & ~1023u;
 
-    const size_t budget = 216 * 1024;   // + 1 KB alignment slack + ~9.5 KB static <= 227 KB
+    size_t budget = 216 * 1024;         // + 1 KB alignment slack + ~9.5 KB static <= 227 KB
+    size_t a2_bytes = 0;
+    if (a->dyn_x || a->dyn_w) {
+        DASR_REQUIRE(a->dyn_x && a->dyn_w && d->epi == DASR_EPI_SEAN && SWZ == 128 && !a->gb_s,
+                     "the K-DYN extension needs dyn_x and dyn_w, the SEAN epilogue, Cin %% 64 == 0 and no gb_s");
+        k.dyn = 1;
+        k.a2_tx_bytes = (uint32_t)k.RB * k.Wp * 32;
+        k.b2_tx_bytes = (uint32_t)n_tile * 32;
+        a2_bytes = (k.a2_tx_bytes + 1023u) & ~(size_t)1023u;
+        budget -= a2_bytes;
+    }
     const size_t all_b = (size_t)k.nch * k.taps * k.b_stage_bytes;
     k.SA = 2;
     if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
@@ -811,7 +890,9 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         k.SB = sb;
         DASR_REQUIRE(sb >= 1, "not enough shared memory for the weight ring");
     }
-    const size_t smem_bytes = (size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes + 1024;
+    if (k.dyn) DASR_REQUIRE(!k.b_resident, "the K-DYN extension streams its weights (resident mode not supported)");
+    k.a2_off = (uint32_t)((size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes);
+    const size_t smem_bytes = (size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes + a2_bytes + 1024;
 
     // outputs
     k.Ho = d->H; k.Wo = d->W;
@@ -831,6 +912,9 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.resid_f32 = a->resid_f32;
     k.out_aux_f32 = a->out_aux_f32;
     k.nslots = k.n_strips * k.tiles_per_strip;
+#ifdef DASR_PROFILE
+    k.dbg = g_host_dbg;
+#endif
     if (d->epi == DASR_EPI_STATS)
         DASR_REQUIRE(n_tile <= 64, "STATS epilogue supports Cout tiles up to 64 (shared-memory partials)");
     k.w_img_rows = d->w_img_rows;
@@ -854,6 +938,23 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         int rc = encode_tmap_bf16(&mB, a->w, 2, dims, str, box, SWZ);
         if (rc) return rc;
     }
-    if (SWZ == 128) return dispatch_n<128, 2>(n_tile, mA, mB, k, smem_bytes, stream);
-    return dispatch_n<64, 2>(n_tile, mA, mB, k, smem_bytes, stream);
+    CUtensorMap mA2 = mA, mB2 = mB;
+    if (k.dyn) {
+        {
+            uint64_t dims[4] = {16, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+            uint64_t str[3] = {32, (uint64_t)d->W * 32, (uint64_t)d->H * d->W * 32};
+            uint32_t box[4] = {16, (uint32_t)k.Wp, (uint32_t)k.RB, 1};
+            int rc = encode_tmap_bf16(&mA2, a->dyn_x, 4, dims, str, box, 32);
+            if (rc) return rc;
+        }
+        {
+            uint64_t dims[2] = {(uint64_t)k.taps * 16, (uint64_t)d->B * n_tile};
+            uint64_t str[1] = {(uint64_t)k.taps * 16 * 2};
+            uint32_t box[2] = {16, (uint32_t)n_tile};
+            int rc = encode_tmap_bf16(&mB2, a->dyn_w, 2, dims, str, box, 32);
+            if (rc) return rc;
+        }
+    }
+    if (SWZ == 128) return dispatch_n<128, 2>(n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    return dispatch_n<64, 2>(n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
 }

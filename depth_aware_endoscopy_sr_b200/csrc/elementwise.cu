@@ -470,6 +470,47 @@ __global__ void __launch_bounds__(256) dynconv_labels_kernel(const __nv_bfloat16
     }
 }
 
+// masks NCHW fp32 [B,K,H,W] -> NHWC bf16 [B,H,W,16]: the A operand of the K-DYN extension of the SEAN GEMM
+__global__ void build_mask16_kernel(const float* __restrict__ masks, uint4* __restrict__ out, int K, int HW, size_t npix) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / HW, p = i - b * HW;
+        __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            v[k] = __float2bfloat16(k < K ? __ldg(masks + (b * K + k) * (size_t)HW + p) : 0.f);
+        const uint4* src = reinterpret_cast<const uint4*>(v);
+        out[2 * i] = src[0];
+        out[2 * i + 1] = src[1];
+    }
+}
+
+// table T[n][k][tap][c] (bf16) -> GEMM-B weights of the dynamic convolution: wdyn[n][c][tap*16 + k] (k >= K zero),
+// n = (SEAN instance, image).  One block per n.
+__global__ void __launch_bounds__(256) table_to_dynweights_kernel(const __nv_bfloat16* __restrict__ table,
+                                                                  __nv_bfloat16* __restrict__ wdyn, int K, int C2) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    __nv_bfloat16* ts = reinterpret_cast<__nv_bfloat16*>(smraw);       // [K][9][C2]
+    const size_t n = blockIdx.x;
+    const int tsz8 = K * 9 * C2 / 8;
+    const uint4* tg = reinterpret_cast<const uint4*>(table + n * (size_t)K * 9 * C2);
+    for (int i = threadIdx.x; i < tsz8; i += blockDim.x) reinterpret_cast<uint4*>(ts)[i] = __ldg(tg + i);
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(wdyn + n * (size_t)C2 * 9 * 16);
+    const int items = C2 * 9 * 2;                                       // 16-byte pieces: (c, tap, 8 k's)
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        const int kg = it & 1;
+        const int tap = (it >> 1) % 9;
+        const int c = it / 18;
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = kg * 8 + j;
+            v[j] = k < K ? ts[(k * 9 + tap) * C2 + c] : __float2bfloat16(0.f);
+        }
+        dst[it] = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 // general (non one-hot) masks: exact linear form, slow path kept for API completeness
 __global__ void dynconv_masks_kernel(const __nv_bfloat16* __restrict__ table, const float* __restrict__ masks,
                                      uint4* __restrict__ out, int B, int K, int H, int W, int C2) {
@@ -624,6 +665,25 @@ extern "C" int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs
     const int gx = grid_for((size_t)B * K * L, 256, 64);
     style_mix_batched_kernel<<<dim3(gx, nS), 256, 0, (cudaStream_t)stream>>>(
         depth_vec, (const float* const*)A_ptrs, (const float* const*)a_ptrs, (__nv_bfloat16*)stp, B, K, L);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_build_mask16(const float* masks, void* mask16, int B, int K, int H, int W, void* stream) {
+    DASR_REQUIRE(masks && mask16 && B > 0, "bad arguments");
+    DASR_REQUIRE(K >= 1 && K <= 16, "mask image: at most 16 depth masks (got %d)", K);
+    const size_t npix = (size_t)B * H * W;
+    build_mask16_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(masks, (uint4*)mask16, K, H * W, npix);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream) {
+    DASR_REQUIRE(table && wdyn && n > 0, "bad arguments");
+    DASR_REQUIRE(K >= 1 && K <= 16 && nf2 % 8 == 0, "dynamic-conv weights: K <= 16, 2*nf multiple of 8");
+    const size_t smem = (size_t)K * 9 * nf2 * 2;
+    DASR_REQUIRE(smem <= 48 * 1024, "table too large");
+    table_to_dynweights_kernel<<<n, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, (__nv_bfloat16*)wdyn, K, nf2);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -399,29 +399,26 @@ class Engine:
                     stp_all.numel() * 2 + table_all.numel() * 2 + self._ws_all.numel() * 2,
                     lambda: L.conv_fwd(stp_all, self._ws_all, self._zero_bias, table_all, Cout=self._ws_rows, ks=1,
                                        w_img_rows=self._ws_rows))
-        return stp_all, table_all
+        # GEMM-B form of every table for the K-DYN extension of the SEAN GEMM: [nS][B*2nf][9*16]
+        nf2 = self._ws_rows // 9
+        wdyn_all = torch.empty(nS, B * nf2, 9 * 16, device=vec.device, dtype=BF16)
+        self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
+                    lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, s)))
+        return stp_all, table_all, wdyn_all
 
-    def _sean_inputs(self, n: str, sean, depth, labels, masks, flag, tables):
-        """actv and gb_s of one SEAN instance (they depend on the network inputs only, not on x)."""
+    def _sean_actv(self, sean, depth):
+        """actv = ReLU(mlp_mask(depth)) of one SEAN instance (normalization.py:37-40,61)."""
         lib = L.load()
         B, _, H, W = depth.shape
         nf2 = 2 * sean.norm_nc
-        K, lat = sean.label_nc, sean.len_latent
         s = L.stream_ptr()
-        table = tables[1][self._sean_index[n]]
-        gb_s = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
-        # K-DYN algorithmic bytes (SURVEY.md 8(d)): write gb_s + read labels (u8) + read the table
-        self._timed("dynconv", "hbm", 0, gb_s.numel() * 2 + B * H * W + table.numel() * 2,
-                    lambda: L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag),
-                                                         L.ptr(gb_s), B, K, H, W, nf2, s)))
-        # actv last: it is the operand the SEAN convolution reads first, so it is still L2-resident (126 MB L2)
         actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
         self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
                     lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight),
                                                       L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
-        return actv, gb_s
+        return actv
 
-    def _dgb(self, p: str, blk, x, x32, depth, labels, masks, flag, tables):
+    def _dgb(self, p: str, blk, x, x32, depth, mask16, tables):
         """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834).  ``x`` is the bf16 copy of the block input
         (GEMM operand), ``x32`` its fp32 residual stream (None for the first block: the bf16 tensor is exact).
         Returns (bf16 output, fp32 output)."""
@@ -439,12 +436,14 @@ class Engine:
             self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
                         lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), None, B, nf,
                                                                   H * W, nslots, s)))
-            actv, gb_s = self._sean_inputs(n, sean, depth, labels, masks, flag, tables)
+            actv = self._sean_actv(sean, depth)
+            wdyn = tables[2][self._sean_index[n]]     # K-DYN runs inside the SEAN GEMM as a K extension
             if j == 1:
-                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], gb_s=gb_s)
+                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], dyn_x=mask16,
+                                 dyn_w=wdyn)
             else:
-                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm[1], gb_s=gb_s,
-                                 resid=x if x32 is None else None, resid_f32=x32, out_aux_f32=out32)
+                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm[1], dyn_x=mask16,
+                                 dyn_w=wdyn, resid=x if x32 is None else None, resid_f32=x32, out_aux_f32=out32)
         return cur, out32
 
     def _classic(self, p: str, x):
@@ -483,7 +482,7 @@ class Engine:
         f0 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
         L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g),
                                     L.ptr(enc.layer1.bias), L.ptr(f0), B, h, w, s))
-        vec = labels = flag = tables = None
+        vec = labels = flag = tables = mask16 = None
         if not net.isBaseline:
             e2 = self._conv(f0, "encoder.layer2", subsample=2, act=L.ACT_LRELU)
             e3 = self._conv(e2, "encoder.layer3", subsample=2, act=L.ACT_LRELU)
@@ -500,6 +499,8 @@ class Engine:
             flag = torch.zeros(1, device=dev, dtype=torch.int32)
             L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
             tables = self.style_tables(vec)
+            mask16 = torch.empty(B, h, w, 16, device=dev, dtype=BF16)
+            L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(mask16), B, K, h, w, s))
             if cap is not None:
                 cap.update(e5=e5, depthVec=vec, labels=labels, flag=flag)
 
@@ -513,7 +514,7 @@ class Engine:
                 if x.shape[1] != h or x.shape[2] != w:
                     raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
                                               "%d at x%d) are not implemented yet" % (i, net.scale))
-                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, labels, masks, flag, tables)
+                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, mask16, tables)
             return self._classic("classic-residual%d" % (i + 1), x), None
 
         for i, pos in order:

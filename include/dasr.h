@@ -90,6 +90,10 @@ typedef struct {
     const float* resid_f32; /* DASR_EPI_SEAN: fp32 NHWC residual (the trunk's fp32 residual stream); used
                                instead of `resid` when not NULL                                     */
     float* out_aux_f32;   /* DASR_EPI_SEAN: optional fp32 NHWC copy of the output                    */
+    const void* dyn_x;    /* DASR_EPI_SEAN: K-DYN folded into the GEMM (instead of gb_s): the depth-mask image NHWC
+                             bf16 [B,H,W,16] (dasr_build_mask16) ...                                            */
+    const void* dyn_w;    /* ... and the per-image dynamic filters bf16 [B*Cout][ks*ks*16] (dasr_table_to_dynweights):
+                             gamma/beta += sum_{tap,k} mask[p+tap][k] * T[b][k][tap][:]                          */
 } dasr_conv_args;
 
 int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream);
@@ -281,6 +285,13 @@ int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs, const voi
  * bias by dasr_pack_weights).  table bf16 [B][K][9][2nf]; out NHWC bf16 [B,H,W,2nf].                  */
 int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* masks, const int32_t* flag,
                      void* out, int B, int K, int H, int W, int nf2, void* stream);
+
+/* K-DYN folded into the SEAN GEMM (dasr_conv_args.dyn_x / dyn_w).  dasr_build_mask16: masks NCHW fp32 [B,K,H,W]
+ * (K <= 16) -> NHWC bf16 [B,H,W,16] (one-hot masks are exact in bf16; other values are rounded like every other
+ * activation).  dasr_table_to_dynweights: the n = (instances x images) tables bf16 [n][K][9][2nf] -> GEMM-B
+ * weights bf16 [n][2nf][9*16] (column tap*16 + k, zero for k >= K).                                          */
+int dasr_build_mask16(const float* masks, void* mask16, int B, int K, int H, int W, void* stream);
+int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream);
 
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
  * stats [B][nslots][C][2] (partial sum, sumsq over H*W; summed here in slot order) ->

@@ -49,6 +49,9 @@ def run(name, B, H, Cin, Cout, ks, epi, **kw):
     print("== %-34s %.3f ms  %.0f TFLOP/s   per-CTA cycles (avg over 148):" % (name, ms, fl / ms / 1e9))
     print("   " + "  ".join("%s=%dk" % (NAMES[i], buf[i] / 148 / 1000) for i in range(8)), flush=True)
 
+DBG = int(os.environ.get("DASR_DBG", "0"))
+lib.dasr_prof_set(DBG)
+print("#### ablation knob DASR_DBG=%d (bit 0: no epilogue global loads, bit 1: no epilogue global stores)" % DBG)
 run("trunk 64->64 stats B64@64", 64, 64, 64, 64, 3, L.EPI_STATS)
 run("sean 128->128 B64@64", 64, 64, 128, 128, 3, L.EPI_SEAN, act=L.ACT_RELU)
 run("classic 32->32 B64@256", 64, 256, 32, 32, 3, L.EPI_STORE, act=L.ACT_RELU)
