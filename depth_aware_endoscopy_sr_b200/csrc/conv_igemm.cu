@@ -56,6 +56,7 @@ struct ConvK {
     int B, H, W, Cin, Cout;
     int kh, kw, pad_h, pad_w, taps;
     int Wt, Wp, RB;
+    unsigned wp_magic;             // floor(2^32 / Wp) + 1: q / Wp == __umulhi(q, wp_magic)
     int n_strips, tiles_per_strip, ntn, total_tiles;
     int nch;                       // Cin / KC
     int SA, SB, b_resident;
@@ -187,7 +188,7 @@ template <int N_TILE, int NB>
 __device__ __forceinline__ void sean_load(const ConvK& p, SeanOps& o, int img, int q0, int w0, int m, int blk, int c0) {
     constexpr int NF = N_TILE / 2;
     const int q = q0 + blk * 128 + m;
-    const int h = q / p.Wp;
+    const int h = (int)__umulhi((unsigned)q, p.wp_magic);
     const int wl = q - h * p.Wp;
     const int w = w0 + wl;
     o.valid = (h < p.H) && (wl < p.Wt) && (w < p.W);
@@ -279,7 +280,10 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
     }
 }
 
-template <int SWZ, int N_TILE, int NB>
+// EPI (the epilogue variant) is a template parameter: with a run-time switch the epilogue warps executed ~1500
+// instructions per 128x16 accumulator piece (ncu source view) and were ISSUE-bound, which also starved the MMA
+// issuer that shares a scheduler with them.
+template <int SWZ, int N_TILE, int NB, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const ConvK p) {
@@ -562,7 +566,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t aph = (acc_it / NACC) & 1;
             const float* bias_t = bias_s + nt * N_TILE;
 
-            if (p.epi == DASR_EPI_SEAN) {
+            if (EPI == DASR_EPI_SEAN) {
                 // (mean, scale) of this image for the nf = N_TILE/2 normalised channels
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 if (et < N_TILE) norm_s[et] = __ldg(p.norm + (size_t)img * N_TILE + et);
@@ -575,7 +579,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             tc_fence_after();
             const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
 
-            if (p.epi == DASR_EPI_SEAN) {
+            if (EPI == DASR_EPI_SEAN) {
                 sean_epilogue<N_TILE, NB>(p, t_acc, bias_t, norm_s, img, q0, w0, m, half);
                 tc_fence_before();
                 __syncwarp();
@@ -586,13 +590,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
             for (int blk = 0; blk < NB; blk++) {
                 const int q = q0 + blk * 128 + m;
-                const int h = q / p.Wp;
+                const int h = (int)__umulhi((unsigned)q, p.wp_magic);     // q / Wp (exact for q < 2^32 / Wp)
                 const int wl = q - h * p.Wp;
                 const int w = w0 + wl;
                 bool valid = (h < p.H) && (wl < p.Wt) && (w < p.W);
                 const uint32_t t_blk = t_acc + blk * N_TILE;
 
-                if (p.epi == DASR_EPI_STORE || p.epi == DASR_EPI_STATS) {
+                if (EPI == DASR_EPI_STORE || EPI == DASR_EPI_STATS) {
                     int ho = h, wo = w;
                     if (p.subsample == 2) {
                         valid = valid && !(h & 1) && !(w & 1);
@@ -614,7 +618,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_t[c0 + j];
-                        if (p.epi == DASR_EPI_STORE) {
+                        if (EPI == DASR_EPI_STORE) {
                             if (rp) {
                                 float rr[16];
                                 unpack8(r0, rr);
@@ -663,7 +667,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                             }
                         }
                     }
-                } else if (p.epi == DASR_EPI_SHUFFLE2) {
+                } else if (EPI == DASR_EPI_SHUFFLE2) {
                     const int Cq = p.Cout >> 2;  // channels after the shuffle
 #pragma unroll 1
                     for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
@@ -705,7 +709,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
             acc_it++;
-            if (p.epi == DASR_EPI_STATS) {
+            if (EPI == DASR_EPI_STATS) {
                 // one statistics slot per (image, tile): the four row quadrants are added in a fixed order
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 if (et < N_TILE) {
@@ -734,10 +738,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int SWZ, int N_TILE, int NB>
+template <int SWZ, int N_TILE, int NB, int EPI>
 static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
                   const ConvK& k, size_t smem_bytes, cudaStream_t stream) {
-    auto fn = conv_halo_kernel<SWZ, N_TILE, NB>;
+    auto fn = conv_halo_kernel<SWZ, N_TILE, NB, EPI>;
     static bool configured[64] = {false};
     int dev = 0;
     DASR_CUDA_OK(cudaGetDevice(&dev));
@@ -751,16 +755,25 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMa
     return DASR_OK;
 }
 
+// only the (epilogue, N tile) pairs the network uses are instantiated
 template <int SWZ, int NB>
-static int dispatch_n(int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2,
+static int dispatch_n(int epi, int n_tile, const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2,
                       const CUtensorMap& mB2, const ConvK& k, size_t smem, cudaStream_t s) {
-    switch (n_tile) {
-        case 16: return launch<SWZ, 16, NB>(mA, mB, mA2, mB2, k, smem, s);
-        case 32: return launch<SWZ, 32, NB>(mA, mB, mA2, mB2, k, smem, s);
-        case 64: return launch<SWZ, 64, NB>(mA, mB, mA2, mB2, k, smem, s);
-        case 128: return launch<SWZ, 128, NB>(mA, mB, mA2, mB2, k, smem, s);
-    }
-    return fail(DASR_ERR_BAD_ARG, "unsupported N tile %d", n_tile);
+#define DASR_CASE(E, N) \
+    if (epi == (E) && n_tile == (N)) return launch<SWZ, N, NB, E>(mA, mB, mA2, mB2, k, smem, s)
+    DASR_CASE(DASR_EPI_STORE, 16);
+    DASR_CASE(DASR_EPI_STORE, 32);
+    DASR_CASE(DASR_EPI_STORE, 64);
+    DASR_CASE(DASR_EPI_STORE, 128);
+    DASR_CASE(DASR_EPI_STATS, 32);
+    DASR_CASE(DASR_EPI_STATS, 64);
+    DASR_CASE(DASR_EPI_SEAN, 64);
+    DASR_CASE(DASR_EPI_SEAN, 128);
+    DASR_CASE(DASR_EPI_SHUFFLE2, 64);
+    DASR_CASE(DASR_EPI_SHUFFLE2, 128);
+    DASR_CASE(DASR_EPI_NCHW_F32, 16);
+#undef DASR_CASE
+    return fail(DASR_ERR_BAD_ARG, "unsupported epilogue %d with N tile %d", epi, n_tile);
 }
 
 }  // namespace dasr
@@ -844,6 +857,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.n_strips = (d->W + max_wt - 1) / max_wt;
     k.Wt = (d->W + k.n_strips - 1) / k.n_strips;
     k.Wp = k.Wt + k.kw - 1;
+    k.wp_magic = (unsigned)((1ull << 32) / (unsigned)k.Wp) + 1u;
     const int span = (d->H - 1) * k.Wp + k.Wt;  // padded-flat positions that contain valid outputs
     const int blocks = (span + 127) / 128;
     k.tiles_per_strip = (blocks + NB - 1) / NB;
@@ -955,6 +969,6 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
             if (rc) return rc;
         }
     }
-    if (SWZ == 128) return dispatch_n<128, 2>(n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
-    return dispatch_n<64, 2>(n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    if (SWZ == 128) return dispatch_n<128, 2>(d->epi, n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    return dispatch_n<64, 2>(d->epi, n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
 }
