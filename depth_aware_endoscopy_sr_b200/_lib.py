@@ -29,7 +29,7 @@ class ConvDesc(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s", "actmask",
-                                          "gamma_out", "resid_f32", "out_aux_f32", "dyn_x", "dyn_w")]
+                                          "gamma_out", "resid_f32", "out_aux_f32", "norm_out", "normk_out", "dyn_x", "dyn_w")]
 
 
 class UnpackDesc(C.Structure):
@@ -183,13 +183,14 @@ def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, *, Cout: int, ks: int,
              epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
              resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None, kw: int = 0,
-             actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0, dyn_x=None, dyn_w=None) -> torch.Tensor:
+             actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0, dyn_x=None, dyn_w=None, norm_out=None, normk_out=None) -> torch.Tensor:
     """x: NHWC bf16 [B,H,W,Cin]."""
     B, H, W, Cin = x.shape
     d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, kw, mask_slope, w_img_rows)
     a = ConvArgs(ptr(x, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
                  ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(actmask, torch.bfloat16),
                  ptr(gamma_out, torch.bfloat16), ptr(resid_f32, torch.float32), ptr(out_aux_f32, torch.float32),
+                 ptr(norm_out, torch.float32), ptr(normk_out, torch.float32),
                  ptr(dyn_x, torch.bfloat16), ptr(dyn_w, torch.bfloat16))
     check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
     return out

@@ -177,18 +177,17 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     stats = torch.empty(B, nslots, nf, 2, device=dev, dtype=torch.float32)
     norm = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
     normk = torch.empty(B, nf, device=dev, dtype=torch.float32)
-    y = eng._conv(x, conv_name, epi=L.EPI_STATS, stats=stats)
-    L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm), L.ptr(normk), B, nf, H * W, nslots, s))
+    y = eng._conv(x, conv_name, epi=L.EPI_STATS, stats=stats)      # coefficients are finalised inside the SEAN conv
     actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
     L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B,
                               H, W, nf2, s))
     gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
     if first:
-        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm, dyn_x=mask16, dyn_w=wdyn,
-                        gamma_out=gamma)
+        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, stats=stats, norm_out=norm, normk_out=normk,
+                        dyn_x=mask16, dyn_w=wdyn, gamma_out=gamma)
     else:
-        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm, dyn_x=mask16, dyn_w=wdyn,
-                        resid=resid.data, gamma_out=gamma)
+        out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, stats=stats, norm_out=norm, normk_out=normk,
+                        dyn_x=mask16, dyn_w=wdyn, resid=resid.data, gamma_out=gamma)
     del table, stats
     o = _T(out, "handled")
     tp.use(cur)

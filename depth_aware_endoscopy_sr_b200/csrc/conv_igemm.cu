@@ -80,6 +80,8 @@ struct ConvK {
     int nslots;                    // STATS: partial-sum slots per image
     int n_bias;                    // padded Cout (bias entries staged in shared memory)
     int dbg;                       // profile build only (see DBG)
+    float* norm_out;               // SEAN with fused finalize: optional copies of (mean, scale) [B][nf][2] ...
+    float* normk_out;              // ... and of k [B][nf] for the backward pass
     // K-DYN folded into the GEMM (SEAN epilogue only): after the main K loop, 9 more taps of K = 16 over the
     // mask image `aux16` (NHWC bf16 [B,H,W,16], 32-byte swizzled rows) with the PER-IMAGE filters wdyn
     // ([B*Cout][taps*16]) accumulate the dynamic convolution gb_s straight into the same TMEM accumulators.
@@ -569,7 +571,44 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (EPI == DASR_EPI_SEAN) {
                 // (mean, scale) of this image for the nf = N_TILE/2 normalised channels
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
-                if (et < N_TILE) norm_s[et] = __ldg(p.norm + (size_t)img * N_TILE + et);
+                if (p.norm) {
+                    if (et < N_TILE) norm_s[et] = __ldg(p.norm + (size_t)img * N_TILE + et);
+                } else if (et < N_TILE / 2) {
+                    // fused dasr_instats_finalize: the per-tile partial sums of the producing convolution
+                    // ([B][nslots][nf][2], 17 slots at 64x64) are reduced here in slot order -- bit-reproducible --
+                    // while the MMAs of this tile are still running; no separate finalize launch
+                    constexpr int NF = N_TILE / 2;
+                    const float2* sp = reinterpret_cast<const float2*>(p.stats) + (size_t)img * p.nslots * NF + et;
+                    float a1 = 0.f, a2 = 0.f;
+                    for (int sl = 0; sl < p.nslots; sl += 8) {
+                        float2 v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            v[u] = (sl + u < p.nslots) ? __ldg(sp + (size_t)(sl + u) * NF) : make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            a1 += v[u].x;
+                            a2 += v[u].y;
+                        }
+                    }
+                    const float inv_hw = 1.f / (float)(p.H * p.W);
+                    const float mean = a1 * inv_hw;
+                    const float var = fmaxf(a2 * inv_hw - mean * mean, 0.f);
+                    const float eps = 1e-5f;
+                    // IN(IN(y)) = (y - mean) * (var+eps)^-1/2 * (var/(var+eps) + eps)^-1/2
+                    const float r1 = rsqrtf(var + eps);
+                    const float r2 = rsqrtf(var * r1 * r1 + eps);
+                    norm_s[2 * et] = mean;
+                    norm_s[2 * et + 1] = r1 * r2;
+                    if (p.norm_out && tps == 0 && strip == 0) {      // saved for the backward pass
+                        p.norm_out[((size_t)img * NF + et) * 2] = mean;
+                        p.norm_out[((size_t)img * NF + et) * 2 + 1] = r1 * r2;
+                        if (p.normk_out) {
+                            const float a = var + eps, rr = var / a + eps;
+                            p.normk_out[(size_t)img * NF + et] = 1.f / a + eps / (a * a * rr);
+                        }
+                    }
+                }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
             }
 
@@ -844,7 +883,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     }
     if (d->epi == DASR_EPI_SEAN) {
         DASR_REQUIRE(k.ntn == 1 && n_tile >= 32, "SEAN epilogue needs Cout = 2*nf in {64,128}");
-        DASR_REQUIRE(a->y && a->norm, "SEAN epilogue needs y and norm");
+        DASR_REQUIRE(a->y && (a->norm || a->stats), "SEAN epilogue needs y and norm (or the statistics partials)");
     }
     if (d->epi == DASR_EPI_STATS) DASR_REQUIRE(a->stats, "STATS epilogue needs a stats buffer");
     k.n_bias = k.ntn * n_tile;
@@ -926,6 +965,8 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     k.resid_f32 = a->resid_f32;
     k.out_aux_f32 = a->out_aux_f32;
     k.nslots = k.n_strips * k.tiles_per_strip;
+    k.norm_out = a->norm_out;
+    k.normk_out = a->normk_out;
 #ifdef DASR_PROFILE
     k.dbg = g_host_dbg;
 #endif

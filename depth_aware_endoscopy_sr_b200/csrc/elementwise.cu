@@ -227,84 +227,95 @@ __global__ void build_aux_kernel(const uint8_t* __restrict__ labels, const float
 }
 
 // ------------------------------------------------------------------------------------ actv
-// Store-bandwidth kernel (2*C bytes per pixel out, 4 bytes in).  Block = (image, band of kActvRows rows): the
-// zero-padded depth halo of the band sits in shared memory (no bounds checks in the loop).  Thread = (8-channel
-// group g, pixel slot): its 72 weights + 8 biases live in REGISTERS as float2 pairs and every tap is 4 packed
-// FFMA2 (fma.rn.f32x2, two fp32 FMAs per instruction on sm_100); a slot walks a run of consecutive pixels of one
-// row with a sliding 3x3 window (3 shared-memory loads per pixel).  Lanes 0..G-1 of a pixel write one contiguous
-// 2*C-byte row.  v1 -> v2: 242 -> ~75 instructions per (pixel, 8 channels), grid sized to whole waves.
+// Store-bandwidth kernel (2*C bytes per pixel out, 4 bytes in).  Persistent blocks over (image, 2-row band) items; the
+// zero-padded depth halo of the band sits in shared memory.  A pixel is produced by C/4 consecutive lanes (a full
+// warp at C = 128): lane = 4 channels, whose 36 weights + 4 biases live in registers as float2 pairs, every tap is
+// two packed FFMA2 (fma.rn.f32x2), and the lanes of a pixel write one contiguous 2*C-byte row.  A slot walks a run
+// of pixels of one row two at a time with a sliding 3x4 window (6 broadcast shared-memory loads per pixel pair, 8
+// independent FMA chains).  v1: 242 instructions per (pixel, 8 channels), 64 us; v2 (8 channels per lane, 125
+// registers, 16 warps/SM): 33 us; v3 (4 channels per lane, 2 pixels in flight): see profiles/.
 constexpr int kActvRows = 2;
-template <int G>
+template <int C>
 __global__ void __launch_bounds__(256) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
-                                                   const float* __restrict__ bias, uint4* __restrict__ out, int H,
+                                                   const float* __restrict__ bias, uint2* __restrict__ out, int H,
                                                    int W, int n_items) {
-    constexpr int SLOTS = 256 / G;
-    extern __shared__ float dsm[];                 // (rows + 2) x (W + 2), zero padded
+    constexpr int LPP = C / 4;                     // lanes per pixel
+    constexpr int SLOTS = 256 / LPP;
+    extern __shared__ float dsm[];                 // (rows + 2) x (W + 4), zero padded
     const int bands = (H + kActvRows - 1) / kActvRows;
-    const int LW = W + 2;
-    const int g = threadIdx.x % G, slot = threadIdx.x / G;
-    float2 wr[9][4], br[4];
+    const int LW = W + 4;
+    const int g = threadIdx.x % LPP, slot = threadIdx.x / LPP;
+    float2 wr[9][2], br[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        br[j] = make_float2(__ldg(bias + g * 8 + 2 * j), __ldg(bias + g * 8 + 2 * j + 1));
+    for (int j = 0; j < 2; j++) {
+        br[j] = make_float2(__ldg(bias + g * 4 + 2 * j), __ldg(bias + g * 4 + 2 * j + 1));
 #pragma unroll
         for (int t = 0; t < 9; t++)
-            wr[t][j] = make_float2(__ldg(w + (g * 8 + 2 * j) * 9 + t), __ldg(w + (g * 8 + 2 * j + 1) * 9 + t));
+            wr[t][j] = make_float2(__ldg(w + (g * 4 + 2 * j) * 9 + t), __ldg(w + (g * 4 + 2 * j + 1) * 9 + t));
     }
+    const int seg = 16;
+    const int segs_per_row = (W + seg - 1) / seg;
     // persistent over (image, band) items: the weights (identical for every image) are loaded once per block
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int b = item / bands, band = item - b * bands;
-    const int h0 = band * kActvRows;
-    const int rows = min(kActvRows, H - h0);
-    const float* dp = depth + (size_t)b * H * W;
-    __syncthreads();
-    for (int i = threadIdx.x; i < (rows + 2) * LW; i += 256) {
-        const int r = i / LW, c = i - r * LW;
-        const int hh = h0 + r - 1, ww = c - 1;
-        dsm[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(dp + hh * W + ww) : 0.f;
-    }
-    __syncthreads();
-    // runs: each row is cut into segments of `seg` pixels; slot s takes run s, s + SLOTS, ...
-    const int seg = 8;
-    const int segs_per_row = (W + seg - 1) / seg;
-    const int nruns = rows * segs_per_row;
-    uint4* op = out + ((size_t)b * H + h0) * W * G;
-    for (int run = slot; run < nruns; run += SLOTS) {
-        const int r = run / segs_per_row;
-        const int x0 = (run - r * segs_per_row) * seg;
-        const int x1 = min(x0 + seg, W);
-        const float* d0 = dsm + r * LW + x0;       // window row 0, column x-1 (padded coordinates)
-        float win[3][3];
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            win[t][1] = d0[t * LW];
-            win[t][2] = d0[t * LW + 1];
+        const int b = item / bands, band = item - b * bands;
+        const int h0 = band * kActvRows;
+        const int rows = min(kActvRows, H - h0);
+        const float* dp = depth + (size_t)b * H * W;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (rows + 2) * LW; i += 256) {
+            const int r = i / LW, c = i - r * LW;
+            const int hh = h0 + r - 1, ww = c - 1;
+            dsm[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(dp + hh * W + ww) : 0.f;
         }
-        for (int x = x0; x < x1; x++) {
+        __syncthreads();
+        const int nruns = rows * segs_per_row;
+        uint2* op = out + ((size_t)b * H + h0) * W * LPP;
+        for (int run = slot; run < nruns; run += SLOTS) {
+            const int r = run / segs_per_row;
+            const int x0 = (run - r * segs_per_row) * seg;
+            const int x1 = min(x0 + seg, W);
+            const float* d0 = dsm + r * LW + x0;       // window row 0, image column x0 - 1 (padded coordinates)
+            float win[3][4];
 #pragma unroll
             for (int t = 0; t < 3; t++) {
-                win[t][0] = win[t][1];
-                win[t][1] = win[t][2];
-                win[t][2] = d0[t * LW + (x - x0) + 2];
+                win[t][2] = d0[t * LW];
+                win[t][3] = d0[t * LW + 1];
             }
-            float2 acc[4];
+            for (int x = x0; x < x1; x += 2) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[j] = br[j];
-#pragma unroll
-            for (int t = 0; t < 3; t++)
-#pragma unroll
-                for (int u = 0; u < 3; u++) {
-                    const float2 d2 = make_float2(win[t][u], win[t][u]);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) acc[j] = __ffma2_rn(d2, wr[t * 3 + u][j], acc[j]);
+                for (int t = 0; t < 3; t++) {
+                    win[t][0] = win[t][2];
+                    win[t][1] = win[t][3];
+                    win[t][2] = d0[t * LW + (x - x0) + 2];
+                    win[t][3] = d0[t * LW + (x - x0) + 3];
                 }
-            uint4 o;
-            __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+                float2 acc[2][2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) oh[j] = __floats2bfloat162_rn(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
-            op[((size_t)r * W + x) * G + g] = o;
+                for (int q = 0; q < 2; q++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++) acc[q][j] = br[j];
+#pragma unroll
+                for (int t = 0; t < 3; t++)
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const float2 d2 = make_float2(win[t][u + q], win[t][u + q]);
+#pragma unroll
+                            for (int j = 0; j < 2; j++) acc[q][j] = __ffma2_rn(d2, wr[t * 3 + u][j], acc[q][j]);
+                        }
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    if (x + q >= x1) break;
+                    uint2 o;
+                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        oh[j] = __floats2bfloat162_rn(fmaxf(acc[q][j].x, 0.f), fmaxf(acc[q][j].y, 0.f));
+                    op[((size_t)r * W + x + q) * LPP + g] = o;
+                }
+            }
         }
-    }
     }
 }
 
@@ -639,14 +650,24 @@ extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bi
     DASR_REQUIRE(C == 128 || C == 64, "actv: C (= 2*nf) must be 64 or 128 (got %d)", C);
     DASR_REQUIRE((size_t)H * W < 0x7fffffffull, "frame too large");
     const int bands = (H + kActvRows - 1) / kActvRows;
-    const size_t smem = (size_t)(kActvRows + 2) * (W + 2) * sizeof(float);
+    const size_t smem = (size_t)(kActvRows + 2) * (W + 4) * sizeof(float);
     DASR_REQUIRE(smem <= 48 * 1024, "actv: frame too wide (%d)", W);
     const int n_items = B * bands;
-    const int grid = n_items < 2 * num_sms() ? n_items : 2 * num_sms();     // 2 resident blocks per SM (114 registers)
+    // persistent grid = exactly the blocks that are resident at once (asked from the occupancy calculator)
+    static int per_sm[2] = {0, 0};
+    const int vi = (C == 128) ? 0 : 1;
+    if (per_sm[vi] == 0) {
+        int nb = 0;
+        if (C == 128) DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<128>, 256, smem));
+        else DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<64>, 256, smem));
+        per_sm[vi] = nb > 0 ? nb : 1;
+    }
+    const int cap = per_sm[vi] * num_sms();
+    const int grid = n_items < cap ? n_items : cap;
     if (C == 128)
-        actv_kernel<16><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, n_items);
+        actv_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint2*)out, H, W, n_items);
     else
-        actv_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint4*)out, H, W, n_items);
+        actv_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint2*)out, H, W, n_items);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -426,23 +426,20 @@ class Engine:
         B, H, W, nf = x.shape
         s = L.stream_ptr()
         nslots = L.conv_stats_slots(B, H, W, nf, nf)
-        stats = torch.empty(B, nslots, nf, 2, device=x.device, dtype=torch.float32)
-        norm = torch.empty(2, B, nf, 2, device=x.device, dtype=torch.float32)
+        stats = torch.empty(2, B, nslots, nf, 2, device=x.device, dtype=torch.float32)
         cur = x
         out32 = torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32)
         for j, sean in ((1, blk.norm1), (2, blk.norm2)):
             n = "%s.norm%d" % (p, j)
-            y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats)
-            self._timed("instats_finalize", "hbm", 0, stats.numel() * 4,
-                        lambda: L.check(lib.dasr_instats_finalize(L.ptr(stats), L.ptr(norm[j - 1]), None, B, nf,
-                                                                  H * W, nslots, s)))
+            # conv + per-tile statistics; the double-InstanceNorm coefficients are finalised inside the SEAN conv
+            y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats[j - 1])
             actv = self._sean_actv(sean, depth)
             wdyn = tables[2][self._sean_index[n]]     # K-DYN runs inside the SEAN GEMM as a K extension
             if j == 1:
-                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, norm=norm[0], dyn_x=mask16,
+                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, stats=stats[0], dyn_x=mask16,
                                  dyn_w=wdyn)
             else:
-                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, norm=norm[1], dyn_x=mask16,
+                cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, stats=stats[1], dyn_x=mask16,
                                  dyn_w=wdyn, resid=x if x32 is None else None, resid_f32=x32, out_aux_f32=out32)
         return cur, out32
 

@@ -81,7 +81,10 @@ typedef struct {
     float* stats;         /* DASR_EPI_STATS: [B][dasr_conv_stats_slots()][Cout][2] partial sums (every
                              entry is written; no zeroing needed)                                   */
     const void* y;        /* DASR_EPI_SEAN: conv output to normalise, NHWC bf16 [B,H,W,Cout/2]      */
-    const float* norm;    /* DASR_EPI_SEAN: [B][Cout/2][2] = (mean, scale) from dasr_instats_finalize */
+    const float* norm;    /* DASR_EPI_SEAN: [B][Cout/2][2] = (mean, scale) from dasr_instats_finalize; or NULL with
+                             `stats` = the partial sums [B][slots][Cout/2][2] written by the DASR_EPI_STATS conv of
+                             the same geometry: the finalize step then runs inside this kernel (per tile, in slot
+                             order, hidden behind the MMAs)                                              */
     const void* gb_s;     /* DASR_EPI_SEAN: dynamic-conv term NHWC bf16 [B,H,W,Cout] (or NULL)       */
     const void* actmask;  /* DASR_EPI_STORE: optional NHWC bf16 tensor shaped like out; the result is multiplied
                              by (actmask > 0 ? 1 : mask_slope) last -- ReLU / LeakyReLU backward fused into a
@@ -90,6 +93,8 @@ typedef struct {
     const float* resid_f32; /* DASR_EPI_SEAN: fp32 NHWC residual (the trunk's fp32 residual stream); used
                                instead of `resid` when not NULL                                     */
     float* out_aux_f32;   /* DASR_EPI_SEAN: optional fp32 NHWC copy of the output                    */
+    float* norm_out;      /* DASR_EPI_SEAN with fused finalize: optional [B][Cout/2][2] copy of (mean, scale) ...   */
+    float* normk_out;     /* ... and [B][Cout/2] of k (see dasr_instats_finalize) for the backward pass            */
     const void* dyn_x;    /* DASR_EPI_SEAN: K-DYN folded into the GEMM (instead of gb_s): the depth-mask image NHWC
                              bf16 [B,H,W,16] (dasr_build_mask16) ...                                            */
     const void* dyn_w;    /* ... and the per-image dynamic filters bf16 [B*Cout][ks*ks*16] (dasr_table_to_dynweights):
