@@ -119,8 +119,9 @@ def test_images_are_independent():
             assert torch.equal(one[0], full[b])
 
 
-def test_non_onehot_masks_take_the_general_path():
-    """Overlapping / fractional masks: the dynamic conv must fall back to its exact linear form."""
+def test_non_onehot_masks_stay_linear():
+    """Overlapping / fractional masks: the dynamic convolution is linear in the mask values (they enter the SEAN
+    GEMM as a bf16 image; the values used here are exact in bf16)."""
     from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
     meta = dict(scale=8, latent=256, which=tuple(range(14)))
     sd = fill_state_dict(oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10), seed=6)
