@@ -5,14 +5,14 @@ folding, PixelShuffle row permutation and the ConvTranspose flip are applied by 
 (b) the order of kernel launches that restates ``DepthNet.forward`` (reference codes/models/modules/
 sftmd_arch.py:912-950) and ``SEAN.forward`` (normalization.py:52-92):
 
+    once         st'    = A_i_j(depthVec) for all SEAN instances             dasr_style_mix_batched
+                 T      = alpha * W_s . st'   (tables of per-image dynamic filters)  ONE dasr_conv_fwd (1x1, per-image weights)
+                 wdyn   = T as GEMM-B weights; mask16 = bf16 mask image       dasr_table_to_dynweights / dasr_build_mask16
     per SEAN     actv   = ReLU(conv3x3(depth, 1->2nf))                       dasr_actv_fwd
-                 st'    = A_i_j(depthVec)                                    dasr_style_mix
-                 T      = alpha * W_s . st'   (table of per-image dynamic filters)   dasr_conv_fwd (1x1 GEMM)
-                 gb_s   = dynamic 3x3 conv of the depth mask with T          dasr_dynconv_fwd  (K-DYN)
-    per DGB conv y      = conv3x3(x) + b ; sum / sumsq per (image, channel)   dasr_conv_fwd EPI_STATS
-                 norm   = closed form of InstanceNorm applied twice          dasr_instats_finalize
-                 out    = act(IN(IN(y)) * (1 + gamma) + beta [+ x])          dasr_conv_fwd EPI_SEAN over actv
-                          with [gamma_o|beta_o] as the GEMM and gb_s, the blend and the modulation as epilogue
+    per DGB conv y      = conv3x3(x) + b ; per-tile sum / sumsq per channel   dasr_conv_fwd EPI_STATS
+                 out    = act(IN(IN(y)) * (1 + gamma) + beta [+ x])          dasr_conv_fwd EPI_SEAN over actv:
+                          [gamma_o|beta_o] as the GEMM, K-DYN (dynamic 3x3 conv of mask16 with wdyn) as a K extension
+                          of the same GEMM, the InstanceNorm finalize in the prologue, blend + modulation as epilogue
 
 Activations are NHWC bf16; network input / output are NCHW fp32 like the reference.  Everything is launched on
 torch's current stream; nothing here computes on the host or with torch ops.
