@@ -23,6 +23,8 @@
 // Replaces: nn.Conv2d call sites codes/models/modules/sftmd_arch.py:743-749,812,819,862-864,891-910 and
 // codes/models/modules/normalization.py:41-42,87-89 of the reference.
 #include "dasr_internal.h"
+#include <stdlib.h>
+#include <string.h>
 #include "sm100_ptx.cuh"
 
 namespace dasr {
@@ -340,6 +342,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_s);
+    // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the
+    // previous kernel in the stream; nothing below may run before that kernel has completed and flushed.  Our own
+    // dependents may be scheduled as soon as every CTA of this grid got here (they block at the same point).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int i = threadIdx.x; i < p.n_bias; i += kThreads) bias_s[i] = __ldg(p.bias + i);
     if (threadIdx.x < p.taps) {
         const int t = threadIdx.x / p.kw, u = threadIdx.x - t * p.kw;
@@ -777,6 +784,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// DASR_PDL=0 turns programmatic dependent launch off (A/B measurements)
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DASR_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 template <int SWZ, int N_TILE, int NB, int EPI>
 static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
                   const ConvK& k, size_t smem_bytes, cudaStream_t stream) {
@@ -789,7 +806,18 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMa
         configured[dev & 63] = true;
     }
     int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
-    fn<<<grid, kThreads, smem_bytes, stream>>>(mA, mB, mA2, mB2, k);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    DASR_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, mA, mB, mA2, mB2, k));
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -20,6 +20,8 @@
 // Warp roles: w0 TMA producer (multi-stage ring), w1 MMA issuer (one elected thread), w2 TMEM allocator,
 // w4..7 final flush.
 #include "dasr_internal.h"
+#include <stdlib.h>
+#include <string.h>
 #include "sm100_ptx.cuh"
 
 namespace dasr {
@@ -77,6 +79,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // programmatic dependent launch: the set-up above overlaps the tail of the previous kernel (see conv_igemm.cu)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // this CTA's slice
     const int tapgroup = blockIdx.y / p.n_cchunks;
@@ -356,7 +361,21 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     const size_t smem_bytes = (size_t)k.stages * k.stage_bytes + 1024;
     DASR_REQUIRE(smem_bytes <= 220 * 1024, "shared memory budget exceeded (%zu)", smem_bytes);
     dim3 grid(ksplit, k.n_tapgroups * k.n_cchunks, n_mblocks);
-    conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(mY, mX, k);
+    {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kWgThreads);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        const char* e = getenv("DASR_PDL");
+        cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+        DASR_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel, mY, mX, k));
+    }
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -241,6 +241,9 @@ __global__ void __launch_bounds__(256) actv_kernel(const float* __restrict__ dep
                                                    int W, int n_items) {
     constexpr int LPP = C / 4;                     // lanes per pixel
     constexpr int SLOTS = 256 / LPP;
+    // lets the SEAN conv that follows in the stream (launched with programmatic stream serialization) set up its
+    // barriers / TMEM while this grid drains; it still waits for this grid's completion before reading actv
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ float dsm[];                 // (rows + 2) x (W + 4), zero padded
     const int bands = (H + kActvRows - 1) / kActvRows;
     const int LW = W + 4;
