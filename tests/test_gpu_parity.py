@@ -103,6 +103,22 @@ def test_other_seeds_and_batch():
         assert err <= TOL_PIX_STRESS
 
 
+def test_fp32_residual_stream_option():
+    """Engine.fp32_residual carries an fp32 copy of the trunk's residual stream; both settings meet the tolerance."""
+    z, meta = load_golden("x8_b1_64_init")
+    sd, (lq, depth, masks, gt) = case_tensors(meta)
+    net = _build(meta, sd)
+    st = meta["stride"]
+    errs = {}
+    for flag in (False, True):
+        net.engine().fp32_residual = flag
+        with torch.no_grad():
+            sr = net(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+        errs[flag] = np.abs(sr.numpy()[:, :, ::st, ::st] - z["sr"]).max()
+    print("residual stream bf16 / fp32: max|sr-ref| = %.4g / %.4g" % (errs[False], errs[True]))
+    assert errs[False] <= TOL_PIX and errs[True] <= TOL_PIX
+
+
 def test_images_are_independent():
     """Size-independent property (no op couples batch elements): a batch of 8 frames equals the
     8 frames run one by one -- bit-exact, since every reduction is per image."""
