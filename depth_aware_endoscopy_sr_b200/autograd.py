@@ -160,7 +160,7 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
 
 
 def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, tables,
-                mask16, *, first: bool, resid: Optional[_T]) -> _T:
+                mask16, dT_all, scr_all, *, first: bool, resid: Optional[_T]) -> _T:
     """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
     eng, lib, s = tp.eng, tp.lib, tp.s
     x = cur.data
@@ -218,20 +218,15 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         dA = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
         L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)
         gw, gb = eng._grad_view(n + ".mlp_mask.0.weight"), eng._grad_view(n + ".mlp_mask.0.bias")
-        scr = torch.zeros(nf2, 9 * L.AUX_CH, device=dev, dtype=torch.float32)
+        scr = scr_all[sidx]          # zeroed once per step for all instances
         L.check(lib.dasr_actv_bwd_tc(L.ptr(dA), L.ptr(aux), L.ptr(scr), L.ptr(gw), L.ptr(gb), B, H, W, nf2, s))
-        # ---- style branch: K-DYN backward -> table GEMM backward -> A_i_j backward
-        dT = torch.zeros(B * K, 9 * nf2, device=dev, dtype=torch.float32)
+        # ---- style branch: K-DYN backward into this instance's slice of dT_all; the table GEMM / A_i_j backward of
+        # all instances run batched once every block has back-propagated (bwd_pool)
+        dT = dT_all[sidx]
         # one-hot masks: tensor-core kernel; otherwise (device flag) the exact general-mask kernel -- each is a
         # no-op in the other's case, so no host synchronisation is needed to choose
         L.check(lib.dasr_dynconv_bwd_tc(L.ptr(dgb), L.ptr(aux), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
         L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
-        dWs = eng._dw_view(n + ".table")
-        dstp = torch.empty(B * K, lat, device=dev, dtype=torch.float32)
-        L.check(lib.dasr_table_bwd(L.ptr(dT), L.ptr(stp), L.ptr(pkt.w), L.ptr(dWs), L.ptr(dstp), B * K, 9 * nf2, lat, s))
-        L.check(lib.dasr_style_mix_bwd(L.ptr(dstp), L.ptr(vec), L.ptr(sean.A_i_j.weight),
-                                       L.ptr(eng._grad_view(n + ".A_i_j.weight")),
-                                       L.ptr(eng._grad_view(n + ".A_i_j.bias")), L.ptr(dvec), B, K, lat, s))
         # ---- the block convolution in front of the norm (its bias gradient is exactly zero: IN removes the mean)
         tp.wgrad(dy, x, conv_name)
         tp.dgrad_into(cur, dy, conv_name + ".dg")
@@ -265,7 +260,7 @@ def _forward_train(eng, lq, depth, masks):
 
     tp.ops.append(bwd_first)
 
-    vec = labels = flag = dvec = aux = tables = mask16 = None
+    vec = labels = flag = dvec = aux = tables = mask16 = dT_all = scr_all = None
     if not net.isBaseline:
         e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
         e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
@@ -286,6 +281,15 @@ def _forward_train(eng, lq, depth, masks):
         tp.use(e5)
 
         def bwd_pool():
+            # style branch of ALL SEAN instances: dWs = dT^T stp, dstp = dT Ws, then the A_i_j backward (batched)
+            nS = len(eng._sean_names)
+            N = eng._ws_rows
+            dWs_all = eng._dw_flat[eng._wg_tables_off:eng._wg_tables_off + nS * N * lat]
+            dstp_all = torch.empty(nS, B * K, lat, device=dev, dtype=torch.float32)
+            L.check(lib.dasr_table_bwd_batched(L.ptr(dT_all), L.ptr(tables[0]), L.ptr(eng._ws_all), L.ptr(dWs_all),
+                                               L.ptr(dstp_all), nS, B * K, N, lat, tp.s))
+            L.check(lib.dasr_style_mix_bwd_batched(L.ptr(dstp_all), L.ptr(vec), L.ptr(eng._A_ptrs), L.ptr(eng._dA_ptrs),
+                                                   L.ptr(eng._da_ptrs), L.ptr(dvec), nS, B, K, lat, tp.s))
             de5 = torch.empty_like(e5.data)
             L.check(lib.dasr_region_pool_bwd(L.ptr(dvec), L.ptr(msel), L.ptr(cnt), L.ptr(de5), B, P, lat, K, s))
             tp.accum(e5, de5)
@@ -295,6 +299,8 @@ def _forward_train(eng, lq, depth, masks):
         flag = torch.zeros(1, device=dev, dtype=torch.int32)
         L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
         tables = eng.style_tables(vec)
+        dT_all = torch.zeros(len(eng._sean_names), B * K, eng._ws_rows, device=dev, dtype=torch.float32)
+        scr_all = torch.zeros(len(eng._sean_names), eng._ws_rows // 9, 9 * L.AUX_CH, device=dev, dtype=torch.float32)
         mask16 = torch.empty(B, h, w, 16, device=dev, dtype=BF16)
         L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(mask16), B, K, h, w, s))
         aux = torch.empty(B, h, w, L.AUX_CH, device=dev, dtype=BF16)
@@ -312,9 +318,9 @@ def _forward_train(eng, lq, depth, masks):
             p = "depth-residual%d" % (i + 1)
             blk = net.block(i)
             a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec, aux,
-                            tables, mask16, first=True, resid=None)
+                            tables, mask16, dT_all, scr_all, first=True, resid=None)
             return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec, aux,
-                               tables, mask16, first=False, resid=x)
+                               tables, mask16, dT_all, scr_all, first=False, resid=x)
         p = "classic-residual%d" % (i + 1)
         f = _conv_train(tp, x, p + ".block.0", act="relu")
         # relu(x + conv(f)): the residual add is the conv epilogue; its backward = lazy ReLU mask, then both paths

@@ -157,11 +157,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const uint4* __restrict__ x
     const size_t r0 = blockIdx.x * rows_per_block;
     const size_t r1 = min(r0 + rows_per_block, rows);
     if (pl < LANES)
-        for (size_t r = r0 + pl; r < r1; r += LANES) {
-            float f[8];
-            bunpack8(__ldg(x + r * G + g), f);
+        for (size_t r = r0 + pl; r < r1; r += 4 * (size_t)LANES) {      // four independent 16-byte loads in flight
+            uint4 v[4];
 #pragma unroll
-            for (int j = 0; j < 8; j++) s[j] += f[j];
+            for (int u = 0; u < 4; u++)
+                v[u] = (r + u * (size_t)LANES < r1) ? __ldg(x + (r + u * (size_t)LANES) * G + g) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float f[8];
+                bunpack8(v[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; j++) s[j] += f[j];
+            }
         }
     extern __shared__ float red[];   // [LANES][G*8 + 1]
     const int ld = G * 8 + 1;
@@ -229,12 +236,18 @@ __global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* _
 template <bool AT>
 __global__ void __launch_bounds__(256) gemm_f32_bf16_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Bm,
                                                             float* __restrict__ C, int M, int N, int K, int lda, int ldb,
-                                                            int ldc, int k_per_split, int atomic) {
+                                                            int ldc, int k_per_split, int atomic, int splits,
+                                                            long long sA, long long sB, long long sC) {
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
+    // blockIdx.z = batch * splits + split (a batch of independent GEMMs with strides sA / sB / sC)
+    const int batch = blockIdx.z / splits, split = blockIdx.z - batch * splits;
+    A += (size_t)batch * sA;
+    Bm += (size_t)batch * sB;
+    C += (size_t)batch * sC;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * k_per_split, kend = min(K, kbeg + k_per_split);
+    const int kbeg = split * k_per_split, kend = min(K, kbeg + k_per_split);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     float acc[4][4];
 #pragma unroll
@@ -324,6 +337,56 @@ __global__ void style_mix_bwd_v_kernel(const float* __restrict__ dstp, const flo
         const int b = idx / ((size_t)L * K);
         float s = 0.f;
         for (int j = 0; j < K; j++) s = fmaf(A[j * K + i], dstp[((size_t)b * K + j) * L + c], s);
+        dvec[idx] += s;
+    }
+}
+
+// the same for nS SEAN instances: A / dA / da are device pointer tables, dstp is [nS][B][K][L]; dvec sums the
+// instances in index order (deterministic)
+__global__ void __launch_bounds__(256) style_mix_bwd_a_batched_kernel(const float* __restrict__ dstp,
+                                                                      const float* __restrict__ vec,
+                                                                      float* const* __restrict__ dA_ptrs,
+                                                                      float* const* __restrict__ da_ptrs, int B, int K,
+                                                                      int L) {
+    const int sidx = blockIdx.y;
+    const int j = blockIdx.x / K, i = blockIdx.x % K;
+    const float* ds = dstp + (size_t)sidx * B * K * L;
+    float s = 0.f, sa = 0.f;
+    for (int idx = threadIdx.x; idx < B * L; idx += blockDim.x) {
+        const int b = idx / L, c = idx - b * L;
+        const float d = ds[((size_t)b * K + j) * L + c];
+        s = fmaf(d, vec[((size_t)b * K + i) * L + c], s);
+        sa += d;
+    }
+    __shared__ float r0[256], r1[256];
+    r0[threadIdx.x] = s;
+    r1[threadIdx.x] = sa;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off) {
+            r0[threadIdx.x] += r0[threadIdx.x + off];
+            r1[threadIdx.x] += r1[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        dA_ptrs[sidx][j * K + i] += r0[0];
+        if (i == 0) da_ptrs[sidx][j] += r1[0];
+    }
+}
+__global__ void style_mix_bwd_v_batched_kernel(const float* __restrict__ dstp, const float* const* __restrict__ A_ptrs,
+                                               float* __restrict__ dvec, int nS, int B, int K, int L) {
+    const size_t total = (size_t)B * K * L;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = idx % L;
+        const int i = (idx / L) % K;
+        const int b = idx / ((size_t)L * K);
+        float s = 0.f;
+        for (int sidx = 0; sidx < nS; sidx++) {
+            const float* A = A_ptrs[sidx];
+            const float* ds = dstp + (size_t)sidx * total;
+            for (int j = 0; j < K; j++) s = fmaf(__ldg(A + j * K + i), ds[((size_t)b * K + j) * L + c], s);
+        }
         dvec[idx] += s;
     }
 }
@@ -560,7 +623,7 @@ extern "C" int dasr_colsum(const void* x, float* out, int64_t rows, int C, void*
     DASR_REQUIRE(C % 8 == 0 && C >= 8 && 256 % (C / 8) == 0, "colsum: unsupported C %d", C);
     const int G = C / 8;
     const int lanes = 256 / G;
-    size_t rpb = ((size_t)rows + 2 * 148 - 1) / (2 * 148);
+    size_t rpb = ((size_t)rows + 4 * (size_t)num_sms() - 1) / (4 * (size_t)num_sms());
     if (rpb < (size_t)lanes * 4) rpb = (size_t)lanes * 4;
     const int grid = (int)(((size_t)rows + rpb - 1) / rpb);
     colsum_kernel<<<grid, 256, (size_t)lanes * (C + 1) * sizeof(float), (cudaStream_t)stream>>>((const uint4*)x, out, (size_t)rows, G, rpb);
@@ -588,26 +651,34 @@ extern "C" int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const fl
     return DASR_OK;
 }
 
-extern "C" int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N,
-                              int L, void* stream) {
-    DASR_REQUIRE(dT && stp && Ws && dWs && dstp, "null pointer");
+// nS independent instances in one call (strides between instances: dT BK*N, stp BK*L, Ws / dWs N*L, dstp BK*L)
+extern "C" int dasr_table_bwd_batched(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int nS,
+                                      int BK, int N, int L, void* stream) {
+    DASR_REQUIRE(dT && stp && Ws && dWs && dstp && nS > 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     // dWs [N][L] = dT^T [N][BK] * stp [BK][L]
-    gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, 1), 256, 0, st>>>(
-        dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0);
+    gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, nS), 256, 0, st>>>(
+        dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0, 1, (long long)BK * N, (long long)BK * L,
+        (long long)N * L);
     DASR_LAUNCH_OK();
-    // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles -> split the reduction over N
-    const int tiles = ((L + 63) / 64) * ((BK + 63) / 64);
-    int splits = (num_sms() + tiles - 1) / tiles;
+    // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles per instance -> split the reduction over N
+    const int tiles = ((L + 63) / 64) * ((BK + 63) / 64) * nS;
+    int splits = (2 * num_sms() + tiles - 1) / tiles;
     if (splits > (N + 63) / 64) splits = (N + 63) / 64;
     if (splits < 1) splits = 1;
     const int kps = (((N + splits - 1) / splits) + 15) / 16 * 16;
     splits = (N + kps - 1) / kps;
-    DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)BK * L * sizeof(float), st));
-    gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, splits), 256, 0, st>>>(
-        dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1);
+    DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)nS * BK * L * sizeof(float), st));
+    gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, nS * splits), 256, 0, st>>>(
+        dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1, splits, (long long)BK * N, (long long)N * L,
+        (long long)BK * L);
     DASR_LAUNCH_OK();
     return DASR_OK;
+}
+
+extern "C" int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N,
+                              int L, void* stream) {
+    return dasr_table_bwd_batched(dT, stp, Ws, dWs, dstp, 1, BK, N, L, stream);
 }
 
 extern "C" int dasr_style_mix_bwd(const float* dstp, const float* vec, const float* A, float* dA, float* da, float* dvec,
@@ -616,6 +687,18 @@ extern "C" int dasr_style_mix_bwd(const float* dstp, const float* vec, const flo
     style_mix_bwd_a_kernel<<<K * K, 256, 0, (cudaStream_t)stream>>>(dstp, vec, dA, da, B, K, L);
     DASR_LAUNCH_OK();
     style_mix_bwd_v_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(dstp, A, dvec, B, K, L);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_style_mix_bwd_batched(const float* dstp, const float* vec, const void* A_ptrs, const void* dA_ptrs,
+                                          const void* da_ptrs, float* dvec, int nS, int B, int K, int L, void* stream) {
+    DASR_REQUIRE(dstp && vec && A_ptrs && dA_ptrs && da_ptrs && dvec && nS > 0, "bad arguments");
+    style_mix_bwd_a_batched_kernel<<<dim3(K * K, nS), 256, 0, (cudaStream_t)stream>>>(
+        dstp, vec, (float* const*)dA_ptrs, (float* const*)da_ptrs, B, K, L);
+    DASR_LAUNCH_OK();
+    style_mix_bwd_v_batched_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(
+        dstp, (const float* const*)A_ptrs, dvec, nS, B, K, L);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -209,12 +209,15 @@ class Engine:
                                                        mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf))
                         rows_total += nf
                     self._packed[n + ".table"] = _Packed(ws, None, 9 * 2 * nf, lat, 1)
-                    self._wg[n + ".table"] = (self._wg_total, 9 * 2 * nf, lat)
-                    self._wg_total += 9 * 2 * nf * lat
             else:
                 p = "classic-residual%d" % (i + 1)
                 add_wn(p + ".block.0")
                 add_wn(p + ".block.2")
+        # weight gradients of the style-table GEMMs: one contiguous [nS][9*2nf][lat] block (batched backward)
+        self._wg_tables_off = self._wg_total
+        for n in sean_names:
+            self._wg[n + ".table"] = (self._wg_total, self._ws_rows, self._ws_all.shape[1])
+            self._wg_total += self._ws_rows * self._ws_all.shape[1]
         if net.scale == 8:
             add_wn("upscale1.0", shuffle_r=2)
             add_wn("upscale1.3")
@@ -336,6 +339,13 @@ class Engine:
             elif sp["kind"] == "out9":
                 U(self._dw_view("conv_output"), P("conv_output.weight"), G("conv_output.weight"), mode=L.PACK_ROWTAPS)
         self._unpack_descs = (L.UnpackDesc * len(descs))(*descs)
+        # gradient pointer tables of the batched A_i_j backward (dasr_style_mix_bwd_batched)
+        if self._sean_names:
+            dev = self._g_flat.device
+            self._dA_ptrs = torch.tensor([self._grad_view(n + ".A_i_j.weight").data_ptr() for n in self._sean_names],
+                                         dtype=torch.int64, device=dev)
+            self._da_ptrs = torch.tensor([self._grad_view(n + ".A_i_j.bias").data_ptr() for n in self._sean_names],
+                                         dtype=torch.int64, device=dev)
 
     def _finish_backward(self):
         """Packed-layout gradients -> parameter gradients; returns one tensor (or None) per parameter, all of them

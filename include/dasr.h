@@ -219,9 +219,16 @@ int dasr_actv_bwd_tc(const void* dA, const void* aux, float* scratch, float* dW,
 /* style-table GEMM backward: dWs[n][c] = sum_bk dT[bk][n] stp[bk][c];  dstp[bk][c] = sum_n dT[bk][n] Ws[n][c]    */
 int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N, int L,
                    void* stream);
+/* the same for nS SEAN instances at once (instance strides: dT BK*N, stp BK*L, Ws / dWs N*L, dstp BK*L)      */
+int dasr_table_bwd_batched(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int nS, int BK,
+                           int N, int L, void* stream);
 /* A_i_j backward: dA += , da += , dvec += (accumulating over the SEAN instances)                        */
 int dasr_style_mix_bwd(const float* dstp, const float* vec, const float* A, float* dA, float* da, float* dvec, int B,
                        int K, int L, void* stream);
+/* all nS instances at once: dstp fp32 [nS][B][K][L]; A_ptrs / dA_ptrs / da_ptrs are DEVICE arrays of nS device
+ * pointers (A_i_j.weight, its gradient, the gradient of A_i_j.bias); dvec += the sum over the instances          */
+int dasr_style_mix_bwd_batched(const float* dstp, const float* vec, const void* A_ptrs, const void* dA_ptrs,
+                               const void* da_ptrs, float* dvec, int nS, int B, int K, int L, void* stream);
 int dasr_region_pool_bwd(const float* dvec, const float* msel, const float* cnt, void* de5, int B, int P, int C, int K,
                          void* stream);
 /* mlp_mask backward: dW[c][9] += , db[c] += from dA (NHWC bf16 [B,H,W,C], ReLU mask already applied)      */
