@@ -103,6 +103,21 @@ def test_other_seeds_and_batch():
         assert err <= TOL_PIX_STRESS
 
 
+def test_1080p_frame_matches_oracle():
+    """BASELINE configs[4]: a 135x240 LR frame -> 1080x1920 (two 128-wide strips per row, odd sizes everywhere)."""
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=8, latent=256, which=tuple(range(14)))
+    sd = fill_state_dict(oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10), seed=3)
+    lq, depth, masks = synthetic_inputs(1, 135, 240, scale=8, seed=3)
+    with torch.no_grad():
+        ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=8, which=meta["which"])
+        sr = _build(meta, sd)(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+    assert tuple(sr.shape) == (1, 3, 1080, 1920)
+    err = (sr - ref).abs().max().item()
+    print("1080p frame: max|sr-oracle|=%.4g" % err)
+    assert err <= TOL_PIX_STRESS
+
+
 def test_fp32_residual_stream_option():
     """Engine.fp32_residual carries an fp32 copy of the trunk's residual stream; both settings meet the tolerance."""
     z, meta = load_golden("x8_b1_64_init")

@@ -128,7 +128,8 @@ def _torch_step_reference(sd, meta, inputs, steps, lr):
     lq, depth, masks, gt = [t.cuda() for t in inputs]
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        net = dasr.DepthNet(which_ResBlk_depth=list(meta["which"]), scale=meta["scale"], nb=meta["nb"]).cuda().train()
+        net = dasr.DepthNet(which_ResBlk_depth=list(meta["which"]), scale=meta["scale"], nb=meta["nb"],
+                            depth_latent_ch=meta.get("latent", 256)).cuda().train()
     net.load_state_dict(sd)
     wd = torch.ones(10, device="cuda", requires_grad=True)
     opt = torch.optim.Adam([p for p in net.parameters()] + [wd], lr=lr, betas=(0.9, 0.99))
@@ -189,3 +190,32 @@ def test_train_step_cuda_graph_replays_the_eager_trajectory():
     # ~zero gradients, so compare the bulk
     close = ((traj[True][1] - traj[False][1]).abs() <= 1e-4).float().mean().item()
     assert close >= 0.5, close
+
+
+@pytest.mark.parametrize("scale,which,latent,unused", [(4, list(range(14)), 256, ("upscale1.",)),
+                                                      (2, list(range(16)), 32, ("upscale1.", "upscale2."))])
+def test_training_step_at_x4_and_x2(scale, which, latent, unused):
+    """BASELINE configs[3]: the x4 / x2 variants train through the same kernels (smaller upsampler, 64-channel
+    blocks 15/16, 32-channel latent at x2); parameters the reference never touches get no gradient."""
+    import depth_aware_endoscopy_sr_b200 as dasr
+    torch.manual_seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = dasr.DepthNet(which_ResBlk_depth=which, scale=scale, nb=16, depth_latent_ch=latent).cuda().train()
+    lq, depth, masks, gt = [t.cuda() for t in synthetic_inputs(2, 32, 32, scale=scale, seed=9, with_gt=True)]
+    sr = net(lq, depth, masks)
+    assert tuple(sr.shape) == (2, 3, 32 * scale, 32 * scale)
+    (sr - gt).abs().mean().backward()
+    for name, p in net.named_parameters():
+        if name.startswith(unused) or name.startswith("depth-residual14."):
+            assert p.grad is None, name
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    net.zero_grad(set_to_none=True)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    inputs = [t.cpu() for t in (lq, depth, masks, gt)]
+    ref_losses, _, _ = _torch_step_reference(sd, dict(scale=scale, which=which, nb=16, latent=latent), inputs, steps=3, lr=1e-3)
+    step = dasr.TrainStep(net, num_masks=10, lr=1e-3, betas=(0.9, 0.99))
+    losses = [step(lq, depth, masks, gt)[0].item() for _ in range(3)]
+    assert all(np.isfinite(losses))
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-2)     # same trajectory as torch criteria + torch Adam
