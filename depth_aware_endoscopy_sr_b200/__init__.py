@@ -11,7 +11,7 @@ Public surface (mirrors the reference's own, codes/models/networks.py:15-59):
     FusedAdam                              torch.optim.Adam over one flat buffer (optim.py)
     FlatDataParallel, install_ddp          the data-parallel wrapper the reference applies when opt['dist'] (parallel.py)
     TrainStep                              optimize_parameters() as one device-resident step (trainer.py)
-    depth_masks, tensor2img                getDepthMask / tensor2img of the data and test pipelines on the device (io.py)
+    depth_masks, tensor2img, psnr, ssim    getDepthMask / tensor2img / validation metrics on the device (io.py)
 
 All arithmetic runs in libdasr_b200.so (hand-written sm_100a CUDA, C ABI in include/dasr.h).
 """
@@ -21,8 +21,8 @@ from .loss import L1Loss, dynamic_weight_mask_loss, training_loss  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .parallel import FlatDataParallel, install_ddp, shard_frames  # noqa: F401
 from .trainer import TrainStep  # noqa: F401
-from .io import depth_masks, tensor2img  # noqa: F401
+from .io import depth_masks, tensor2img, psnr, ssim  # noqa: F401
 
 __all__ = ["DepthNet", "SEAN", "Encoder", "Depth_Residual_Block_Mask", "Classic_Residual_Block", "define_G",
            "install", "L1Loss", "dynamic_weight_mask_loss", "training_loss", "FusedAdam", "FlatDataParallel",
-           "install_ddp", "shard_frames", "TrainStep", "depth_masks", "tensor2img"]
+           "install_ddp", "shard_frames", "TrainStep", "depth_masks", "tensor2img", "psnr", "ssim"]

@@ -110,3 +110,149 @@ extern "C" int dasr_tensor2img(const float* sr, uint8_t* img, int B, int H, int 
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ validation metrics
+// PSNR (codes/utils/util.py:646-653 as called from codes/train.py:251-257) and
+// pytorch_ssim.ssim (codes/pytorch_ssim/__init__.py:17-38,65-72) of the validation loop, on the device.
+namespace dasr {
+
+// exact integer sum of squared differences of two uint8 frames [H,W,C] inside a `crop`-pixel border, per frame
+__global__ void __launch_bounds__(256) sqdiff_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                        unsigned long long* __restrict__ out, int H, int W, int C,
+                                                        int crop) {
+    const int f = blockIdx.y;
+    const int Hc = H - 2 * crop, Wc = W - 2 * crop;
+    const size_t n = (size_t)Hc * Wc * C;
+    const uint8_t* pa = a + (size_t)f * H * W * C;
+    const uint8_t* pb = b + (size_t)f * H * W * C;
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t p = i / C;
+        const int x = (int)(p % Wc) + crop, y = (int)(p / Wc) + crop;
+        const size_t idx = ((size_t)y * W + x) * C + c;
+        const int d = (int)pa[idx] - (int)pb[idx];
+        s += (unsigned long long)(d * d);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out + f, s);      // integer atomics: exact and order-independent
+}
+
+// SSIM map of one 16x16 output tile per block: separable 11-tap Gaussian (sigma 1.5, zero padding) of x, y, x^2, y^2,
+// xy in shared memory, then the SSIM formula and a block sum.  part[frame][channel][tile] partial sums.
+constexpr int kSsimT = 16, kSsimR = 5, kSsimP = kSsimT + 2 * kSsimR;    // tile, radius, padded tile (26)
+__global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                                                   float* __restrict__ part, int H, int W, int tiles_x, int tiles_y) {
+    __shared__ float s1[kSsimP][kSsimP + 1], s2[kSsimP][kSsimP + 1];
+    __shared__ float hz[5][kSsimP][kSsimT + 1];       // horizontally filtered rows of the 5 quantities
+    __shared__ float g[11];
+    __shared__ float red[8];
+    const int plane = blockIdx.y;                      // frame * C + channel
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const float* p1 = img1 + (size_t)plane * H * W;
+    const float* p2 = img2 + (size_t)plane * H * W;
+    if (threadIdx.x < 11) {
+        // gaussian(11, 1.5) normalised like the reference (fp32 exp, fp32 sum)
+        float w[11], sum = 0.f;
+        for (int i = 0; i < 11; i++) {
+            w[i] = expf(-(float)((i - 5) * (i - 5)) / (2.f * 1.5f * 1.5f));
+            sum += w[i];
+        }
+        g[threadIdx.x] = w[threadIdx.x] / sum;
+    }
+    const int y0 = ty * kSsimT - kSsimR, x0 = tx * kSsimT - kSsimR;
+    for (int i = threadIdx.x; i < kSsimP * kSsimP; i += 256) {
+        const int r = i / kSsimP, c = i - r * kSsimP;
+        const int y = y0 + r, x = x0 + c;
+        const bool in = (y >= 0 && y < H && x >= 0 && x < W);
+        s1[r][c] = in ? __ldg(p1 + (size_t)y * W + x) : 0.f;
+        s2[r][c] = in ? __ldg(p2 + (size_t)y * W + x) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSsimP * kSsimT; i += 256) {
+        const int r = i / kSsimT, c = i - r * kSsimT;
+        float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+            const float u = s1[r][c + k], v = s2[r][c + k], wk = g[k];
+            a = fmaf(wk, u, a);
+            b = fmaf(wk, v, b);
+            aa = fmaf(wk, u * u, aa);
+            bb = fmaf(wk, v * v, bb);
+            ab = fmaf(wk, u * v, ab);
+        }
+        hz[0][r][c] = a; hz[1][r][c] = b; hz[2][r][c] = aa; hz[3][r][c] = bb; hz[4][r][c] = ab;
+    }
+    __syncthreads();
+    float acc = 0.f;
+    {
+        const int r = threadIdx.x / kSsimT, c = threadIdx.x - r * kSsimT;       // 256 threads = 16 x 16 outputs
+        const int y = ty * kSsimT + r, x = tx * kSsimT + c;
+        if (y < H && x < W) {
+            float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 11; k++)
+#pragma unroll
+                for (int q = 0; q < 5; q++) m[q] = fmaf(g[k], hz[q][r + k][c], m[q]);
+            const float mu1 = m[0], mu2 = m[1];
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float sg1 = m[2] - mu1_sq, sg2 = m[3] - mu2_sq, sg12 = m[4] - mu12;
+            const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+            acc = ((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; i++) t += red[i];
+        part[(size_t)plane * tiles_x * tiles_y + blockIdx.x] = t;
+    }
+}
+
+// out[frame] = mean over the frame's channels and pixels of the SSIM map (tiles added in index order, in double)
+__global__ void ssim_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int per_frame, double inv_n) {
+    const int f = blockIdx.x;
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < per_frame; i += blockDim.x) s += (double)part[(size_t)f * per_frame + i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[f] = (float)(red[0] * inv_n);
+}
+
+}  // namespace dasr
+
+extern "C" int dasr_sqdiff_u8(const uint8_t* a, const uint8_t* b, unsigned long long* out, int F, int H, int W, int C,
+                              int crop, void* stream) {
+    DASR_REQUIRE(a && b && out && F > 0 && crop >= 0 && H > 2 * crop && W > 2 * crop, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DASR_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)F * sizeof(unsigned long long), st));
+    const size_t n = (size_t)(H - 2 * crop) * (W - 2 * crop) * C;
+    size_t gx = (n + 255) / 256;
+    if (gx > (size_t)num_sms() * 8) gx = (size_t)num_sms() * 8;
+    sqdiff_u8_kernel<<<dim3((unsigned)gx, F), 256, 0, st>>>(a, b, out, H, W, C, crop);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_ssim_tiles(int H, int W) { return ((H + kSsimT - 1) / kSsimT) * ((W + kSsimT - 1) / kSsimT); }
+
+extern "C" int dasr_ssim(const float* img1, const float* img2, float* part, float* out, int F, int C, int H, int W,
+                         void* stream) {
+    DASR_REQUIRE(img1 && img2 && part && out && F > 0 && C > 0, "bad arguments");
+    const int tx = (W + kSsimT - 1) / kSsimT, ty = (H + kSsimT - 1) / kSsimT;
+    cudaStream_t st = (cudaStream_t)stream;
+    ssim_kernel<<<dim3(tx * ty, F * C), 256, 0, st>>>(img1, img2, part, H, W, tx, ty);
+    DASR_LAUNCH_OK();
+    ssim_reduce_kernel<<<F, 256, 0, st>>>(part, out, C * tx * ty, 1.0 / ((double)C * H * W));
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}

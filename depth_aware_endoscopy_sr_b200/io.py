@@ -7,7 +7,11 @@
                                            ``[B,3,H,W]`` fp32 RGB -> ``[B,H,W,3]`` uint8 BGR on the device, so only a
                                            quarter of the bytes crosses PCIe and no CPU pass is needed
 
-Both run in libdasr_b200.so; CPU tensors raise.
+    psnr(sr_u8, gt_u8, crop)               ``utils.util.calculate_psnr`` on the uint8 frames of ``tensor2img`` with the
+                                           border crop of codes/train.py:251-257, per frame
+    ssim(img1, img2)                       ``pytorch_ssim.ssim`` (codes/pytorch_ssim/__init__.py), per frame or averaged
+
+All run in libdasr_b200.so; CPU tensors raise.
 """
 from __future__ import annotations
 
@@ -38,3 +42,30 @@ def tensor2img(sr: torch.Tensor, min_max=(0.0, 1.0)) -> torch.Tensor:
     L.check(L.load().dasr_tensor2img(L.ptr(x), L.ptr(img), B, H, W, float(min_max[0]), float(min_max[1]),
                                      L.stream_ptr()))
     return img[0] if squeeze else img
+
+
+def psnr(sr_u8: torch.Tensor, gt_u8: torch.Tensor, crop: int = 0) -> torch.Tensor:
+    """uint8 frames [F,H,W,C] (or [H,W,C]) on the device -> PSNR per frame (float64 tensor on the device),
+    20*log10(255/sqrt(mse)) over the region inside a ``crop``-pixel border; inf for identical frames."""
+    a = (sr_u8.unsqueeze(0) if sr_u8.dim() == 3 else sr_u8).contiguous()
+    b = (gt_u8.unsqueeze(0) if gt_u8.dim() == 3 else gt_u8).contiguous()
+    if a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.shape != b.shape:
+        raise RuntimeError("psnr: two uint8 frame tensors of the same shape are needed")
+    F_, H, W, C = a.shape
+    acc = torch.empty(F_, device=a.device, dtype=torch.int64)
+    L.check(L.load().dasr_sqdiff_u8(L.ptr(a), L.ptr(b), L.ptr(acc), F_, H, W, C, int(crop), L.stream_ptr()))
+    mse = acc.double() / float((H - 2 * crop) * (W - 2 * crop) * C)
+    return 20.0 * torch.log10(255.0 / torch.sqrt(mse))
+
+
+def ssim(img1: torch.Tensor, img2: torch.Tensor, size_average: bool = True) -> torch.Tensor:
+    """fp32 frames [F,C,H,W] in [0,1] on the device -> mean SSIM (scalar) or per-frame SSIM [F]."""
+    a, b = img1.contiguous().float(), img2.contiguous().float()
+    if a.shape != b.shape or a.dim() != 4:
+        raise RuntimeError("ssim: two [F,C,H,W] tensors of the same shape are needed")
+    F_, C, H, W = a.shape
+    lib = L.load()
+    part = torch.empty(F_ * C * lib.dasr_ssim_tiles(H, W), device=a.device, dtype=torch.float32)
+    out = torch.empty(F_, device=a.device, dtype=torch.float32)
+    L.check(lib.dasr_ssim(L.ptr(a), L.ptr(b), L.ptr(part), L.ptr(out), F_, C, H, W, L.stream_ptr()))
+    return out.mean() if size_average else out

@@ -365,6 +365,17 @@ int dasr_depth_masks(const float* depth, uint8_t* labels, float* masks, float* r
  * round_half_even((clamp(x, lo, hi) - lo) / (hi - lo) * 255)                                                     */
 int dasr_tensor2img(const float* sr, uint8_t* img, int B, int H, int W, float lo, float hi, void* stream);
 
+/* Validation metrics.
+ * dasr_sqdiff_u8: out[f] = exact integer sum of (a-b)^2 over frame f ([F,H,W,C] uint8) inside a `crop`-pixel border --
+ * the numerator of util.calculate_psnr (codes/utils/util.py:646-653) as train.py:251-257 calls it.
+ * dasr_ssim: pytorch_ssim.ssim (codes/pytorch_ssim/__init__.py:17-38,65-72; 11x11 Gaussian window, sigma 1.5, zero
+ * padding, C1 = 0.01^2, C2 = 0.03^2) of NCHW fp32 frames [F,C,H,W]; out[f] = mean SSIM of frame f.
+ * part: fp32 scratch [F*C*dasr_ssim_tiles(H,W)].                                                                  */
+int dasr_sqdiff_u8(const uint8_t* a, const uint8_t* b, unsigned long long* out, int F, int H, int W, int C, int crop,
+                   void* stream);
+int dasr_ssim_tiles(int H, int W);
+int dasr_ssim(const float* img1, const float* img2, float* part, float* out, int F, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,3 +43,35 @@ def test_tensor2img_matches_reference_conversion():
         assert np.array_equal(out[b], ref)
     one = bio.tensor2img(sr[0].cuda())
     assert one.shape == (40, 56, 3) and np.array_equal(one.cpu().numpy(), out[0])
+
+
+def test_psnr_and_ssim_match_the_reference_formulas():
+    import math
+    import torch.nn.functional as F
+    from depth_aware_endoscopy_sr_b200 import io as bio
+    g = torch.Generator().manual_seed(3)
+    gt = torch.rand(2, 3, 72, 100, generator=g)
+    sr = (gt + 0.05 * torch.randn(gt.shape, generator=g)).clamp(0, 1)
+    # PSNR as train.py:251-257 computes it from the tensor2img frames with a border crop of `scale` pixels
+    sr8, gt8 = bio.tensor2img(sr.cuda()), bio.tensor2img(gt.cuda())
+    got = bio.psnr(sr8, gt8, crop=8).cpu().numpy()
+    for f in range(2):
+        a = sr8[f].cpu().numpy().astype(np.float64)[8:-8, 8:-8, :]
+        b = gt8[f].cpu().numpy().astype(np.float64)[8:-8, 8:-8, :]
+        ref = 20 * math.log10(255.0 / math.sqrt(np.mean((a - b) ** 2)))
+        assert abs(got[f] - ref) <= 1e-9 * ref
+    assert math.isinf(bio.psnr(gt8, gt8).cpu()[0].item())
+    # SSIM: pytorch_ssim._ssim restated with torch ops (window = outer product of the normalised 1-D Gaussian)
+    w1 = torch.tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
+    w1 = (w1 / w1.sum()).unsqueeze(1)
+    win = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous().double()
+    x, y = sr.double(), gt.double()
+    mu1, mu2 = F.conv2d(x, win, padding=5, groups=3), F.conv2d(y, win, padding=5, groups=3)
+    s1 = F.conv2d(x * x, win, padding=5, groups=3) - mu1 ** 2
+    s2 = F.conv2d(y * y, win, padding=5, groups=3) - mu2 ** 2
+    s12 = F.conv2d(x * y, win, padding=5, groups=3) - mu1 * mu2
+    smap = ((2 * mu1 * mu2 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1 ** 2 + mu2 ** 2 + 0.01 ** 2) * (s1 + s2 + 0.03 ** 2))
+    got = bio.ssim(sr.cuda(), gt.cuda(), size_average=False).cpu().double()
+    ref = smap.mean(dim=(1, 2, 3))
+    assert (got - ref).abs().max().item() <= 2e-5
+    assert abs(bio.ssim(sr.cuda(), gt.cuda()).item() - smap.mean().item()) <= 2e-5
