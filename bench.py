@@ -282,14 +282,48 @@ def run_b200(args):
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
-        clocks = sampler.stop(clk_mark) if rank == 0 else None      # samples span both timed regions
+
+        # ------------------------------------------------ the same with the output step of codes/test.py on the
+        # device: tensor2img (clamp / x255 / round / uint8 / BGR) before the read-back, so a
+        # quarter of the bytes crosses PCIe (reported next to e2e, not instead of it)
+        from depth_aware_endoscopy_sr_b200 import io as dio
+        out_u8 = [torch.empty(B, SCALE * LR, SCALE * LR, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+        def e2e_u8_step(i):
+            slot = i % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_done[slot])
+                for d, h in zip(dev_in[slot], host_sets[i % n_sets]):
+                    d.copy_(h, non_blocking=True)
+                ev_in[slot].record(s_in)
+            cur.wait_event(ev_in[slot])
+            img = dio.tensor2img(net(*dev_in[slot]))
+            ev_done[slot].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[slot])
+                out_u8[slot].copy_(img, non_blocking=True)
+                img.record_stream(s_out)
+
+        for i in range(3):
+            e2e_u8_step(i)
+        e2e_join()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for i in range(K):
+            e2e_u8_step(i)
+        e2e_join()
+        g1.record()
+        barrier()
+        ms_e2e_u8 = g0.elapsed_time(g1)
+        clocks = sampler.stop(clk_mark) if rank == 0 else None      # samples span the timed regions
 
     train = train_pass(args, net, dev, rank, world, barrier) if args.train_steps > 0 else None
 
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, ms_e2e, ms_e2e_u8], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e, ms_e2e_u8 = t.tolist()
     value = B * world * K / (ms_total * 1e-3)
     e2e = B * world * K / (ms_e2e * 1e-3)
 
@@ -316,6 +350,10 @@ def run_b200(args):
                              "rotates over %d sets" % n_sets},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K},
+            "e2e_uint8_frames": {"value": B * world * K / (ms_e2e_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                 "d2h_bytes_per_step": out_u8[0].numel(), "ms_per_step": ms_e2e_u8 / K,
+                                 "note": "net(...) + device-side tensor2img (uint8 BGR frames, what codes/test.py "
+                                         "writes) read back instead of the fp32 tensor"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train}
     print(json.dumps(line), flush=True)
 
