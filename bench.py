@@ -186,6 +186,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _bind_to_gpu_numa_node(local):
+    """Pin this rank (and therefore its pinned host buffers, first-touch) to the CPUs of the NUMA node its GPU hangs
+    off, so that the e2e host<->device copies of 8 ranks do not cross sockets.  Returns a short description."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        with open(base + "/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %s of %s" % (cpulist, bus)
+        return "unchanged (%s)" % cpulist
+    except Exception as e:       # best effort: containers may hide sysfs
+        return "unavailable (%s)" % type(e).__name__
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -197,6 +224,7 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else "single rank"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -346,6 +374,7 @@ def run_b200(args):
             "config": {"workload": "depthNet_SEAN_depthMask x8 inference, batch %d per GPU, synthetic 3x64x64 LR + "
                                    "1x64x64 depth + 10 masks -> 3x512x512, random-init weights" % B,
                        "batch_per_gpu": B, "lr": [LR, LR], "scale": SCALE, "sharding": "frames by rank, no collective",
+                       "host_affinity": numa,
                        "l2": "no flush: one step streams ~3.5 GB of activations (>> 126 MB L2) and the input batch "
                              "rotates over %d sets" % n_sets},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
