@@ -240,22 +240,44 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
         tmem_ld16(t_acc + blk * N_TILE + NF + c0, vb);
         tmem_ld_wait();
         if (!o.valid) continue;
-        float yv[16], gs[16], bs[16], f[16];
+        float yv[16], gs[16], f[16];
         unpack8(o.y0, yv);
         unpack8(o.y1, yv + 8);
-        unpack8(o.g0, gs);
-        unpack8(o.g1, gs + 8);
-        unpack8(o.b0, bs);
-        unpack8(o.b1, bs + 8);
+        // bias / (mean, scale) of the 16 columns with 128-bit shared-memory loads (a scalar LDS per value made this
+        // loop ~530 instructions per step); run-time flags are tested once per step, not once per element
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const float g = __uint_as_float(vg[j]) + bias_t[c0 + j] + gs[j];
-            const float b = __uint_as_float(vb[j]) + bias_t[NF + c0 + j] + bs[j];
-            const float n = (yv[j] - norm_s[2 * (c0 + j)]) * norm_s[2 * (c0 + j) + 1];
-            float t = fmaf(n, 1.f + g, b);
-            if (p.inner_relu) t = fmaxf(t, 0.f);
-            f[j] = t;
-            gs[j] = g;
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 bg = *reinterpret_cast<const float4*>(bias_t + c0 + j4);
+            const float4 bb = *reinterpret_cast<const float4*>(bias_t + NF + c0 + j4);
+            gs[j4] = __uint_as_float(vg[j4]) + bg.x;
+            gs[j4 + 1] = __uint_as_float(vg[j4 + 1]) + bg.y;
+            gs[j4 + 2] = __uint_as_float(vg[j4 + 2]) + bg.z;
+            gs[j4 + 3] = __uint_as_float(vg[j4 + 3]) + bg.w;
+            f[j4] = __uint_as_float(vb[j4]) + bb.x;
+            f[j4 + 1] = __uint_as_float(vb[j4 + 1]) + bb.y;
+            f[j4 + 2] = __uint_as_float(vb[j4 + 2]) + bb.z;
+            f[j4 + 3] = __uint_as_float(vb[j4 + 3]) + bb.w;
+        }
+        if (p.gb_s) {      // dynamic-conv term from memory (when it is not folded into the GEMM)
+            float t0[16];
+            unpack8(o.g0, t0);
+            unpack8(o.g1, t0 + 8);
+#pragma unroll
+            for (int j = 0; j < 16; j++) gs[j] += t0[j];
+            unpack8(o.b0, t0);
+            unpack8(o.b1, t0 + 8);
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] += t0[j];
+        }
+#pragma unroll
+        for (int j2 = 0; j2 < 16; j2 += 2) {
+            const float4 nm = *reinterpret_cast<const float4*>(norm_s + 2 * (c0 + j2));     // (mean, scale) x 2
+            f[j2] = fmaf((yv[j2] - nm.x) * nm.y, 1.f + gs[j2], f[j2]);
+            f[j2 + 1] = fmaf((yv[j2 + 1] - nm.z) * nm.w, 1.f + gs[j2 + 1], f[j2 + 1]);
+        }
+        if (p.inner_relu) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
         }
         if (DBG(p, 2)) continue;
         if (p.gamma_out) store16(p.gamma_out + o.pix * NF + c0, gs);
@@ -274,8 +296,13 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
 #pragma unroll
             for (int j = 0; j < 16; j++) f[j] += rr[j];
         }
+        if (p.act == DASR_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
+            for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == DASR_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+        }
         store16(p.out + o.pix * NF + c0, f);
         if (p.out_aux_f32) {
             stg256f(p.out_aux_f32 + o.pix * NF + c0, f);
@@ -303,8 +330,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __shared__ uint64_t acc_full[2], acc_empty[2];
     __shared__ uint64_t a2_full, a2_empty;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float norm_s[512];         // SEAN: (mean, scale) of the image; STATS: scratch of the fused finalize
-    __shared__ float bias_s[kMaxBias];
+    __shared__ __align__(16) float norm_s[512];         // SEAN: (mean, scale) of the image; STATS: scratch of the fused finalize
+    __shared__ __align__(16) float bias_s[kMaxBias];
     __shared__ uint32_t tap_lo_s[81];     // descriptor-low-word offset of tap (t,u): ((t*Wp + u) * SWZ) >> 4
 
     const uint32_t raw_addr = smem_u32(smem_raw);
