@@ -426,7 +426,7 @@ def train_pass(args, net, dev, rank, world, barrier):
             "gradient_allreduce": None if world == 1 else "one NCCL all-reduce (AVG) of the flat fp32 buffer, %.1f MB"
                                                              % (nparam * 4 / 1e6),
             "cuda_graph": not args.no_graph,
-            "gpu_launches": int(launches) if args.no_graph else int(step.launches_per_step) * Kt}
+            "gpu_launches": int(launches)}
 
 
 def _ncu_traffic(kernel_family):

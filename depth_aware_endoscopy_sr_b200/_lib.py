@@ -159,8 +159,19 @@ def flat_pad(numel: int) -> int:
     return (numel + 3) // 4 * 4
 
 
+_replayed_launches = 0
+
+
+def note_replayed_launches(n: int) -> None:
+    """Kernels of this library executed by a CUDA-graph replay (counted at capture time; a replay does not pass
+    through the C entry points that bump dasr_launch_count)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def launch_count() -> int:
-    return int(load().dasr_launch_count())
+    """Kernels of libdasr_b200.so launched so far in this process, directly or through CUDA-graph replays."""
+    return int(load().dasr_launch_count()) + _replayed_launches
 
 
 def check(rc: int) -> None:

@@ -85,6 +85,7 @@ class TrainStep:
                 dst.copy_(src, non_blocking=True)
         self.optimizer.advance()
         self._g.replay()
+        L.note_replayed_launches(self.launches_per_step)
         return self._static_out
 
     def _step(self, lq, depth, masks, gt):

@@ -118,6 +118,32 @@ def test_1080p_frame_matches_oracle():
     assert err <= TOL_PIX_STRESS
 
 
+def test_cuda_graph_replay_matches_kernel_by_kernel_schedule():
+    """From the third call with one input shape the forward is replayed from a CUDA graph: same bits as the eager
+    schedule, new inputs are honoured, a parameter update drops the recorded schedule."""
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=8, latent=256, which=tuple(range(14)))
+    sd = fill_state_dict(oracle.state_layout(scale=8, nb=16, which=meta["which"], latent=256, K=10), seed=2)
+    net = _build(meta, sd)
+    eng = net.engine()
+    a = [t.cuda() for t in synthetic_inputs(2, 24, 40, scale=8, seed=1)]
+    b = [t.cuda() for t in synthetic_inputs(2, 24, 40, scale=8, seed=2)]
+    with torch.no_grad():
+        eager_a = eng._infer_eager(*a)
+        eager_b = eng._infer_eager(*b)
+        outs = [net(*a) for _ in range(4)]          # calls 3 and 4 are graph replays
+        assert any(e["graph"] is not None for e in eng._graphs.values())
+        for o in outs:
+            assert torch.equal(o, eager_a)
+        assert torch.equal(net(*b), eager_b)        # replay with other inputs
+        assert torch.equal(net(*a), eager_a)
+        # a parameter update invalidates the recorded schedules
+        net.conv_output.bias.add_(0.25)
+        shifted = net(*a)
+        assert len([e for e in eng._graphs.values() if e["graph"] is not None]) == 0
+        assert torch.equal(shifted, eng._infer_eager(*a)) and not torch.equal(shifted, eager_a)
+
+
 def test_fp32_residual_stream_option():
     """Engine.fp32_residual carries an fp32 copy of the trunk's residual stream; both settings meet the tolerance."""
     z, meta = load_golden("x8_b1_64_init")
