@@ -139,6 +139,14 @@ __global__ void __launch_bounds__(256) sqdiff_u8_kernel(const uint8_t* __restric
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out + f, s);      // integer atomics: exact and order-independent
 }
 
+// psnr[f] = 20 log10(255 / sqrt(ssd[f] / n))  (double; +inf for identical frames, like util.calculate_psnr)
+__global__ void psnr_finalize_kernel(const unsigned long long* __restrict__ ssd, double* __restrict__ out, int F, double n) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const double mse = (double)ssd[f] / n;
+    out[f] = ssd[f] == 0ull ? (double)INFINITY : 20.0 * log10(255.0 / sqrt(mse));
+}
+
 // SSIM map of one 16x16 output tile per block: separable 11-tap Gaussian (sigma 1.5, zero padding) of x, y, x^2, y^2,
 // xy in shared memory, then the SSIM formula and a block sum.  part[frame][channel][tile] partial sums.
 constexpr int kSsimT = 16, kSsimR = 5, kSsimP = kSsimT + 2 * kSsimR;    // tile, radius, padded tile (26)
@@ -239,6 +247,17 @@ extern "C" int dasr_sqdiff_u8(const uint8_t* a, const uint8_t* b, unsigned long 
     size_t gx = (n + 255) / 256;
     if (gx > (size_t)num_sms() * 8) gx = (size_t)num_sms() * 8;
     sqdiff_u8_kernel<<<dim3((unsigned)gx, F), 256, 0, st>>>(a, b, out, H, W, C, crop);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_psnr_u8(const uint8_t* a, const uint8_t* b, unsigned long long* ssd, double* psnr, int F, int H, int W,
+                            int C, int crop, void* stream) {
+    DASR_REQUIRE(psnr != nullptr, "null pointer");
+    int rc = dasr_sqdiff_u8(a, b, ssd, F, H, W, C, crop, stream);
+    if (rc) return rc;
+    psnr_finalize_kernel<<<(F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ssd, psnr, F,
+                                                                           (double)(H - 2 * crop) * (W - 2 * crop) * C);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

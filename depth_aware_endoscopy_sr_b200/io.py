@@ -53,9 +53,9 @@ def psnr(sr_u8: torch.Tensor, gt_u8: torch.Tensor, crop: int = 0) -> torch.Tenso
         raise RuntimeError("psnr: two uint8 frame tensors of the same shape are needed")
     F_, H, W, C = a.shape
     acc = torch.empty(F_, device=a.device, dtype=torch.int64)
-    L.check(L.load().dasr_sqdiff_u8(L.ptr(a), L.ptr(b), L.ptr(acc), F_, H, W, C, int(crop), L.stream_ptr()))
-    mse = acc.double() / float((H - 2 * crop) * (W - 2 * crop) * C)
-    return 20.0 * torch.log10(255.0 / torch.sqrt(mse))
+    out = torch.empty(F_, device=a.device, dtype=torch.float64)
+    L.check(L.load().dasr_psnr_u8(L.ptr(a), L.ptr(b), L.ptr(acc), L.ptr(out), F_, H, W, C, int(crop), L.stream_ptr()))
+    return out
 
 
 def ssim(img1: torch.Tensor, img2: torch.Tensor, size_average: bool = True) -> torch.Tensor:
@@ -68,4 +68,8 @@ def ssim(img1: torch.Tensor, img2: torch.Tensor, size_average: bool = True) -> t
     part = torch.empty(F_ * C * lib.dasr_ssim_tiles(H, W), device=a.device, dtype=torch.float32)
     out = torch.empty(F_, device=a.device, dtype=torch.float32)
     L.check(lib.dasr_ssim(L.ptr(a), L.ptr(b), L.ptr(part), L.ptr(out), F_, C, H, W, L.stream_ptr()))
-    return out.mean() if size_average else out
+    if not size_average:
+        return out
+    if F_ == 1:
+        return out[0]
+    return out.mean()      # frames have equal sizes: the mean of the per-frame means is the global mean

@@ -373,6 +373,9 @@ int dasr_tensor2img(const float* sr, uint8_t* img, int B, int H, int W, float lo
  * part: fp32 scratch [F*C*dasr_ssim_tiles(H,W)].                                                                  */
 int dasr_sqdiff_u8(const uint8_t* a, const uint8_t* b, unsigned long long* out, int F, int H, int W, int C, int crop,
                    void* stream);
+/* the same plus psnr[f] = 20 log10(255 / sqrt(ssd[f] / n)) in double (+inf for identical frames)                  */
+int dasr_psnr_u8(const uint8_t* a, const uint8_t* b, unsigned long long* ssd, double* psnr, int F, int H, int W, int C,
+                 int crop, void* stream);
 int dasr_ssim_tiles(int H, int W);
 int dasr_ssim(const float* img1, const float* img2, float* part, float* out, int F, int C, int H, int W, void* stream);
 
