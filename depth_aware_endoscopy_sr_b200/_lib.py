@@ -29,7 +29,8 @@ class ConvDesc(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("x", "w", "bias", "out", "resid", "stats", "y", "norm", "gb_s", "actmask",
-                                          "gamma_out", "resid_f32", "out_aux_f32", "norm_out", "normk_out", "dyn_x", "dyn_w")]
+                                          "gamma_out", "resid_f32", "out_aux_f32", "norm_out", "normk_out", "gen_depth", "gen_w",
+                                          "gen_b", "dyn_x", "dyn_w")]
 
 
 class UnpackDesc(C.Structure):
@@ -76,6 +77,7 @@ def load() -> C.CDLL:
         "dasr_zero_insert2": [vp, vp, i32, i32, i32, i32, vp],
         "dasr_add": [vp, vp, vp, vp, i64, vp],
         "dasr_conv_stats_slots": [C.POINTER(ConvDesc)],
+        "dasr_conv_gen_ok": [i32, i32],
         "dasr_region_pool_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
         "dasr_unpack_grads": [C.POINTER(UnpackDesc), i32, vp],
         "dasr_sean_bwd_slots": [i32],
@@ -127,7 +129,7 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_gen_ok", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize", "dasr_unpack_grads",
             "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd_finalize", "dasr_sean_bwd2", "dasr_colsum",
@@ -200,14 +202,16 @@ def ptr(t: Optional[torch.Tensor], dtype=None) -> Optional[int]:
 def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, *, Cout: int, ks: int,
              epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
              resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None, kw: int = 0,
-             actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0, dyn_x=None, dyn_w=None, norm_out=None, normk_out=None) -> torch.Tensor:
-    """x: NHWC bf16 [B,H,W,Cin]."""
-    B, H, W, Cin = x.shape
+             actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0, dyn_x=None, dyn_w=None, norm_out=None, normk_out=None, gen_depth=None, gen_w=None, gen_b=None,
+             shape=None) -> torch.Tensor:
+    """x: NHWC bf16 [B,H,W,Cin] (or None with gen_depth / shape = (B,H,W,Cin): the kernel generates its A operand)."""
+    B, H, W, Cin = x.shape if x is not None else shape
     d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, kw, mask_slope, w_img_rows)
-    a = ConvArgs(ptr(x, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
+    a = ConvArgs(ptr(x, torch.bfloat16) if x is not None else None, ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
                  ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(actmask, torch.bfloat16),
                  ptr(gamma_out, torch.bfloat16), ptr(resid_f32, torch.float32), ptr(out_aux_f32, torch.float32),
                  ptr(norm_out, torch.float32), ptr(normk_out, torch.float32),
+                 ptr(gen_depth, torch.float32), ptr(gen_w, torch.float32), ptr(gen_b, torch.float32),
                  ptr(dyn_x, torch.bfloat16), ptr(dyn_w, torch.bfloat16))
     check(load().dasr_conv_fwd(C.byref(d), C.byref(a), stream_ptr()))
     return out

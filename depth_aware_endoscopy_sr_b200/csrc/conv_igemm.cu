@@ -89,6 +89,12 @@ struct ConvK {
     // ([B*Cout][taps*16]) accumulate the dynamic convolution gb_s straight into the same TMEM accumulators.
     int dyn;
     uint32_t a2_tx_bytes, b2_tx_bytes, a2_off;
+    // GEN kernels (SEAN epilogue, inference): the A operand actv = ReLU(conv3x3(depth, 1 -> Cin) + b) is GENERATED
+    // inside the kernel by a fourth warpgroup instead of being read from memory (normalization.py:37-40,61)
+    const float* gen_depth;        // [B,1,H,W] fp32
+    const float* gen_w;            // mlp_mask weight [Cin][9] fp32
+    const float* gen_b;            // mlp_mask bias [Cin] fp32
+    uint32_t gen_off;              // depth-halo scratch inside the dynamic shared memory
     int w_img_rows;                // > 0: per-image weights, image b uses rows [b*w_img_rows, +Cout) of the B matrix
 };
 
@@ -314,8 +320,11 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
 // EPI (the epilogue variant) is a template parameter: with a run-time switch the epilogue warps executed ~1500
 // instructions per 128x16 accumulator piece (ncu source view) and were ISSUE-bound, which also starved the MMA
 // issuer that shares a scheduler with them.
-template <int SWZ, int N_TILE, int NB, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+// GEN (SEAN epilogue only): 16 warps -- a fourth warpgroup computes the A operand (actv) of every tile straight into
+// the 128-byte-swizzled shared-memory stages the MMA reads (no actv tensor in HBM, no actv launch); registers are
+// redistributed between the warpgroups with setmaxnreg (roles 56, epilogue 168, generators 120 per thread).
+template <int SWZ, int N_TILE, int NB, int EPI, bool GEN>
+__global__ void __launch_bounds__(GEN ? 512 : kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const ConvK p) {
     constexpr int KC = SWZ / 2;          // channels per K chunk (one swizzle span per pixel row)
@@ -345,7 +354,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.SA; i++) {
-            mbar_init(&a_full[i], 1);
+            mbar_init(&a_full[i], GEN ? 64 : 1);       // GEN: the 64 generator threads of a channel chunk arrive
             mbar_init(&a_empty[i], 1);
         }
         for (int i = 0; i < p.SB; i++) {
@@ -374,7 +383,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // dependents may be scheduled as soon as every CTA of this grid got here (they block at the same point).
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    for (int i = threadIdx.x; i < p.n_bias; i += kThreads) bias_s[i] = __ldg(p.bias + i);
+    for (int i = threadIdx.x; i < p.n_bias; i += (GEN ? 512 : kThreads)) bias_s[i] = __ldg(p.bias + i);
     if (threadIdx.x < p.taps) {
         const int t = threadIdx.x / p.kw, u = threadIdx.x - t * p.kw;
         tap_lo_s[threadIdx.x] = (uint32_t)((t * p.Wp + u) * SWZ) >> 4;
@@ -383,9 +392,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-
     const int tiles_per_img = p.n_strips * p.tiles_per_strip * p.ntn;
 
+    // GEN: the register file is redistributed between the warpgroups at the top of each warpgroup-level branch
+    // (setmaxnreg applies to the code it dominates): roles 56, epilogue 168, generators 120 registers per thread
+    if (warp < 4) {
+    if (GEN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
     if (warp == 0) {
         // ===================================================== A producer: one halo box per K chunk
         // (elect.sync under a warp-uniform branch: ptxas then issues TMA/MMA straight from uniform registers;
@@ -402,7 +414,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int q0 = tps * (NB * 128);
                 const int r0 = q0 / p.Wp;
                 const int w0 = strip * p.Wt;
-                for (int c = 0; c < p.nch; c++) {
+                for (int c = 0; c < (GEN ? 0 : p.nch); c++) {
                     const int sa = a_it % p.SA;
                     const uint32_t ph = (a_it / p.SA) & 1;
                     PROF_LAP(1);
@@ -578,7 +590,87 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             PROF_LAP(3);
             PROF_FLUSH(0, 4);
         }
-    } else if (warp >= 4) {
+    }
+    } else if (GEN && warp >= 12) {
+        // ===================================================== A generator (warps 12..15): actv tiles in shared memory
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 120;\n");
+        // thread = (channel chunk c = stage, 16-byte piece g of the 128-byte pixel row, one of 8 row runs)
+        const int gt = threadIdx.x - 384;
+        const int c = gt >> 6;
+        const int g = gt & 7;
+        const int run = (gt & 63) >> 3;
+        float2 wr[9][4], br[4];
+        {
+            const int ch0 = c * 64 + g * 8;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                br[j] = make_float2(__ldg(p.gen_b + ch0 + 2 * j), __ldg(p.gen_b + ch0 + 2 * j + 1));
+#pragma unroll
+                for (int t = 0; t < 9; t++)
+                    wr[t][j] = make_float2(__ldg(p.gen_w + (ch0 + 2 * j) * 9 + t), __ldg(p.gen_w + (ch0 + 2 * j + 1) * 9 + t));
+            }
+        }
+        float* dsm = reinterpret_cast<float*>(smem + p.gen_off);      // (RB + 2) x (Wp + 2) depth halo, zero padded
+        const int DW = p.Wp + 2;
+        const int nrows = p.RB * p.Wp;
+        const int per_run = (nrows + 7) >> 3;
+        uint8_t* stage = a_smem + (size_t)c * p.a_stage_bytes;
+        uint32_t t_it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, t_it++) {
+            const int img = tile / tiles_per_img;
+            int r = tile - img * tiles_per_img;
+            const int strip = r / (p.tiles_per_strip * p.ntn);
+            r -= strip * (p.tiles_per_strip * p.ntn);
+            const int tps = r / p.ntn;
+            const int q0 = tps * (NB * 128);
+            const int y0 = q0 / p.Wp - p.pad_h;           // image row / column of patch position (0, 0)
+            const int x0 = strip * p.Wt - p.pad_w;
+            asm volatile("bar.sync 2, 128;\n" ::: "memory");          // the previous tile's readers are done
+            const float* dp = p.gen_depth + (size_t)img * p.H * p.W;
+            for (int i = gt; i < (p.RB + 2) * DW; i += 128) {
+                const int rr = i / DW, cc = i - rr * DW;
+                const int hh = y0 - 1 + rr, ww = x0 - 1 + cc;
+                dsm[i] = (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) ? __ldg(dp + (size_t)hh * p.W + ww) : 0.f;
+            }
+            asm volatile("bar.sync 2, 128;\n" ::: "memory");
+            mbar_wait(&a_empty[c], (t_it & 1) ^ 1);
+            const int pr0 = run * per_run, pr1 = min(nrows, pr0 + per_run);
+            // (two pixels per iteration -- 8 FMA chains -- measured slower: 155 vs 138 us; the generator is bound by the
+            // issue slots it shares with the epilogue warps, not by latency)
+            int pi = pr0 / p.Wp, pj = pr0 - pi * p.Wp;
+            for (int pr = pr0; pr < pr1; pr++) {
+                const int hh = y0 + pi, ww = x0 + pj;
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) {         // outside the image actv is ZERO (padding)
+                    const float* d0 = dsm + pi * DW + pj;               // window origin = (hh - 1, ww - 1)
+                    float2 acc[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[j] = br[j];
+#pragma unroll
+                    for (int t = 0; t < 3; t++)
+#pragma unroll
+                        for (int u = 0; u < 3; u++) {
+                            const float d = d0[t * DW + u];
+                            const float2 d2 = make_float2(d, d);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[j] = __ffma2_rn(d2, wr[t * 3 + u][j], acc[j]);
+                        }
+                    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) oh[j] = __floats2bfloat162_rn(fmaxf(acc[j].x, 0.f), fmaxf(acc[j].y, 0.f));
+                }
+                // 128-byte swizzle of the K-major operand: 16-byte piece index XOR (row & 7)
+                *reinterpret_cast<uint4*>(stage + (size_t)pr * 128 + ((g ^ (pr & 7)) << 4)) = o;
+                if (++pj == p.Wp) {
+                    pj = 0;
+                    pi++;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor-core reads
+            mbar_arrive(&a_full[c]);
+        }
+    } else if (warp >= 4 && warp < 12) {
+        if (GEN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
         // ===================================================== epilogue warps (8: 2 per TMEM lane quadrant)
         // warp w may only read TMEM lanes 32*(w%4)..+31; the two warps of a quadrant take the even / odd
         // 16-column chunks.  Operands that live in HBM (residual, y, gb_s) are requested BEFORE the TMEM load
@@ -821,10 +913,10 @@ static bool pdl_enabled() {
     return v != 0;
 }
 
-template <int SWZ, int N_TILE, int NB, int EPI>
+template <int SWZ, int N_TILE, int NB, int EPI, bool GEN = false>
 static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
                   const ConvK& k, size_t smem_bytes, cudaStream_t stream) {
-    auto fn = conv_halo_kernel<SWZ, N_TILE, NB, EPI>;
+    auto fn = conv_halo_kernel<SWZ, N_TILE, NB, EPI, GEN>;
     static bool configured[64] = {false};
     int dev = 0;
     DASR_CUDA_OK(cudaGetDevice(&dev));
@@ -836,7 +928,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMa
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(GEN ? 512 : kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -861,6 +953,10 @@ static int dispatch_n(int epi, int n_tile, const CUtensorMap& mA, const CUtensor
     DASR_CASE(DASR_EPI_STORE, 128);
     DASR_CASE(DASR_EPI_STATS, 32);
     DASR_CASE(DASR_EPI_STATS, 64);
+    if (epi == DASR_EPI_SEAN && n_tile == 128 && k.gen_depth) {
+        if (SWZ == 128) return launch<128, 128, NB, DASR_EPI_SEAN, true>(mA, mB, mA2, mB2, k, smem, s);
+        return fail(DASR_ERR_BAD_ARG, "the in-kernel actv generator needs Cin = 128");
+    }
     DASR_CASE(DASR_EPI_SEAN, 64);
     DASR_CASE(DASR_EPI_SEAN, 128);
     DASR_CASE(DASR_EPI_SHUFFLE2, 64);
@@ -890,6 +986,20 @@ extern "C" int dasr_prof_read(unsigned long long* host_out, int reset) {
 }
 #endif
 
+// 1 if the SEAN conv of this geometry can generate its A operand in-kernel (two A stages fit), else 0
+extern "C" int dasr_conv_gen_ok(int H, int W) {
+    const int NB = 2, max_wt = 128;
+    const int n_strips = (W + max_wt - 1) / max_wt;
+    const int Wt = (W + n_strips - 1) / n_strips;
+    const int Wp = Wt + 2;
+    const int RB = (Wp - 1 + NB * 128 + 2 * Wp + 2 + Wp - 1) / Wp;
+    const size_t a_stage = (((size_t)RB * Wp * 128) + 1023u) & ~(size_t)1023u;
+    const size_t a2 = (((size_t)RB * Wp * 32) + 1023u) & ~(size_t)1023u;
+    const size_t gen = (((size_t)(RB + 3) * (Wp + 2) * 4) + 1023u) & ~(size_t)1023u;
+    (void)H;
+    return (2 * a_stage + 2 * 16384 + a2 + gen <= 216 * 1024) ? 1 : 0;
+}
+
 extern "C" int dasr_conv_stats_slots(const dasr_conv_desc* d) {
     DASR_REQUIRE(d && d->W > 0 && d->H > 0 && (d->ks == 1 || d->ks == 3 || d->ks == 9), "bad descriptor");
     const int NB = 2, max_wt = 128;
@@ -908,7 +1018,12 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     DASR_REQUIRE(d->ks == 1 || d->ks == 3 || d->ks == 9, "ks must be 1, 3 or 9 (got %d)", d->ks);
     DASR_REQUIRE(d->Cin % 32 == 0 && d->Cin >= 32, "Cin must be a multiple of 32 (got %d)", d->Cin);
     DASR_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, "bad shape");
-    DASR_REQUIRE(a->x && a->w && a->bias && a->out, "null tensor pointer");
+    const bool gen = a->gen_depth != nullptr;
+    DASR_REQUIRE((a->x || gen) && a->w && a->bias && a->out, "null tensor pointer");
+    if (gen)
+        DASR_REQUIRE(a->gen_w && a->gen_b && d->epi == DASR_EPI_SEAN && d->Cin == 128 && d->Cout == 128 && d->ks == 3 && a->dyn_x,
+                     "the in-kernel actv generator needs gen_w / gen_b, the SEAN epilogue with the K-DYN extension and "
+                     "Cin = Cout = 128");
 
     ConvK k;
     memset(&k, 0, sizeof k);
@@ -975,6 +1090,14 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         a2_bytes = (k.a2_tx_bytes + 1023u) & ~(size_t)1023u;
         budget -= a2_bytes;
     }
+    size_t gen_bytes = 0;
+    if (gen) {
+        k.gen_depth = a->gen_depth;
+        k.gen_w = a->gen_w;
+        k.gen_b = a->gen_b;
+        gen_bytes = (((size_t)(k.RB + 3) * (k.Wp + 2) * sizeof(float)) + 1023u) & ~(size_t)1023u;   // + one row of slack
+        budget -= gen_bytes;
+    }
     const size_t all_b = (size_t)k.nch * k.taps * k.b_stage_bytes;
     k.SA = 2;
     if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
@@ -1000,7 +1123,10 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     }
     if (k.dyn) DASR_REQUIRE(!k.b_resident, "the K-DYN extension streams its weights (resident mode not supported)");
     k.a2_off = (uint32_t)((size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes);
-    const size_t smem_bytes = (size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes + a2_bytes + 1024;
+    k.gen_off = k.a2_off + (uint32_t)a2_bytes;
+    if (gen) DASR_REQUIRE(k.SA == 2 && k.nch == 2, "the in-kernel actv generator needs two A stages (one per channel chunk); "
+                          "use dasr_conv_gen_ok() to test a geometry");
+    const size_t smem_bytes = (size_t)k.SA * k.a_stage_bytes + (size_t)k.SB * k.b_stage_bytes + a2_bytes + gen_bytes + 1024;
 
     // outputs
     k.Ho = d->H; k.Wo = d->W;
@@ -1035,7 +1161,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
         uint32_t box[4] = {(uint32_t)KC, (uint32_t)k.Wp, (uint32_t)k.RB, 1};
-        int rc = encode_tmap_bf16(&mA, a->x, 4, dims, str, box, SWZ);
+        int rc = encode_tmap_bf16(&mA, gen ? a->out : a->x, 4, dims, str, box, SWZ);     // unused when generating
         if (rc) return rc;
     }
     {

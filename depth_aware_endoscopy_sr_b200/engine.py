@@ -48,6 +48,12 @@ class Engine:
         # error is set by the bf16 GEMM operands) and costs 5 % of the step (128 B of epilogue traffic per pixel and
         # block).  True: carry an fp32 copy next to the bf16 GEMM operand (SEAN epilogue resid_f32 / out_aux_f32).
         self.fp32_residual = False
+        # Option (inference): generate actv = ReLU(mlp_mask(depth)) inside the SEAN conv (GEN kernel: a fourth
+        # warpgroup writes the swizzled A stages, registers redistributed with setmaxnreg) instead of a separate
+        # kernel + a 67 MB tensor per SEAN instance.  Measured at B=64: 138 us against 92 + 34 us for the two-kernel
+        # form -- the generator competes with the epilogue warps for issue slots and sits on the MMA's critical
+        # path -- so it is OFF by default; it saves 3.5 GB of activation memory at B=64.
+        self.fuse_actv = os.environ.get("DASR_FUSE_ACTV", "0") == "1"
         self.use_graphs = os.environ.get("DASR_INFER_GRAPH", "1") != "0"   # replay inference from a CUDA graph (see infer)
         self.max_graphs = 3
         # larger batches are device-bound when issued kernel by kernel (B=64 at 64x64: 6.3 ms of kernels against 2.7 ms
@@ -375,25 +381,26 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------ helpers
     def _conv(self, x, name, *, epi=L.EPI_STORE, act=L.ACT_NONE, subsample=1, out=None, **kw):
+        """``x`` None: the kernel generates its A operand (``gen_depth`` / ``shape`` in kw)."""
         pk = self._packed[name]
-        B, H, W, _ = x.shape
+        B, H, W, cin = x.shape if x is not None else kw["shape"]
+        dev = x.device if x is not None else kw["gen_depth"].device
         if out is None:
             if epi == L.EPI_SHUFFLE2:
-                out = torch.empty(B, 2 * H, 2 * W, pk.cout // 4, device=x.device, dtype=BF16)
+                out = torch.empty(B, 2 * H, 2 * W, pk.cout // 4, device=dev, dtype=BF16)
             elif epi == L.EPI_SEAN:
-                out = torch.empty(B, H, W, pk.cout // 2, device=x.device, dtype=BF16)
+                out = torch.empty(B, H, W, pk.cout // 2, device=dev, dtype=BF16)
             elif subsample == 2:
-                out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=x.device, dtype=BF16)
+                out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=dev, dtype=BF16)
             else:
-                out = torch.empty(B, H, W, pk.cout, device=x.device, dtype=BF16)
+                out = torch.empty(B, H, W, pk.cout, device=dev, dtype=BF16)
         if self.profile is None:
             return L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act, subsample=subsample,
                               **kw)
-        cin = x.shape[3]
         flops = 2.0 * B * H * W * pk.cout * cin * pk.ks * pk.ks           # algorithmic (stride-1 grid)
         if subsample == 2:
             flops /= 4.0
-        nbytes = x.numel() * 2 + out.numel() * out.element_size() + pk.w.numel() * 2
+        nbytes = (x.numel() * 2 if x is not None else 0) + out.numel() * out.element_size() + pk.w.numel() * 2
         for t in (kw.get("resid"), kw.get("y"), kw.get("gb_s")):
             if t is not None:
                 nbytes += t.numel() * 2
@@ -452,19 +459,27 @@ class Engine:
         stats = torch.empty(2, B, nslots, nf, 2, device=x.device, dtype=torch.float32)
         cur = x
         out32 = torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32) if self.fp32_residual else None
+        # actv generated inside the SEAN conv (no actv tensor, no actv launch) when the geometry leaves room for it
+        gen = self.fuse_actv and nf == 64 and lib.dasr_conv_gen_ok(H, W) == 1
         for j, sean in ((1, blk.norm1), (2, blk.norm2)):
             n = "%s.norm%d" % (p, j)
             # conv + per-tile statistics; the double-InstanceNorm coefficients are finalised inside the SEAN conv
             y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats[j - 1])
-            actv = self._sean_actv(sean, depth)
             wdyn = tables[2][self._sean_index[n]]     # K-DYN runs inside the SEAN GEMM as a K extension
+            if gen:
+                actv = None
+                akw = dict(shape=(B, H, W, 2 * nf), gen_depth=depth, gen_w=sean.mlp_mask[0].weight,
+                           gen_b=sean.mlp_mask[0].bias)
+            else:
+                actv = self._sean_actv(sean, depth)
+                akw = {}
             if j == 1:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, stats=stats[0], dyn_x=mask16,
-                                 dyn_w=wdyn)
+                                 dyn_w=wdyn, **akw)
             else:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, stats=stats[1], dyn_x=mask16,
                                  dyn_w=wdyn, resid=x if x32 is None else None, resid_f32=x32,
-                                 out_aux_f32=out32)
+                                 out_aux_f32=out32, **akw)
         return cur, out32
 
     def _classic(self, p: str, x):

@@ -95,6 +95,11 @@ typedef struct {
     float* out_aux_f32;   /* DASR_EPI_SEAN: optional fp32 NHWC copy of the output                    */
     float* norm_out;      /* DASR_EPI_SEAN with fused finalize: optional [B][Cout/2][2] copy of (mean, scale) ...   */
     float* normk_out;     /* ... and [B][Cout/2] of k (see dasr_instats_finalize) for the backward pass            */
+    const float* gen_depth; /* DASR_EPI_SEAN + dyn_x, Cin = Cout = 128: generate the A operand inside the kernel instead of
+                               reading x:  x = ReLU(conv3x3(gen_depth [B,1,H,W] fp32, gen_w [Cin][9]) + gen_b [Cin])
+                               -- SEAN's mlp_mask (normalization.py:37-40,61); x may then be NULL (inference)        */
+    const float* gen_w;
+    const float* gen_b;
     const void* dyn_x;    /* DASR_EPI_SEAN: K-DYN folded into the GEMM (instead of gb_s): the depth-mask image NHWC
                              bf16 [B,H,W,16] (dasr_build_mask16) ...                                            */
     const void* dyn_w;    /* ... and the per-image dynamic filters bf16 [B*Cout][ks*ks*16] (dasr_table_to_dynweights):
@@ -105,6 +110,9 @@ int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream
 /* number of partial-statistics slots per image the DASR_EPI_STATS epilogue writes for this shape (> 0),
  * or a negative dasr_status                                                                         */
 int dasr_conv_stats_slots(const dasr_conv_desc* d);
+/* 1 if a 3x3, 128 -> 128 DASR_EPI_SEAN convolution over HxW frames can generate its A operand in-kernel (gen_depth):
+ * it needs two A stages in shared memory, which wide strips do not leave room for                              */
+int dasr_conv_gen_ok(int H, int W);
 
 /* Weight gradient of a stride-1 "same" convolution with a kh x kw kernel (autograd of the nn.Conv2d call sites
  * above; reference codes/models/F_model_depthCond.py:191):

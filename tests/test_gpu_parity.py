@@ -144,6 +144,23 @@ def test_cuda_graph_replay_matches_kernel_by_kernel_schedule():
         assert torch.equal(shifted, eng._infer_eager(*a)) and not torch.equal(shifted, eager_a)
 
 
+def test_in_kernel_actv_generator_option():
+    """Engine.fuse_actv: the SEAN conv generates its A operand (actv) in-kernel; same result as the two-kernel form
+    up to bf16 rounding of identical arithmetic (it IS the same arithmetic: bit-equal)."""
+    z, meta = load_golden("x8_b2_32_init")
+    sd, (lq, depth, masks, gt) = case_tensors(meta)
+    net = _build(meta, sd)
+    outs = {}
+    for flag in (False, True):
+        net.engine().fuse_actv = flag
+        with torch.no_grad():
+            outs[flag] = net.engine()._infer_eager(lq.cuda(), depth.cuda(), masks.cuda())
+    st = meta["stride"]
+    err = np.abs(outs[True].cpu().numpy()[:, :, ::st, ::st] - z["sr"]).max()
+    assert err <= TOL_PIX
+    assert torch.equal(outs[True], outs[False])
+
+
 def test_fp32_residual_stream_option():
     """Engine.fp32_residual carries an fp32 copy of the trunk's residual stream; both settings meet the tolerance."""
     z, meta = load_golden("x8_b1_64_init")
