@@ -317,6 +317,62 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
     }
 }
 
+// STATS epilogue of one tile for one thread: store y = acc + bias (bf16) and accumulate, per column, the sum and the
+// sum of squares of the STORED values over this warp's 32 rows of BOTH M blocks in registers; one butterfly reduction
+// per 16-column chunk and tile (v1 reduced every M block separately: twice the shuffles on the critical epilogue).
+template <int N_TILE, int NB>
+__device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, const float* bias_t, float* red_s, int img,
+                                               int q0, int w0, int nt, int m, int half, int ew, int lane) {
+    if (half * 16 >= N_TILE) return;
+    bool valid[NB];
+    size_t pix[NB];
+#pragma unroll
+    for (int blk = 0; blk < NB; blk++) {
+        const int q = q0 + blk * 128 + m;
+        const int h = (int)__umulhi((unsigned)q, p.wp_magic);
+        const int wl = q - h * p.Wp;
+        const int w = w0 + wl;
+        valid[blk] = (h < p.H) && (wl < p.Wt) && (w < p.W);
+        pix[blk] = ((size_t)img * p.H + h) * p.W + w;
+    }
+#pragma unroll 1
+    for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
+        float s1[16], s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) s1[j] = s2[j] = 0.f;
+#pragma unroll
+        for (int blk = 0; blk < NB; blk++) {
+            uint32_t v[16];
+            tmem_ld16(t_acc + blk * N_TILE + c0, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_t[c0 + j];
+            // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
+            const uint4 o0 = pack8(f), o1 = pack8(f + 8);
+            if (valid[blk]) {
+                if (!DBG(p, 2)) stg256(p.out + pix[blk] * p.Cout + nt * N_TILE + c0, o0, o1);
+                unpack8(o0, f);
+                unpack8(o1, f + 8);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    s1[j] += f[j];
+                    s2[j] = fmaf(f[j], f[j], s2[j]);
+                }
+            }
+        }
+        warp_colsum16(s1, lane);
+        warp_colsum16(s2, lane);
+        if (!(lane & 1)) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            // per-tile partials of this warp's row quadrant: (ew, column) has exactly one owner lane -> deterministic
+            float* rp2 = red_s + (ew * N_TILE + c0 + col) * 2;
+            rp2[0] = s1[0];
+            rp2[1] = s2[0];
+        }
+    }
+}
+
 // EPI (the epilogue variant) is a template parameter: with a run-time switch the epilogue warps executed ~1500
 // instructions per 128x16 accumulator piece (ncu source view) and were ISSUE-bound, which also starved the MMA
 // issuer that shares a scheduler with them.
@@ -752,8 +808,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 acc_it++;
                 continue;
             }
+            if (EPI == DASR_EPI_STATS)
+                stats_epilogue<N_TILE, NB>(p, t_acc, bias_t, norm_s, img, q0, w0, nt, m, half, ew, lane);
 #pragma unroll 1
-            for (int blk = 0; blk < NB; blk++) {
+            for (int blk = 0; blk < (EPI == DASR_EPI_STATS ? 0 : NB); blk++) {
                 const int q = q0 + blk * 128 + m;
                 const int h = (int)__umulhi((unsigned)q, p.wp_magic);     // q / Wp (exact for q < 2^32 / Wp)
                 const int wl = q - h * p.Wp;
@@ -761,7 +819,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 bool valid = (h < p.H) && (wl < p.Wt) && (w < p.W);
                 const uint32_t t_blk = t_acc + blk * N_TILE;
 
-                if (EPI == DASR_EPI_STORE || EPI == DASR_EPI_STATS) {
+                if (EPI == DASR_EPI_STORE) {      // (EPI_STATS has its own function, stats_epilogue)
                     int ho = h, wo = w;
                     if (p.subsample == 2) {
                         valid = valid && !(h & 1) && !(w & 1);
@@ -783,7 +841,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_t[c0 + j];
-                        if (EPI == DASR_EPI_STORE) {
+                        {
                             if (rp) {
                                 float rr[16];
                                 unpack8(r0, rr);
@@ -801,35 +859,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 for (int j = 0; j < 16; j++) f[j] *= (mm[j] > 0.f ? 1.f : p.mask_slope);
                             }
                             if (valid && !DBG(p, 2)) store16(op + c0, f);
-                        } else {
-                            // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
-                            uint4 o0 = pack8(f), o1 = pack8(f + 8);
-                            if (valid && !DBG(p, 2)) stg256(op + c0, o0, o1);
-                            float s1[16], s2[16];
-                            unpack8(o0, s1);
-                            unpack8(o1, s1 + 8);
-#pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                const float x = valid ? s1[j] : 0.f;
-                                s1[j] = x;
-                                s2[j] = x * x;
-                            }
-                            warp_colsum16(s1, lane);
-                            warp_colsum16(s2, lane);
-                            if (!(lane & 1)) {
-                                const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 +
-                                                ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                                // per-tile partials of this warp's row quadrant in shared memory: (ew, column) has
-                                // exactly one owner lane, the M blocks are added in order -> deterministic
-                                float* rp2 = norm_s + (ew * N_TILE + c0 + col) * 2;
-                                if (blk == 0) {
-                                    rp2[0] = s1[0];
-                                    rp2[1] = s2[0];
-                                } else {
-                                    rp2[0] += s1[0];
-                                    rp2[1] += s2[0];
-                                }
-                            }
                         }
                     }
                 } else if (EPI == DASR_EPI_SHUFFLE2) {
