@@ -41,6 +41,11 @@ struct WgK {
     uint32_t a_blk_bytes, b_blk_bytes, stage_bytes, a_lbo, b_lbo;
     uint32_t a_tx, b_tx;                // bytes one TMA box really transfers (blocks are padded to 1 KB)
     int stages;
+    // stacked taps (Cin fits ONE smem block): the column blocks of the B operand of one MMA are the SAME X block
+    // viewed stack_lbo bytes further down each (the next horizontal / vertical tap), so stack_g taps are one MMA of
+    // N = stack_g * Nc instead of stack_g MMAs of N = Nc (tools/umma_probe.cu test 7)
+    int stack_g;
+    uint32_t stack_lbo;
     float* dw;
     int ldw;
     // per-image mode (K-DYN backward): grid.x = B * ksplit_i, every CTA reduces over the pixels of ONE image and
@@ -49,7 +54,14 @@ struct WgK {
     int per_image, ksplit_i, n_valid;
     long long dw_img_stride;
     const int* skip_flag;               // optional device int: the whole kernel is a no-op when *skip_flag != 0
+    int dbg;                            // -DDASR_PROFILE ablation knob (env DASR_WG_DBG): 1 no flush, 2 no MMA, 4 no TMA
 };
+
+#ifdef DASR_PROFILE
+#define WG_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define WG_DBG(p, bit) 0
+#endif
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX, const WgK p) {
@@ -113,6 +125,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                 const int rt = r / p.n_strips, strip = r - rt * p.n_strips;
                 const int s = it % p.stages;
                 mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
+                if (WG_DBG(p, 4)) {
+                    mbar_arrive(&full[s]);
+                    continue;
+                }
                 mbar_expect_tx(&full[s], p.a_blocks * p.a_tx + p.b_blocks * p.b_tx);
                 uint8_t* sa = smem + (size_t)s * p.stage_bytes;
                 uint8_t* sb = sa + a_bytes_stage;
@@ -126,11 +142,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
     } else if (warp == 1) {
         if (elect_one()) {
             // MN-major operands: idesc bits 15 (A) and 16 (B); descriptor = addr>>4 | LBO>>4 <<16 | SBO>>4 <<32 | ...
-            const uint32_t idesc = make_idesc_bf16(p.Mb, p.Nc) | (1u << 15) | (1u << 16);
+            const uint32_t mn_major = (1u << 15) | (1u << 16);
+            const int g = p.stack_g;                              // taps per MMA
+            const int g_last = ntaps - ((ntaps - 1) / g) * g;     // taps of the last group of the slice
+            const uint32_t idesc_full = make_idesc_bf16(p.Mb, g * p.Nc) | mn_major;
+            const uint32_t idesc_last = make_idesc_bf16(p.Mb, g_last * p.Nc) | mn_major;
             const uint32_t hi_a = ((8u * p.swz_a) >> 4) | (1u << 14) | ((p.swz_a == 128 ? 2u : 4u) << 29);
             const uint32_t hi_b = ((8u * p.swz_b) >> 4) | (1u << 14) | ((p.swz_b == 128 ? 2u : 4u) << 29);
             const uint32_t lo_a_flags = ((p.a_lbo >> 4) & 0x3FFFu) << 16;
-            const uint32_t lo_b_flags = ((p.b_lbo >> 4) & 0x3FFFu) << 16;
+            const uint32_t lo_b_flags = (((g > 1 ? p.stack_lbo : p.b_lbo) >> 4) & 0x3FFFu) << 16;
             const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
             const int ksteps = p.Wt >> 4;
             const uint32_t a_kstep = (16u * p.swz_a) >> 4, b_kstep = (16u * p.swz_b) >> 4;
@@ -142,14 +162,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                 const uint32_t sa_lo = smem_lo + ((uint32_t)s * p.stage_bytes >> 4);
                 const uint32_t sb_lo = sa_lo + (a_bytes_stage >> 4);
 #pragma unroll 1
-                for (int r = 0; r < p.TR; r++) {
+                for (int r = 0; r < (WG_DBG(p, 2) ? 0 : p.TR); r++) {
                     const uint32_t a_row = sa_lo + (((uint32_t)(r * p.Wt) * p.swz_a) >> 4);
 #pragma unroll 1
-                    for (int tp = 0; tp < ntaps; tp++) {
+                    for (int tp = 0; tp < ntaps; tp += g) {
                         const int tap = tap0 + tp;
                         const int t = tap / p.kw, u = tap - t * p.kw;
                         const uint32_t b_row = sb_lo + (((uint32_t)((r + t - t_first) * p.Wp + u) * p.swz_b) >> 4);
                         const uint32_t d = tmem_base + tp * p.Nc;
+                        const uint32_t idesc = (tp + g >= ntaps) ? idesc_last : idesc_full;
                         const uint32_t acc0 = (it | r) != 0;
 #pragma unroll 4
                         for (int ks = 0; ks < ksteps; ks++) {
@@ -174,7 +195,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
         }
     } else if (warp >= 4) {
         // ===================================================== flush: TMEM -> red.global.add.f32
-        if (n_my > 0) {
+        if (n_my > 0 && !WG_DBG(p, 1)) {
             mbar_wait(&acc_full, 0);
             tc_fence_after();
             const int ew = warp & 3;
@@ -277,8 +298,27 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     }
     DASR_REQUIRE(k.taps_per_slice >= 1, "slice does not fit TMEM");
     if (d->kw > 1) DASR_REQUIRE(k.taps_per_slice == d->kw, "kernel row does not fit one TMEM slice (kw %d, Cin chunk %d)", d->kw, k.Nc);
+    // stacked taps: one MMA covers a whole kernel row (or up to 256 / Nc vertical taps) when X is one smem block
+    k.stack_g = 1;
+    k.stack_lbo = 0;
+    {
+        const char* e = getenv("DASR_WG_STACK");
+        const bool allow = !(e && e[0] == '0');
+        if (allow && k.b_blocks == 1) {
+            if (d->kw > 1 && d->kw * k.Nc <= 256) {
+                k.stack_g = d->kw;
+                k.stack_lbo = (uint32_t)k.swz_b;                     // next pixel of the patch row
+                // the whole kernel in one CTA when its columns fit TMEM: dY and X are read once instead of kh times
+                if (d->kh * d->kw * k.Nc <= 512) k.taps_per_slice = d->kh * d->kw;
+            } else if (d->kw == 1 && k.taps_per_slice > 1) {
+                k.stack_g = 256 / k.Nc < k.taps_per_slice ? 256 / k.Nc : k.taps_per_slice;
+                // stack_lbo = Wp * swz_b, set below once the strip width is known
+            }
+        }
+    }
     k.n_tapgroups = (d->kh * d->kw + k.taps_per_slice - 1) / k.taps_per_slice;
-    const int dt = (d->kw > 1) ? 0 : (k.taps_per_slice - 1);   // extra patch rows spanned by one slice
+    // extra patch rows spanned by one slice
+    const int dt = (d->kw > 1) ? (k.taps_per_slice / d->kw - 1) : (k.taps_per_slice - 1);
 
     // K tiles
     const int max_wt = 128;
@@ -287,6 +327,10 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     k.n_strips = (d->W + k.Wt - 1) / k.Wt;
     k.Wp = k.Wt + d->kw - 1;
     DASR_REQUIRE(k.Wp <= 256, "strip too wide");
+    if (d->kw == 1 && k.stack_g > 1) {
+        k.stack_lbo = (uint32_t)k.Wp * k.swz_b;                      // next row of the patch
+        if ((k.stack_lbo >> 4) > 0x3FFFu) k.stack_g = 1;
+    }
     const size_t budget = 200 * 1024;
     int TR = 8;
     for (;; TR >>= 1) {
@@ -322,6 +366,9 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     if (ksplit < 1) ksplit = 1;
     if (ksplit > k.ktiles_total) ksplit = k.ktiles_total;
     k.skip_flag = o.skip_flag;
+#ifdef DASR_PROFILE
+    if (const char* e = getenv("DASR_WG_DBG")) k.dbg = atoi(e);
+#endif
     if (o.per_image) {
         const int tiles_per_img = k.n_rowtiles * k.n_strips;
         int ks_i = num_sms() / (slices * d->B);

@@ -149,7 +149,10 @@ __global__ void probe_tma4d(const __grid_constant__ CUtensorMap map, int c0, int
 template <int SWZ>
 __global__ void __launch_bounds__(128, 1)
 probe_mnmajor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int R, int M, int N,
-              int shift, float* D) {
+              int shift, float* D, int stack = 0) {
+    // stack > 0 ("stacked taps"): X has only CB channels (ONE smem block); the N/CB column blocks of the B operand
+    // are the same block viewed `stack` rows further down each: LBO = stack * SWZ bytes.
+    //   D[m][g*CB + c] = sum_r dY[r][m] * X[r + shift + g*stack][c]
     constexpr int CB = SWZ / 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -172,9 +175,10 @@ probe_mnmajor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t tmem = tmem_base_s;
     if (warp == 1) {
         if (elect_one()) {
-            mbar_expect_tx(&bar_full, (M / CB) * blkA + (N / CB) * blkB);
+            const int nbB = stack ? 1 : N / CB;
+            mbar_expect_tx(&bar_full, (M / CB) * blkA + nbB * blkB);
             for (int j = 0; j < M / CB; j++) tma_load_2d(sA + j * blkA, &mapA, &bar_full, j * CB, 0);
-            for (int j = 0; j < N / CB; j++) tma_load_2d(sB + j * blkB, &mapB, &bar_full, j * CB, 0);
+            for (int j = 0; j < nbB; j++) tma_load_2d(sB + j * blkB, &mapB, &bar_full, j * CB, 0);
             if (!mbar_wait_bounded(&bar_full, 0)) { D[0] = -12345.f; }
             tc_fence_after();
             // instruction descriptor: bf16 x bf16 -> f32, A and B MN-major (bits 15, 16)
@@ -185,7 +189,8 @@ probe_mnmajor(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 const uint32_t a_addr = smem_u32(sA) + k0 * SWZ;
                 const uint32_t b_addr = smem_u32(sB) + (k0 + shift) * SWZ;
                 const uint64_t da = uint64_t((a_addr & 0x3FFFFu) >> 4) | (uint64_t(blkA >> 4) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-                const uint64_t db = uint64_t((b_addr & 0x3FFFFu) >> 4) | (uint64_t(blkB >> 4) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+                const uint32_t lbo_b = stack ? (uint32_t)stack * SWZ : blkB;
+                const uint64_t db = uint64_t((b_addr & 0x3FFFFu) >> 4) | (uint64_t(lbo_b >> 4) << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
                 umma_bf16(tmem, da, db, idesc, k0 > 0);
             }
             umma_commit(&bar_mma);
@@ -291,11 +296,12 @@ static int run_gemm(int N, int r, int bo_mode, const char* tag, bool dump) {
 }
 
 template <int SWZ>
-static void run_mnmajor(int R, int M, int N, int shift) {
+static void run_mnmajor(int R, int M, int N, int shift, int stack = 0) {
     const int CB = SWZ / 2;
+    const int Nx = stack ? CB : N;      // channels X really has
     const int RB = R + 80;
     auto hA = rand_bf16((size_t)R * M, 5 + shift);
-    auto hB = rand_bf16((size_t)RB * N, 9 + N);
+    auto hB = rand_bf16((size_t)RB * Nx, 9 + N);
     __nv_bfloat16 *dA, *dB;
     float* dD;
     CK(cudaMalloc(&dA, hA.size() * 2));
@@ -306,14 +312,14 @@ static void run_mnmajor(int R, int M, int N, int shift) {
     CK(cudaMemset(dD, 0xFF, 128 * N * 4));
     uint64_t dimsA[2] = {(uint64_t)M, (uint64_t)R}, strA[1] = {(uint64_t)M * 2};
     uint32_t boxA[2] = {(uint32_t)CB, (uint32_t)R};
-    uint64_t dimsB[2] = {(uint64_t)N, (uint64_t)RB}, strB[1] = {(uint64_t)N * 2};
+    uint64_t dimsB[2] = {(uint64_t)Nx, (uint64_t)RB}, strB[1] = {(uint64_t)Nx * 2};
     uint32_t boxB[2] = {(uint32_t)CB, (uint32_t)RB};
     CUtensorMapSwizzle sw = SWZ == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap mA = make_map(dA, 2, dimsA, strA, boxA, nullptr, sw);
     CUtensorMap mB = make_map(dB, 2, dimsB, strB, boxB, nullptr, sw);
     size_t smem = (size_t)(M / CB) * R * SWZ + (size_t)(N / CB) * RB * SWZ + 4096;
     CK(cudaFuncSetAttribute(probe_mnmajor<SWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    probe_mnmajor<SWZ><<<1, 128, smem>>>(mA, mB, R, M, N, shift, dD);
+    probe_mnmajor<SWZ><<<1, 128, smem>>>(mA, mB, R, M, N, shift, dD, stack);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         printf("mnmajor SWZ=%d M=%d N=%d shift=%d : CUDA ERROR %s\n", SWZ, M, N, shift, cudaGetErrorString(e));
@@ -329,13 +335,17 @@ static void run_mnmajor(int R, int M, int N, int shift) {
             const int lane = hyp == 0 ? m : hyp == 1 ? (m / 16) * 32 + (m % 16) : m * 2;
             for (int n = 0; n < N; n++) {
                 float ref = 0;
-                for (int r = 0; r < R; r++) ref += bf2f(hA[(size_t)r * M + m]) * bf2f(hB[(size_t)(r + shift) * N + n]);
+                if (stack) {
+                    const int g = n / CB, c = n % CB;
+                    for (int r = 0; r < R; r++) ref += bf2f(hA[(size_t)r * M + m]) * bf2f(hB[(size_t)(r + shift + g * stack) * Nx + c]);
+                } else
+                    for (int r = 0; r < R; r++) ref += bf2f(hA[(size_t)r * M + m]) * bf2f(hB[(size_t)(r + shift) * N + n]);
                 float d = fabsf(ref - hD[lane * N + n]);
                 if (!(d <= 1e-3f)) bad++;
                 if (d > maxerr) maxerr = d;
             }
         }
-        printf("mnmajor SWZ=%d R=%d M=%d N=%d shift=%d lane-hyp=%d : %s (bad=%d/%d maxerr=%g)\n", SWZ, R, M, N, shift, hyp,
+        printf("mnmajor SWZ=%d R=%d M=%d N=%d shift=%d stack=%d lane-hyp=%d : %s (bad=%d/%d maxerr=%g)\n", SWZ, R, M, N, shift, stack, hyp,
                bad ? "FAIL" : "PASS", bad, M * N, maxerr);
         if (!bad) break;
     }
@@ -440,6 +450,15 @@ int main(int argc, char** argv) {
         for (int shift : {0, 1, 5, 66}) run_mnmajor<64>(64, 128, 32, shift);
         run_mnmajor<64>(64, 32, 32, 3);
         run_mnmajor<64>(64, 64, 128, 1);
+    } else if (test == 7) {
+        // stacked taps: the N blocks of B are ONE X block at row offsets g*stack (LBO = stack rows)
+        for (int shift : {0, 1, 66}) run_mnmajor<64>(64, 128, 96, shift, 1);      // 3 horizontal taps x 32 ch
+        run_mnmajor<64>(64, 64, 96, 2, 1);
+        run_mnmajor<64>(32, 64, 160, 0, 10);                                      // 5 vertical taps, Wp = 10
+        run_mnmajor<64>(32, 64, 128, 3, 13);
+        for (int shift : {0, 1, 67}) run_mnmajor<128>(64, 64, 192, shift, 1);     // 3 horizontal taps x 64 ch
+        run_mnmajor<128>(64, 128, 192, 5, 1);
+        run_mnmajor<128>(32, 128, 128, 5, 7);
     }
     return 0;
 }
