@@ -82,8 +82,7 @@ def load() -> C.CDLL:
         "dasr_unpack_grads": [C.POINTER(UnpackDesc), i32, vp],
         "dasr_sean_bwd_slots": [i32],
         "dasr_sean_bwd1": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
-        "dasr_sean_bwd_finalize": [vp, vp, vp, vp, i32, i32, i32, vp],
-        "dasr_sean_bwd2": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "dasr_sean_bwd2": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_colsum": [vp, vp, i64, i32, vp],
         "dasr_dynconv_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_table_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
@@ -132,7 +131,7 @@ def load() -> C.CDLL:
 EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_gen_ok", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize", "dasr_unpack_grads",
-            "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd_finalize", "dasr_sean_bwd2", "dasr_colsum",
+            "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd2", "dasr_colsum",
             "dasr_dynconv_bwd", "dasr_table_bwd", "dasr_style_mix_bwd", "dasr_region_pool_bwd", "dasr_actv_bwd",
             "dasr_unshuffle_actgrad", "dasr_out9_bwd_prep", "dasr_nchw3_to_nhwc32", "dasr_actgrad",
             "dasr_zero_insert2_to", "dasr_loss_rows", "dasr_loss_fwd", "dasr_loss_finalize", "dasr_loss_bwd",

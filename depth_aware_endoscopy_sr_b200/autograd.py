@@ -11,7 +11,7 @@ returns one gradient per parameter (``None`` for parameters the reference never 
                        LeakyReLU mask and the residual accumulation fused into the epilogue
     weight gradients   dasr_conv_wgrad (tcgen05, MN-major operands) into one flat fp32 buffer in the packed
                        layout, then dasr_unpack_grads (weight-norm backward, SEAN alpha blend, index maps)
-    SEAN / IN          dasr_sean_bwd1 / _finalize / _bwd2;   K-DYN  dasr_dynconv_bwd + dasr_table_bwd +
+    SEAN / IN          dasr_sean_bwd1 / _bwd2;   K-DYN  dasr_dynconv_bwd + dasr_table_bwd +
                        dasr_style_mix_bwd;   pooling  dasr_region_pool_bwd;   mlp_mask  dasr_actv_bwd
     tail               dasr_unshuffle_actgrad (PixelShuffle + LeakyReLU), dasr_out9_bwd_prep (clamp + im2row)
 
@@ -202,18 +202,17 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         dgb = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
         dn = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
         dskip = torch.empty(B, H, W, nf, device=dev, dtype=BF16) if resid is not None else None
-        part = torch.empty(B, slots, nf, 2, device=dev, dtype=torch.float32)
+        part = torch.empty(B, slots, nf, 4, device=dev, dtype=torch.float32)
         L.check(lib.dasr_sean_bwd1(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(norm), L.ptr(gamma), L.ptr(dgb), L.ptr(dn),
                                    L.ptr(dskip), L.ptr(part), B, HW, nf, s))
         if resid is not None:
             tp.accum(resid, dskip)
-        coef = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
-        L.check(lib.dasr_sean_bwd_finalize(L.ptr(part), L.ptr(norm), L.ptr(normk), L.ptr(coef), B, nf, HW, s))
         dy = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
-        L.check(lib.dasr_sean_bwd2(L.ptr(dn), L.ptr(y), L.ptr(norm), L.ptr(coef), L.ptr(dy), B, HW, nf, s))
+        # pass 2 also adds the [gamma_o; beta_o] bias gradient (column sums of dgb, accumulated by pass 1)
+        L.check(lib.dasr_sean_bwd2(L.ptr(dn), L.ptr(y), L.ptr(norm), L.ptr(normk), L.ptr(part), L.ptr(dy),
+                                   L.ptr(eng._db_view(n + ".gb_o")), B, HW, nf, s))
         # ---- gamma_o / beta_o convolution and mlp_mask
         tp.wgrad(dgb, actv, n + ".gb_o")
-        tp.bias_grad(dgb, n + ".gb_o")
         pkd = eng._packed[n + ".gb_o.dg"]
         dA = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
         L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)

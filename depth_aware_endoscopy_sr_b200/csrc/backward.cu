@@ -2,7 +2,7 @@
 // total_loss.backward() at codes/models/F_model_depthCond.py:191).  All activations NHWC bf16, all
 // reductions fp32 with a fixed summation order per block (cross-block sums use fp32 atomics where noted).
 //
-//   sean_bwd1 / sean_bwd_finalize / sean_bwd2   SEAN modulate + double InstanceNorm backward
+//   sean_bwd1 / sean_bwd2   SEAN modulate + double InstanceNorm backward (+ [gamma_o; beta_o] bias gradient)
 //                                               (normalization.py:56,87-89; sftmd_arch.py:813,820,828,832-833)
 //   colsum            bias gradients (sum over pixels of a gradient tensor)
 //   dynconv_bwd       K-DYN backward: per-image table gradient dT (normalization.py:81-85 restated)
@@ -49,14 +49,15 @@ __global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict_
     constexpr int LANES = 256 / G;
     const int b = blockIdx.y, slot = blockIdx.x;
     const int g = threadIdx.x % G, pl = threadIdx.x / G;
-    float mean[8], scale[8], s1[8], t2[8];
+    float mean[8], scale[8], acc[4][8];          // acc: sum dn, sum dn*n, sum dz*n (dgamma), sum dz (dbeta)
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         mean[j] = __ldg(norm + ((size_t)b * NF + g * 8 + j) * 2);
         scale[j] = __ldg(norm + ((size_t)b * NF + g * 8 + j) * 2 + 1);
-        s1[j] = t2[j] = 0.f;
+        acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = 0.f;
     }
     const int p0 = slot * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+#pragma unroll 2
     for (int pix = p0 + pl; pix < p1; pix += LANES) {
         const size_t i = ((size_t)b * HW + pix) * G + g;
         float d[8], a[8], yv[8], gm[8], dg[8], dnv[8];
@@ -71,8 +72,10 @@ __global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict_
             d[j] = dz;
             dg[j] = dz * n;
             dnv[j] = dz * (1.f + gm[j]);
-            s1[j] += dnv[j];
-            t2[j] += dnv[j] * n;
+            acc[0][j] += dnv[j];
+            acc[1][j] += dnv[j] * n;
+            acc[2][j] += dg[j];
+            acc[3][j] += dz;
         }
         const size_t o = ((size_t)b * HW + pix) * (2 * G);
         dgb[o + g] = bpack8(dg);
@@ -80,59 +83,80 @@ __global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict_
         dn_out[i] = bpack8(dnv);
         if (dskip) dskip[i] = bpack8(d);
     }
-    __shared__ float red[2][LANES][NF + 1];
+    // lanes of a warp that share g (stride G) first, then the 8 warps through shared memory
+    __shared__ float red[4][8][NF];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        red[0][pl][g * 8 + j] = s1[j];
-        red[1][pl][g * 8 + j] = t2[j];
+    for (int w = 0; w < 4; w++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            float v = acc[w][j];
+#pragma unroll
+            for (int off = G; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            acc[w][j] = v;
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < G) {
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) red[w][warp][g * 8 + j] = acc[w][j];
     }
     __syncthreads();
-    if (threadIdx.x < 2 * NF) {
+    if (threadIdx.x < 4 * NF) {
         const int which = threadIdx.x / NF, c = threadIdx.x - which * NF;
-        float s = 0.f;
-        for (int l = 0; l < LANES; l++) s += red[which][l][c];
-        part[(((size_t)b * nslots + slot) * NF + c) * 2 + which] = s;
+        float sum = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; l++) sum += red[which][l][c];
+        part[(((size_t)b * nslots + slot) * NF + c) * 4 + which] = sum;
     }
 }
 
-// coef[b][c] = (c1, c2):  dy = scale * (dn - c1) + c2 * n,  c1 = S1 / N,  c2 = -k * T2 / (N * scale)
-// with k = 1/a + eps/(a^2 r), a = var + eps, r = var/a + eps   (norm[b][c] = (mean, scale); normk[b][c] = k)
-__global__ void sean_bwd_finalize_kernel(const float* __restrict__ part, const float* __restrict__ norm,
-                                         const float* __restrict__ normk, float* __restrict__ coef, int n, int C,
-                                         int nslots, float inv_hw) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int b = i / C, c = i - b * C;
-    const float2* sp = reinterpret_cast<const float2*>(part) + (size_t)b * nslots * C + c;
-    float s1 = 0.f, t2 = 0.f;
-    for (int s = 0; s < nslots; s++) {
-        const float2 v = __ldg(sp + (size_t)s * C);
-        s1 += v.x;
-        t2 += v.y;
-    }
-    const float scale = norm[2 * i + 1], k = normk[i];
-    coef[2 * i] = s1 * inv_hw;
-    coef[2 * i + 1] = -k * t2 * inv_hw / scale;
-}
-
+// pass 2.  Prologue (per CTA, from the partial sums of pass 1):
+//   coef[c] = (c1, c2):  dy = scale * (dn - c1) + c2 * n,  c1 = S1 / N,  c2 = -k * T2 / (N * scale)
+// with k = 1/a + eps/(a^2 r), a = var + eps, r = var/a + eps   (norm[b][c] = (mean, scale); normk[b][c] = k);
+// the first CTA of every image also adds the image's share of the [gamma_o; beta_o] bias gradient to dbias.
 template <int G>
 __global__ void __launch_bounds__(256) sean_bwd2_kernel(const uint4* __restrict__ dn, const uint4* __restrict__ y,
-                                                        const float* __restrict__ norm, const float* __restrict__ coef,
-                                                        uint4* __restrict__ dy, int HW, int pix_per_block) {
+                                                        const float* __restrict__ norm, const float* __restrict__ normk,
+                                                        const float* __restrict__ part, uint4* __restrict__ dy,
+                                                        float* __restrict__ dbias, int HW, int pix_per_block,
+                                                        int nslots) {
     constexpr int NF = G * 8;
     constexpr int LANES = 256 / G;
     const int b = blockIdx.y;
     const int g = threadIdx.x % G, pl = threadIdx.x / G;
+    __shared__ float sums[2][NF];
+    if (threadIdx.x < 4 * NF) {
+        const int which = threadIdx.x / NF, c = threadIdx.x - which * NF;
+        if (which < 2 || (dbias && blockIdx.x == 0)) {
+            const float* sp = part + ((size_t)b * nslots * NF + c) * 4 + which;
+            float s0 = 0.f, s1 = 0.f;
+            int sl = 0;
+            for (; sl + 1 < nslots; sl += 2) {
+                s0 += __ldg(sp + (size_t)sl * NF * 4);
+                s1 += __ldg(sp + (size_t)(sl + 1) * NF * 4);
+            }
+            if (sl < nslots) s0 += __ldg(sp + (size_t)sl * NF * 4);
+            if (which < 2)
+                sums[which][c] = s0 + s1;
+            else
+                atomicAdd(dbias + (which - 2) * NF + c, s0 + s1);
+        }
+    }
+    __syncthreads();
+    const float inv_hw = 1.f / (float)HW;
     float mean[8], scale[8], c1[8], c2[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const size_t k = (size_t)b * NF + g * 8 + j;
+        const int c = g * 8 + j;
+        const size_t k = (size_t)b * NF + c;
         mean[j] = __ldg(norm + k * 2);
         scale[j] = __ldg(norm + k * 2 + 1);
-        c1[j] = __ldg(coef + k * 2);
-        c2[j] = __ldg(coef + k * 2 + 1);
+        c1[j] = sums[0][c] * inv_hw;
+        c2[j] = -__ldg(normk + k) * sums[1][c] * inv_hw / scale[j];
     }
     const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+#pragma unroll 2
     for (int pix = p0 + pl; pix < p1; pix += LANES) {
         const size_t i = ((size_t)b * HW + pix) * G + g;
         float d[8], yv[8];
@@ -569,16 +593,15 @@ static inline int grid_for(size_t n, int block, int cap = 148 * 16) {
 
 using namespace dasr;
 
-extern "C" int dasr_sean_bwd_slots(int HW) {
-    // pixels per block chosen so that an image gives ~16 blocks (>= 256 pixels each)
-    int ppb = (HW + 15) / 16;
-    if (ppb < 256) ppb = 256;
-    return (HW + ppb - 1) / ppb;
-}
 static int sean_ppb(int HW) {
-    int ppb = (HW + 15) / 16;
-    if (ppb < 256) ppb = 256;
+    // pixels per block: ~32 blocks per image, at least 128 pixels each (a 64x64 image at B = 16 gives 512 CTAs)
+    int ppb = (HW + 31) / 32;
+    if (ppb < 128) ppb = 128;
     return ppb;
+}
+extern "C" int dasr_sean_bwd_slots(int HW) {
+    const int ppb = sean_ppb(HW);
+    return (HW + ppb - 1) / ppb;
 }
 
 extern "C" int dasr_sean_bwd1(const void* dout, const void* act_out, const void* y, const float* norm, const void* gamma,
@@ -595,25 +618,16 @@ extern "C" int dasr_sean_bwd1(const void* dout, const void* act_out, const void*
     return DASR_OK;
 }
 
-extern "C" int dasr_sean_bwd_finalize(const float* part, const float* norm, const float* normk, float* coef, int B,
-                                      int nf, int HW, void* stream) {
-    DASR_REQUIRE(part && norm && normk && coef, "null pointer");
-    const int n = B * nf, slots = dasr_sean_bwd_slots(HW);
-    sean_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(part, norm, normk, coef, n, nf, slots, 1.f / (float)HW);
-    DASR_LAUNCH_OK();
-    return DASR_OK;
-}
-
-extern "C" int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, const float* coef, void* dy, int B,
-                              int HW, int nf, void* stream) {
-    DASR_REQUIRE(dn && y && norm && coef && dy, "null pointer");
+extern "C" int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, const float* normk, const float* part,
+                              void* dy, float* dbias, int B, int HW, int nf, void* stream) {
+    DASR_REQUIRE(dn && y && norm && normk && part && dy, "null pointer");
     DASR_REQUIRE(nf == 64 || nf == 32, "nf must be 32 or 64 (got %d)", nf);
     const int ppb = sean_ppb(HW), slots = (HW + ppb - 1) / ppb;
     dim3 grid(slots, B);
     if (nf == 64)
-        sean_bwd2_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, coef, (uint4*)dy, HW, ppb);
+        sean_bwd2_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, normk, part, (uint4*)dy, dbias, HW, ppb, slots);
     else
-        sean_bwd2_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, coef, (uint4*)dy, HW, ppb);
+        sean_bwd2_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, normk, part, (uint4*)dy, dbias, HW, ppb, slots);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

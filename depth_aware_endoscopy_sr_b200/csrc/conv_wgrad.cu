@@ -54,6 +54,7 @@ struct WgK {
     int per_image, ksplit_i, n_valid;
     long long dw_img_stride;
     const int* skip_flag;               // optional device int: the whole kernel is a no-op when *skip_flag != 0
+    int col_first, col_count;           // flush window inside every tap's Nc columns (default: all of them)
     int dbg;                            // -DDASR_PROFILE ablation knob (env DASR_WG_DBG): 1 no flush, 2 no MMA, 4 no TMA
 };
 
@@ -217,6 +218,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                 float* dst_img = p.dw + (size_t)my_img * p.dw_img_stride + (size_t)(tap0 + tp) * p.Cout + o;
                 const int ncols = p.per_image ? min(p.Nc, p.n_valid - cb0) : p.Nc;
                 for (int c0 = 0; c0 < ncols; c0 += 16) {
+                    if (c0 + 16 <= p.col_first || c0 >= p.col_first + p.col_count) continue;
                     uint32_t v[16];
                     tmem_ld16(t_row + tp * p.Nc + c0, v);
                     tmem_ld_wait();
@@ -232,6 +234,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                             // scalar red was its own L2 request (7.2 M per launch, 80 % of the kernel time)
 #pragma unroll
                             for (int j = 0; j < 16; j += 4)
+                                if (c0 + j >= p.col_first && c0 + j < p.col_first + p.col_count)
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j),
                                              "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
                                              "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
@@ -254,6 +257,7 @@ using namespace dasr;
 
 struct WgOpts {
     int per_image = 0, n_valid = 0;
+    int col_first = 0, col_count = 0;       // flush window (multiples of 4); 0 / 0 = every column
     long long dw_img_stride = 0;
     const int* skip_flag = nullptr;
 };
@@ -366,6 +370,9 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     if (ksplit < 1) ksplit = 1;
     if (ksplit > k.ktiles_total) ksplit = k.ktiles_total;
     k.skip_flag = o.skip_flag;
+    k.col_first = o.col_count ? o.col_first : 0;
+    k.col_count = o.col_count ? o.col_count : k.Nc;
+    DASR_REQUIRE(k.col_first % 4 == 0 && k.col_count % 4 == 0, "flush window must be a multiple of 4 columns");
 #ifdef DASR_PROFILE
     if (const char* e = getenv("DASR_WG_DBG")) k.dbg = atoi(e);
 #endif
@@ -470,7 +477,14 @@ extern "C" int dasr_actv_bwd_tc(const void* dA, const void* aux, float* scratch,
     DASR_REQUIRE(dA && aux && scratch && dW && db, "null pointer");
     dasr_wgrad_desc d;
     d.B = B; d.H = H; d.W = W; d.Cout = C; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.reserved = 0;
-    int rc = wgrad_launch(&d, dA, aux, scratch, WgOpts(), stream);
+    // only the depth (hi, lo, lo2) and the constant-one channel are read back: flush those four columns per tap
+    static_assert(DASR_AUX_DEPTH_HI % 4 == 0 && DASR_AUX_DEPTH_LO2 == DASR_AUX_DEPTH_HI + 3 &&
+                      DASR_AUX_ONE > DASR_AUX_DEPTH_HI && DASR_AUX_ONE < DASR_AUX_DEPTH_LO2,
+                  "the four auxiliary channels of the mlp_mask gradient must share one 16-byte group");
+    WgOpts o;
+    o.col_first = DASR_AUX_DEPTH_HI;
+    o.col_count = 4;
+    int rc = wgrad_launch(&d, dA, aux, scratch, o, stream);
     if (rc) return rc;
     actv_bwd_gather_kernel<<<(C * 9 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, dW, db, C);
     DASR_LAUNCH_OK();

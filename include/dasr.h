@@ -192,16 +192,16 @@ int dasr_unpack_grads(const dasr_unpack_desc* descs, int n, void* stream);
  * Backward, memory-bound kernels (backward.cu)
  * ------------------------------------------------------------------------------------------------ */
 /* SEAN modulate + double-InstanceNorm backward (normalization.py:56,87-89; sftmd_arch.py:813,820,828,832-833).
- * pass 1: dz = dout * [act_out > 0]; n = (y-mean)*scale; dgb = [dz*n | dz]; dn = dz*(1+gamma);
- *         part[b][slot][c] = (sum dn, sum dn*n); dskip = dz (optional).  All NHWC bf16 [B,HW,nf] but dgb [B,HW,2nf].
- * finalize: coef[b][c] = (S1/N, -k*T2/(N*scale)).   pass 2: dy = scale*(dn - c1) + c2*n.                  */
+ * pass 1: dz = dout * [act_out > 0]; n = (y-mean)*scale; dgb = [dz*n | dz]; dn = dz*(1+gamma); dskip = dz (optional);
+ *         part[b][slot][c] = (sum dn, sum dn*n, sum dz*n, sum dz) over the slot's pixels, fp32 [B][slots][nf][4].
+ *         All tensors NHWC bf16 [B,HW,nf] but dgb [B,HW,2nf].
+ * pass 2: coef = (S1/N, -k*T2/(N*scale)) from part (per CTA); dy = scale*(dn - c1) + c2*n; dbias (optional, fp32
+ *         [2nf]) += the bias gradient of the [gamma_o; beta_o] convolution (sum over b, p of dgb).              */
 int dasr_sean_bwd_slots(int HW);
 int dasr_sean_bwd1(const void* dout, const void* act_out, const void* y, const float* norm, const void* gamma,
                    void* dgb, void* dn, void* dskip, float* part, int B, int HW, int nf, void* stream);
-int dasr_sean_bwd_finalize(const float* part, const float* norm, const float* normk, float* coef, int B, int nf,
-                           int HW, void* stream);
-int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, const float* coef, void* dy, int B, int HW,
-                   int nf, void* stream);
+int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, const float* normk, const float* part, void* dy,
+                   float* dbias, int B, int HW, int nf, void* stream);
 /* out[c] += sum over rows of x[row][c] (x bf16 [rows][C]) -- bias gradients                               */
 int dasr_colsum(const void* x, float* out, int64_t rows, int C, void* stream);
 /* K-DYN backward: dT[b][k][tap][c] += sum_p dgb[b,p,c] * mask[b,k,p+tap-1] (labels fast path like the forward) */
@@ -318,7 +318,7 @@ int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf
  * norm [B][C][2] = (mean, (v+eps)^-1/2 (v/(v+eps)+eps)^-1/2)                                          */
 int dasr_instats_finalize(const float* stats, float* norm, float* normk, int B, int C, int HW, int nslots,
                           void* stream);
-/* normk [B][C] (optional, NULL): k = 1/a + eps/(a^2 r) with a = v+eps, r = v/a+eps, used by dasr_sean_bwd_finalize */
+/* normk [B][C] (optional, NULL): k = 1/a + eps/(a^2 r) with a = v+eps, r = v/a+eps, used by dasr_sean_bwd2 */
 
 /* ------------------------------------------------------------------------------------------------
  * Training step behind the generator (train.cu)

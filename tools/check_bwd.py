@@ -84,7 +84,7 @@ if __name__ == "__main__":
 
 
 def sean_bwd_case(B=2, H=16, W=16, nf=64):
-    """sean_bwd1 / finalize / bwd2 against autograd of IN(IN(y)) * (1 + gamma) + beta -> relu."""
+    """sean_bwd1 / bwd2 against autograd of IN(IN(y)) * (1 + gamma) + beta -> relu."""
     lib = L.load()
     s = L.stream_ptr()
     HW = H * W
@@ -114,14 +114,16 @@ def sean_bwd_case(B=2, H=16, W=16, nf=64):
     dgb = torch.empty(B, H, W, 2 * nf, device=dev, dtype=torch.bfloat16)
     dn = torch.empty(B, H, W, nf, device=dev, dtype=torch.bfloat16)
     dskip = torch.empty(B, H, W, nf, device=dev, dtype=torch.bfloat16)
-    part = torch.empty(B, slots, nf, 2, device=dev)
+    part = torch.empty(B, slots, nf, 4, device=dev)
     L.check(lib.dasr_sean_bwd1(L.ptr(dout), L.ptr(act_out), L.ptr(y), L.ptr(norm), L.ptr(gamma), L.ptr(dgb), L.ptr(dn),
                                L.ptr(dskip), L.ptr(part), B, HW, nf, s))
-    coef = torch.empty(B, nf, 2, device=dev)
-    L.check(lib.dasr_sean_bwd_finalize(L.ptr(part), L.ptr(norm), L.ptr(normk), L.ptr(coef), B, nf, HW, s))
     dy = torch.empty(B, H, W, nf, device=dev, dtype=torch.bfloat16)
-    L.check(lib.dasr_sean_bwd2(L.ptr(dn), L.ptr(y), L.ptr(norm), L.ptr(coef), L.ptr(dy), B, HW, nf, s))
+    dbias = torch.zeros(2 * nf, device=dev)
+    L.check(lib.dasr_sean_bwd2(L.ptr(dn), L.ptr(y), L.ptr(norm), L.ptr(normk), L.ptr(part), L.ptr(dy), L.ptr(dbias), B,
+                               HW, nf, s))
     torch.cuda.synchronize()
+    report("sean_bwd dbias gamma", dbias[:nf], gr.grad.sum(dim=(0, 1, 2)), 1e-2)
+    report("sean_bwd dbias beta", dbias[nf:], br.grad.sum(dim=(0, 1, 2)), 1e-2)
     report("sean_bwd dgamma nf%d %dx%d" % (nf, H, W), dgb[..., :nf], gr.grad, 1e-2)
     report("sean_bwd dbeta", dgb[..., nf:], br.grad, 1e-2)
     report("sean_bwd dskip", dskip, br.grad, 1e-2)
