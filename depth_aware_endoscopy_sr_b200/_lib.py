@@ -97,7 +97,7 @@ def load() -> C.CDLL:
         "dasr_actgrad": [vp, vp, vp, i64, C.c_float, vp],
         "dasr_zero_insert2_to": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
         "dasr_mask_labels": [vp, vp, vp, i32, i32, i32, i32, vp],
-        "dasr_actv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_actv_fwd": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_style_mix": [vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_dynconv_fwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_instats_finalize": [vp, vp, vp, i32, i32, i32, i32, vp],

@@ -180,7 +180,7 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     y = eng._conv(x, conv_name, epi=L.EPI_STATS, stats=stats)      # coefficients are finalised inside the SEAN conv
     actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
     L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B,
-                              H, W, nf2, s))
+                              H, W, nf2, 0, s))
     gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
     if first:
         out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, stats=stats, norm_out=norm, normk_out=normk,

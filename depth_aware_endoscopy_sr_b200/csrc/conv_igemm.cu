@@ -379,8 +379,16 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
 // GEN (SEAN epilogue only): 16 warps -- a fourth warpgroup computes the A operand (actv) of every tile straight into
 // the 128-byte-swizzled shared-memory stages the MMA reads (no actv tensor in HBM, no actv launch); registers are
 // redistributed between the warpgroups with setmaxnreg (roles 56, epilogue 168, generators 120 per thread).
+// LEAN (SEAN epilogue without the generator): the kernel is compiled for 128 registers per thread (launch bound of
+// 512 threads, launched with 384) and setmaxnreg moves them to where they are needed (roles 40, epilogue 168), so
+// that 16 K registers of the SM stay free: the actv kernel of the NEXT SEAN instance (side stream, 256 threads x 64
+// registers) can then be resident next to this kernel instead of waiting for it (Engine._ActvPrefetch).
+#ifndef DASR_LEAN_ROLE_REGS
+#define DASR_LEAN_ROLE_REGS 40
+#define DASR_LEAN_EPI_REGS 168
+#endif
 template <int SWZ, int N_TILE, int NB, int EPI, bool GEN>
-__global__ void __launch_bounds__(GEN ? 512 : kThreads, 1)
+__global__ void __launch_bounds__(GEN || EPI == DASR_EPI_SEAN ? 512 : kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const ConvK p) {
     constexpr int KC = SWZ / 2;          // channels per K chunk (one swizzle span per pixel row)
@@ -454,6 +462,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // (setmaxnreg applies to the code it dominates): roles 56, epilogue 168, generators 120 registers per thread
     if (warp < 4) {
     if (GEN) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+    else if (EPI == DASR_EPI_SEAN) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(DASR_LEAN_ROLE_REGS));
     if (warp == 0) {
         // ===================================================== A producer: one halo box per K chunk
         // (elect.sync under a warp-uniform branch: ptxas then issues TMA/MMA straight from uniform registers;
@@ -727,6 +736,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else if (warp >= 4 && warp < 12) {
         if (GEN) asm volatile("setmaxnreg.inc.sync.aligned.u32 168;\n");
+        else if (EPI == DASR_EPI_SEAN) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(DASR_LEAN_EPI_REGS));
         // ===================================================== epilogue warps (8: 2 per TMEM lane quadrant)
         // warp w may only read TMEM lanes 32*(w%4)..+31; the two warps of a quadrant take the even / odd
         // 16-column chunks.  Operands that live in HBM (residual, y, gb_s) are requested BEFORE the TMEM load

@@ -9,6 +9,7 @@
 //   dynconv         K-DYN: depth-guided dynamic 3x3 convolution, apply step      (normalization.py:81-85 restated)
 //   instats_finalize double InstanceNorm closed form                             (sftmd_arch.py:813 + normalization.py:56)
 #include "dasr_internal.h"
+#include <stdlib.h>
 #include <string.h>
 
 namespace dasr {
@@ -235,8 +236,11 @@ __global__ void build_aux_kernel(const uint8_t* __restrict__ labels, const float
 // independent FMA chains).  v1: 242 instructions per (pixel, 8 channels), 64 us; v2 (8 channels per lane, 125
 // registers, 16 warps/SM): 33 us; v3 (4 channels per lane, 2 pixels in flight): see profiles/.
 constexpr int kActvRows = 2;
-template <int C>
-__global__ void __launch_bounds__(256) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
+// MINB = resident blocks per SM the register budget is compiled for: 3 (<= 85 registers) when the kernel has the
+// device to itself; 4 (64 registers) for the "background" launches of Engine._ActvPrefetch, which run ONE block per
+// SM next to a convolution kernel that leaves 16 K registers free (conv_igemm.cu, LEAN)
+template <int C, int MINB>
+__global__ void __launch_bounds__(256, MINB) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
                                                    const float* __restrict__ bias, uint2* __restrict__ out, int H,
                                                    int W, int n_items) {
     constexpr int LPP = C / 4;                     // lanes per pixel
@@ -647,32 +651,40 @@ extern "C" int dasr_build_aux(const uint8_t* labels, const float* depth, void* a
     return DASR_OK;
 }
 
+template <int C, int MINB>
+static int actv_launch(const float* depth, const float* w, const float* bias, void* out, int H, int W, int n_items,
+                       size_t smem, int ctas_per_sm, cudaStream_t stream) {
+    // persistent grid = the blocks that are resident at once (asked from the occupancy calculator), or fewer
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int nb = 0;
+        DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<C, MINB>, 256, smem));
+        per_sm = nb > 0 ? nb : 1;
+    }
+    const int ctas = (ctas_per_sm > 0 && ctas_per_sm < per_sm) ? ctas_per_sm : per_sm;
+    const int cap = ctas * num_sms();
+    const int grid = n_items < cap ? n_items : cap;
+    actv_kernel<C, MINB><<<grid, 256, smem, stream>>>(depth, w, bias, (uint2*)out, H, W, n_items);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
 extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bias, void* out, int B, int H, int W,
-                             int C, void* stream) {
+                             int C, int ctas_per_sm, void* stream) {
     DASR_REQUIRE(depth && w && bias && out && C % 8 == 0, "bad arguments");
     DASR_REQUIRE(C == 128 || C == 64, "actv: C (= 2*nf) must be 64 or 128 (got %d)", C);
     DASR_REQUIRE((size_t)H * W < 0x7fffffffull, "frame too large");
+    DASR_REQUIRE(ctas_per_sm >= 0, "ctas_per_sm must be >= 0 (0 = as many as fit)");
     const int bands = (H + kActvRows - 1) / kActvRows;
     const size_t smem = (size_t)(kActvRows + 2) * (W + 4) * sizeof(float);
     DASR_REQUIRE(smem <= 48 * 1024, "actv: frame too wide (%d)", W);
     const int n_items = B * bands;
-    // persistent grid = exactly the blocks that are resident at once (asked from the occupancy calculator)
-    static int per_sm[2] = {0, 0};
-    const int vi = (C == 128) ? 0 : 1;
-    if (per_sm[vi] == 0) {
-        int nb = 0;
-        if (C == 128) DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<128>, 256, smem));
-        else DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<64>, 256, smem));
-        per_sm[vi] = nb > 0 ? nb : 1;
-    }
-    const int cap = per_sm[vi] * num_sms();
-    const int grid = n_items < cap ? n_items : cap;
-    if (C == 128)
-        actv_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint2*)out, H, W, n_items);
-    else
-        actv_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(depth, w, bias, (uint2*)out, H, W, n_items);
-    DASR_LAUNCH_OK();
-    return DASR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctas_per_sm == 1)
+        return C == 128 ? actv_launch<128, 4>(depth, w, bias, out, H, W, n_items, smem, 1, st)
+                        : actv_launch<64, 4>(depth, w, bias, out, H, W, n_items, smem, 1, st);
+    return C == 128 ? actv_launch<128, 3>(depth, w, bias, out, H, W, n_items, smem, ctas_per_sm, st)
+                    : actv_launch<64, 3>(depth, w, bias, out, H, W, n_items, smem, ctas_per_sm, st);
 }
 
 extern "C" int dasr_style_mix(const float* depth_vec, const float* A, const float* a, void* stp, int B, int K, int L,

@@ -6,7 +6,7 @@
 
 namespace dasr {
 
-constexpr int kPackBatch = 28;
+constexpr int kPackBatch = 320;      // descriptors per launch: the 32 KB kernel-parameter space of CUDA 12.1+ (sm_70+)
 
 struct PackBatch {
     dasr_pack_desc d[kPackBatch];
@@ -135,7 +135,7 @@ __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ 
 //   w_eff[a] = f * (g[a] / ||v[a]||) * v[a]      (f = alpha | 1 - alpha | 1; g absent for plain convs)
 // i.e. weight-norm backward (sftmd_arch.py:740,851 -> torch._weight_norm backward) and the SEAN blend
 // (normalization.py:87-88).  One block per (descriptor, dim0 index a).
-constexpr int kUnpackBatch = 16;
+constexpr int kUnpackBatch = 224;
 struct UnpackBatch {
     dasr_unpack_desc d[kUnpackBatch];
     int n;

@@ -54,6 +54,10 @@ class Engine:
         # form -- the generator competes with the epilogue warps for issue slots and sits on the MMA's critical
         # path -- so it is OFF by default; it saves 3.5 GB of activation memory at B=64.
         self.fuse_actv = os.environ.get("DASR_FUSE_ACTV", "0") == "1"
+        # actv of the next SEAN instances is produced on a low-priority side stream while the trunk convolutions run
+        # (it depends on the depth map only); three rotating buffers.  DASR_ACTV_OVERLAP=0 keeps one stream.
+        self.actv_overlap = os.environ.get("DASR_ACTV_OVERLAP", "1") == "1"
+        self._side_streams = {}
         self.use_graphs = os.environ.get("DASR_INFER_GRAPH", "1") != "0"   # replay inference from a CUDA graph (see infer)
         self.max_graphs = 3
         # larger batches are device-bound when issued kernel by kernel (B=64 at 64x64: 6.3 ms of kernels against 2.7 ms
@@ -436,19 +440,65 @@ class Engine:
                     lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, s)))
         return stp_all, table_all, wdyn_all
 
-    def _sean_actv(self, sean, depth):
+    def _sean_actv(self, sean, depth, out=None, ctas_per_sm=0):
         """actv = ReLU(mlp_mask(depth)) of one SEAN instance (normalization.py:37-40,61)."""
         lib = L.load()
         B, _, H, W = depth.shape
         nf2 = 2 * sean.norm_nc
         s = L.stream_ptr()
-        actv = torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
+        actv = out if out is not None else torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
         self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
                     lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight),
-                                                      L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2, s)))
+                                                      L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2,
+                                                      ctas_per_sm, s)))
         return actv
 
-    def _dgb(self, p: str, blk, x, x32, depth, mask16, tables):
+    class _ActvPrefetch:
+        """Produces actv of the SEAN instances, in network order, on a side stream ``ahead`` instances in front of the
+        main stream.  take() makes the main stream wait for the next instance and returns its buffer; done() (after
+        the SEAN conv that reads it was launched) hands the buffer back for instance k + ahead."""
+
+        def __init__(self, eng, seans, depth, nf2, ahead=3):
+            dev = depth.device
+            self.eng, self.seans, self.depth = eng, seans, depth
+            st = eng._side_streams.get(dev.index)
+            if st is None:
+                st = eng._side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=0)
+            self.side = st
+            self.main = torch.cuda.current_stream(dev)
+            B, _, H, W = depth.shape
+            self.bufs = [torch.empty(B, H, W, nf2, device=dev, dtype=BF16) for _ in range(min(ahead, len(seans)))]
+            self.ready = [None] * len(seans)
+            self.k = 0
+            fork = torch.cuda.Event()
+            fork.record(self.main)
+            self.side.wait_event(fork)
+            for i in range(len(self.bufs)):
+                self._issue(i)
+
+        def _issue(self, i):
+            with torch.cuda.stream(self.side):
+                # one block per SM: it fits beside the convolution kernels and never keeps their blocks waiting
+                self.eng._sean_actv(self.seans[i], self.depth, out=self.bufs[i % len(self.bufs)], ctas_per_sm=1)
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            self.ready[i] = ev
+
+        def take(self):
+            self.main.wait_event(self.ready[self.k])
+            return self.bufs[self.k % len(self.bufs)]
+
+        def done(self):
+            k = self.k
+            self.k += 1
+            nxt = k + len(self.bufs)
+            if nxt < len(self.seans):
+                free = torch.cuda.Event()
+                free.record(self.main)
+                self.side.wait_event(free)
+                self._issue(nxt)
+
+    def _dgb(self, p: str, blk, x, x32, depth, mask16, tables, prefetch=None):
         """Depth_Residual_Block_Mask.forward (sftmd_arch.py:826-834).  ``x`` is the bf16 copy of the block input
         (GEMM operand), ``x32`` its fp32 residual stream (None for the first block: the bf16 tensor is exact).
         Returns (bf16 output, fp32 output)."""
@@ -470,6 +520,9 @@ class Engine:
                 actv = None
                 akw = dict(shape=(B, H, W, 2 * nf), gen_depth=depth, gen_w=sean.mlp_mask[0].weight,
                            gen_b=sean.mlp_mask[0].bias)
+            elif prefetch is not None:
+                actv = prefetch.take()
+                akw = {}
             else:
                 actv = self._sean_actv(sean, depth)
                 akw = {}
@@ -480,6 +533,8 @@ class Engine:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, stats=stats[1], dyn_x=mask16,
                                  dyn_w=wdyn, resid=x if x32 is None else None, resid_f32=x32,
                                  out_aux_f32=out32, **akw)
+            if prefetch is not None and not gen:
+                prefetch.done()
         return cur, out32
 
     def _classic(self, p: str, x):
@@ -585,12 +640,20 @@ class Engine:
         x, x32 = fea_bef, None      # x32: fp32 residual stream of the trunk (bf16 copies feed the GEMMs)
         order = net.block_order()
 
+        prefetch = None
+        if self.actv_overlap and self.profile is None and cap is None and not self.fuse_actv:
+            seans = [sn for i, _pos in order if i in net.which_ResBlk_depth
+                     for sn in (net.block(i).norm1, net.block(i).norm2)]
+            if seans:
+                prefetch = Engine._ActvPrefetch(self, seans, depth, 2 * seans[0].norm_nc)
+
         def run_block(i, x, x32):
             if i in net.which_ResBlk_depth:
                 if x.shape[1] != h or x.shape[2] != w:
                     raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
                                               "%d at x%d) are not implemented yet" % (i, net.scale))
-                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, mask16, tables)
+                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, mask16, tables,
+                                 prefetch=prefetch)
             return self._classic("classic-residual%d" % (i + 1), x), None
 
         for i, pos in order:

@@ -279,9 +279,11 @@ int dasr_mask_labels(const float* masks, uint8_t* labels, int32_t* flag_not_oneh
                      int W, void* stream);
 
 /* SEAN depth branch first layer (normalization.py:37-40,61): actv = ReLU(conv3x3(depth, 1->C) + b),
- * depth NCHW fp32 [B,1,H,W], w fp32 [C][9], out NHWC bf16 [B,H,W,C]                                  */
+ * depth NCHW fp32 [B,1,H,W], w fp32 [C][9], out NHWC bf16 [B,H,W,C].  ctas_per_sm: 0 = a persistent grid that
+ * fills the device; 1 = one block per SM, compiled for 64 registers, meant to run on a side stream NEXT TO a
+ * convolution kernel (the SEAN convolution leaves 16 K registers and ~5 KB of shared memory per SM free)   */
 int dasr_actv_fwd(const float* depth, const float* w, const float* bias, void* out, int B, int H, int W,
-                  int C, void* stream);
+                  int C, int ctas_per_sm, void* stream);
 
 /* SEAN label mixing (normalization.py:27,80): stp[b][j][:] = sum_i A[j][i] depth_vec[b][i][:] + a[j]
  * depth_vec fp32 [B,K,L] -> stp bf16 [B*K][L].  The style table (normalization.py:81-85 restated,

@@ -23,7 +23,7 @@ def t(fn, n=20):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-fa = lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(w), L.ptr(b), L.ptr(actv), B, H, W, nf2, s))
+fa = lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(w), L.ptr(b), L.ptr(actv), B, H, W, nf2, 0, s))
 fd = lambda: L.check(lib.dasr_dynconv_fwd(L.ptr(table), L.ptr(labels), L.ptr(masks), L.ptr(flag), L.ptr(gbs), B, K, H, W, nf2, s))
 mb = actv.numel() * 2 / 1e6
 ua, ud = t(fa), t(fd)
