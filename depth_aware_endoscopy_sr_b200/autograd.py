@@ -160,7 +160,7 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
 
 
 def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, tables,
-                mask16, dT_all, scr_all, *, first: bool, resid: Optional[_T]) -> _T:
+                mask16, dT_all, scr_all, *, first: bool, resid: Optional[_T], actv_pre=None) -> _T:
     """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
     eng, lib, s = tp.eng, tp.lib, tp.s
     x = cur.data
@@ -178,9 +178,12 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     norm = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
     normk = torch.empty(B, nf, device=dev, dtype=torch.float32)
     y = eng._conv(x, conv_name, epi=L.EPI_STATS, stats=stats)      # coefficients are finalised inside the SEAN conv
-    actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
-    L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B,
-                              H, W, nf2, 0, s))
+    if actv_pre is not None:
+        actv = actv_pre          # produced on the side stream (the caller made this stream wait for it)
+    else:
+        actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+        L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias),
+                                  L.ptr(actv), B, H, W, nf2, 0, s))
     gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
     if first:
         out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, stats=stats, norm_out=norm, normk_out=normk,
@@ -310,16 +313,45 @@ def _forward_train(eng, lq, depth, masks):
     fea_bef = _conv_train(tp, h1, "head.2", act="lrelu")
     order = net.block_order()
 
+    # actv of every SEAN instance depends on the depth map only (and is kept for the backward pass): all of them are
+    # produced on the engine's side stream, one block per SM, beside the convolutions of the main stream
+    # (Engine._ActvPrefetch is the inference counterpart with rotating buffers)
+    actv_pre = {}
+    if eng.actv_overlap and not net.isBaseline:
+        dgb_blocks = [i for i, _pos in order if i in net.which_ResBlk_depth]
+        side = eng._side_streams.get(dev.index)
+        if side is None:
+            side = eng._side_streams[dev.index] = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        for i in dgb_blocks:
+            blk = net.block(i)
+            nf2 = 2 * blk.norm1.norm_nc
+            pair = [torch.empty(B, h, w, nf2, device=dev, dtype=BF16) for _ in range(2)]
+            with torch.cuda.stream(side):
+                for sean, buf in zip((blk.norm1, blk.norm2), pair):
+                    L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias),
+                                              L.ptr(buf), B, h, w, nf2, 1, side.cuda_stream))
+                ev = torch.cuda.Event()
+                ev.record(side)
+            actv_pre[i] = (pair, ev)
+
     def run_block(i, x):
         if i in net.which_ResBlk_depth:
             if x.data.shape[1] != h or x.data.shape[2] != w:
                 raise NotImplementedError("depth-guided blocks above LR resolution are not implemented")
             p = "depth-residual%d" % (i + 1)
             blk = net.block(i)
+            pre = (None, None)
+            if i in actv_pre:
+                pre, ev = actv_pre.pop(i)
+                torch.cuda.current_stream(dev).wait_event(ev)
             a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec, aux,
-                            tables, mask16, dT_all, scr_all, first=True, resid=None)
+                            tables, mask16, dT_all, scr_all, first=True, resid=None, actv_pre=pre[0])
             return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec, aux,
-                               tables, mask16, dT_all, scr_all, first=False, resid=x)
+                               tables, mask16, dT_all, scr_all, first=False, resid=x, actv_pre=pre[1])
         p = "classic-residual%d" % (i + 1)
         f = _conv_train(tp, x, p + ".block.0", act="relu")
         # relu(x + conv(f)): the residual add is the conv epilogue; its backward = lazy ReLU mask, then both paths

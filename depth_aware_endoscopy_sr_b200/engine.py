@@ -454,45 +454,49 @@ class Engine:
         return actv
 
     class _ActvPrefetch:
-        """Produces actv of the SEAN instances, in network order, on a side stream ``ahead`` instances in front of the
-        main stream.  take() makes the main stream wait for the next instance and returns its buffer; done() (after
-        the SEAN conv that reads it was launched) hands the buffer back for instance k + ahead."""
+        """Produces actv of the SEAN instances, in network order, on a side stream, one depth-guided block (two
+        instances) at a time and ``ahead`` blocks in front of the main stream.  take() makes the main stream wait for
+        the next block's pair and returns its two buffers; done() (after the block's kernels were launched) hands the
+        buffers back for block k + ahead.  One cross-stream wait and one record per BLOCK: the four convolutions of a
+        block stay an unbroken programmatic-dependent-launch chain."""
 
-        def __init__(self, eng, seans, depth, nf2, ahead=3):
+        def __init__(self, eng, blocks, depth, nf2, ahead=2):
             dev = depth.device
-            self.eng, self.seans, self.depth = eng, seans, depth
+            self.eng, self.blocks, self.depth = eng, blocks, depth
             st = eng._side_streams.get(dev.index)
             if st is None:
-                st = eng._side_streams[dev.index] = torch.cuda.Stream(device=dev, priority=0)
+                st = eng._side_streams[dev.index] = torch.cuda.Stream(device=dev)
             self.side = st
             self.main = torch.cuda.current_stream(dev)
             B, _, H, W = depth.shape
-            self.bufs = [torch.empty(B, H, W, nf2, device=dev, dtype=BF16) for _ in range(min(ahead, len(seans)))]
-            self.ready = [None] * len(seans)
+            self.slots = [[torch.empty(B, H, W, nf2, device=dev, dtype=BF16) for _ in range(2)]
+                          for _ in range(min(ahead, len(blocks)))]
+            self.ready = [None] * len(blocks)
             self.k = 0
             fork = torch.cuda.Event()
             fork.record(self.main)
             self.side.wait_event(fork)
-            for i in range(len(self.bufs)):
+            for i in range(len(self.slots)):
                 self._issue(i)
 
         def _issue(self, i):
             with torch.cuda.stream(self.side):
-                # one block per SM: it fits beside the convolution kernels and never keeps their blocks waiting
-                self.eng._sean_actv(self.seans[i], self.depth, out=self.bufs[i % len(self.bufs)], ctas_per_sm=1)
+                for sean, buf in zip(self.blocks[i], self.slots[i % len(self.slots)]):
+                    # one block per SM: it fits beside the convolution kernels and never keeps their blocks waiting
+                    self.eng._sean_actv(sean, self.depth, out=buf, ctas_per_sm=1)
                 ev = torch.cuda.Event()
                 ev.record(self.side)
             self.ready[i] = ev
 
         def take(self):
             self.main.wait_event(self.ready[self.k])
-            return self.bufs[self.k % len(self.bufs)]
+            return self.slots[self.k % len(self.slots)]
 
         def done(self):
             k = self.k
             self.k += 1
-            nxt = k + len(self.bufs)
-            if nxt < len(self.seans):
+            nxt = k + len(self.slots)
+            if nxt < len(self.blocks):
                 free = torch.cuda.Event()
                 free.record(self.main)
                 self.side.wait_event(free)
@@ -511,6 +515,7 @@ class Engine:
         out32 = torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32) if self.fp32_residual else None
         # actv generated inside the SEAN conv (no actv tensor, no actv launch) when the geometry leaves room for it
         gen = self.fuse_actv and nf == 64 and lib.dasr_conv_gen_ok(H, W) == 1
+        pre = prefetch.take() if (prefetch is not None and not gen) else None
         for j, sean in ((1, blk.norm1), (2, blk.norm2)):
             n = "%s.norm%d" % (p, j)
             # conv + per-tile statistics; the double-InstanceNorm coefficients are finalised inside the SEAN conv
@@ -520,8 +525,8 @@ class Engine:
                 actv = None
                 akw = dict(shape=(B, H, W, 2 * nf), gen_depth=depth, gen_w=sean.mlp_mask[0].weight,
                            gen_b=sean.mlp_mask[0].bias)
-            elif prefetch is not None:
-                actv = prefetch.take()
+            elif pre is not None:
+                actv = pre[j - 1]
                 akw = {}
             else:
                 actv = self._sean_actv(sean, depth)
@@ -533,8 +538,8 @@ class Engine:
                 cur = self._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, act=L.ACT_RELU, y=y, stats=stats[1], dyn_x=mask16,
                                  dyn_w=wdyn, resid=x if x32 is None else None, resid_f32=x32,
                                  out_aux_f32=out32, **akw)
-            if prefetch is not None and not gen:
-                prefetch.done()
+        if pre is not None:
+            prefetch.done()
         return cur, out32
 
     def _classic(self, p: str, x):
@@ -641,11 +646,12 @@ class Engine:
         order = net.block_order()
 
         prefetch = None
-        if self.actv_overlap and self.profile is None and cap is None and not self.fuse_actv:
-            seans = [sn for i, _pos in order if i in net.which_ResBlk_depth
-                     for sn in (net.block(i).norm1, net.block(i).norm2)]
-            if seans:
-                prefetch = Engine._ActvPrefetch(self, seans, depth, 2 * seans[0].norm_nc)
+        # (the instrumented pass of bench.py times kernels one by one: no overlap there unless forced by a probe)
+        if (self.actv_overlap and (self.profile is None or self.actv_overlap == "force") and cap is None
+                and not self.fuse_actv):
+            blocks = [(net.block(i).norm1, net.block(i).norm2) for i, _pos in order if i in net.which_ResBlk_depth]
+            if blocks:
+                prefetch = Engine._ActvPrefetch(self, blocks, depth, 2 * blocks[0][0].norm_nc)
 
         def run_block(i, x, x32):
             if i in net.which_ResBlk_depth:
