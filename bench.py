@@ -32,6 +32,25 @@ import threading
 import time
 import warnings
 
+# stdout carries exactly ONE JSON line.  NCCL prints its version banner (NCCL_DEBUG=VERSION|WARN|INFO) with a plain
+# printf to fd 1, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the
+# original stdout.
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -183,7 +202,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _bind_to_gpu_numa_node(local):
@@ -384,7 +403,7 @@ def run_b200(args):
                                  "note": "net(...) + device-side tensor2img (uint8 BGR frames, what codes/test.py "
                                          "writes) read back instead of the fp32 tensor"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def train_pass(args, net, dev, rank, world, barrier):
@@ -489,6 +508,7 @@ def roofline_pass(net, dev_sets, B):
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
