@@ -129,8 +129,8 @@ class DepthNet(nn.Module):
             raise NotImplementedError("ablation variants (ablate_depth_matrix / ablate_depth_block) are out of scope")
         if in_nc != 3 or out_nc != 3 or nf != 64:
             raise NotImplementedError("the B200 kernels are specialised for in_nc=out_nc=3, nf=64 (every shipped yml)")
-        if scale not in (2, 4, 8):
-            raise NotImplementedError("scale %r: only x2, x4 and x8 are implemented" % (scale,))
+        if scale not in (2, 3, 4, 8):
+            raise NotImplementedError("scale %r: the reference builds x2, x3, x4 and x8" % (scale,))
         if use_trainable_params is None:
             use_trainable_params = True
         self.scale = scale
@@ -164,7 +164,8 @@ class DepthNet(nn.Module):
         self.upscale2 = nn.Sequential(_wn(_conv3(ch_last2_upscale, 32 * 4)), nn.PixelShuffle(2),
                                       nn.LeakyReLU(0.2, inplace=True), _wn(_conv3(32, 32)),
                                       nn.LeakyReLU(0.2, inplace=True))
-        self.upscale3 = nn.Sequential(_wn(_conv3(ch_last_upscale, 32 * 4)), nn.PixelShuffle(2),
+        final_scale = 3 if scale == 3 else 2
+        self.upscale3 = nn.Sequential(_wn(_conv3(ch_last_upscale, 32 * final_scale ** 2)), nn.PixelShuffle(final_scale),
                                       nn.LeakyReLU(0.2, inplace=True))
         self.conv_output = nn.Conv2d(32, out_nc, kernel_size=9, stride=1, padding=4, bias=True)
         self._engine = None

@@ -120,7 +120,16 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
     eng = tp.eng
     lib = tp.lib
     acts = {"none": L.ACT_NONE, "relu": L.ACT_RELU, "lrelu": L.ACT_LRELU}
-    if shuffle:
+    r = 2 if shuffle is True else int(shuffle)        # PixelShuffle factor (0: none)
+    if r == 3:
+        # x3 tail: plain conv into the shuffled channel order (+ activation), then PixelShuffle(3) as a copy
+        u = eng._conv(x.data, name, act=acts[act])
+        B_, H_, W_, C_ = u.shape
+        out = torch.empty(B_, 3 * H_, 3 * W_, C_ // 9, device=u.device, dtype=BF16)
+        L.check(lib.dasr_pixel_shuffle(L.ptr(u), L.ptr(out), B_, H_, W_, C_ // 9, 3, tp.s))
+        del u
+        o = _T(out, "handled")
+    elif shuffle:
         out = eng._conv(x.data, name, epi=L.EPI_SHUFFLE2, act=acts[act])
         o = _T(out, "handled")
     else:
@@ -136,8 +145,8 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
         if shuffle:
             o.grad = None
             B, H2, W2, Cq = o.data.shape
-            dy = torch.empty(B, H2 // 2, W2 // 2, 4 * Cq, device=g.device, dtype=BF16)
-            L.check(lib.dasr_unshuffle_actgrad(L.ptr(g), L.ptr(o.data), L.ptr(dy), B, H2 // 2, W2 // 2, Cq, 0.2, s))
+            dy = torch.empty(B, H2 // r, W2 // r, r * r * Cq, device=g.device, dtype=BF16)
+            L.check(lib.dasr_unshuffle_actgrad(L.ptr(g), L.ptr(o.data), L.ptr(dy), B, H2 // r, W2 // r, Cq, 0.2, r, s))
         else:
             dy = tp.take(o)
         if subsample == 2:      # gradient on the stride-1 grid of the forward kernel
@@ -397,7 +406,7 @@ def _forward_train(eng, lq, depth, masks):
         x = _conv_train(tp, x, "upscale2.0", act="lrelu", shuffle=True)
         x = _conv_train(tp, x, "upscale2.3", act="lrelu")
     x = run_block(order[-1][0], x)
-    u3 = _conv_train(tp, x, "upscale3.0", act="lrelu", shuffle=True)
+    u3 = _conv_train(tp, x, "upscale3.0", act="lrelu", shuffle=3 if net.scale == 3 else True)
     Bo, Ho, Wo, _ = u3.data.shape
     sr = torch.empty(B, 3, Ho, Wo, device=dev, dtype=torch.float32)
     pk = eng._packed["conv_output"]

@@ -466,24 +466,47 @@ __global__ void __launch_bounds__(128) actv_bwd_kernel(const __nv_bfloat16* __re
 }
 
 // ------------------------------------------------------------------------------------ PixelShuffle + LeakyReLU backward
-// dconv[b,h,w,s*Cq + c] = dps[b,2h+i,2w+j,c] * (ps_out[b,2h+i,2w+j,c] > 0 ? 1 : slope),  s = 2i + j
+// dconv[b,h,w,s*Cq + c] = dps[b,r*h+i,r*w+j,c] * (ps_out[b,r*h+i,r*w+j,c] > 0 ? 1 : slope),  s = r*i + j
+// (the convolution in front of the shuffle is packed in this "shuffled" channel order, DASR_PACK_* shuffle_r)
 __global__ void unshuffle_actgrad_kernel(const uint4* __restrict__ dps, const uint4* __restrict__ ps_out,
-                                         uint4* __restrict__ dconv, int B, int H, int W, int Gq, float slope) {
-    const size_t total = (size_t)B * H * W * 4 * Gq;   // uint4 items of the output
+                                         uint4* __restrict__ dconv, int B, int H, int W, int Gq, float slope, int r) {
+    const int r2 = r * r;
+    const size_t total = (size_t)B * H * W * r2 * Gq;   // uint4 items of the output
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int g = idx % Gq;
-        const int s = (idx / Gq) % 4;
-        const size_t pix = idx / ((size_t)Gq * 4);
+        const int s = (idx / Gq) % r2;
+        const size_t pix = idx / ((size_t)Gq * r2);
         const int w = pix % W;
         const int h = (pix / W) % H;
         const int b = pix / ((size_t)W * H);
-        const size_t src = ((((size_t)b * 2 * H + 2 * h + (s >> 1)) * 2 * W) + 2 * w + (s & 1)) * Gq + g;
+        const int i = s / r, j = s - i * r;
+        const size_t src = ((((size_t)b * r * H + r * h + i) * r * W) + r * w + j) * Gq + g;
         float d[8], o[8];
         bunpack8(__ldg(dps + src), d);
         bunpack8(__ldg(ps_out + src), o);
 #pragma unroll
-        for (int j = 0; j < 8; j++) d[j] *= (o[j] > 0.f ? 1.f : slope);
+        for (int k = 0; k < 8; k++) d[k] *= (o[k] > 0.f ? 1.f : slope);
         dconv[idx] = bpack8(d);
+    }
+}
+
+// PixelShuffle(r) of an NHWC tensor whose channels are in the shuffled order above (sftmd_arch.py:904-908, the x3
+// tail): out[b, r*h+i, r*w+j, c] = in[b, h, w, (r*i+j)*Cq + c].  (r = 2 never runs this: it is the store addressing
+// of the convolution's EPI_SHUFFLE2 epilogue.)
+__global__ void pixel_shuffle_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int Gq,
+                                     int r) {
+    const int r2 = r * r;
+    const size_t total = (size_t)B * H * W * r2 * Gq;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % Gq;
+        const int s = (idx / Gq) % r2;
+        const size_t pix = idx / ((size_t)Gq * r2);
+        const int w = pix % W;
+        const int h = (pix / W) % H;
+        const int b = pix / ((size_t)W * H);
+        const int i = s / r, j = s - i * r;
+        const size_t dst = ((((size_t)b * r * H + r * h + i) * r * W) + r * w + j) * Gq + g;
+        out[dst] = __ldg(in + idx);
     }
 }
 
@@ -636,7 +659,7 @@ extern "C" int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, 
 
 extern "C" int dasr_colsum(const void* x, float* out, int64_t rows, int C, void* stream) {
     DASR_REQUIRE(x && out && rows > 0, "bad arguments");
-    DASR_REQUIRE(C % 8 == 0 && C >= 8 && 256 % (C / 8) == 0, "colsum: unsupported C %d", C);
+    DASR_REQUIRE(C % 8 == 0 && C >= 8 && C / 8 <= 256, "colsum: unsupported C %d", C);   // 256 % G != 0: spare threads idle
     const int G = C / 8;
     const int lanes = 256 / G;
     size_t rpb = ((size_t)rows + 4 * (size_t)num_sms() - 1) / (4 * (size_t)num_sms());
@@ -738,10 +761,20 @@ extern "C" int dasr_actv_bwd(const void* dA, const float* depth, float* dW, floa
 }
 
 extern "C" int dasr_unshuffle_actgrad(const void* dps, const void* ps_out, void* dconv, int B, int H, int W, int Cq,
-                                      float slope, void* stream) {
+                                      float slope, int r, void* stream) {
     DASR_REQUIRE(dps && ps_out && dconv && Cq % 8 == 0, "bad arguments");
-    const size_t total = (size_t)B * H * W * 4 * (Cq / 8);
-    unshuffle_actgrad_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)dps, (const uint4*)ps_out, (uint4*)dconv, B, H, W, Cq / 8, slope);
+    DASR_REQUIRE(r == 2 || r == 3, "PixelShuffle factor must be 2 or 3 (got %d)", r);
+    const size_t total = (size_t)B * H * W * r * r * (Cq / 8);
+    unshuffle_actgrad_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)dps, (const uint4*)ps_out, (uint4*)dconv, B, H, W, Cq / 8, slope, r);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_pixel_shuffle(const void* in, void* out, int B, int H, int W, int Cq, int r, void* stream) {
+    DASR_REQUIRE(in && out && Cq % 8 == 0 && B > 0 && H > 0 && W > 0, "bad arguments");
+    DASR_REQUIRE(r == 2 || r == 3, "PixelShuffle factor must be 2 or 3 (got %d)", r);
+    const size_t total = (size_t)B * H * W * r * r * (Cq / 8);
+    pixel_shuffle_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, Cq / 8, r);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

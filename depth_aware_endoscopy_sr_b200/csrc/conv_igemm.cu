@@ -961,6 +961,18 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMa
     DASR_CUDA_OK(cudaGetDevice(&dev));
     if (!configured[dev & 63]) {
         DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 10 * 1024));
+        if (EPI == DASR_EPI_SEAN) {
+            // setmaxnreg.inc blocks until the CTA's register pool (registers at launch x threads) can serve it: the
+            // redistribution below must fit the pool ptxas actually gave this kernel, or the epilogue warps hang
+            cudaFuncAttributes fa;
+            DASR_CUDA_OK(cudaFuncGetAttributes(&fa, fn));
+            const int threads = GEN ? 512 : kThreads;
+            const int need = GEN ? (128 * 56 + 256 * 168 + 128 * 120)
+                                 : (128 * DASR_LEAN_ROLE_REGS + 256 * DASR_LEAN_EPI_REGS);
+            DASR_REQUIRE(fa.numRegs * threads >= need,
+                         "SEAN convolution compiled with %d registers per thread: the setmaxnreg redistribution needs "
+                         "%d registers per CTA (rebuild with the launch bounds of conv_igemm.cu)", fa.numRegs, need);
+        }
         configured[dev & 63] = true;
     }
     int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
@@ -1085,6 +1097,8 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         k.ntn = 1;
     } else {
         n_tile = d->Cout >= 128 ? 128 : d->Cout;
+        // Cout = 288 (the x3 tail, 32 * 3^2 channels in front of PixelShuffle(3)): nine N tiles of 32
+        if (d->Cout > 128 && d->Cout % 128 != 0) n_tile = (d->Cout % 64 == 0) ? 64 : 32;
         DASR_REQUIRE(n_tile == 16 || n_tile == 32 || n_tile == 64 || n_tile == 128,
                      "Cout must be 16, 32, 64 or a multiple of 128 (got %d)", d->Cout);
         DASR_REQUIRE(d->Cout % n_tile == 0, "Cout %d not a multiple of the N tile %d", d->Cout, n_tile);

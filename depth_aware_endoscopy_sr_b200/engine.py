@@ -242,7 +242,7 @@ class Engine:
         if net.scale >= 4:
             add_wn("upscale2.0", shuffle_r=2)
             add_wn("upscale2.3")
-        add_wn("upscale3.0", shuffle_r=2)
+        add_wn("upscale3.0", shuffle_r=3 if net.scale == 3 else 2)
         wq = torch.zeros(9 * 32, 32, device=device, dtype=BF16)
         bq = torch.zeros(3, device=device, dtype=torch.float32)
         self._descs.append(L.pack_desc(P("conv_output.weight"), wq, bias=P("conv_output.bias"), dst_bias=bq,
@@ -683,7 +683,14 @@ class Engine:
             x = self._conv(x, "upscale2.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
             x = self._conv(x, "upscale2.3", act=L.ACT_LRELU)
         x, _ = run_block(order[-1][0], x, None)
-        x = self._conv(x, "upscale3.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
+        if net.scale == 3:
+            # 64 -> 288 convolution (shuffled channel order, LeakyReLU commutes with the permutation), then
+            # PixelShuffle(3) as a copy kernel (sftmd_arch.py:904-908)
+            u = self._conv(x, "upscale3.0", act=L.ACT_LRELU)
+            x = torch.empty(B, 3 * u.shape[1], 3 * u.shape[2], u.shape[3] // 9, device=dev, dtype=BF16)
+            L.check(lib.dasr_pixel_shuffle(L.ptr(u), L.ptr(x), B, u.shape[1], u.shape[2], u.shape[3] // 9, 3, s))
+        else:
+            x = self._conv(x, "upscale3.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
         out = torch.empty(B, 3, x.shape[1], x.shape[2], device=dev, dtype=torch.float32)
         if net.min != 0.0 or net.max != 1.0:
             raise NotImplementedError("the fused output epilogue clamps to [0,1] (the only range define_G builds)")

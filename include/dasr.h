@@ -241,9 +241,13 @@ int dasr_region_pool_bwd(const float* dvec, const float* msel, const float* cnt,
                          void* stream);
 /* mlp_mask backward: dW[c][9] += , db[c] += from dA (NHWC bf16 [B,H,W,C], ReLU mask already applied)      */
 int dasr_actv_bwd(const void* dA, const float* depth, float* dW, float* db, int B, int H, int W, int C, void* stream);
-/* PixelShuffle(2) + LeakyReLU backward: dps/ps_out NHWC bf16 [B,2H,2W,Cq] -> dconv NHWC bf16 [B,H,W,4Cq]     */
+/* PixelShuffle(r) + LeakyReLU backward (r = 2 | 3): dps/ps_out NHWC bf16 [B,rH,rW,Cq] -> dconv NHWC bf16
+ * [B,H,W,r*r*Cq] in the shuffled channel order s*Cq + c, s = r*i + j (DASR_PACK_* shuffle_r)                 */
 int dasr_unshuffle_actgrad(const void* dps, const void* ps_out, void* dconv, int B, int H, int W, int Cq, float slope,
-                           void* stream);
+                           int r, void* stream);
+/* PixelShuffle(r) forward of an NHWC bf16 tensor in that channel order (sftmd_arch.py:904-908; the x3 tail --
+ * for r = 2 the shuffle is the store addressing of DASR_EPI_SHUFFLE2): in [B,H,W,r*r*Cq] -> out [B,rH,rW,Cq]  */
+int dasr_pixel_shuffle(const void* in, void* out, int B, int H, int W, int Cq, int r, void* stream);
 /* clamp backward + horizontal im2row of d(sr): dout, sr NCHW fp32 [B,3,H,W] -> aprime NHWC bf16 [B,H,W,32];
  * dbias[3] += sum of the masked gradient                                                                 */
 int dasr_out9_bwd_prep(const float* dout, const float* sr, void* aprime, float* dbias, int B, int H, int W, void* stream);

@@ -14,7 +14,7 @@ from oracle import depthnet_oracle as oracle  # noqa: E402  (the checker; tests 
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 INIT_CASES = ["x8_b1_64_init", "x8_b2_32_init"]   # the reference's own random init (strict tolerance)
-CASES = ["x8_b2_16", "x8_b1_64", "x8_b1_24x40", "x4_b1_24", "x2_b1_32"]
+CASES = ["x8_b2_16", "x8_b1_64", "x8_b1_24x40", "x4_b1_24", "x2_b1_32", "x3_b1_24"]
 
 
 def load_golden(name):

@@ -40,6 +40,8 @@ CASES = {
     "x8_b1_24x40": (8, list(range(14)), 256, 1, 24, 40, 2, 2),
     "x4_b1_24": (4, list(range(14)), 256, 1, 24, 24, 3, 1),
     "x2_b1_32": (2, list(range(16)), 32, 1, 32, 32, 4, 1),
+    # x3 (options/train/train_depthNet_SEAN_depthMask_endoscene_x3.yml:48-63): 16 depth-guided blocks, PixelShuffle(3)
+    "x3_b1_24": (3, list(range(16)), 256, 1, 24, 24, 5, 1),
 }
 
 
@@ -136,5 +138,7 @@ def run_case(name, scale, which, latent, B, h, w, seed, stride, init="synthetic"
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = sys.argv[1:]            # optional: regenerate just the named cases
     for name, args in CASES.items():
-        run_case(name, *args)
+        if not only or name in only:
+            run_case(name, *args)

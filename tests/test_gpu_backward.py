@@ -37,7 +37,7 @@ def kb():
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64, 3, 3), (2, 64, 64, 128, 128, 3, 3), (1, 24, 40, 64, 32, 3, 3),
                                    (1, 24, 40, 32, 64, 3, 3), (1, 31, 31, 128, 256, 3, 3), (1, 135, 240, 64, 64, 3, 3),
                                    (1, 64, 64, 32, 32, 9, 1), (2, 64, 64, 32, 128, 3, 3), (1, 24, 40, 32, 32, 3, 3),
-                                   (1, 135, 240, 32, 32, 3, 3), (1, 40, 300, 32, 32, 9, 1), (3, 64, 64, 64, 128, 3, 3)])
+                                   (1, 135, 240, 32, 32, 3, 3), (1, 40, 300, 32, 32, 9, 1), (3, 64, 64, 64, 128, 3, 3), (1, 24, 24, 64, 288, 3, 3)])
 def test_conv_wgrad_kernel(kb, shape):
     B, H, W, Cin, Cout, kh, kw = shape
     kb.failures.clear()

@@ -71,7 +71,7 @@ def test_forward_matches_reference_golden(name):
     assert err_pre <= 2 * tol * max(1.0, np.abs(z["pre_clamp"]).max())
 
 
-@pytest.mark.parametrize("name", INIT_CASES + ["x8_b2_16", "x8_b1_24x40", "x4_b1_24", "x2_b1_32"])
+@pytest.mark.parametrize("name", INIT_CASES + ["x8_b2_16", "x8_b1_24x40", "x4_b1_24", "x2_b1_32", "x3_b1_24"])
 def test_forward_matches_oracle_full_frame(name):
     """Full-resolution comparison + PSNR delta against the CPU oracle (itself pinned to the goldens)."""
     _z, meta = load_golden(name)

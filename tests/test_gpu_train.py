@@ -193,10 +193,12 @@ def test_train_step_cuda_graph_replays_the_eager_trajectory():
 
 
 @pytest.mark.parametrize("scale,which,latent,unused", [(4, list(range(14)), 256, ("upscale1.",)),
-                                                      (2, list(range(16)), 32, ("upscale1.", "upscale2."))])
+                                                      (2, list(range(16)), 32, ("upscale1.", "upscale2.")),
+                                                      (3, list(range(16)), 256, ("upscale1.", "upscale2."))])
 def test_training_step_at_x4_and_x2(scale, which, latent, unused):
-    """BASELINE configs[3]: the x4 / x2 variants train through the same kernels (smaller upsampler, 64-channel
-    blocks 15/16, 32-channel latent at x2); parameters the reference never touches get no gradient."""
+    """BASELINE configs[3]: the x4 / x2 (/ x3: PixelShuffle(3) tail) variants train through the same kernels (smaller
+    upsampler, 64-channel blocks 15/16, 32-channel latent at x2); parameters the reference never touches get no
+    gradient."""
     import depth_aware_endoscopy_sr_b200 as dasr
     torch.manual_seed(5)
     with warnings.catch_warnings():

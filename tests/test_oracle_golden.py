@@ -27,7 +27,7 @@ def test_oracle_forward_matches_reference(name):
     assert np.abs(sr.numpy()[:, :, ::st, ::st] - z["sr"]).max() <= 1e-4
 
 
-@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24", "x2_b1_32"])
+@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24"])
 def test_oracle_loss_and_gradients_match_reference(name):
     z, meta = load_golden(name)
     sd, (lq, depth, masks, gt) = case_tensors(meta)

@@ -232,7 +232,7 @@ def misc_bwd_case():
     ps.backward(dps)
     dconv = torch.empty(B, H, W, 4 * Cq, device=dev, dtype=torch.bfloat16)
     dps_a, ps_a = nhwc(dps).to(torch.bfloat16), nhwc(ps.detach()).to(torch.bfloat16)   # keep the operands alive
-    L.check(lib.dasr_unshuffle_actgrad(L.ptr(dps_a), L.ptr(ps_a), L.ptr(dconv), B, H, W, Cq, 0.2, s))
+    L.check(lib.dasr_unshuffle_actgrad(L.ptr(dps_a), L.ptr(ps_a), L.ptr(dconv), B, H, W, Cq, 0.2, 2, s))
     torch.cuda.synchronize()
     # our channel order is s*Cq + c (packed / permuted), torch's is c*4 + s
     ref = conv.grad.reshape(B, Cq, 4, H, W).permute(0, 3, 4, 2, 1).reshape(B, H, W, 4 * Cq)
