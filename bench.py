@@ -450,9 +450,9 @@ def train_pass(args, net, dev, rank, world, barrier):
 
 def _ncu_traffic(kernel_family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/r01_conv_ncu_full_v5_summary.csv), or None."""
+    `ncu --set full` capture (profiles/r01_conv_ncu_full_v6_summary.csv), or None."""
     col = {"conv3x3_128to128_sean": 2}.get(kernel_family)
-    path = os.path.join(ROOT, "profiles", "r01_conv_ncu_full_v5_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r01_conv_ncu_full_v6_summary.csv")
     if col is None or not os.path.exists(path):
         return None
     import csv
