@@ -561,7 +561,7 @@ class Engine:
         """Inference.  A forward is ~100 kernel launches; issued from Python that is 2.7 ms of host time, more than
         the kernels of a single 1080p frame need (1.5 ms), so for small batches (``graph_max_pixels``) the schedule is
         replayed from a CUDA graph from the third call with the same input shape on (static input / output buffers;
-        the result is returned as a copy): 2.7 -> 0.94 ms per 64x64 frame, 2.7 -> 1.5 ms per 1080p frame.  ``cap`` /
+        the result is returned as a copy): 2.7 -> 0.85 ms per 64x64 frame, 2.7 -> 1.3 ms per 1080p frame.  ``cap`` /
         ``profile`` / an ongoing stream capture use the kernel-by-kernel schedule."""
         if (not self.use_graphs or cap is not None or self.profile is not None or not lq.is_cuda
                 or lq.shape[0] * lq.shape[2] * lq.shape[3] > self.graph_max_pixels
