@@ -38,6 +38,9 @@ int fail(int code, const char* fmt, ...);
 // cuTensorMapEncodeTiled for a bf16 tensor (rank <= 4). swizzle_bytes in {32, 64, 128}.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+// the same for an fp32 tensor (destination of the bulk tensor reductions of conv_wgrad.cu)
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 int num_sms();
 void count_launch();   // bumps the counter behind dasr_launch_count()
