@@ -71,7 +71,7 @@ def load() -> C.CDLL:
         "dasr_check_device": [],
         "dasr_conv_fwd": [C.POINTER(ConvDesc), C.POINTER(ConvArgs), vp],
         "dasr_conv_out9": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
-        "dasr_conv_wgrad": [C.POINTER(WgradDesc), vp, vp, vp, vp],
+        "dasr_conv_wgrad": [C.POINTER(WgradDesc), vp, vp, vp, vp, vp],
         "dasr_pack_weights": [C.POINTER(PackDesc), i32, vp, vp],
         "dasr_conv_first": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_zero_insert2": [vp, vp, i32, i32, i32, i32, vp],
@@ -217,13 +217,15 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Te
     return out
 
 
-def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int = 3, kw: int = 3) -> torch.Tensor:
-    """dw[Cout][kh*kw*Cin] (fp32, zeroed by the caller) += weight gradient; dy / x NHWC bf16."""
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int = 3, kw: int = 3,
+               db: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw[Cout][kh*kw*Cin] (fp32, zeroed by the caller) += weight gradient; dy / x NHWC bf16.
+    db (optional, fp32 [Cout]) += the bias gradient (column sums of dy), fused into the same kernel."""
     B, H, W, Cout = dy.shape
     Cin = x.shape[3]
     d = WgradDesc(B, H, W, Cout, Cin, kh, kw, 0)
     check(load().dasr_conv_wgrad(C.byref(d), ptr(dy, torch.bfloat16), ptr(x, torch.bfloat16), ptr(dw, torch.float32),
-                                 stream_ptr()))
+                                 ptr(db, torch.float32) if db is not None else None, stream_ptr()))
     return dw
 
 

@@ -102,9 +102,10 @@ class Tape:
         t.grad = out
 
     # ------------------------------------------------------------------ weight-gradient helpers
-    def wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, kh=3, kw=3):
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, kh=3, kw=3, bias=False):
+        """Weight gradient (and, with ``bias``, the bias gradient in the same kernel)."""
         dw = self.eng._dw_view(wname)
-        L.conv_wgrad(dy, x, dw, kh, kw)
+        L.conv_wgrad(dy, x, dw, kh, kw, db=self.eng._db_view(wname) if bias else None)
 
     def bias_grad(self, dy: torch.Tensor, wname: str):
         db = self.eng._db_view(wname)
@@ -155,9 +156,7 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
             full = torch.empty(B, H, W, Co, device=dy.device, dtype=BF16)
             L.check(lib.dasr_zero_insert2_to(L.ptr(dy), L.ptr(full), B, Ho, Wo, Co, H, W, s))
             dy = full
-        tp.wgrad(dy, x.data, name)
-        if bias_grad:
-            tp.bias_grad(dy, name)
+        tp.wgrad(dy, x.data, name, bias=bias_grad)
         if need_dgrad:
             if convt_src is not None:
                 tp.dgrad_into(convt_src, dy, name + ".dg", subsample=2)
@@ -266,8 +265,7 @@ def _forward_train(eng, lq, depth, masks):
         dy = tp.take(f0)
         lq32 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
         L.check(lib.dasr_nchw3_to_nhwc32(L.ptr(lq), L.ptr(lq32), B, h, w, s))
-        tp.wgrad(dy, lq32, "encoder.layer1")
-        tp.bias_grad(dy, "encoder.layer1")
+        tp.wgrad(dy, lq32, "encoder.layer1", bias=True)
 
     tp.ops.append(bwd_first)
 
@@ -372,8 +370,7 @@ def _forward_train(eng, lq, depth, masks):
 
         def bwd_res():
             dy = tp.take(o)
-            tp.wgrad(dy, f.data, p + ".block.2")
-            tp.bias_grad(dy, p + ".block.2")
+            tp.wgrad(dy, f.data, p + ".block.2", bias=True)
             tp.accum(x, dy)
             tp.dgrad_into(f, dy, p + ".block.2.dg")
 

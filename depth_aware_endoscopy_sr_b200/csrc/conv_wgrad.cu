@@ -56,6 +56,10 @@ struct WgK {
     const int* skip_flag;               // optional device int: the whole kernel is a no-op when *skip_flag != 0
     int col_first, col_count;           // flush window inside every tap's Nc columns (default: all of them)
     int tma_flush;                      // flush through cp.reduce.async.bulk.tensor (mapW) instead of per-lane red
+    // bias gradient db[o] += sum_pixels dY[p][o], fused: the CTAs of slice 0 issue one more MMA per K step whose B
+    // operand is a constant block of ones (16 columns) -- the column sum of the A operand already in shared memory
+    float* db;
+    uint32_t ones_off;                  // byte offset of the 2 KB block of bf16 ones behind the pipeline stages
     int dbg;                            // -DDASR_PROFILE ablation knob (env DASR_WG_DBG): 1 no flush, 2 no MMA, 4 no TMA
 };
 
@@ -90,6 +94,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
         tma_prefetch_desc(&mapX);
     }
     if (warp == 2) tmem_alloc<512>(&tmem_base_s);
+    if (p.db) {
+        uint32_t* ones = reinterpret_cast<uint32_t*>(smem + p.ones_off);
+        for (int i = threadIdx.x; i < 512; i += kWgThreads) ones[i] = 0x3F803F80u;        // bf16 1.0 x 2
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                      // read by tcgen05.mma
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -118,6 +127,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
     }
     if (p.skip_flag && *p.skip_flag != 0) kt_end = kt_begin;     // uniform over the grid: nothing to do
     const int n_my = kt_end > kt_begin ? (kt_end - kt_begin + kt_step - 1) / kt_step : 0;
+    const bool do_bias = p.db != nullptr && blockIdx.y == 0;      // tap group 0, channel chunk 0
 
     if (warp == 0) {
         if (elect_one()) {
@@ -155,6 +165,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
             const uint32_t lo_a_flags = ((p.a_lbo >> 4) & 0x3FFFu) << 16;
             const uint32_t lo_b_flags = (((g > 1 ? p.stack_lbo : p.b_lbo) >> 4) & 0x3FFFu) << 16;
             const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+            const uint32_t idesc_ones = make_idesc_bf16(p.Mb, 16) | mn_major;
+            const uint32_t ones_lo = smem_lo + (p.ones_off >> 4);        // every element is 1: LBO irrelevant
             const int ksteps = p.Wt >> 4;
             const uint32_t a_kstep = (16u * p.swz_a) >> 4, b_kstep = (16u * p.swz_b) >> 4;
             uint32_t it = 0;
@@ -191,6 +203,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                                 : "memory");
                         }
                     }
+                    if (do_bias) {
+                        const uint32_t d = tmem_base + ntaps * p.Nc;
+                        const uint32_t acc0 = (it | r) != 0;
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            const uint32_t a_lo = (a_row + ks * a_kstep) | lo_a_flags;
+                            const uint32_t accum = acc0 | (ks != 0);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+                                "setp.ne.b32 p, %6, 0;\n\t"
+                                "mov.b64 da, {%1, %3};\n\t"
+                                "mov.b64 db, {%2, %4};\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d),
+                                "r"(a_lo), "r"(ones_lo), "r"(hi_a), "r"(hi_b), "r"(idesc_ones), "r"(accum)
+                                : "memory");
+                        }
+                    }
                 }
                 umma_commit(&empty[s]);
             }
@@ -215,6 +244,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
             const int o = ca0 + m;
             row_ok = row_ok && (o < p.Cout);
             const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16);
+            if (do_bias) {
+                uint32_t v[16];
+                tmem_ld16(t_row + ntaps * p.Nc, v);
+                tmem_ld_wait();
+                if (row_ok) atomicAdd(p.db + o, __uint_as_float(v[0]));
+            }
             if (p.tma_flush) {
                 // Bulk tensor reductions: the slice goes TMEM -> registers -> 128-byte-swizzled [128 rows][32 floats]
                 // tiles in the (now idle) pipeline stages -> ONE cp.reduce.async.bulk.tensor (fp32 add, performed at
@@ -325,6 +360,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
 using namespace dasr;
 
 struct WgOpts {
+    float* db = nullptr;                    // fused bias gradient (or NULL)
     int per_image = 0, n_valid = 0;
     int col_first = 0, col_count = 0;       // flush window (multiples of 4); 0 / 0 = every column
     long long dw_img_stride = 0;
@@ -500,7 +536,15 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
         DASR_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured[dev & 63] = true;
     }
-    const size_t smem_bytes = (size_t)k.stages * k.stage_bytes + 1024;
+    k.db = nullptr;
+    k.ones_off = 0;
+    if (o.db) {
+        DASR_REQUIRE(!o.per_image && k.taps_per_slice * k.Nc + 16 <= 512,
+                     "fused bias gradient: no TMEM column left (taps %d x %d columns)", k.taps_per_slice, k.Nc);
+        k.db = o.db;
+        k.ones_off = (uint32_t)(((size_t)k.stages * k.stage_bytes + 1023) & ~(size_t)1023);
+    }
+    const size_t smem_bytes = (size_t)k.stages * k.stage_bytes + 1024 + (o.db ? 3072 : 0);
     DASR_REQUIRE(smem_bytes <= 220 * 1024, "shared memory budget exceeded (%zu)", smem_bytes);
     dim3 grid(ksplit, k.n_tapgroups * k.n_cchunks, n_mblocks);
     {
@@ -522,8 +566,11 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     return DASR_OK;
 }
 
-extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, void* stream) {
-    return wgrad_launch(d, dy, x, dw, WgOpts(), stream);
+extern "C" int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, float* db,
+                               void* stream) {
+    WgOpts o;
+    o.db = db;
+    return wgrad_launch(d, dy, x, dw, o, stream);
 }
 
 // K-DYN backward on the tensor cores: per image, dT[b][k][tap][c] += sum_p dgb[b,p,c] * onehot[b, p+tap-1, k]

@@ -118,11 +118,13 @@ int dasr_conv_gen_ok(int H, int W);
  * above; reference codes/models/F_model_depthCond.py:191):
  *   dw[o][(t*kw+u)*Cin + i] += sum_{b,h,w} dy[b,h,w,o] * x[b,h+t-kh/2,w+u-kw/2,i]
  * dy NHWC bf16 [B,H,W,Cout], x NHWC bf16 [B,H,W,Cin], dw fp32 [Cout][kh*kw*Cin] in the packed GEMM-B layout
- * of dasr_pack_weights (accumulated with fp32 atomics: the caller zeroes it).  Channels multiples of 32.     */
+ * of dasr_pack_weights (accumulated with fp32 atomics: the caller zeroes it).  Channels multiples of 32.
+ * db (optional, fp32 [Cout]): the bias gradient db[o] += sum_{b,h,w} dy[b,h,w,o], computed by the same kernel
+ * (one more MMA per K step against a block of ones) instead of a separate pass over dy.                      */
 typedef struct {
     int32_t B, H, W, Cout, Cin, kh, kw, reserved;
 } dasr_wgrad_desc;
-int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, void* stream);
+int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, float* db, void* stream);
 
 /* conv_output + clamp (sftmd_arch.py:910,948-950): 9x9, Cin = 32 -> Cout = 3, zero padding 4.
  * x NHWC bf16 [B,H,W,32]; wq packed by DASR_PACK_ROWTAPS ([9][32][32] bf16); bias fp32 [3];

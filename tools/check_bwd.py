@@ -51,11 +51,20 @@ def wgrad_case(B, H, W, Cin, Cout, kh=3, kw=3, time=False):
     xa, dya = nhwc(x).to(torch.bfloat16), nhwc(dy).to(torch.bfloat16)
     dw = torch.zeros(Cout, kh * kw * Cin, device=dev)
     L.conv_wgrad(dya, xa, dw, kh, kw)
+    # the same with the fused bias gradient (one more MMA per K step against a block of ones)
+    dw2 = torch.zeros(Cout, kh * kw * Cin, device=dev)
+    fused_bias = kh * kw * min(Cin, 128) // (1 if kw == 1 else kh) + 16 <= 512
+    db = torch.zeros(Cout, device=dev)
+    if fused_bias:
+        L.conv_wgrad(dya, xa, dw2, kh, kw, db=db)
     torch.cuda.synchronize()
     w = torch.zeros(Cout, Cin, kh, kw, device=dev, requires_grad=True)
     F.conv2d(bf(x), w, None, padding=(kh // 2, kw // 2)).backward(bf(dy))
     ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin)      # [o][(t,u),i]
     report("wgrad B%d %dx%d %d->%d k%dx%d" % (B, H, W, Cin, Cout, kh, kw), dw, ref, 2e-3)
+    if fused_bias:
+        report("   + fused bias: dw", dw2, ref, 2e-3)
+        report("   + fused bias: db", db, bf(dy).sum(dim=(0, 2, 3)), 2e-3)
     if time:
         ms = timeit(lambda: L.conv_wgrad(dya, xa, dw, kh, kw))
         print("     %.3f ms  %.0f TFLOP/s" % (ms, 2.0 * B * H * W * Cout * Cin * kh * kw / ms / 1e9), flush=True)
