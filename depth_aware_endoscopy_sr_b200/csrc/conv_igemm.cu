@@ -976,8 +976,7 @@ static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMa
         configured[dev & 63] = true;
     }
     int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEN ? 512 : kThreads);
     cfg.dynamicSmemBytes = smem_bytes;

@@ -548,8 +548,7 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     DASR_REQUIRE(smem_bytes <= 220 * 1024, "shared memory budget exceeded (%zu)", smem_bytes);
     dim3 grid(ksplit, k.n_tapgroups * k.n_cchunks, n_mblocks);
     {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(kWgThreads);
         cfg.dynamicSmemBytes = smem_bytes;
