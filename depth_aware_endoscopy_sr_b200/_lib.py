@@ -24,7 +24,7 @@ PACK_CONV, PACK_CONVT, PACK_STYLE, PACK_ROWTAPS, PACK_DGRAD, PACK_DGRAD_CONVT, P
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("B", "H", "W", "Cin", "Cout", "ks", "epi", "act", "subsample", "clamp01", "inner_relu", "kw")] + \
-               [("mask_slope", C.c_float), ("w_img_rows", C.c_int32)]
+               [("mask_slope", C.c_float), ("w_img_rows", C.c_int32), ("unshuffle", C.c_int32)]
 
 
 class ConvArgs(C.Structure):
@@ -203,10 +203,11 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Te
              epi: int = EPI_STORE, act: int = ACT_NONE, subsample: int = 1, clamp01: int = 0, inner_relu: int = 0,
              resid=None, stats=None, y=None, norm=None, gb_s=None, resid_f32=None, out_aux_f32=None, kw: int = 0,
              actmask=None, mask_slope: float = 0.0, gamma_out=None, w_img_rows: int = 0, dyn_x=None, dyn_w=None, norm_out=None, normk_out=None, gen_depth=None, gen_w=None, gen_b=None,
-             shape=None) -> torch.Tensor:
+             shape=None, unshuffle: int = 0) -> torch.Tensor:
     """x: NHWC bf16 [B,H,W,Cin] (or None with gen_depth / shape = (B,H,W,Cin): the kernel generates its A operand)."""
     B, H, W, Cin = x.shape if x is not None else shape
-    d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, kw, mask_slope, w_img_rows)
+    d = ConvDesc(B, H, W, Cin, Cout, ks, epi, act, subsample, clamp01, inner_relu, kw, mask_slope, w_img_rows,
+                 unshuffle)
     a = ConvArgs(ptr(x, torch.bfloat16) if x is not None else None, ptr(w, torch.bfloat16), ptr(bias, torch.float32), ptr(out), ptr(resid),
                  ptr(stats), ptr(y), ptr(norm), ptr(gb_s), ptr(actmask, torch.bfloat16),
                  ptr(gamma_out, torch.bfloat16), ptr(resid_f32, torch.float32), ptr(out_aux_f32, torch.float32),

@@ -96,6 +96,7 @@ struct ConvK {
     const float* gen_b;            // mlp_mask bias [Cin] fp32
     uint32_t gen_off;              // depth-halo scratch inside the dynamic shared memory
     int w_img_rows;                // > 0: per-image weights, image b uses rows [b*w_img_rows, +Cout) of the B matrix
+    int unshuffle;                 // EPI_STORE: space-to-depth store addressing (PixelShuffle(2) backward)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -838,6 +839,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     }
                     const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
                     __nv_bfloat16* op = p.out + pix * p.Cout + nt * N_TILE;
+                    if (p.unshuffle)        // pixel (ho, wo) -> channel block 2*(ho%2) + wo%2 of pixel (ho/2, wo/2)
+                        op = p.out + ((((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * 4 +
+                                      ((ho & 1) * 2 + (wo & 1))) * p.Cout + nt * N_TILE;
                     const __nv_bfloat16* rp = p.resid ? p.resid + pix * p.Cout + nt * N_TILE : nullptr;
                     const __nv_bfloat16* mp = p.actmask ? p.actmask + pix * p.Cout + nt * N_TILE : nullptr;
 #pragma unroll 1
@@ -1209,6 +1213,10 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     if (d->epi == DASR_EPI_STATS)
         DASR_REQUIRE(n_tile <= 64, "STATS epilogue supports Cout tiles up to 64 (shared-memory partials)");
     k.w_img_rows = d->w_img_rows;
+    k.unshuffle = d->unshuffle;
+    if (d->unshuffle)
+        DASR_REQUIRE(d->unshuffle == 2 && d->epi == DASR_EPI_STORE && k.subsample == 1 && d->H % 2 == 0 && d->W % 2 == 0,
+                     "unshuffle store: factor 2, EPI_STORE, stride 1 and even frame sizes only");
 
     // tensor maps
     CUtensorMap mA, mB;

@@ -70,6 +70,10 @@ typedef struct {
     float mask_slope;             /* DASR_EPI_STORE with actmask: factor where actmask <= 0         */
     int32_t w_img_rows;           /* 0, or Cout: per-image weights -- image b uses rows [b*Cout, (b+1)*Cout) of w (a
                                      batch of independent GEMMs in one launch: the 26 style-table GEMMs)  */
+    int32_t unshuffle;            /* DASR_EPI_STORE only, 0 | 2: store pixel (h, w) of the [B,H,W,Cout] result at
+                                     out[b, h/2, w/2, (2*(h%2) + w%2)*Cout + c] (out NHWC [B,H/2,W/2,4*Cout]) -- the
+                                     backward of PixelShuffle(2) as store addressing; resid / actmask keep the
+                                     [B,H,W,Cout] indexing (the LeakyReLU mask of the shuffled tensor)        */
 } dasr_conv_desc;
 
 typedef struct {
