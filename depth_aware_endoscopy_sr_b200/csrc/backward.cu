@@ -702,7 +702,9 @@ extern "C" int dasr_table_bwd_batched(const float* dT, const void* stp, const vo
     DASR_LAUNCH_OK();
     // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles per instance -> split the reduction over N
     const int tiles = ((L + 63) / 64) * ((BK + 63) / 64) * nS;
-    int splits = (2 * num_sms() + tiles - 1) / tiles;
+    // ~8 resident blocks per SM: the kernel has no software pipelining, so it needs the warps to hide its load latency
+    // (2 blocks per SM: 147 us for the 26 instances of a training step at B = 16; 8: 110 - 135 us)
+    int splits = (8 * num_sms() + tiles - 1) / tiles;
     if (splits > (N + 63) / 64) splits = (N + 63) / 64;
     if (splits < 1) splits = 1;
     const int kps = (((N + splits - 1) / splits) + 15) / 16 * 16;
