@@ -41,7 +41,7 @@ class UnpackDesc(C.Structure):
 
 
 class WgradDesc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "Cout", "Cin", "kh", "kw", "reserved")]
+    _fields_ = [(n, C.c_int32) for n in ("B", "H", "W", "Cout", "Cin", "kh", "kw", "ksplit_div")]
 
 
 class PackDesc(C.Structure):
@@ -219,12 +219,13 @@ def conv_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Te
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, kh: int = 3, kw: int = 3,
-               db: Optional[torch.Tensor] = None) -> torch.Tensor:
+               db: Optional[torch.Tensor] = None, ksplit_div: int = 0) -> torch.Tensor:
     """dw[Cout][kh*kw*Cin] (fp32, zeroed by the caller) += weight gradient; dy / x NHWC bf16.
-    db (optional, fp32 [Cout]) += the bias gradient (column sums of dy), fused into the same kernel."""
+    db (optional, fp32 [Cout]) += the bias gradient (column sums of dy), fused into the same kernel.
+    ksplit_div > 1: that many times fewer split-K CTAs (side-stream launches, see include/dasr.h)."""
     B, H, W, Cout = dy.shape
     Cin = x.shape[3]
-    d = WgradDesc(B, H, W, Cout, Cin, kh, kw, 0)
+    d = WgradDesc(B, H, W, Cout, Cin, kh, kw, int(ksplit_div))
     check(load().dasr_conv_wgrad(C.byref(d), ptr(dy, torch.bfloat16), ptr(x, torch.bfloat16), ptr(dw, torch.float32),
                                  ptr(db, torch.float32) if db is not None else None, stream_ptr()))
     return dw

@@ -20,6 +20,7 @@ the data-parallel wrapper all-reduces (parallel.py).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Dict, List, Optional
 
@@ -54,6 +55,12 @@ class Tape:
         self.lib = L.load()
         self.ops = []
         self.s = L.stream_ptr()
+        # weight gradients are leaves of the backward: with ``Engine.wgrad_overlap`` they are issued on a side stream
+        # and fill the wave tails / launch gaps of the data-gradient chain (begin_backward / join_backward)
+        self.wg_side = None
+        self.wg_main = None
+        self._held = []
+        self._wg_next = 0
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def use(self, t: _T) -> _T:
@@ -115,7 +122,60 @@ class Tape:
     def wgrad(self, dy: torch.Tensor, x: torch.Tensor, wname: str, kh=3, kw=3, bias=False):
         """Weight gradient (and, with ``bias``, the bias gradient in the same kernel)."""
         dw = self.eng._dw_view(wname)
-        L.conv_wgrad(dy, x, dw, kh, kw, db=self.eng._db_view(wname) if bias else None)
+        db = self.eng._db_view(wname) if bias else None
+        if self.wg_side is None:
+            L.conv_wgrad(dy, x, dw, kh, kw, db=db)
+            return
+        side = self.wg_side[self._wg_next % len(self.wg_side)]
+        self._wg_next += 1
+        ev = torch.cuda.Event()
+        ev.record(self.wg_main)             # dy (and the zeroed flat buffers) are ready at this point of the main stream
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            L.conv_wgrad(dy, x, dw, kh, kw, db=db, ksplit_div=self.eng.wgrad_ksplit_div)
+        # the caching allocator orders reuse on the main stream only: keep both operands alive until the join
+        self._held.append((dy, x))
+
+    @contextlib.contextmanager
+    def leaf(self, *tensors):
+        """Run a leaf chain of the backward (kernels whose results only reach parameter gradients) on the next side
+        stream; yields the raw stream to launch on.  ``tensors``: every operand allocated on the main stream."""
+        if self.wg_side is None or not self.eng.leaf_overlap:
+            yield self.s
+            return
+        side = self.wg_side[self._wg_next % len(self.wg_side)]
+        self._wg_next += 1
+        ev = torch.cuda.Event()
+        ev.record(self.wg_main)
+        side.wait_event(ev)
+        self._held.append(tensors)
+        with torch.cuda.stream(side):
+            yield side.cuda_stream
+
+    def sync_leaves(self):
+        """Main stream waits for everything issued on the side streams so far (before a consumer on the main stream)."""
+        if self.wg_side is not None:
+            for side in self.wg_side[:max(1, min(self._wg_next, len(self.wg_side)))]:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                self.wg_main.wait_event(ev)
+
+    def begin_backward(self, device):
+        self.s = L.stream_ptr()
+        # kernel-by-kernel issue is host-bound (the cross-stream events only add host time: 13.7 -> 17 ms per step), so
+        # the side streams are used inside a CUDA-graph capture (TrainStep(graph=True)) or when forced
+        eng = self.eng
+        if eng.wgrad_overlap and (eng.overlap_eager or torch.cuda.is_current_stream_capturing()):
+            self.wg_main = torch.cuda.current_stream(device)
+            self.wg_side = self.eng._wgrad_streams(device)
+            self._wg_next = 0
+
+    def join_backward(self):
+        """Main stream waits for the weight gradients of the side stream (before unpack / all-reduce)."""
+        if self.wg_side is not None:
+            self.sync_leaves()
+            self._held.clear()
+            self.wg_side = None
 
     def bias_grad(self, dy: torch.Tensor, wname: str):
         db = self.eng._db_view(wname)
@@ -240,17 +300,20 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         tp.wgrad(dgb, actv, n + ".gb_o")
         pkd = eng._packed[n + ".gb_o.dg"]
         dA = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
-        L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)
         gw, gb = eng._grad_view(n + ".mlp_mask.0.weight"), eng._grad_view(n + ".mlp_mask.0.bias")
         scr = scr_all[sidx]          # zeroed once per step for all instances
-        L.check(lib.dasr_actv_bwd_tc(L.ptr(dA), L.ptr(aux), L.ptr(scr), L.ptr(gw), L.ptr(gb), B, H, W, nf2, s))
+        dT = dT_all[sidx]
+        # everything below only reaches parameter gradients (mlp_mask, the style tables): a leaf chain
+        with tp.leaf(dgb, actv, dA) as s2:
+            L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)
+            L.check(lib.dasr_actv_bwd_tc(L.ptr(dA), L.ptr(aux), L.ptr(scr), L.ptr(gw), L.ptr(gb), B, H, W, nf2, s2))
         # ---- style branch: K-DYN backward into this instance's slice of dT_all; the table GEMM / A_i_j backward of
         # all instances run batched once every block has back-propagated (bwd_pool)
-        dT = dT_all[sidx]
         # one-hot masks: tensor-core kernel; otherwise (device flag) the exact general-mask kernel -- each is a
         # no-op in the other's case, so no host synchronisation is needed to choose
-        L.check(lib.dasr_dynconv_bwd_tc(L.ptr(dgb), L.ptr(aux), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
-        L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s))
+        with tp.leaf(dgb) as s2:
+            L.check(lib.dasr_dynconv_bwd_tc(L.ptr(dgb), L.ptr(aux), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s2))
+            L.check(lib.dasr_dynconv_bwd(L.ptr(dgb), None, L.ptr(masks), L.ptr(flag), L.ptr(dT), B, K, H, W, nf2, s2))
         # ---- the block convolution in front of the norm (its bias gradient is exactly zero: IN removes the mean)
         tp.wgrad(dy, x, conv_name)
         tp.dgrad_into(cur, dy, conv_name + ".dg")
@@ -305,6 +368,7 @@ def _forward_train(eng, lq, depth, masks):
 
         def bwd_pool():
             # style branch of ALL SEAN instances: dWs = dT^T stp, dstp = dT Ws, then the A_i_j backward (batched)
+            tp.sync_leaves()             # dT_all is complete once the K-DYN leaf chains have run
             nS = len(eng._sean_names)
             N = eng._ws_rows
             dWs_all = eng._dw_flat[eng._wg_tables_off:eng._wg_tables_off + nS * N * lat]
@@ -456,14 +520,18 @@ class _DepthNetFn(torch.autograd.Function):
         if tp is None:
             raise RuntimeError("DepthNet backward called twice (activations are released after the first pass)")
         ctx.tape = None
-        tp.s = L.stream_ptr()
         dsr = dsr.contiguous().float()
+        tp.begin_backward(dsr.device)
         eng._begin_backward(dsr.device)
         tp.bwd_out(dsr)
         for op in reversed(tp.ops):
             op()
+        tp.join_backward()
         grads = eng._finish_backward()
+        # break the tape <-> closure reference cycles now: left to Python's cyclic GC, the tail activations the closures
+        # hold (0.32 GB per step at B=16) pile up for several steps and the caching allocator keeps growing
         tp.ops = None
+        tp.bwd_out = None
         return (None, None, None, None) + tuple(grads)
 
 

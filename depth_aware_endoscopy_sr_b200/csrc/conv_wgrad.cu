@@ -475,6 +475,11 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     const int slices = k.n_tapgroups * k.n_cchunks * n_mblocks;
     int ksplit = (2 * num_sms()) / slices;      // a CTA owns all 512 TMEM columns -> one CTA per SM; 2 waves
     if (ksplit > num_sms() / slices && slices <= num_sms()) ksplit = num_sms() / slices;
+    // ksplit_div = d: d times fewer split-K CTAs per launch (each reduces d times more pixels and the launch flushes
+    // d times fewer partial dW slices): fewer SM-microseconds per gradient at a longer latency, which is the better
+    // trade when the gradient runs beside the data-gradient chain on a side stream
+    const int ks_div = d->ksplit_div > 1 ? d->ksplit_div : 1;
+    ksplit = (ksplit + ks_div - 1) / ks_div;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > k.ktiles_total) ksplit = k.ktiles_total;
     k.skip_flag = o.skip_flag;
@@ -486,7 +491,7 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
 #endif
     if (o.per_image) {
         const int tiles_per_img = k.n_rowtiles * k.n_strips;
-        int ks_i = num_sms() / (slices * d->B);
+        int ks_i = num_sms() / (slices * d->B * ks_div);
         if (ks_i < 1) ks_i = 1;
         if (ks_i > tiles_per_img) ks_i = tiles_per_img;
         k.per_image = 1;
@@ -581,7 +586,7 @@ extern "C" int dasr_dynconv_bwd_tc(const void* dgb, const void* aux, const int32
     DASR_REQUIRE(dgb && aux && dT, "null pointer");
     DASR_REQUIRE(K >= 1 && K <= 16, "K-DYN backward: at most 16 depth masks (got %d)", K);
     dasr_wgrad_desc d;
-    d.B = B; d.H = H; d.W = W; d.Cout = nf2; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.reserved = 0;
+    d.B = B; d.H = H; d.W = W; d.Cout = nf2; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.ksplit_div = 0;
     WgOpts o;
     o.per_image = 1;
     o.n_valid = K;
@@ -610,7 +615,7 @@ extern "C" int dasr_actv_bwd_tc(const void* dA, const void* aux, float* scratch,
                                 int W, int C, void* stream) {
     DASR_REQUIRE(dA && aux && scratch && dW && db, "null pointer");
     dasr_wgrad_desc d;
-    d.B = B; d.H = H; d.W = W; d.Cout = C; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.reserved = 0;
+    d.B = B; d.H = H; d.W = W; d.Cout = C; d.Cin = DASR_AUX_CH; d.kh = 3; d.kw = 3; d.ksplit_div = 0;
     // only the depth (hi, lo, lo2) and the constant-one channel are read back: flush those four columns per tap
     static_assert(DASR_AUX_DEPTH_HI % 4 == 0 && DASR_AUX_DEPTH_LO2 == DASR_AUX_DEPTH_HI + 3 &&
                       DASR_AUX_ONE > DASR_AUX_DEPTH_HI && DASR_AUX_ONE < DASR_AUX_DEPTH_LO2,

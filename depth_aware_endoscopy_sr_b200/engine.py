@@ -58,6 +58,21 @@ class Engine:
         # (it depends on the depth map only); three rotating buffers.  DASR_ACTV_OVERLAP=0 keeps one stream.
         self.actv_overlap = os.environ.get("DASR_ACTV_OVERLAP", "1") == "1"
         self._side_streams = {}
+        # Training backward: the weight gradients (leaves of the backward) are issued round-robin on side streams, so
+        # their CTAs fill the wave tails of the data-gradient chain (256 tiles on 148 SMs at B=16) and their launch /
+        # prologue / flush latency is off the critical path; beside other kernels a gradient is split over half as
+        # many CTAs (half the partial-dW flushes and SM-microseconds, twice the latency -- hidden by the four
+        # streams).  Measured at B=16: 7.72 (one stream) -> 7.44 (1 side stream) -> 7.25 ms (4 streams, split / 2);
+        # split / 3 and / 4 are slower again (7.66, 7.78).  DASR_WGRAD_OVERLAP=0 keeps one stream.
+        self.wgrad_overlap = os.environ.get("DASR_WGRAD_OVERLAP", "1") == "1"
+        self.wgrad_streams = max(1, int(os.environ.get("DASR_WGRAD_STREAMS", "6")))
+        self.wgrad_ksplit_div = max(1, int(os.environ.get("DASR_WG_KSPLIT_DIV", "2")))
+        # the other leaf chains of a SEAN backward (gamma_o/beta_o data gradient -> mlp_mask gradient, K-DYN backward)
+        # go to the side streams as well: the critical chain of an instance is then sean_bwd1 -> sean_bwd2 -> one
+        # 64 -> 64 data gradient.  7.31 -> 6.83 ms (4 streams), 6.77 ms (6 streams).  DASR_LEAF_OVERLAP=0: main stream.
+        self.leaf_overlap = os.environ.get("DASR_LEAF_OVERLAP", "1") == "1"
+        self.overlap_eager = os.environ.get("DASR_OVERLAP_EAGER", "0") == "1"    # side streams outside a graph capture too
+        self._wg_streams = {}
         self.use_graphs = os.environ.get("DASR_INFER_GRAPH", "1") != "0"   # replay inference from a CUDA graph (see infer)
         self.max_graphs = 3
         # larger batches are device-bound when issued kernel by kernel (B=64 at 64x64: 6.3 ms of kernels against 2.7 ms
@@ -299,6 +314,12 @@ class Engine:
     def _grad_view(self, pname):
         off, shape, n = self._goff[pname]
         return self._g_flat[off:off + n].view(shape)
+
+    def _wgrad_streams(self, device):
+        st = self._wg_streams.get(device.index)
+        if st is None:
+            st = self._wg_streams[device.index] = [torch.cuda.Stream(device=device) for _ in range(self.wgrad_streams)]
+        return st
 
     def _begin_backward(self, device):
         """Zero the flat buffers the backward kernels accumulate into (one memset each)."""

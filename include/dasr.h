@@ -124,9 +124,12 @@ int dasr_conv_gen_ok(int H, int W);
  * dy NHWC bf16 [B,H,W,Cout], x NHWC bf16 [B,H,W,Cin], dw fp32 [Cout][kh*kw*Cin] in the packed GEMM-B layout
  * of dasr_pack_weights (accumulated with fp32 atomics: the caller zeroes it).  Channels multiples of 32.
  * db (optional, fp32 [Cout]): the bias gradient db[o] += sum_{b,h,w} dy[b,h,w,o], computed by the same kernel
- * (one more MMA per K step against a block of ones) instead of a separate pass over dy.                      */
+ * (one more MMA per K step against a block of ones) instead of a separate pass over dy.
+ * ksplit_div: 0 / 1 = the latency-optimal split-K (one CTA per SM); d > 1 = d times fewer CTAs, each reducing d
+ * times more pixels (fewer partial-dW flushes, fewer SM-microseconds, longer latency): for gradients issued on a
+ * side stream beside other kernels.                                                                            */
 typedef struct {
-    int32_t B, H, W, Cout, Cin, kh, kw, reserved;
+    int32_t B, H, W, Cout, Cin, kh, kw, ksplit_div;
 } dasr_wgrad_desc;
 int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, float* dw, float* db, void* stream);
 

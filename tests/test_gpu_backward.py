@@ -161,6 +161,40 @@ def test_full_depth_gradients_are_in_the_bf16_class(name):
     assert g["depth-residual14.conv1.0.weight"] is None
 
 
+def test_side_stream_backward_equals_the_one_stream_backward():
+    """The weight gradients and the other leaf chains of the backward run on side streams inside a captured training
+    step (Engine.wgrad_overlap / leaf_overlap); forced here kernel by kernel, with every combination of stream count
+    and split-K divisor, the gradients must equal the one-stream backward up to the order of the fp32 atomics."""
+    import warnings
+    import depth_aware_endoscopy_sr_b200 as dasr
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    torch.manual_seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = dasr.DepthNet(which_ResBlk_depth=[0, 1], scale=8, nb=5).cuda().train()
+    lq, depth, masks, gt = [t.cuda() for t in synthetic_inputs(2, 32, 32, scale=8, seed=9, with_gt=True)]
+    eng = net.engine()
+
+    def run(**kw):
+        for k, v in kw.items():
+            setattr(eng, k, v)
+        eng._wg_streams = {}
+        net.zero_grad(set_to_none=True)
+        sr = net(lq, depth, masks)
+        (sr - gt).abs().mean().backward()
+        torch.cuda.synchronize()
+        return sr.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+
+    sr0, g0 = run(overlap_eager=False)
+    for streams, div, leaf in ((1, 1, False), (3, 2, True), (6, 2, True), (2, 3, True)):
+        sr1, g1 = run(overlap_eager=True, wgrad_overlap=True, wgrad_streams=streams, wgrad_ksplit_div=div, leaf_overlap=leaf)
+        assert torch.equal(sr0, sr1)
+        assert g0.keys() == g1.keys()
+        for k in g0:
+            err = (g0[k] - g1[k]).abs().max().item()
+            assert err <= 1e-4 * g0[k].abs().max().item() + 1e-9, (streams, div, leaf, k, err)
+
+
 def test_backward_twice_raises_and_weights_repack_after_update():
     from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
     import depth_aware_endoscopy_sr_b200 as dasr
