@@ -47,7 +47,7 @@ class WgradDesc(C.Structure):
 class PackDesc(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("v", "g", "alpha", "bias", "bias2", "dst", "dst_bias")] + \
                [(n, C.c_int32) for n in ("dim0", "dim1", "ks", "mode", "alpha_mode", "shuffle_r", "row_offset",
-                                         "rows_per_tap")]
+                                         "rows_per_tap")] + [("dst_plane_stride", C.c_int64)]
 
 
 _lib = None
@@ -69,6 +69,8 @@ def load() -> C.CDLL:
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     sigs = {
         "dasr_check_device": [],
+        "dasr_set_planes": [i32],
+        "dasr_get_planes": [],
         "dasr_conv_fwd": [C.POINTER(ConvDesc), C.POINTER(ConvArgs), vp],
         "dasr_conv_out9": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_conv_wgrad": [C.POINTER(WgradDesc), vp, vp, vp, vp, vp],
@@ -104,7 +106,7 @@ def load() -> C.CDLL:
         "dasr_instats_finalize": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_style_mix_batched": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_build_mask16": [vp, vp, i32, i32, i32, i32, vp],
-        "dasr_table_to_dynweights": [vp, vp, i32, i32, i32, vp],
+        "dasr_table_to_dynweights": [vp, vp, i32, i32, i32, i32, vp],
         "dasr_build_aux": [vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_dynconv_bwd_tc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_actv_bwd_tc": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
@@ -129,7 +131,7 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_gen_ok", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_set_planes", "dasr_get_planes", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_gen_ok", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize", "dasr_unpack_grads",
             "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd2", "dasr_colsum",
@@ -175,6 +177,63 @@ def note_replayed_launches(n: int) -> None:
 def launch_count() -> int:
     """Kernels of libdasr_b200.so launched so far in this process, directly or through CUDA-graph replays."""
     return int(load().dasr_launch_count()) + _replayed_launches
+
+
+# ------------------------------------------------------------------------------------------------ act tensors
+# "act" tensors (NHWC bf16 activations, packed weights).  With dasr_set_planes(3) -- the fp32-split precise mode the
+# parity tests use, see include/dasr.h -- every act tensor is 3 consecutive bf16 planes; the host code keeps working
+# with the plane-0 view (same shape as in the product configuration) and the kernels find the other planes at a
+# stride of the tensor's own element count.
+def planes() -> int:
+    return int(load().dasr_get_planes())
+
+
+def set_planes(n: int) -> None:
+    check(load().dasr_set_planes(int(n)))
+
+
+def act_empty(*shape, device) -> torch.Tensor:
+    n = planes()
+    if n == 1:
+        return torch.empty(*shape, device=device, dtype=torch.bfloat16)
+    return torch.empty(n, *shape, device=device, dtype=torch.bfloat16)[0]
+
+
+def act_zeros(*shape, device) -> torch.Tensor:
+    n = planes()
+    if n == 1:
+        return torch.zeros(*shape, device=device, dtype=torch.bfloat16)
+    return torch.zeros(n, *shape, device=device, dtype=torch.bfloat16)[0]
+
+
+def act_like(t: torch.Tensor) -> torch.Tensor:
+    return act_empty(*t.shape, device=t.device)
+
+
+def act_planes(t: torch.Tensor) -> torch.Tensor:
+    """[planes, *shape] view of an act tensor allocated by act_empty / act_zeros (tests / probes)."""
+    n = planes()
+    return torch.as_strided(t, (n,) + tuple(t.shape), (t.numel(),) + tuple(t.stride()), t.storage_offset())
+
+
+def act_value(t: torch.Tensor) -> torch.Tensor:
+    """fp32 value of an act tensor: the sum of its planes, lowest plane first (exact)."""
+    pl = act_planes(t).float()
+    v = pl[-1].clone()
+    for k in range(pl.shape[0] - 2, -1, -1):
+        v += pl[k]
+    return v
+
+
+def act_from(x: torch.Tensor) -> torch.Tensor:
+    """act tensor holding the fp32 tensor ``x`` (bf16-rounded with one plane, exact with three)."""
+    t = act_empty(*x.shape, device=x.device)
+    pl = act_planes(t)
+    r = x.float().clone()
+    for k in range(pl.shape[0]):
+        pl[k] = r.to(torch.bfloat16)
+        r -= pl[k].float()
+    return t
 
 
 def check(rc: int) -> None:
@@ -245,7 +304,10 @@ def pack_weights(descs: Sequence[PackDesc], scratch: torch.Tensor) -> None:
 
 
 def pack_desc(v, dst, *, g=None, alpha=None, alpha_mode=0, bias=None, bias2=None, dst_bias=None, mode=PACK_CONV,
-              shuffle_r=0, row_offset=0, rows_per_tap=0) -> PackDesc:
+              shuffle_r=0, row_offset=0, rows_per_tap=0, dst_stride=None) -> PackDesc:
+    """dst_stride: element count of the WHOLE destination matrix when ``dst`` is a row slice of it (plane stride of
+    the fp32-split mode; ignored otherwise)."""
     return PackDesc(ptr(v, torch.float32), ptr(g, torch.float32), ptr(alpha, torch.float32), ptr(bias, torch.float32),
                     ptr(bias2, torch.float32), ptr(dst, torch.bfloat16), ptr(dst_bias, torch.float32),
-                    v.shape[0], v.shape[1], v.shape[2], mode, alpha_mode, shuffle_r, row_offset, rows_per_tap)
+                    v.shape[0], v.shape[1], v.shape[2], mode, alpha_mode, shuffle_r, row_offset, rows_per_tap,
+                    int(dst_stride if dst_stride is not None else dst.numel()))

@@ -73,7 +73,7 @@ class Tape:
         if t.grad is None:
             t.grad = g
         else:
-            out = torch.empty_like(g)
+            out = L.act_like(g)
             L.check(self.lib.dasr_add(L.ptr(t.grad), None, L.ptr(g), L.ptr(out), g.numel(), self.s))
             t.grad = out
 
@@ -84,7 +84,7 @@ class Tape:
             raise RuntimeError("tape: tensor without gradient")
         t.grad = None
         if t.act in ("relu", "lrelu") and not t.masked:
-            out = torch.empty_like(g)
+            out = L.act_like(g)
             L.check(self.lib.dasr_actgrad(L.ptr(g), L.ptr(t.data), L.ptr(out), g.numel(), t.slope, self.s))
             g = out
         return g
@@ -98,9 +98,9 @@ class Tape:
         last = t.pending == 0
         B, H, W, _ = dy.shape
         if subsample == 2:
-            out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=dy.device, dtype=BF16)
+            out = L.act_empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=dy.device)
         else:
-            out = torch.empty(B, H, W, pk.cout, device=dy.device, dtype=BF16)
+            out = L.act_empty(B, H, W, pk.cout, device=dy.device)
         mask = None
         slope = 0.0
         if last and t.act in ("relu", "lrelu") and not t.masked:
@@ -111,7 +111,7 @@ class Tape:
             # the only gradient contribution of a PixelShuffle(2) + LeakyReLU output: write it space-to-depth with
             # the LeakyReLU mask applied -- exactly the tensor the shuffle convolution's backward consumes
             # (replaces the dasr_unshuffle_actgrad pass: 3 x 80 us per training step at B = 16)
-            out = torch.empty(B, H // 2, W // 2, 4 * pk.cout, device=dy.device, dtype=BF16)
+            out = L.act_empty(B, H // 2, W // 2, 4 * pk.cout, device=dy.device)
             mask, slope, unshuffle = t.data, 0.2, 2
             t.unshuffled = True
         L.conv_fwd(dy, pk.w, eng._zero_bias, out, Cout=pk.cout, ks=ks, kw=kw, subsample=subsample, resid=t.grad,
@@ -196,7 +196,7 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
         # x3 tail: plain conv into the shuffled channel order (+ activation), then PixelShuffle(3) as a copy
         u = eng._conv(x.data, name, act=acts[act])
         B_, H_, W_, C_ = u.shape
-        out = torch.empty(B_, 3 * H_, 3 * W_, C_ // 9, device=u.device, dtype=BF16)
+        out = L.act_empty(B_, 3 * H_, 3 * W_, C_ // 9, device=u.device)
         L.check(lib.dasr_pixel_shuffle(L.ptr(u), L.ptr(out), B_, H_, W_, C_ // 9, 3, tp.s))
         del u
         o = _T(out, "handled")
@@ -220,14 +220,14 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
         elif shuffle:
             o.grad = None
             B, H2, W2, Cq = o.data.shape
-            dy = torch.empty(B, H2 // r, W2 // r, r * r * Cq, device=g.device, dtype=BF16)
+            dy = L.act_empty(B, H2 // r, W2 // r, r * r * Cq, device=g.device)
             L.check(lib.dasr_unshuffle_actgrad(L.ptr(g), L.ptr(o.data), L.ptr(dy), B, H2 // r, W2 // r, Cq, 0.2, r, s))
         else:
             dy = tp.take(o)
         if subsample == 2:      # gradient on the stride-1 grid of the forward kernel
             B, Ho, Wo, Co = dy.shape
             H, W = x.data.shape[1], x.data.shape[2]
-            full = torch.empty(B, H, W, Co, device=dy.device, dtype=BF16)
+            full = L.act_empty(B, H, W, Co, device=dy.device)
             L.check(lib.dasr_zero_insert2_to(L.ptr(dy), L.ptr(full), B, Ho, Wo, Co, H, W, s))
             dy = full
         tp.wgrad(dy, x.data, name, bias=bias_grad)
@@ -263,10 +263,10 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
     if actv_pre is not None:
         actv = actv_pre          # produced on the side stream (the caller made this stream wait for it)
     else:
-        actv = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+        actv = L.act_empty(B, H, W, nf2, device=dev)
         L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias),
                                   L.ptr(actv), B, H, W, nf2, 0, s))
-    gamma = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
+    gamma = L.act_empty(B, H, W, nf, device=dev)
     if first:
         out = eng._conv(actv, n + ".gb_o", epi=L.EPI_SEAN, inner_relu=1, y=y, stats=stats, norm_out=norm, normk_out=normk,
                         dyn_x=mask16, dyn_w=wdyn, gamma_out=gamma)
@@ -284,22 +284,22 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         dout = o.grad
         o.grad = None
         slots = lib.dasr_sean_bwd_slots(HW)
-        dgb = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
-        dn = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
-        dskip = torch.empty(B, H, W, nf, device=dev, dtype=BF16) if resid is not None else None
+        dgb = L.act_empty(B, H, W, nf2, device=dev)
+        dn = L.act_empty(B, H, W, nf, device=dev)
+        dskip = L.act_empty(B, H, W, nf, device=dev) if resid is not None else None
         part = torch.empty(B, slots, nf, 4, device=dev, dtype=torch.float32)
         L.check(lib.dasr_sean_bwd1(L.ptr(dout), L.ptr(out), L.ptr(y), L.ptr(norm), L.ptr(gamma), L.ptr(dgb), L.ptr(dn),
                                    L.ptr(dskip), L.ptr(part), B, HW, nf, s))
         if resid is not None:
             tp.accum(resid, dskip)
-        dy = torch.empty(B, H, W, nf, device=dev, dtype=BF16)
+        dy = L.act_empty(B, H, W, nf, device=dev)
         # pass 2 also adds the [gamma_o; beta_o] bias gradient (column sums of dgb, accumulated by pass 1)
         L.check(lib.dasr_sean_bwd2(L.ptr(dn), L.ptr(y), L.ptr(norm), L.ptr(normk), L.ptr(part), L.ptr(dy),
                                    L.ptr(eng._db_view(n + ".gb_o")), B, HW, nf, s))
         # ---- gamma_o / beta_o convolution and mlp_mask
         tp.wgrad(dgb, actv, n + ".gb_o")
         pkd = eng._packed[n + ".gb_o.dg"]
-        dA = torch.empty(B, H, W, nf2, device=dev, dtype=BF16)
+        dA = L.act_empty(B, H, W, nf2, device=dev)
         gw, gb = eng._grad_view(n + ".mlp_mask.0.weight"), eng._grad_view(n + ".mlp_mask.0.bias")
         scr = scr_all[sidx]          # zeroed once per step for all instances
         dT = dT_all[sidx]
@@ -333,14 +333,14 @@ def _forward_train(eng, lq, depth, masks):
     enc = net.encoder
 
     # ---- encoder
-    f0d = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
+    f0d = L.act_empty(B, h, w, 32, device=dev)
     L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g), L.ptr(enc.layer1.bias),
                                 L.ptr(f0d), B, h, w, s))
     f0 = _T(f0d, "lrelu")
 
     def bwd_first():
         dy = tp.take(f0)
-        lq32 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
+        lq32 = L.act_empty(B, h, w, 32, device=dev)
         L.check(lib.dasr_nchw3_to_nhwc32(L.ptr(lq), L.ptr(lq32), B, h, w, s))
         tp.wgrad(dy, lq32, "encoder.layer1", bias=True)
 
@@ -351,7 +351,7 @@ def _forward_train(eng, lq, depth, masks):
         e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
         e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
         h3, w3 = e3.data.shape[1], e3.data.shape[2]
-        zd = torch.empty(B, 2 * h3 - 1, 2 * w3 - 1, 128, device=dev, dtype=BF16)
+        zd = L.act_empty(B, 2 * h3 - 1, 2 * w3 - 1, 128, device=dev)
         L.check(lib.dasr_zero_insert2(L.ptr(e3.data), L.ptr(zd), B, h3, w3, 128, s))
         z = _T(zd, "none")
         e4 = _conv_train(tp, z, "encoder.layer4", act="lrelu", convt_src=e3)
@@ -377,7 +377,7 @@ def _forward_train(eng, lq, depth, masks):
                                                L.ptr(dstp_all), nS, B * K, N, lat, tp.s))
             L.check(lib.dasr_style_mix_bwd_batched(L.ptr(dstp_all), L.ptr(vec), L.ptr(eng._A_ptrs), L.ptr(eng._dA_ptrs),
                                                    L.ptr(eng._da_ptrs), L.ptr(dvec), nS, B, K, lat, tp.s))
-            de5 = torch.empty_like(e5.data)
+            de5 = L.act_like(e5.data)
             L.check(lib.dasr_region_pool_bwd(L.ptr(dvec), L.ptr(msel), L.ptr(cnt), L.ptr(de5), B, P, lat, K, s))
             tp.accum(e5, de5)
 
@@ -414,7 +414,7 @@ def _forward_train(eng, lq, depth, masks):
         for i in dgb_blocks:
             blk = net.block(i)
             nf2 = 2 * blk.norm1.norm_nc
-            pair = [torch.empty(B, h, w, nf2, device=dev, dtype=BF16) for _ in range(2)]
+            pair = [L.act_empty(B, h, w, nf2, device=dev) for _ in range(2)]
             with torch.cuda.stream(side):
                 for sean, buf in zip((blk.norm1, blk.norm2), pair):
                     L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight), L.ptr(sean.mlp_mask[0].bias),
@@ -459,7 +459,7 @@ def _forward_train(eng, lq, depth, masks):
     for i, pos in order:
         if pos == "trunk":
             x = run_block(i, x)
-    addd = torch.empty_like(x.data)
+    addd = L.act_like(x.data)
     L.check(lib.dasr_add(L.ptr(x.data), None, L.ptr(fea_bef.data), L.ptr(addd), addd.numel(), s))
     add = _T(addd, "none")
     xa, xb = tp.use(x), tp.use(fea_bef)
@@ -489,7 +489,7 @@ def _forward_train(eng, lq, depth, masks):
     tp.use(u3)
 
     def bwd_out(dsr):
-        ap = torch.empty(Bo, Ho, Wo, 32, device=dev, dtype=BF16)
+        ap = L.act_empty(Bo, Ho, Wo, 32, device=dev)
         L.check(lib.dasr_out9_bwd_prep(L.ptr(dsr), L.ptr(sr), L.ptr(ap), L.ptr(eng._grad_view("conv_output.bias")), Bo,
                                        Ho, Wo, s))
         tp.wgrad(ap, u3.data, "conv_output", kh=9, kw=1)

@@ -45,10 +45,12 @@ __global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict_
                                                         const uint4* __restrict__ y, const float* __restrict__ norm,
                                                         const uint4* __restrict__ gamma, uint4* __restrict__ dgb,
                                                         uint4* __restrict__ dn_out, uint4* __restrict__ dskip,
-                                                        float* __restrict__ part, int HW, int pix_per_block, int nslots) {
+                                                        float* __restrict__ part, int HW, int pix_per_block, int nslots,
+                                                        int npl) {
     constexpr int NF = G * 8;
     constexpr int LANES = 256 / G;
     const int b = blockIdx.y, slot = blockIdx.x;
+    const size_t ps8 = (size_t)gridDim.y * HW * G;          // plane stride of the [B,HW,nf] tensors (uint4 units)
     const int g = threadIdx.x % G, pl = threadIdx.x / G;
     float mean[8], scale[8], acc[4][8];          // acc: sum dn, sum dn*n, sum dz*n (dgamma), sum dz (dbeta)
 #pragma unroll
@@ -62,10 +64,16 @@ __global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict_
     for (int pix = p0 + pl; pix < p1; pix += LANES) {
         const size_t i = ((size_t)b * HW + pix) * G + g;
         float d[8], a[8], yv[8], gm[8], dg[8], dnv[8];
-        bunpack8(__ldg(dout + i), d);
-        bunpack8(__ldg(act_out + i), a);
-        bunpack8(__ldg(y + i), yv);
-        bunpack8(__ldg(gamma + i), gm);
+        bunpack8(__ldg(act_out + i), a);      // sign only: plane 0
+        if (npl == 1) {
+            bunpack8(__ldg(dout + i), d);
+            bunpack8(__ldg(y + i), yv);
+            bunpack8(__ldg(gamma + i), gm);
+        } else {
+            pl_load8(dout, i, ps8, npl, d);
+            pl_load8(y, i, ps8, npl, yv);
+            pl_load8(gamma, i, ps8, npl, gm);
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const float dz = a[j] > 0.f ? d[j] : 0.f;
@@ -79,10 +87,20 @@ __global__ void __launch_bounds__(256) sean_bwd1_kernel(const uint4* __restrict_
             acc[3][j] += dz;
         }
         const size_t o = ((size_t)b * HW + pix) * (2 * G);
-        dgb[o + g] = bpack8(dg);
-        dgb[o + G + g] = bpack8(d);
-        dn_out[i] = bpack8(dnv);
-        if (dskip) dskip[i] = bpack8(d);
+        if (npl == 1) {
+            dgb[o + g] = bpack8(dg);
+            dgb[o + G + g] = bpack8(d);
+            dn_out[i] = bpack8(dnv);
+            if (dskip) dskip[i] = bpack8(d);
+        } else {
+            float t[8];
+            pl_store8(dgb, o + g, 2 * ps8, npl, dg);
+#pragma unroll
+            for (int j = 0; j < 8; j++) t[j] = d[j];
+            pl_store8(dgb, o + G + g, 2 * ps8, npl, t);
+            pl_store8(dn_out, i, ps8, npl, dnv);
+            if (dskip) pl_store8(dskip, i, ps8, npl, d);
+        }
     }
     // lanes of a warp that share g (stride G) first, then the 8 warps through shared memory
     __shared__ float red[4][8][NF];
@@ -121,10 +139,11 @@ __global__ void __launch_bounds__(256) sean_bwd2_kernel(const uint4* __restrict_
                                                         const float* __restrict__ norm, const float* __restrict__ normk,
                                                         const float* __restrict__ part, uint4* __restrict__ dy,
                                                         float* __restrict__ dbias, int HW, int pix_per_block,
-                                                        int nslots) {
+                                                        int nslots, int npl) {
     constexpr int NF = G * 8;
     constexpr int LANES = 256 / G;
     const int b = blockIdx.y;
+    const size_t ps8 = (size_t)gridDim.y * HW * G;
     const int g = threadIdx.x % G, pl = threadIdx.x / G;
     __shared__ float sums[2][NF];
     if (threadIdx.x < 4 * NF) {
@@ -161,14 +180,20 @@ __global__ void __launch_bounds__(256) sean_bwd2_kernel(const uint4* __restrict_
     for (int pix = p0 + pl; pix < p1; pix += LANES) {
         const size_t i = ((size_t)b * HW + pix) * G + g;
         float d[8], yv[8];
-        bunpack8(__ldg(dn + i), d);
-        bunpack8(__ldg(y + i), yv);
+        if (npl == 1) {
+            bunpack8(__ldg(dn + i), d);
+            bunpack8(__ldg(y + i), yv);
+        } else {
+            pl_load8(dn, i, ps8, npl, d);
+            pl_load8(y, i, ps8, npl, yv);
+        }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const float n = (yv[j] - mean[j]) * scale[j];
             d[j] = scale[j] * (d[j] - c1[j]) + c2[j] * n;
         }
-        dy[i] = bpack8(d);
+        if (npl == 1) dy[i] = bpack8(d);
+        else pl_store8(dy, i, ps8, npl, d);
     }
 }
 
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* _
                                                           const uint8_t* __restrict__ labels,
                                                           const float* __restrict__ masks, const int* __restrict__ flag,
                                                           float* __restrict__ dT, int K, int H, int W, int C2,
-                                                          int rows_per_block) {
+                                                          int rows_per_block, int npl, size_t ps) {
     extern __shared__ float acc[];   // [K*9][C2]
     const int bands = (H + rows_per_block - 1) / rows_per_block;
     const int b = blockIdx.x / bands, band = blockIdx.x % bands;
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* _
     const bool general = (labels == nullptr) || (flag != nullptr && *flag != 0);
     for (int y = h0; y < h1; y++)
         for (int x = 0; x < W; x++) {
-            const float v = __bfloat162float(dgb[(((size_t)b * H + y) * W + x) * C2 + c]);
+            const float v = pl_load1(dgb, (((size_t)b * H + y) * W + x) * C2 + c, ps, npl);
 #pragma unroll
             for (int t = 0; t < 3; t++)
 #pragma unroll
@@ -262,7 +287,8 @@ template <bool AT>
 __global__ void __launch_bounds__(256) gemm_f32_bf16_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Bm,
                                                             float* __restrict__ C, int M, int N, int K, int lda, int ldb,
                                                             int ldc, int k_per_split, int atomic, int splits,
-                                                            long long sA, long long sB, long long sC) {
+                                                            long long sA, long long sB, long long sC, int npl,
+                                                            size_t psB) {
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -291,7 +317,7 @@ __global__ void __launch_bounds__(256) gemm_f32_bf16_kernel(const float* __restr
             As[kk][r] = v;
             const int kb = idx >> 6, c = idx & 63;
             const int kq = k0 + kb, n = n0 + c;
-            Bs[kb][c] = (kq < kend && n < N) ? __bfloat162float(Bm[(size_t)kq * ldb + n]) : 0.f;
+            Bs[kb][c] = (kq < kend && n < N) ? pl_load1(Bm, (size_t)kq * ldb + n, psB, npl) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -420,7 +446,7 @@ __global__ void style_mix_bwd_v_batched_kernel(const float* __restrict__ dstp, c
 // de5[b][p][c] = sum_k msel[b][k][p] * dvec[b][k][c] / (cnt[b][k] + 1e-10)      (msel, cnt saved by the forward)
 __global__ void region_pool_bwd_kernel(const float* __restrict__ dvec, const float* __restrict__ msel,
                                        const float* __restrict__ cnt, __nv_bfloat16* __restrict__ de5, int B, int P, int C,
-                                       int K) {
+                                       int K, int npl) {
     const size_t total = (size_t)B * P * C;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int c = idx % C;
@@ -431,7 +457,7 @@ __global__ void region_pool_bwd_kernel(const float* __restrict__ dvec, const flo
             const float m = msel[((size_t)b * K + k) * P + p];
             if (m != 0.f) s += m * dvec[((size_t)b * K + k) * C + c] / (cnt[b * K + k] + 1e-10f);
         }
-        de5[idx] = __float2bfloat16(s);
+        pl_store1(de5, idx, total, npl, s);
     }
 }
 
@@ -469,7 +495,8 @@ __global__ void __launch_bounds__(128) actv_bwd_kernel(const __nv_bfloat16* __re
 // dconv[b,h,w,s*Cq + c] = dps[b,r*h+i,r*w+j,c] * (ps_out[b,r*h+i,r*w+j,c] > 0 ? 1 : slope),  s = r*i + j
 // (the convolution in front of the shuffle is packed in this "shuffled" channel order, DASR_PACK_* shuffle_r)
 __global__ void unshuffle_actgrad_kernel(const uint4* __restrict__ dps, const uint4* __restrict__ ps_out,
-                                         uint4* __restrict__ dconv, int B, int H, int W, int Gq, float slope, int r) {
+                                         uint4* __restrict__ dconv, int B, int H, int W, int Gq, float slope, int r,
+                                         int npl) {
     const int r2 = r * r;
     const size_t total = (size_t)B * H * W * r2 * Gq;   // uint4 items of the output
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -482,11 +509,13 @@ __global__ void unshuffle_actgrad_kernel(const uint4* __restrict__ dps, const ui
         const int i = s / r, j = s - i * r;
         const size_t src = ((((size_t)b * r * H + r * h + i) * r * W) + r * w + j) * Gq + g;
         float d[8], o[8];
-        bunpack8(__ldg(dps + src), d);
-        bunpack8(__ldg(ps_out + src), o);
+        if (npl == 1) bunpack8(__ldg(dps + src), d);
+        else pl_load8(dps, src, total, npl, d);
+        bunpack8(__ldg(ps_out + src), o);       // sign only: plane 0
 #pragma unroll
         for (int k = 0; k < 8; k++) d[k] *= (o[k] > 0.f ? 1.f : slope);
-        dconv[idx] = bpack8(d);
+        if (npl == 1) dconv[idx] = bpack8(d);
+        else pl_store8(dconv, idx, total, npl, d);
     }
 }
 
@@ -515,7 +544,7 @@ __global__ void pixel_shuffle_kernel(const uint4* __restrict__ in, uint4* __rest
 // channels used;  dbias[co] += sum g
 __global__ void __launch_bounds__(256) out9_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ sr,
                                                             __nv_bfloat16* __restrict__ aprime, float* __restrict__ dbias,
-                                                            int B, int H, int W) {
+                                                            int B, int H, int W, int npl) {
     const size_t plane = (size_t)H * W;
     const size_t total = (size_t)B * plane;
     float sb[3] = {0.f, 0.f, 0.f};
@@ -544,8 +573,13 @@ __global__ void __launch_bounds__(256) out9_bwd_prep_kernel(const float* __restr
             }
         }
         uint4* op = reinterpret_cast<uint4*>(aprime + pix * 32);
+        if (npl == 1) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) op[q] = bpack8(out + 8 * q);
+            for (int q = 0; q < 4; q++) op[q] = bpack8(out + 8 * q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) pl_store8(reinterpret_cast<uint4*>(aprime), pix * 4 + q, total * 4, npl, out + 8 * q);
+        }
     }
     __shared__ float red[3][256];
     for (int co = 0; co < 3; co++) red[co][threadIdx.x] = sb[co];
@@ -559,32 +593,42 @@ __global__ void __launch_bounds__(256) out9_bwd_prep_kernel(const float* __restr
 }
 
 // x NCHW fp32 [B,3,H,W] -> NHWC bf16 [B,H,W,32] (channels 3..31 zero)
-__global__ void nchw3_to_nhwc32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+__global__ void nchw3_to_nhwc32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                       int npl) {
     const size_t plane = (size_t)H * W;
     const size_t total = (size_t)B * plane;
     for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
         const size_t b = pix / plane, p = pix - b * plane;
         float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 3; c++) f[c] = __ldg(x + (b * 3 + c) * plane + p);
-        uint4* op = reinterpret_cast<uint4*>(out + pix * 32);
-        op[0] = bpack8(f);
         const uint4 z = make_uint4(0, 0, 0, 0);
-        op[1] = z;
-        op[2] = z;
-        op[3] = z;
+        for (int k = 0; k < npl; k++) {
+            uint4* op = reinterpret_cast<uint4*>(out + ((size_t)k * total + pix) * 32);
+            const uint4 u = bpack8(f);
+            op[0] = u;
+            op[1] = z;
+            op[2] = z;
+            op[3] = z;
+            float t[8];
+            bunpack8(u, t);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] -= t[j];
+        }
     }
 }
 
 // out = d * (act_out > 0 ? 1 : slope)      (ReLU / LeakyReLU backward, out of place)
 __global__ void actgrad_kernel(const uint4* __restrict__ d, const uint4* __restrict__ act_out, uint4* __restrict__ out,
-                               size_t n8, float slope) {
+                               size_t n8, float slope, int npl) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         float g[8], a[8];
-        bunpack8(__ldg(d + i), g);
-        bunpack8(__ldg(act_out + i), a);
+        if (npl == 1) bunpack8(__ldg(d + i), g);
+        else pl_load8(d, i, n8, npl, g);
+        bunpack8(__ldg(act_out + i), a);        // sign only: plane 0
 #pragma unroll
         for (int j = 0; j < 8; j++) g[j] *= (a[j] > 0.f ? 1.f : slope);
-        out[i] = bpack8(g);
+        if (npl == 1) out[i] = bpack8(g);
+        else pl_store8(out, i, n8, npl, g);
     }
 }
 
@@ -636,9 +680,9 @@ extern "C" int dasr_sean_bwd1(const void* dout, const void* act_out, const void*
     const int ppb = sean_ppb(HW), slots = (HW + ppb - 1) / ppb;
     dim3 grid(slots, B);
     if (nf == 64)
-        sean_bwd1_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint4*)act_out, (const uint4*)y, norm, (const uint4*)gamma, (uint4*)dgb, (uint4*)dn, (uint4*)dskip, part, HW, ppb, slots);
+        sean_bwd1_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint4*)act_out, (const uint4*)y, norm, (const uint4*)gamma, (uint4*)dgb, (uint4*)dn, (uint4*)dskip, part, HW, ppb, slots, planes());
     else
-        sean_bwd1_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint4*)act_out, (const uint4*)y, norm, (const uint4*)gamma, (uint4*)dgb, (uint4*)dn, (uint4*)dskip, part, HW, ppb, slots);
+        sean_bwd1_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dout, (const uint4*)act_out, (const uint4*)y, norm, (const uint4*)gamma, (uint4*)dgb, (uint4*)dn, (uint4*)dskip, part, HW, ppb, slots, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -650,9 +694,9 @@ extern "C" int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, 
     const int ppb = sean_ppb(HW), slots = (HW + ppb - 1) / ppb;
     dim3 grid(slots, B);
     if (nf == 64)
-        sean_bwd2_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, normk, part, (uint4*)dy, dbias, HW, ppb, slots);
+        sean_bwd2_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, normk, part, (uint4*)dy, dbias, HW, ppb, slots, planes());
     else
-        sean_bwd2_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, normk, part, (uint4*)dy, dbias, HW, ppb, slots);
+        sean_bwd2_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)dn, (const uint4*)y, norm, normk, part, (uint4*)dy, dbias, HW, ppb, slots, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -660,6 +704,7 @@ extern "C" int dasr_sean_bwd2(const void* dn, const void* y, const float* norm, 
 extern "C" int dasr_colsum(const void* x, float* out, int64_t rows, int C, void* stream) {
     DASR_REQUIRE(x && out && rows > 0, "bad arguments");
     DASR_REQUIRE(C % 8 == 0 && C >= 8 && C / 8 <= 256, "colsum: unsupported C %d", C);   // 256 % G != 0: spare threads idle
+    DASR_REQUIRE(planes() == 1, "colsum has no fp32-split form (bias gradients come from the weight-gradient kernel)");
     const int G = C / 8;
     const int lanes = 256 / G;
     size_t rpb = ((size_t)rows + 4 * (size_t)num_sms() - 1) / (4 * (size_t)num_sms());
@@ -685,7 +730,7 @@ extern "C" int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const fl
     }
     DASR_REQUIRE(smem <= 100 * 1024, "table too large");
     const int bands = (H + rows - 1) / rows;
-    dynconv_bwd_kernel<<<B * bands, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dgb, labels, masks, flag, dT, K, H, W, nf2, rows);
+    dynconv_bwd_kernel<<<B * bands, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dgb, labels, masks, flag, dT, K, H, W, nf2, rows, planes(), (size_t)B * H * W * nf2);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -698,7 +743,7 @@ extern "C" int dasr_table_bwd_batched(const float* dT, const void* stp, const vo
     // dWs [N][L] = dT^T [N][BK] * stp [BK][L]
     gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, nS), 256, 0, st>>>(
         dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0, 1, (long long)BK * N, (long long)BK * L,
-        (long long)N * L);
+        (long long)N * L, planes(), (size_t)nS * BK * L);
     DASR_LAUNCH_OK();
     // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles per instance -> split the reduction over N
     const int tiles = ((L + 63) / 64) * ((BK + 63) / 64) * nS;
@@ -712,7 +757,7 @@ extern "C" int dasr_table_bwd_batched(const float* dT, const void* stp, const vo
     DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)nS * BK * L * sizeof(float), st));
     gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, nS * splits), 256, 0, st>>>(
         dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1, splits, (long long)BK * N, (long long)N * L,
-        (long long)BK * L);
+        (long long)BK * L, planes(), (size_t)nS * N * L);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -747,7 +792,7 @@ extern "C" int dasr_style_mix_bwd_batched(const float* dstp, const float* vec, c
 extern "C" int dasr_region_pool_bwd(const float* dvec, const float* msel, const float* cnt, void* de5, int B, int P, int C,
                                     int K, void* stream) {
     DASR_REQUIRE(dvec && msel && cnt && de5, "null pointer");
-    region_pool_bwd_kernel<<<grid_for((size_t)B * P * C, 256), 256, 0, (cudaStream_t)stream>>>(dvec, msel, cnt, (__nv_bfloat16*)de5, B, P, C, K);
+    region_pool_bwd_kernel<<<grid_for((size_t)B * P * C, 256), 256, 0, (cudaStream_t)stream>>>(dvec, msel, cnt, (__nv_bfloat16*)de5, B, P, C, K, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -755,6 +800,7 @@ extern "C" int dasr_region_pool_bwd(const float* dvec, const float* msel, const 
 extern "C" int dasr_actv_bwd(const void* dA, const float* depth, float* dW, float* db, int B, int H, int W, int C,
                              void* stream) {
     DASR_REQUIRE(dA && depth && dW && db && C <= 128, "bad arguments");
+    DASR_REQUIRE(planes() == 1, "dasr_actv_bwd has no fp32-split form (use dasr_actv_bwd_tc)");
     const int rows = 8;
     const int bands = (H + rows - 1) / rows;
     actv_bwd_kernel<<<B * bands, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dA, depth, dW, db, H, W, C, rows);
@@ -767,7 +813,7 @@ extern "C" int dasr_unshuffle_actgrad(const void* dps, const void* ps_out, void*
     DASR_REQUIRE(dps && ps_out && dconv && Cq % 8 == 0, "bad arguments");
     DASR_REQUIRE(r == 2 || r == 3, "PixelShuffle factor must be 2 or 3 (got %d)", r);
     const size_t total = (size_t)B * H * W * r * r * (Cq / 8);
-    unshuffle_actgrad_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)dps, (const uint4*)ps_out, (uint4*)dconv, B, H, W, Cq / 8, slope, r);
+    unshuffle_actgrad_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)dps, (const uint4*)ps_out, (uint4*)dconv, B, H, W, Cq / 8, slope, r, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -775,6 +821,7 @@ extern "C" int dasr_unshuffle_actgrad(const void* dps, const void* ps_out, void*
 extern "C" int dasr_pixel_shuffle(const void* in, void* out, int B, int H, int W, int Cq, int r, void* stream) {
     DASR_REQUIRE(in && out && Cq % 8 == 0 && B > 0 && H > 0 && W > 0, "bad arguments");
     DASR_REQUIRE(r == 2 || r == 3, "PixelShuffle factor must be 2 or 3 (got %d)", r);
+    B *= planes();          // fp32-split planes are extra images of a copy kernel
     const size_t total = (size_t)B * H * W * r * r * (Cq / 8);
     pixel_shuffle_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, (uint4*)out, B, H, W, Cq / 8, r);
     DASR_LAUNCH_OK();
@@ -784,20 +831,21 @@ extern "C" int dasr_pixel_shuffle(const void* in, void* out, int B, int H, int W
 extern "C" int dasr_out9_bwd_prep(const float* dout, const float* sr, void* aprime, float* dbias, int B, int H, int W,
                                   void* stream) {
     DASR_REQUIRE(dout && sr && aprime && dbias, "null pointer");
-    out9_bwd_prep_kernel<<<grid_for((size_t)B * H * W, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(dout, sr, (__nv_bfloat16*)aprime, dbias, B, H, W);
+    out9_bwd_prep_kernel<<<grid_for((size_t)B * H * W, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(dout, sr, (__nv_bfloat16*)aprime, dbias, B, H, W, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
 
 extern "C" int dasr_actgrad(const void* d, const void* act_out, void* out, int64_t n, float slope, void* stream) {
     DASR_REQUIRE(d && act_out && out && n % 8 == 0, "bad arguments");
-    actgrad_kernel<<<grid_for((size_t)n / 8, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)d, (const uint4*)act_out, (uint4*)out, (size_t)n / 8, slope);
+    actgrad_kernel<<<grid_for((size_t)n / 8, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const uint4*)d, (const uint4*)act_out, (uint4*)out, (size_t)n / 8, slope, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
 
 extern "C" int dasr_zero_insert2_to(const void* x, void* out, int B, int H, int W, int C, int Ho, int Wo, void* stream) {
     DASR_REQUIRE(x && out && C % 8 == 0, "bad arguments");
+    B *= planes();          // fp32-split planes are extra images of a copy kernel
     zero_insert2_to_kernel<<<grid_for((size_t)B * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, B, H, W, C / 8, Ho, Wo);
     DASR_LAUNCH_OK();
     return DASR_OK;
@@ -805,7 +853,7 @@ extern "C" int dasr_zero_insert2_to(const void* x, void* out, int B, int H, int 
 
 extern "C" int dasr_nchw3_to_nhwc32(const float* x, void* out, int B, int H, int W, void* stream) {
     DASR_REQUIRE(x && out, "null pointer");
-    nchw3_to_nhwc32_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, B, H, W);
+    nchw3_to_nhwc32_kernel<<<grid_for((size_t)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, B, H, W, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

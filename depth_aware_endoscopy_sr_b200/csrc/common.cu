@@ -82,6 +82,9 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_planes{1};
+int planes() { return g_planes.load(std::memory_order_relaxed); }
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -98,6 +101,14 @@ int num_sms() {
 extern "C" const char* dasr_last_error(void) { return dasr::g_err; }
 extern "C" int dasr_version(void) { return 100; }
 extern "C" int64_t dasr_launch_count(void) { return (int64_t)dasr::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int dasr_set_planes(int n) {
+    if (n != 1 && n != 2 && n != dasr::kMaxPlanes)
+        return dasr::fail(DASR_ERR_BAD_ARG, "planes must be 1 (bf16 storage), 2 or %d (fp32 split); got %d", dasr::kMaxPlanes, n);
+    dasr::g_planes.store(n);
+    return DASR_OK;
+}
+extern "C" int dasr_get_planes(void) { return dasr::planes(); }
 
 extern "C" int dasr_check_device(void) {
     int dev = 0;

@@ -48,6 +48,11 @@ __device__ unsigned long long g_prof[16];
 #define PROF_FLUSH(base, n)
 #endif
 
+#ifdef DASR_CONV_PRECISE_TU
+constexpr bool kPrecTU = true;      // this translation unit instantiates the fp32-split (PREC) kernels
+#else
+constexpr bool kPrecTU = false;
+#endif
 constexpr int kMaxBStages = 96;
 constexpr int kMaxAStages = 4;
 constexpr int kThreads = 384;   // 4 role warps + 8 epilogue warps
@@ -97,6 +102,13 @@ struct ConvK {
     uint32_t gen_off;              // depth-halo scratch inside the dynamic shared memory
     int w_img_rows;                // > 0: per-image weights, image b uses rows [b*w_img_rows, +Cout) of the B matrix
     int unshuffle;                 // EPI_STORE: space-to-depth store addressing (PixelShuffle(2) backward)
+    // fp32-split planes (PREC kernels, dasr_set_planes > 1; dasr_internal.h): the K loop runs the cross terms
+    // (ta[i], tb[i]) of the operand planes, the epilogues read plane sums and write plane splits
+    int npl, n_terms;
+    unsigned char ta[6], tb[6];
+    int w_plane_rows;              // rows of ONE plane of the packed weight matrix
+    int dynw_plane_rows;           // rows of one plane of the dynamic filters (B * N_TILE)
+    size_t ps_out;                 // plane stride (elements) of out / resid / y / gamma_out
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -149,6 +161,39 @@ __device__ __forceinline__ void load16(const __nv_bfloat16* p, float* f) {
 }
 __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* f) {
     stg256(p, pack8(f), pack8(f + 8));
+}
+
+// plane-aware forms of load16 / store16 (PREC kernels): sum of the planes / split into planes; ps = plane stride
+template <bool PREC>
+__device__ __forceinline__ void add_planes16(const __nv_bfloat16* p, size_t ps, int npl, float* f) {
+    if (PREC) {
+        for (int k = 1; k < npl; k++) {
+            float t[16];
+            load16(p + (size_t)k * ps, t);
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] += t[j];
+        }
+    }
+}
+template <bool PREC>
+__device__ __forceinline__ void store16p(__nv_bfloat16* p, size_t ps, int npl, const float* f) {
+    const uint4 a = pack8(f), b = pack8(f + 8);
+    stg256(p, a, b);
+    if (PREC) {
+        float r[16], t[16];
+        uint4 ua = a, ub = b;
+#pragma unroll
+        for (int j = 0; j < 16; j++) r[j] = f[j];
+        for (int k = 1; k < npl; k++) {
+            unpack8(ua, t);
+            unpack8(ub, t + 8);
+#pragma unroll
+            for (int j = 0; j < 16; j++) r[j] -= t[j];
+            ua = pack8(r);
+            ub = pack8(r + 8);
+            stg256(p + (size_t)k * ps, ua, ub);
+        }
+    }
 }
 
 // Reduce 16 per-thread values over the 32 lanes of a warp (recursive halving).  On return lane L holds in
@@ -227,7 +272,7 @@ __device__ __forceinline__ void sean_load(const ConvK& p, SeanOps& o, int img, i
     }
 }
 
-template <int N_TILE, int NB>
+template <int N_TILE, int NB, bool PREC>
 __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, const float* bias_t, const float* norm_s,
                                               int img, int q0, int w0, int m, int half) {
     constexpr int NF = N_TILE / 2;
@@ -250,6 +295,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
         float yv[16], gs[16], f[16];
         unpack8(o.y0, yv);
         unpack8(o.y1, yv + 8);
+        add_planes16<PREC>(p.y + o.pix * NF + c0, p.ps_out, p.npl, yv);
         // bias / (mean, scale) of the 16 columns with 128-bit shared-memory loads (a scalar LDS per value made this
         // loop ~530 instructions per step); run-time flags are tested once per step, not once per element
 #pragma unroll
@@ -287,7 +333,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
             for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
         }
         if (DBG(p, 2)) continue;
-        if (p.gamma_out) store16(p.gamma_out + o.pix * NF + c0, gs);
+        if (p.gamma_out) store16p<PREC>(p.gamma_out + o.pix * NF + c0, p.ps_out, p.npl, gs);
         if (p.resid_f32) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -300,6 +346,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
             float rr[16];
             unpack8(o.r0, rr);
             unpack8(o.r1, rr + 8);
+            add_planes16<PREC>(p.resid + o.pix * NF + c0, p.ps_out, p.npl, rr);
 #pragma unroll
             for (int j = 0; j < 16; j++) f[j] += rr[j];
         }
@@ -310,7 +357,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
 #pragma unroll
             for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
         }
-        store16(p.out + o.pix * NF + c0, f);
+        store16p<PREC>(p.out + o.pix * NF + c0, p.ps_out, p.npl, f);
         if (p.out_aux_f32) {
             stg256f(p.out_aux_f32 + o.pix * NF + c0, f);
             stg256f(p.out_aux_f32 + o.pix * NF + c0 + 8, f + 8);
@@ -321,7 +368,7 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
 // STATS epilogue of one tile for one thread: store y = acc + bias (bf16) and accumulate, per column, the sum and the
 // sum of squares of the STORED values over this warp's 32 rows of BOTH M blocks in registers; one butterfly reduction
 // per 16-column chunk and tile (v1 reduced every M block separately: twice the shuffles on the critical epilogue).
-template <int N_TILE, int NB>
+template <int N_TILE, int NB, bool PREC>
 __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, const float* bias_t, float* red_s, int img,
                                                int q0, int w0, int nt, int m, int half, int ew, int lane) {
     if (half * 16 >= N_TILE) return;
@@ -352,9 +399,13 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
             // statistics of the values as stored (bf16-rounded), so IN(y) is self-consistent
             const uint4 o0 = pack8(f), o1 = pack8(f + 8);
             if (valid[blk]) {
+                if (PREC) {      // the planes hold the fp32 value: statistics of f itself
+                    store16p<true>(p.out + pix[blk] * p.Cout + nt * N_TILE + c0, p.ps_out, p.npl, f);
+                } else {
                 if (!DBG(p, 2)) stg256(p.out + pix[blk] * p.Cout + nt * N_TILE + c0, o0, o1);
                 unpack8(o0, f);
                 unpack8(o1, f + 8);
+                }
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     s1[j] += f[j];
@@ -388,7 +439,7 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
 #define DASR_LEAN_ROLE_REGS 40
 #define DASR_LEAN_EPI_REGS 168
 #endif
-template <int SWZ, int N_TILE, int NB, int EPI, bool GEN>
+template <int SWZ, int N_TILE, int NB, int EPI, bool GEN, bool PREC>
 __global__ void __launch_bounds__(GEN || EPI == DASR_EPI_SEAN ? 512 : kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const ConvK p) {
@@ -458,6 +509,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     const int tiles_per_img = p.n_strips * p.tiles_per_strip * p.ntn;
+    const int nch_t = PREC ? p.nch * p.n_terms : p.nch;      // K chunks x plane cross terms
 
     // GEN: the register file is redistributed between the warpgroups at the top of each warpgroup-level branch
     // (setmaxnreg applies to the code it dominates): roles 56, epilogue 168, generators 120 registers per thread
@@ -480,7 +532,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int q0 = tps * (NB * 128);
                 const int r0 = q0 / p.Wp;
                 const int w0 = strip * p.Wt;
-                for (int c = 0; c < (GEN ? 0 : p.nch); c++) {
+                for (int cc = 0; cc < (GEN ? 0 : nch_t); cc++) {
+                    const int term = PREC ? cc / p.nch : 0;
+                    const int c = cc - term * p.nch;
                     const int sa = a_it % p.SA;
                     const uint32_t ph = (a_it / p.SA) & 1;
                     PROF_LAP(1);
@@ -488,7 +542,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     PROF_LAP(0);
                     mbar_expect_tx(&a_full[sa], p.a_tx_bytes);
                     tma_load_4d(a_smem + (size_t)sa * p.a_stage_bytes, &mapA, &a_full[sa], c * KC,
-                                w0 - p.pad_w, r0 - p.pad_h, img);
+                                w0 - p.pad_w, r0 - p.pad_h, img + (PREC ? (int)p.ta[term] * p.B : 0));
                     a_it++;
                 }
                 if (p.dyn) {       // the mask patch of this tile (single buffer, released by the MMA issuer)
@@ -510,7 +564,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int nt = tile % p.ntn;
                 const int wrow0 = p.w_img_rows ? (tile / tiles_per_img) * p.w_img_rows : 0;
                 if (p.b_resident && !first) continue;
-                for (int c = 0; c < p.nch; c++) {
+                for (int cc = 0; cc < nch_t; cc++) {
+                    const int term = PREC ? cc / p.nch : 0;
+                    const int c = cc - term * p.nch;
+                    const int wrow = wrow0 + nt * N_TILE + (PREC ? (int)p.tb[term] * p.w_plane_rows : 0);
                     for (int tap = 0; tap < p.taps; tap++) {
                         int sb;
                         if (p.b_resident) {
@@ -525,11 +582,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         }
                         mbar_expect_tx(&b_full[sb], p.b_tx_bytes);
                         tma_load_2d(b_smem + (size_t)sb * p.b_stage_bytes, &mapB, &b_full[sb],
-                                    tap * p.Cin + c * KC, wrow0 + nt * N_TILE);
+                                    tap * p.Cin + c * KC, wrow);
                     }
                 }
                 if (p.dyn) {       // this image's dynamic filters, one [Cout x 16] tile per tap through the same ring
                     const int img = tile / tiles_per_img;
+                    for (int pl = 0; pl < (PREC ? p.npl : 1); pl++)     // the mask image is exact: one plane
                     for (int tap = 0; tap < p.taps; tap++) {
                         const int sb = b_it % p.SB;
                         const uint32_t ph = (b_it / p.SB) & 1;
@@ -537,7 +595,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         b_it++;
                         mbar_expect_tx(&b_full[sb], p.b2_tx_bytes);
                         tma_load_2d(b_smem + (size_t)sb * p.b_stage_bytes, &mapB2, &b_full[sb], tap * 16,
-                                    img * N_TILE);
+                                    img * N_TILE + pl * p.dynw_plane_rows);
                     }
                 }
                 first = false;
@@ -576,7 +634,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 PROF_LAP(0);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
-                for (int c = 0; c < p.nch; c++) {
+                for (int c = 0; c < nch_t; c++) {
                     const int sa = a_it % p.SA;
                     PROF_LAP(3);
                     mbar_wait(&a_full[sa], (a_it / p.SA) & 1);
@@ -632,7 +690,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     tc_fence_after();
                     const uint32_t a2_lo_tile = a2_lo0 + (uint32_t)soff * (32u >> 4);
 #pragma unroll 1
-                    for (int tap = 0; tap < p.taps; tap++) {
+                    for (int ti = 0; ti < (PREC ? p.taps * p.npl : p.taps); ti++) {
+                        const int tap = PREC ? ti % p.taps : ti;
                         const int sb = b_it % p.SB;
                         PROF_LAP(3);
                         mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
@@ -812,7 +871,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
 
             if (EPI == DASR_EPI_SEAN) {
-                sean_epilogue<N_TILE, NB>(p, t_acc, bias_t, norm_s, img, q0, w0, m, half);
+                sean_epilogue<N_TILE, NB, PREC>(p, t_acc, bias_t, norm_s, img, q0, w0, m, half);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -820,7 +879,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 continue;
             }
             if (EPI == DASR_EPI_STATS)
-                stats_epilogue<N_TILE, NB>(p, t_acc, bias_t, norm_s, img, q0, w0, nt, m, half, ew, lane);
+                stats_epilogue<N_TILE, NB, PREC>(p, t_acc, bias_t, norm_s, img, q0, w0, nt, m, half, ew, lane);
 #pragma unroll 1
             for (int blk = 0; blk < (EPI == DASR_EPI_STATS ? 0 : NB); blk++) {
                 const int q = q0 + blk * 128 + m;
@@ -860,6 +919,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 float rr[16];
                                 unpack8(r0, rr);
                                 unpack8(r1, rr + 8);
+                                if (valid) add_planes16<PREC>(rp + c0, p.ps_out, p.npl, rr);
 #pragma unroll
                                 for (int j = 0; j < 16; j++) f[j] += rr[j];
                             }
@@ -872,7 +932,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                                 for (int j = 0; j < 16; j++) f[j] *= (mm[j] > 0.f ? 1.f : p.mask_slope);
                             }
-                            if (valid && !DBG(p, 2)) store16(op + c0, f);
+                            if (valid && !DBG(p, 2)) store16p<PREC>(op + c0, p.ps_out, p.npl, f);
                         }
                     }
                 } else if (EPI == DASR_EPI_SHUFFLE2) {
@@ -890,7 +950,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 16; j++)
                                 f[j] = apply_act(__uint_as_float(v[j]) + bias_t[c0 + j], p.act);
-                            if (!DBG(p, 2)) store16(p.out + pix * Cq + c, f);
+                            if (!DBG(p, 2)) store16p<PREC>(p.out + pix * Cq + c, p.ps_out, p.npl, f);
                         }
                     }
                 } else {  // DASR_EPI_NCHW_F32
@@ -956,10 +1016,10 @@ static bool pdl_enabled() {
     return v != 0;
 }
 
-template <int SWZ, int N_TILE, int NB, int EPI, bool GEN = false>
+template <int SWZ, int N_TILE, int NB, int EPI, bool GEN = false, bool PREC = kPrecTU>
 static int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
                   const ConvK& k, size_t smem_bytes, cudaStream_t stream) {
-    auto fn = conv_halo_kernel<SWZ, N_TILE, NB, EPI, GEN>;
+    auto fn = conv_halo_kernel<SWZ, N_TILE, NB, EPI, GEN, PREC>;
     static bool configured[64] = {false};
     int dev = 0;
     DASR_CUDA_OK(cudaGetDevice(&dev));
@@ -1007,21 +1067,48 @@ static int dispatch_n(int epi, int n_tile, const CUtensorMap& mA, const CUtensor
     DASR_CASE(DASR_EPI_STORE, 128);
     DASR_CASE(DASR_EPI_STATS, 32);
     DASR_CASE(DASR_EPI_STATS, 64);
+#ifndef DASR_CONV_PRECISE_TU
     if (epi == DASR_EPI_SEAN && n_tile == 128 && k.gen_depth) {
         if (SWZ == 128) return launch<128, 128, NB, DASR_EPI_SEAN, true>(mA, mB, mA2, mB2, k, smem, s);
         return fail(DASR_ERR_BAD_ARG, "the in-kernel actv generator needs Cin = 128");
     }
+#endif
     DASR_CASE(DASR_EPI_SEAN, 64);
     DASR_CASE(DASR_EPI_SEAN, 128);
     DASR_CASE(DASR_EPI_SHUFFLE2, 64);
     DASR_CASE(DASR_EPI_SHUFFLE2, 128);
+#ifndef DASR_CONV_PRECISE_TU
     DASR_CASE(DASR_EPI_NCHW_F32, 16);
+#endif
 #undef DASR_CASE
     return fail(DASR_ERR_BAD_ARG, "unsupported epilogue %d with N tile %d", epi, n_tile);
 }
 
+// the kernel instantiations of this translation unit (plain bf16 storage, or -- conv_igemm_precise.cu -- the
+// fp32-split PREC variants): called by dasr_conv_fwd with the finished kernel parameters
+#ifdef DASR_CONV_PRECISE_TU
+int conv_dispatch_precise(int epi, int n_tile, int NB, int SWZ, const CUtensorMap& mA, const CUtensorMap& mB,
+                          const CUtensorMap& mA2, const CUtensorMap& mB2, const ConvK& k, size_t smem_bytes,
+                          cudaStream_t stream) {
+#else
+int conv_dispatch_precise(int epi, int n_tile, int NB, int SWZ, const CUtensorMap& mA, const CUtensorMap& mB,
+                          const CUtensorMap& mA2, const CUtensorMap& mB2, const ConvK& k, size_t smem_bytes,
+                          cudaStream_t stream);
+static int conv_dispatch(int epi, int n_tile, int NB, int SWZ, const CUtensorMap& mA, const CUtensorMap& mB,
+                         const CUtensorMap& mA2, const CUtensorMap& mB2, const ConvK& k, size_t smem_bytes,
+                         cudaStream_t stream) {
+#endif
+    if (NB == 4) {       // Cin = 32 -> 64-byte swizzle
+        if (n_tile == 32) return launch<64, 32, 4, DASR_EPI_STORE>(mA, mB, mA2, mB2, k, smem_bytes, stream);
+        return launch<64, 16, 4, DASR_EPI_STORE>(mA, mB, mA2, mB2, k, smem_bytes, stream);
+    }
+    if (SWZ == 128) return dispatch_n<128, 2>(epi, n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    return dispatch_n<64, 2>(epi, n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
+}
+
 }  // namespace dasr
 
+#ifndef DASR_CONV_PRECISE_TU
 using namespace dasr;
 
 #ifdef DASR_PROFILE
@@ -1079,8 +1166,19 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
                      "the in-kernel actv generator needs gen_w / gen_b, the SEAN epilogue with the K-DYN extension and "
                      "Cin = Cout = 128");
 
+    const int npl = planes();
     ConvK k;
     memset(&k, 0, sizeof k);
+    k.npl = npl;
+    {
+        const PlaneTerms t = plane_terms(npl, npl);
+        k.n_terms = t.n;
+        for (int i = 0; i < t.n; i++) { k.ta[i] = t.a[i]; k.tb[i] = t.b[i]; }
+    }
+    if (npl > 1)
+        DASR_REQUIRE(!gen && !a->gb_s && !a->resid_f32 && !a->out_aux_f32 && !a->norm && d->epi != DASR_EPI_NCHW_F32,
+                     "fp32-split planes: the in-kernel actv generator, gb_s, the fp32 residual stream, an external "
+                     "norm buffer and the NCHW fp32 epilogue are not available");
     k.B = d->B; k.H = d->H; k.W = d->W; k.Cin = d->Cin; k.Cout = d->Cout;
     k.kh = d->ks; k.kw = d->kw > 0 ? d->kw : d->ks;
     k.pad_h = k.kh / 2; k.pad_w = k.kw / 2; k.taps = k.kh * k.kw;
@@ -1162,7 +1260,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
     DASR_REQUIRE((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes <= budget,
                  "A tile (%u bytes) does not fit in shared memory", k.a_stage_bytes);
-    const bool may_reside = (k.ntn == 1) && (d->w_img_rows == 0);    // per-image weights always stream
+    const bool may_reside = (k.ntn == 1) && (d->w_img_rows == 0) && npl == 1;    // per-image weights always stream
     if (may_reside && k.nch * k.taps <= kMaxBStages &&
         (size_t)k.SA * k.a_stage_bytes + all_b <= budget) {
         k.b_resident = 1;
@@ -1214,6 +1312,11 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         DASR_REQUIRE(n_tile <= 64, "STATS epilogue supports Cout tiles up to 64 (shared-memory partials)");
     k.w_img_rows = d->w_img_rows;
     k.unshuffle = d->unshuffle;
+    // plane strides: every plane of an act tensor is a full copy of its logical shape
+    k.ps_out = (size_t)d->B * k.Ho * k.Wo * (d->epi == DASR_EPI_SEAN ? d->Cout / 2 : d->epi == DASR_EPI_SHUFFLE2 ? d->Cout / 4 : d->Cout);
+    k.w_plane_rows = k.ntn * n_tile * (d->w_img_rows ? d->B : 1);
+    k.dynw_plane_rows = d->B * n_tile;
+    if (npl > 1) DASR_REQUIRE(k.ntn * n_tile == d->Cout, "fp32-split planes need Cout (%d) to be a multiple of the N tile", d->Cout);
     if (d->unshuffle)
         DASR_REQUIRE(d->unshuffle == 2 && d->epi == DASR_EPI_STORE && k.subsample == 1 && d->H % 2 == 0 && d->W % 2 == 0,
                      "unshuffle store: factor 2, EPI_STORE, stride 1 and even frame sizes only");
@@ -1221,7 +1324,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     // tensor maps
     CUtensorMap mA, mB;
     {
-        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B * npl};   // planes follow each other
         uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
         uint32_t box[4] = {(uint32_t)KC, (uint32_t)k.Wp, (uint32_t)k.RB, 1};
         int rc = encode_tmap_bf16(&mA, gen ? a->out : a->x, 4, dims, str, box, SWZ);     // unused when generating
@@ -1229,7 +1332,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     }
     {
         const uint64_t ktot = (uint64_t)k.taps * d->Cin;
-        const uint64_t rows = (uint64_t)k.ntn * n_tile * (d->w_img_rows ? d->B : 1);
+        const uint64_t rows = (uint64_t)k.ntn * n_tile * (d->w_img_rows ? d->B : 1) * npl;
         if (d->w_img_rows) DASR_REQUIRE(d->w_img_rows == k.ntn * n_tile, "per-image weights: w_img_rows must equal the padded Cout");
         uint64_t dims[2] = {ktot, rows};
         uint64_t str[1] = {ktot * 2};
@@ -1247,17 +1350,14 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
             if (rc) return rc;
         }
         {
-            uint64_t dims[2] = {(uint64_t)k.taps * 16, (uint64_t)d->B * n_tile};
+            uint64_t dims[2] = {(uint64_t)k.taps * 16, (uint64_t)d->B * n_tile * npl};
             uint64_t str[1] = {(uint64_t)k.taps * 16 * 2};
             uint32_t box[2] = {16, (uint32_t)n_tile};
             int rc = encode_tmap_bf16(&mB2, a->dyn_w, 2, dims, str, box, 32);
             if (rc) return rc;
         }
     }
-    if (NB == 4) {       // Cin = 32 -> 64-byte swizzle
-        if (n_tile == 32) return launch<64, 32, 4, DASR_EPI_STORE>(mA, mB, mA2, mB2, k, smem_bytes, stream);
-        return launch<64, 16, 4, DASR_EPI_STORE>(mA, mB, mA2, mB2, k, smem_bytes, stream);
-    }
-    if (SWZ == 128) return dispatch_n<128, 2>(d->epi, n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
-    return dispatch_n<64, 2>(d->epi, n_tile, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    if (npl > 1) return conv_dispatch_precise(d->epi, n_tile, NB, SWZ, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    return conv_dispatch(d->epi, n_tile, NB, SWZ, mA, mB, mA2, mB2, k, smem_bytes, stream);
 }
+#endif  // DASR_CONV_PRECISE_TU

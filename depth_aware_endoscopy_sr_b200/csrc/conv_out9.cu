@@ -34,6 +34,8 @@ constexpr int ZS_STRIDE = 29;
 constexpr int ZS_ROWS = 136;
 constexpr int kThreads = 256;
 constexpr size_t SMEM_BYTES = 2 * (size_t)A_BYTES + 9 * W_TAP_BYTES + ZS_ROWS * ZS_STRIDE * 4 + 1024;
+// fp32-split planes: one patch buffer, the weights of all planes resident
+constexpr size_t SMEM_BYTES_PL = (size_t)A_BYTES + kMaxPlanes * 9 * W_TAP_BYTES + ZS_ROWS * ZS_STRIDE * 4 + 1024;
 }  // namespace out9
 
 struct Out9K {
@@ -42,6 +44,9 @@ struct Out9K {
     int clamp01;
     const float* bias;
     float* out;
+    // fp32-split planes (dasr_internal.h): cross terms of the x / weight planes, a_stages patch buffers
+    int npl, n_terms, a_stages;
+    unsigned char ta[6], tb[6];
 };
 
 __global__ void __launch_bounds__(out9::kThreads, 1)
@@ -54,8 +59,8 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* a_smem = smem;
-    uint8_t* w_smem = smem + 2 * (size_t)A_BYTES;
-    float* zs = reinterpret_cast<float*>(w_smem + 9 * W_TAP_BYTES);
+    uint8_t* w_smem = smem + p.a_stages * (size_t)A_BYTES;
+    float* zs = reinterpret_cast<float*>(w_smem + p.npl * 9 * W_TAP_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -83,17 +88,20 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     if (warp == 0) {
         if (elect_one()) {
-            mbar_expect_tx(&w_full, 9 * W_TAP_BYTES);
-            for (int t = 0; t < 9; t++) tma_load_2d(w_smem + t * W_TAP_BYTES, &mapW, &w_full, 0, t * NCOL);
+            mbar_expect_tx(&w_full, p.npl * 9 * W_TAP_BYTES);
+            for (int t = 0; t < 9 * p.npl; t++) tma_load_2d(w_smem + t * W_TAP_BYTES, &mapW, &w_full, 0, t * NCOL);
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int img = tile / tiles_per_img;
                 const int r = tile - img * tiles_per_img;
                 const int row = r / p.n_strips, strip = r - row * p.n_strips;
-                const int s = it & 1;
-                mbar_wait(&a_empty[s], ((it >> 1) & 1) ^ 1);
-                mbar_expect_tx(&a_full[s], A_BYTES);
-                tma_load_4d(a_smem + (size_t)s * A_BYTES, &mapA, &a_full[s], 0, strip * TW - 4, row * TH - 4, img);
+                for (int term = 0; term < p.n_terms; term++, it++) {
+                    const int s = it % p.a_stages;
+                    mbar_wait(&a_empty[s], ((it / p.a_stages) & 1) ^ 1);
+                    mbar_expect_tx(&a_full[s], A_BYTES);
+                    tma_load_4d(a_smem + (size_t)s * A_BYTES, &mapA, &a_full[s], 0, strip * TW - 4, row * TH - 4,
+                                img + (int)p.ta[term] * p.B);
+                }
             }
         }
     } else if (warp == 1) {
@@ -103,29 +111,33 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint32_t w_base = smem_u32(w_smem);
             mbar_wait(&w_full, 0);
             tc_fence_after();
-            uint32_t it = 0;
+            uint32_t it = 0, ia = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 mbar_wait(&acc_empty[s], ph ^ 1);
-                mbar_wait(&a_full[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(a_smem + (size_t)s * A_BYTES);
                 const uint32_t d_base = tmem_base + s * 256;
+                for (int term = 0; term < p.n_terms; term++, ia++) {
+                    const int sa = ia % p.a_stages;
+                    mbar_wait(&a_full[sa], (ia / p.a_stages) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_smem + (size_t)sa * A_BYTES);
+                    const uint32_t wt_base = w_base + (uint32_t)p.tb[term] * 9 * W_TAP_BYTES;
 #pragma unroll 1
-                for (int blk = 0; blk < NBLK; blk++) {
+                    for (int blk = 0; blk < NBLK; blk++) {
 #pragma unroll
-                    for (int t = 0; t < 9; t++) {
+                        for (int t = 0; t < 9; t++) {
 #pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const uint32_t aa = a_base + (uint32_t)(blk * 128 + t * PW) * 64 + k * 32;
-                            const uint32_t bb = w_base + t * W_TAP_BYTES + k * 32;
-                            umma_bf16(d_base + blk * NCOL, desc_hi | ((aa & 0x3FFFFu) >> 4),
-                                      desc_hi | ((bb & 0x3FFFFu) >> 4), idesc, (t | k) != 0);
+                            for (int k = 0; k < 2; k++) {
+                                const uint32_t aa = a_base + (uint32_t)(blk * 128 + t * PW) * 64 + k * 32;
+                                const uint32_t bb = wt_base + t * W_TAP_BYTES + k * 32;
+                                umma_bf16(d_base + blk * NCOL, desc_hi | ((aa & 0x3FFFFu) >> 4),
+                                          desc_hi | ((bb & 0x3FFFFu) >> 4), idesc, (term | t | k) != 0);
+                            }
                         }
                     }
+                    umma_commit(&a_empty[sa]);
                 }
-                umma_commit(&a_empty[s]);
                 umma_commit(&acc_full[s]);
             }
         }
@@ -204,16 +216,23 @@ extern "C" int dasr_conv_out9(const void* x, const void* wq, const float* bias, 
     k.clamp01 = clamp01;
     k.bias = bias;
     k.out = out;
+    k.npl = planes();
+    k.a_stages = k.npl > 1 ? 1 : 2;
+    {
+        const PlaneTerms t = plane_terms(k.npl, k.npl);
+        k.n_terms = t.n;
+        for (int i = 0; i < t.n; i++) { k.ta[i] = t.a[i]; k.tb[i] = t.b[i]; }
+    }
     CUtensorMap mA, mW;
     {
-        uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        uint64_t dims[4] = {(uint64_t)CIN, (uint64_t)W, (uint64_t)H, (uint64_t)B * k.npl};
         uint64_t str[3] = {(uint64_t)CIN * 2, (uint64_t)W * CIN * 2, (uint64_t)H * W * CIN * 2};
         uint32_t box[4] = {(uint32_t)CIN, (uint32_t)PW, (uint32_t)PH, 1};
         int rc = encode_tmap_bf16(&mA, x, 4, dims, str, box, 64);
         if (rc) return rc;
     }
     {
-        uint64_t dims[2] = {(uint64_t)CIN, (uint64_t)9 * NCOL};
+        uint64_t dims[2] = {(uint64_t)CIN, (uint64_t)9 * NCOL * k.npl};
         uint64_t str[1] = {(uint64_t)CIN * 2};
         uint32_t box[2] = {(uint32_t)CIN, (uint32_t)NCOL};
         int rc = encode_tmap_bf16(&mW, wq, 2, dims, str, box, 64);
@@ -227,7 +246,7 @@ extern "C" int dasr_conv_out9(const void* x, const void* wq, const float* bias, 
         configured[dev & 63] = true;
     }
     const int grid = k.total_tiles < num_sms() ? k.total_tiles : num_sms();
-    conv_out9_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(mA, mW, k);
+    conv_out9_kernel<<<grid, kThreads, k.npl > 1 ? SMEM_BYTES_PL : SMEM_BYTES, stream>>>(mA, mW, k);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

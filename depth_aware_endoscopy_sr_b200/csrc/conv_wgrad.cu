@@ -61,6 +61,10 @@ struct WgK {
     float* db;
     uint32_t ones_off;                  // byte offset of the 2 KB block of bf16 ones behind the pipeline stages
     int dbg;                            // -DDASR_PROFILE ablation knob (env DASR_WG_DBG): 1 no flush, 2 no MMA, 4 no TMA
+    // fp32-split planes (dasr_internal.h): the reduction runs over the cross terms (ta[i], tb[i]) of the dY / X planes
+    // -- planes are extra "images" of the same tensor map
+    int n_terms;
+    unsigned char ta[6], tb[6];
 };
 
 #ifdef DASR_PROFILE
@@ -132,6 +136,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
     if (warp == 0) {
         if (elect_one()) {
             uint32_t it = 0;
+            for (int term = 0; term < p.n_terms; term++)
             for (int kt = kt_begin; kt < kt_end; kt += kt_step, it++) {
                 const int img = kt / tiles_per_img;
                 const int r = kt - img * tiles_per_img;
@@ -146,10 +151,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                 uint8_t* sa = smem + (size_t)s * p.stage_bytes;
                 uint8_t* sb = sa + a_bytes_stage;
                 for (int j = 0; j < p.a_blocks; j++)
-                    tma_load_4d(sa + (size_t)j * p.a_blk_bytes, &mapY, &full[s], ca0 + j * p.cb_a, strip * p.Wt, rt * p.TR, img);
+                    tma_load_4d(sa + (size_t)j * p.a_blk_bytes, &mapY, &full[s], ca0 + j * p.cb_a, strip * p.Wt, rt * p.TR,
+                                img + (int)p.ta[term] * p.B);
                 for (int j = 0; j < p.b_blocks; j++)
                     tma_load_4d(sb + (size_t)j * p.b_blk_bytes, &mapX, &full[s], cb0 + j * p.cb_b, strip * p.Wt - p.pad_w,
-                                rt * p.TR + t_first - p.pad_h, img);
+                                rt * p.TR + t_first - p.pad_h, img + (int)p.tb[term] * p.B);
             }
         }
     } else if (warp == 1) {
@@ -170,6 +176,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
             const int ksteps = p.Wt >> 4;
             const uint32_t a_kstep = (16u * p.swz_a) >> 4, b_kstep = (16u * p.swz_b) >> 4;
             uint32_t it = 0;
+            for (int term = 0; term < p.n_terms; term++)
             for (int kt = kt_begin; kt < kt_end; kt += kt_step, it++) {
                 const int s = it % p.stages;
                 mbar_wait(&full[s], (it / p.stages) & 1);
@@ -203,7 +210,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constan
                                 : "memory");
                         }
                     }
-                    if (do_bias) {
+                    if (do_bias && p.tb[term] == 0) {      // every dY plane exactly once
                         const uint32_t d = tmem_base + ntaps * p.Nc;
                         const uint32_t acc0 = (it | r) != 0;
 #pragma unroll 4
@@ -362,6 +369,7 @@ using namespace dasr;
 struct WgOpts {
     float* db = nullptr;                    // fused bias gradient (or NULL)
     int per_image = 0, n_valid = 0;
+    int x_planes = 0;                       // planes of the X operand (0 = planes(); 1 for the exact auxiliary tensor)
     int col_first = 0, col_count = 0;       // flush window (multiples of 4); 0 / 0 = every column
     long long dw_img_stride = 0;
     const int* skip_flag = nullptr;
@@ -383,6 +391,12 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
     k.kh = d->kh; k.kw = d->kw; k.pad_h = d->kh / 2; k.pad_w = d->kw / 2;
     k.dw = dw;
     k.ldw = d->kh * d->kw * d->Cin;
+    const int npl_y = planes(), npl_x = o.x_planes > 0 ? o.x_planes : planes();
+    {
+        const PlaneTerms t = plane_terms(npl_y, npl_x);
+        k.n_terms = t.n;
+        for (int i = 0; i < t.n; i++) { k.ta[i] = t.a[i]; k.tb[i] = t.b[i]; }
+    }
 
     // operand blocks
     k.swz_a = (d->Cout % 64 == 0) ? 128 : 64;
@@ -503,14 +517,14 @@ static int wgrad_launch(const dasr_wgrad_desc* d, const void* dy, const void* x,
 
     CUtensorMap mY, mX;
     {
-        uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B * npl_y};
         uint64_t str[3] = {(uint64_t)d->Cout * 2, (uint64_t)d->W * d->Cout * 2, (uint64_t)d->H * d->W * d->Cout * 2};
         uint32_t box[4] = {(uint32_t)k.cb_a, (uint32_t)k.Wt, (uint32_t)k.TR, 1};
         int rc = encode_tmap_bf16(&mY, dy, 4, dims, str, box, k.swz_a);
         if (rc) return rc;
     }
     {
-        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B * npl_x};
         uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
         uint32_t box[4] = {(uint32_t)k.cb_b, (uint32_t)k.Wp, (uint32_t)k.PR, 1};
         int rc = encode_tmap_bf16(&mX, x, 4, dims, str, box, k.swz_b);
@@ -592,6 +606,7 @@ extern "C" int dasr_dynconv_bwd_tc(const void* dgb, const void* aux, const int32
     o.n_valid = K;
     o.dw_img_stride = (long long)K * 9 * nf2;
     o.skip_flag = flag;
+    o.x_planes = 1;
     return wgrad_launch(&d, dgb, aux, dT, o, stream);
 }
 
@@ -623,6 +638,7 @@ extern "C" int dasr_actv_bwd_tc(const void* dA, const void* aux, float* scratch,
     WgOpts o;
     o.col_first = DASR_AUX_DEPTH_HI;
     o.col_count = 4;
+    o.x_planes = 1;
     int rc = wgrad_launch(&d, dA, aux, scratch, o, stream);
     if (rc) return rc;
     actv_bwd_gather_kernel<<<(C * 9 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scratch, dW, db, C);

@@ -36,7 +36,7 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
 // ------------------------------------------------------------------------------------ conv_first
 __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ v,
                                                          const float* __restrict__ g, const float* __restrict__ bias,
-                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+                                                         __nv_bfloat16* __restrict__ out, int B, int H, int W, int npl) {
     __shared__ float ws[27][32];  // [ci*9 + tap][co]
     __shared__ float bs[32];
     if (threadIdx.x < 32) {
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
                 for (int j = 0; j < 8; j++) acc[j] = fmaf(in[i], ws[i][c0 + j], acc[j]);
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[j] = lrelu02(acc[j]);
-            op[c0 / 8] = pack8f(acc);
+            if (npl == 1) op[c0 / 8] = pack8f(acc);
+            else pl_store8(reinterpret_cast<uint4*>(out), pix * 4 + c0 / 8, npix * 4, npl, acc);
         }
     }
 }
@@ -99,9 +100,17 @@ __global__ void zero_insert2_kernel(const uint4* __restrict__ x, uint4* __restri
 }
 
 __global__ void add_kernel(const uint4* __restrict__ a, const float4* __restrict__ a32, const uint4* __restrict__ b,
-                           uint4* __restrict__ out, size_t n8) {
+                           uint4* __restrict__ out, size_t n8, int npl) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         float fa[8], fb[8];
+        if (npl > 1) {       // fp32-split planes: plane sums in, split out
+            pl_load8(a, i, n8, npl, fa);
+            pl_load8(b, i, n8, npl, fb);
+#pragma unroll
+            for (int j = 0; j < 8; j++) fa[j] += fb[j];
+            pl_store8(out, i, n8, npl, fa);
+            continue;
+        }
         if (a32) {
             const float4 lo = __ldg(a32 + 2 * i), hi = __ldg(a32 + 2 * i + 1);
             fa[0] = lo.x; fa[1] = lo.y; fa[2] = lo.z; fa[3] = lo.w;
@@ -122,7 +131,8 @@ constexpr int kPoolMaxPos = 8192;
 __global__ void __launch_bounds__(256) region_pool_kernel(const __nv_bfloat16* __restrict__ e5,
                                                           const float* __restrict__ masks, float* __restrict__ vec,
                                                           float* __restrict__ msel_out, float* __restrict__ cnt_out,
-                                                          int hf, int wf, int C, int K, int H, int W) {
+                                                          int hf, int wf, int C, int K, int H, int W, int npl,
+                                                          size_t ps) {
     __shared__ float msel[kPoolMaxPos];
     __shared__ float cnt_s;
     const int b = blockIdx.x / K, k = blockIdx.x % K;
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(256) region_pool_kernel(const __nv_bfloat16* _
         float s = 0.f;
         for (int p = 0; p < P; p++) {
             const float m = msel[p];
-            if (m != 0.f) s = fmaf(m, __bfloat162float(ep[(size_t)p * C + c]), s);
+            if (m != 0.f) s = fmaf(m, pl_load1(ep, (size_t)p * C + c, ps, npl), s);
         }
         vec[((size_t)b * K + k) * C + c] = s * inv;
     }
@@ -239,10 +249,10 @@ constexpr int kActvRows = 2;
 // MINB = resident blocks per SM the register budget is compiled for: 3 (<= 85 registers) when the kernel has the
 // device to itself; 4 (64 registers) for the "background" launches of Engine._ActvPrefetch, which run ONE block per
 // SM next to a convolution kernel that leaves 16 K registers free (conv_igemm.cu, LEAN)
-template <int C, int MINB>
+template <int C, int MINB, bool PL>
 __global__ void __launch_bounds__(256, MINB) actv_kernel(const float* __restrict__ depth, const float* __restrict__ w,
                                                    const float* __restrict__ bias, uint2* __restrict__ out, int H,
-                                                   int W, int n_items) {
+                                                   int W, int n_items, int npl, size_t ps2) {
     constexpr int LPP = C / 4;                     // lanes per pixel
     constexpr int SLOTS = 256 / LPP;
     // lets the SEAN conv that follows in the stream (launched with programmatic stream serialization) set up its
@@ -320,6 +330,21 @@ __global__ void __launch_bounds__(256, MINB) actv_kernel(const float* __restrict
                     for (int j = 0; j < 2; j++)
                         oh[j] = __floats2bfloat162_rn(fmaxf(acc[q][j].x, 0.f), fmaxf(acc[q][j].y, 0.f));
                     op[((size_t)r * W + x + q) * LPP + g] = o;
+                    if (PL) {          // fp32-split planes: the remainders of the fp32 value
+                        float2 rem[2];
+#pragma unroll
+                        for (int j = 0; j < 2; j++) rem[j] = make_float2(fmaxf(acc[q][j].x, 0.f), fmaxf(acc[q][j].y, 0.f));
+                        for (int k = 1; k < npl; k++) {
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const float2 t = __bfloat1622float2(oh[j]);
+                                rem[j].x -= t.x;
+                                rem[j].y -= t.y;
+                                oh[j] = __floats2bfloat162_rn(rem[j].x, rem[j].y);
+                            }
+                            op[(size_t)k * ps2 + ((size_t)r * W + x + q) * LPP + g] = o;
+                        }
+                    }
                 }
             }
         }
@@ -329,7 +354,7 @@ __global__ void __launch_bounds__(256, MINB) actv_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------ style mix
 // stp[b][j][c] = sum_i A[j][i] st[b][i][c] + a[j]   -> bf16 (GEMM A operand of the table GEMM)
 __global__ void style_mix_kernel(const float* __restrict__ st, const float* __restrict__ A, const float* __restrict__ a,
-                                 __nv_bfloat16* __restrict__ stp, int B, int K, int L) {
+                                 __nv_bfloat16* __restrict__ stp, int B, int K, int L, int npl) {
     const size_t total = (size_t)B * K * L;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = i % L;
@@ -337,14 +362,14 @@ __global__ void style_mix_kernel(const float* __restrict__ st, const float* __re
         const int b = i / ((size_t)L * K);
         float s = a[j];
         for (int q = 0; q < K; q++) s = fmaf(A[j * K + q], st[((size_t)b * K + q) * L + c], s);
-        stp[i] = __float2bfloat16(s);
+        pl_store1(stp, i, total, npl, s);
     }
 }
 
 // all SEAN instances of the network in one launch: stp[s][b][j][c] with per-instance A_i_j weights (pointer tables)
 __global__ void style_mix_batched_kernel(const float* __restrict__ st, const float* const* __restrict__ A_ptrs,
                                          const float* const* __restrict__ a_ptrs, __nv_bfloat16* __restrict__ stp,
-                                         int B, int K, int L) {
+                                         int B, int K, int L, int npl) {
     const int sidx = blockIdx.y;
     const float* A = A_ptrs[sidx];
     const float* a = a_ptrs[sidx];
@@ -356,7 +381,7 @@ __global__ void style_mix_batched_kernel(const float* __restrict__ st, const flo
         const int b = i / ((size_t)L * K);
         float s = __ldg(a + j);
         for (int q = 0; q < K; q++) s = fmaf(__ldg(A + j * K + q), st[((size_t)b * K + q) * L + c], s);
-        dst[i] = __float2bfloat16(s);
+        pl_store1(dst, i, total * gridDim.y, npl, s);
     }
 }
 
@@ -505,15 +530,19 @@ __global__ void build_mask16_kernel(const float* __restrict__ masks, uint4* __re
 // table T[n][k][tap][c] (bf16) -> GEMM-B weights of the dynamic convolution: wdyn[n][c][tap*16 + k] (k >= K zero),
 // n = (SEAN instance, image).  One block per n.
 __global__ void __launch_bounds__(256) table_to_dynweights_kernel(const __nv_bfloat16* __restrict__ table,
-                                                                  __nv_bfloat16* __restrict__ wdyn, int K, int C2) {
+                                                                  __nv_bfloat16* __restrict__ wdyn, int K, int C2,
+                                                                  int group, int npl) {
     extern __shared__ __align__(16) uint8_t smraw[];
     __nv_bfloat16* ts = reinterpret_cast<__nv_bfloat16*>(smraw);       // [K][9][C2]
-    const size_t n = blockIdx.x;
+    // fp32-split planes: blockIdx.y = plane; table planes are outermost ([npl][n]...), the planes of wdyn sit inside
+    // every group of `group` images ([n / group][npl][group]...: one SEAN instance = one weight matrix with planes)
+    const size_t n = blockIdx.x, pl = blockIdx.y;
     const int tsz8 = K * 9 * C2 / 8;
-    const uint4* tg = reinterpret_cast<const uint4*>(table + n * (size_t)K * 9 * C2);
+    const uint4* tg = reinterpret_cast<const uint4*>(table + (pl * gridDim.x + n) * (size_t)K * 9 * C2);
     for (int i = threadIdx.x; i < tsz8; i += blockDim.x) reinterpret_cast<uint4*>(ts)[i] = __ldg(tg + i);
     __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(wdyn + n * (size_t)C2 * 9 * 16);
+    const size_t nd = ((n / group) * npl + pl) * group + n % group;
+    uint4* dst = reinterpret_cast<uint4*>(wdyn + nd * (size_t)C2 * 9 * 16);
     const int items = C2 * 9 * 2;                                       // 16-byte pieces: (c, tap, 8 k's)
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int kg = it & 1;
@@ -604,13 +633,14 @@ extern "C" int dasr_conv_first(const float* x, const float* v, const float* g, c
                                int H, int W, void* stream) {
     DASR_REQUIRE(x && v && bias && out && B > 0 && H > 0 && W > 0, "bad arguments");
     const size_t npix = (size_t)B * H * W;
-    conv_first_kernel<<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(x, v, g, bias, (__nv_bfloat16*)out, B, H, W);
+    conv_first_kernel<<<grid_for(npix, 128), 128, 0, (cudaStream_t)stream>>>(x, v, g, bias, (__nv_bfloat16*)out, B, H, W, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
 
 extern "C" int dasr_zero_insert2(const void* x, void* out, int B, int H, int W, int C, void* stream) {
     DASR_REQUIRE(x && out && C % 8 == 0, "bad arguments (C must be a multiple of 8)");
+    B *= planes();          // fp32-split planes are extra images of a copy kernel
     const size_t total = (size_t)B * (2 * H - 1) * (2 * W - 1) * (C / 8);
     zero_insert2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, B, H, W, C / 8);
     DASR_LAUNCH_OK();
@@ -619,7 +649,8 @@ extern "C" int dasr_zero_insert2(const void* x, void* out, int B, int H, int W, 
 
 extern "C" int dasr_add(const void* a, const float* a32, const void* b, void* out, int64_t n, void* stream) {
     DASR_REQUIRE((a || a32) && b && out && n % 8 == 0, "bad arguments (n must be a multiple of 8)");
-    add_kernel<<<grid_for((size_t)n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const float4*)a32, (const uint4*)b, (uint4*)out, (size_t)n / 8);
+    DASR_REQUIRE(planes() == 1 || (a && !a32), "fp32-split planes: no fp32 residual operand");
+    add_kernel<<<grid_for((size_t)n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const float4*)a32, (const uint4*)b, (uint4*)out, (size_t)n / 8, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -628,7 +659,7 @@ extern "C" int dasr_region_pool_fwd(const void* e5, const float* masks, float* d
                                     int B, int hf, int wf, int C, int K, int H, int W, void* stream) {
     DASR_REQUIRE(e5 && masks && depth_vec, "null pointer");
     DASR_REQUIRE(hf * wf <= kPoolMaxPos, "feature map %dx%d too large for region pooling (max %d positions)", hf, wf, kPoolMaxPos);
-    region_pool_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)e5, masks, depth_vec, msel, cnt, hf, wf, C, K, H, W);
+    region_pool_kernel<<<B * K, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)e5, masks, depth_vec, msel, cnt, hf, wf, C, K, H, W, planes(), (size_t)B * hf * wf * C);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -651,20 +682,20 @@ extern "C" int dasr_build_aux(const uint8_t* labels, const float* depth, void* a
     return DASR_OK;
 }
 
-template <int C, int MINB>
+template <int C, int MINB, bool PL = false>
 static int actv_launch(const float* depth, const float* w, const float* bias, void* out, int H, int W, int n_items,
-                       size_t smem, int ctas_per_sm, cudaStream_t stream) {
+                       size_t smem, int ctas_per_sm, cudaStream_t stream, size_t ps2 = 0) {
     // persistent grid = the blocks that are resident at once (asked from the occupancy calculator), or fewer
     static int per_sm = 0;
     if (per_sm == 0) {
         int nb = 0;
-        DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<C, MINB>, 256, smem));
+        DASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, actv_kernel<C, MINB, PL>, 256, smem));
         per_sm = nb > 0 ? nb : 1;
     }
     const int ctas = (ctas_per_sm > 0 && ctas_per_sm < per_sm) ? ctas_per_sm : per_sm;
     const int cap = ctas * num_sms();
     const int grid = n_items < cap ? n_items : cap;
-    actv_kernel<C, MINB><<<grid, 256, smem, stream>>>(depth, w, bias, (uint2*)out, H, W, n_items);
+    actv_kernel<C, MINB, PL><<<grid, 256, smem, stream>>>(depth, w, bias, (uint2*)out, H, W, n_items, planes(), ps2);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -680,6 +711,11 @@ extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bi
     DASR_REQUIRE(smem <= 48 * 1024, "actv: frame too wide (%d)", W);
     const int n_items = B * bands;
     cudaStream_t st = (cudaStream_t)stream;
+    if (planes() > 1) {       // fp32-split planes: the same kernel with the plane-split store compiled in
+        const size_t ps2 = (size_t)B * H * W * (C / 4);
+        return C == 128 ? actv_launch<128, 3, true>(depth, w, bias, out, H, W, n_items, smem, ctas_per_sm, st, ps2)
+                        : actv_launch<64, 3, true>(depth, w, bias, out, H, W, n_items, smem, ctas_per_sm, st, ps2);
+    }
     if (ctas_per_sm == 1)
         return C == 128 ? actv_launch<128, 4>(depth, w, bias, out, H, W, n_items, smem, 1, st)
                         : actv_launch<64, 4>(depth, w, bias, out, H, W, n_items, smem, 1, st);
@@ -690,7 +726,7 @@ extern "C" int dasr_actv_fwd(const float* depth, const float* w, const float* bi
 extern "C" int dasr_style_mix(const float* depth_vec, const float* A, const float* a, void* stp, int B, int K, int L,
                               void* stream) {
     DASR_REQUIRE(depth_vec && A && a && stp, "null pointer");
-    style_mix_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(depth_vec, A, a, (__nv_bfloat16*)stp, B, K, L);
+    style_mix_kernel<<<grid_for((size_t)B * K * L, 256), 256, 0, (cudaStream_t)stream>>>(depth_vec, A, a, (__nv_bfloat16*)stp, B, K, L, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -700,7 +736,7 @@ extern "C" int dasr_style_mix_batched(const float* depth_vec, const void* A_ptrs
     DASR_REQUIRE(depth_vec && A_ptrs && a_ptrs && stp && nS > 0, "bad arguments");
     const int gx = grid_for((size_t)B * K * L, 256, 64);
     style_mix_batched_kernel<<<dim3(gx, nS), 256, 0, (cudaStream_t)stream>>>(
-        depth_vec, (const float* const*)A_ptrs, (const float* const*)a_ptrs, (__nv_bfloat16*)stp, B, K, L);
+        depth_vec, (const float* const*)A_ptrs, (const float* const*)a_ptrs, (__nv_bfloat16*)stp, B, K, L, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -714,12 +750,14 @@ extern "C" int dasr_build_mask16(const float* masks, void* mask16, int B, int K,
     return DASR_OK;
 }
 
-extern "C" int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream) {
+extern "C" int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, int group, void* stream) {
     DASR_REQUIRE(table && wdyn && n > 0, "bad arguments");
+    if (group <= 0) group = n;
+    DASR_REQUIRE(n % group == 0, "table_to_dynweights: n (%d) must be a multiple of the group size (%d)", n, group);
     DASR_REQUIRE(K >= 1 && K <= 16 && nf2 % 8 == 0, "dynamic-conv weights: K <= 16, 2*nf multiple of 8");
     const size_t smem = (size_t)K * 9 * nf2 * 2;
     DASR_REQUIRE(smem <= 48 * 1024, "table too large");
-    table_to_dynweights_kernel<<<n, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, (__nv_bfloat16*)wdyn, K, nf2);
+    table_to_dynweights_kernel<<<dim3(n, planes()), 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)table, (__nv_bfloat16*)wdyn, K, nf2, group, planes());
     DASR_LAUNCH_OK();
     return DASR_OK;
 }
@@ -728,6 +766,7 @@ extern "C" int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const 
                                 void* out, int B, int K, int H, int W, int nf2, void* stream) {
     DASR_REQUIRE(table && out && (labels || masks), "null pointer");
     DASR_REQUIRE(nf2 % 8 == 0, "2*nf must be a multiple of 8");
+    DASR_REQUIRE(planes() == 1, "the stand-alone K-DYN kernel has no fp32-split form (the network folds K-DYN into the SEAN GEMM)");
     if (labels) {
         const int rows = 2;
         const size_t smem = (size_t)(K + 1) * 9 * nf2 * 2 + (size_t)(rows + 2) * (W + 2);

@@ -51,8 +51,10 @@ __global__ void pack_scale_kernel(const PackBatch pb, float* __restrict__ scratc
     }
 }
 
-__global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ scratch) {
+// (npl > 1: every packed weight is split into npl bf16 planes, d.dst_plane_stride elements apart -- dasr_internal.h)
+__global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ scratch, int npl) {
     const dasr_pack_desc& d = pb.d[blockIdx.y];
+    const size_t ps = (size_t)d.dst_plane_stride;
     const int ks = d.ks, taps = ks * ks;
     if (d.mode >= DASR_PACK_DGRAD) {
         // data-gradient layouts: walk the SOURCE linearly (coalesced reads), scatter to dst
@@ -71,12 +73,12 @@ __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ 
                     const int r2 = d.shuffle_r * d.shuffle_r;
                     no = (a % r2) * (d.dim0 / r2) + a / r2;
                 }
-                dstd[(size_t)b * (taps * Ot) + (size_t)(taps - 1 - tap) * Ot + d.row_offset + no] = __float2bfloat16(w);
+                pl_store1(dstd, (size_t)b * (taps * Ot) + (size_t)(taps - 1 - tap) * Ot + d.row_offset + no, ps, npl, w);
             } else if (d.mode == DASR_PACK_DGRAD_CONVT) {   // a = i, b = o
-                dstd[(size_t)a * (taps * d.dim1) + (size_t)tap * d.dim1 + b] = __float2bfloat16(w);
+                pl_store1(dstd, (size_t)a * (taps * d.dim1) + (size_t)tap * d.dim1 + b, ps, npl, w);
             } else {                                     // OUT9_DGRAD: a = o (3), b = i (32), tap = t*9 + u
                 const int t = tap / ks, u = tap - t * ks;
-                dstd[(size_t)b * (ks * 32) + (size_t)(ks - 1 - t) * 32 + u * d.dim0 + a] = __float2bfloat16(w);
+                pl_store1(dstd, (size_t)b * (ks * 32) + (size_t)(ks - 1 - t) * 32 + u * d.dim0 + a, ps, npl, w);
             }
         }
         return;
@@ -96,13 +98,13 @@ __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ 
         if (d.mode == DASR_PACK_STYLE) {
             w = d.v[(((size_t)o * I + c) * ks + t) * ks + u] * sc[o];
             const int row = tap * d.rows_per_tap + d.row_offset + o;
-            dst[(size_t)row * I + c] = __float2bfloat16(w);
+            pl_store1(dst, (size_t)row * I + c, ps, npl, w);
             continue;
         }
         if (d.mode == DASR_PACK_ROWTAPS) {
             // K-OUT9 operand: one [32][I] matrix per vertical tap t, row = u*O + o (horizontal taps folded into N)
             w = d.v[(((size_t)o * I + c) * ks + t) * ks + u] * sc[o];
-            dst[((size_t)t * 32 + u * O + o) * I + c] = __float2bfloat16(w);
+            pl_store1(dst, ((size_t)t * 32 + u * O + o) * I + c, ps, npl, w);
             if (kk == 0 && d.dst_bias) d.dst_bias[o] = d.bias ? d.bias[o] : 0.f;
             continue;
         }
@@ -117,7 +119,7 @@ __global__ void pack_write_kernel(const PackBatch pb, const float* __restrict__ 
             row = (o % r2) * (O / r2) + o / r2;
         }
         row += d.row_offset;
-        dst[(size_t)row * K + kk] = __float2bfloat16(w);
+        pl_store1(dst, (size_t)row * K + kk, ps, npl, w);
         if (kk == 0 && d.dst_bias) {
             float f = 1.f;
             if (d.alpha_mode == 1) f = *d.alpha;
@@ -269,6 +271,7 @@ extern "C" int dasr_pack_weights(const dasr_pack_desc* descs, int n, float* scra
             const dasr_pack_desc& d = pb.d[i];
             DASR_REQUIRE(d.v && d.dst && d.dim0 > 0 && d.dim1 > 0 && d.ks > 0, "bad pack descriptor %d", start + i);
             DASR_REQUIRE(d.alpha_mode == 0 || d.alpha, "descriptor %d: alpha_mode without alpha", start + i);
+            DASR_REQUIRE(planes() == 1 || d.dst_plane_stride > 0, "descriptor %d: dst_plane_stride missing (fp32-split planes)", start + i);
             pb.scale_off[i] = scale_base + rows;
             rows += d.dim0;
             int e = d.dim0 * d.dim1 * d.ks * d.ks;
@@ -278,7 +281,7 @@ extern "C" int dasr_pack_weights(const dasr_pack_desc* descs, int n, float* scra
         DASR_LAUNCH_OK();
         int bx = (max_elems + 255) / 256;
         if (bx > 256) bx = 256;
-        pack_write_kernel<<<dim3(bx, pb.n), 256, 0, stream>>>(pb, scratch);
+        pack_write_kernel<<<dim3(bx, pb.n), 256, 0, stream>>>(pb, scratch, planes());
         DASR_LAUNCH_OK();
         scale_base += rows;
     }

@@ -137,7 +137,7 @@ class Engine:
             blk0 = net.block(next(i for i, _ in net.block_order() if i in net.which_ResBlk_depth))
             nf0, lat0 = blk0.nf, blk0.norm1.len_latent
             self._ws_rows = 9 * 2 * nf0
-            self._ws_all = torch.zeros(len(sean_names) * self._ws_rows, lat0, device=device, dtype=BF16)
+            self._ws_all = L.act_zeros(len(sean_names) * self._ws_rows, lat0, device=device)
             seans = [getattr(net.block(int(n.split(".")[0][len("depth-residual"):]) - 1), n.split(".")[1]) for n in sean_names]
             self._A_ptrs = torch.tensor([m.A_i_j.weight.data_ptr() for m in seans], dtype=torch.int64, device=device)
             self._a_ptrs = torch.tensor([m.A_i_j.bias.data_ptr() for m in seans], dtype=torch.int64, device=device)
@@ -154,7 +154,7 @@ class Engine:
                 rows, kdim, co = v.shape[1], v.shape[2] * v.shape[3] * v.shape[0], v.shape[1]
             else:   # PACK_DGRAD_CONVT: [I][O][k][k] -> rows = I
                 rows, kdim, co = v.shape[0], v.shape[2] * v.shape[3] * v.shape[1], v.shape[0]
-            dst = torch.zeros(rows, kdim, device=device, dtype=BF16)
+            dst = L.act_zeros(rows, kdim, device=device)
             self._descs_bwd.append(L.pack_desc(v, dst, g=g, mode=mode, shuffle_r=shuffle_r))
             rows_bwd += v.shape[0]
             self._packed[name + ".dg"] = _Packed(dst, None, co, kdim // (v.shape[2] * v.shape[3]), v.shape[2])
@@ -165,7 +165,7 @@ class Engine:
             cin = v.shape[1] if mode != L.PACK_CONVT else v.shape[0]
             ks = v.shape[2]
             rows = rows_pad or cout
-            dst = torch.zeros(rows, ks * ks * cin, device=device, dtype=BF16)
+            dst = L.act_zeros(rows, ks * ks * cin, device=device)
             dbias = torch.zeros(rows, device=device, dtype=torch.float32)
             self._descs.append(L.pack_desc(v, dst, g=g, bias=bias, dst_bias=dbias, mode=mode, shuffle_r=shuffle_r))
             rows_total += v.shape[0]
@@ -209,7 +209,7 @@ class Engine:
                     ag, ab = P(n + ".alpha_gamma"), P(n + ".alpha_beta")
                     lat = blk.norm1.len_latent
                     # [gamma_o | beta_o] stacked along N, scaled by (1 - alpha); bias = blend of both branches
-                    wo = torch.zeros(2 * nf, 9 * 2 * nf, device=device, dtype=BF16)
+                    wo = L.act_zeros(2 * nf, 9 * 2 * nf, device=device)
                     bo = torch.zeros(2 * nf, device=device, dtype=torch.float32)
                     for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
                         self._descs.append(L.pack_desc(P("%s.mlp_%s_o.weight" % (n, x)), wo, alpha=al, alpha_mode=2,
@@ -219,7 +219,7 @@ class Engine:
                         rows_total += nf
                     self._packed[n + ".gb_o"] = _Packed(wo, bo, 2 * nf, 2 * nf, 3)
                     reserve(n + ".gb_o", 2 * nf, 9 * 2 * nf)
-                    wod = torch.zeros(2 * nf, 9 * 2 * nf, device=device, dtype=BF16)
+                    wod = L.act_zeros(2 * nf, 9 * 2 * nf, device=device)
                     for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
                         self._descs_bwd.append(L.pack_desc(P("%s.mlp_%s_o.weight" % (n, x)), wod, alpha=al, alpha_mode=2,
                                                            mode=L.PACK_DGRAD, row_offset=off, rows_per_tap=2 * nf))
@@ -239,7 +239,8 @@ class Engine:
                     ws = self._ws_all[k0:k0 + self._ws_rows]
                     for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
                         self._descs.append(L.pack_desc(P("%s.mlp_%s_s.weight" % (n, x)), ws, alpha=al, alpha_mode=1,
-                                                       mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf))
+                                                       mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf,
+                                                       dst_stride=self._ws_all.numel()))
                         rows_total += nf
                     self._packed[n + ".table"] = _Packed(ws, None, 9 * 2 * nf, lat, 1)
             else:
@@ -258,7 +259,7 @@ class Engine:
             add_wn("upscale2.0", shuffle_r=2)
             add_wn("upscale2.3")
         add_wn("upscale3.0", shuffle_r=3 if net.scale == 3 else 2)
-        wq = torch.zeros(9 * 32, 32, device=device, dtype=BF16)
+        wq = L.act_zeros(9 * 32, 32, device=device)
         bq = torch.zeros(3, device=device, dtype=torch.float32)
         self._descs.append(L.pack_desc(P("conv_output.weight"), wq, bias=P("conv_output.bias"), dst_bias=bq,
                                        mode=L.PACK_ROWTAPS))
@@ -266,7 +267,7 @@ class Engine:
         self._packed["conv_output"] = _Packed(wq, bq, 3, 32, 9)
         self._wg["conv_output"] = (self._wg_total, 32, 9 * 32)      # gradient laid out [u*3+co][t*32+ci]
         self._wg_total += 32 * 9 * 32
-        wqd = torch.zeros(32, 9 * 32, device=device, dtype=BF16)
+        wqd = L.act_zeros(32, 9 * 32, device=device)
         self._descs_bwd.append(L.pack_desc(P("conv_output.weight"), wqd, mode=L.PACK_OUT9_DGRAD))
         rows_bwd += 3
         self._packed["conv_output.dg"] = _Packed(wqd, None, 32, 32, 9)
@@ -291,9 +292,11 @@ class Engine:
             return
         device = next(self.net.parameters()).device
         ptrs = tuple(k[0] for k in key)
-        if self._device != device or getattr(self, "_ptrs", None) != ptrs:
-            self._build_pack_plan(device)
+        if self._device != device or getattr(self, "_ptrs", None) != ptrs or getattr(self, "_planes", 1) != L.planes():
+            self._build_pack_plan(device)      # (also when the storage mode changed: plain bf16 <-> fp32-split planes)
             self._ptrs = ptrs
+            self._planes = L.planes()
+            self._graphs.clear()
             self._key = self._key_bwd = None
         if key != self._key:
             L.pack_weights(self._descs, self._scratch)
@@ -412,13 +415,13 @@ class Engine:
         dev = x.device if x is not None else kw["gen_depth"].device
         if out is None:
             if epi == L.EPI_SHUFFLE2:
-                out = torch.empty(B, 2 * H, 2 * W, pk.cout // 4, device=dev, dtype=BF16)
+                out = L.act_empty(B, 2 * H, 2 * W, pk.cout // 4, device=dev)
             elif epi == L.EPI_SEAN:
-                out = torch.empty(B, H, W, pk.cout // 2, device=dev, dtype=BF16)
+                out = L.act_empty(B, H, W, pk.cout // 2, device=dev)
             elif subsample == 2:
-                out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=dev, dtype=BF16)
+                out = L.act_empty(B, (H + 1) // 2, (W + 1) // 2, pk.cout, device=dev)
             else:
-                out = torch.empty(B, H, W, pk.cout, device=dev, dtype=BF16)
+                out = L.act_empty(B, H, W, pk.cout, device=dev)
         if self.profile is None:
             return L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act, subsample=subsample,
                               **kw)
@@ -445,21 +448,22 @@ class Engine:
         nS = len(self._sean_names)
         B, K, lat = vec.shape
         s = L.stream_ptr()
-        stp_all = torch.empty(nS, 1, B * K, lat, device=vec.device, dtype=BF16)
+        stp_all = L.act_empty(nS, 1, B * K, lat, device=vec.device)
         self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp_all.numel() * 2,
                     lambda: L.check(lib.dasr_style_mix_batched(L.ptr(vec), L.ptr(self._A_ptrs), L.ptr(self._a_ptrs),
                                                                L.ptr(stp_all), nS, B, K, lat, s)))
-        table_all = torch.empty(nS, 1, B * K, self._ws_rows, device=vec.device, dtype=BF16)
+        table_all = L.act_empty(nS, 1, B * K, self._ws_rows, device=vec.device)
         self._timed("style_table_gemm", "tensor", 2.0 * nS * B * K * lat * self._ws_rows,
                     stp_all.numel() * 2 + table_all.numel() * 2 + self._ws_all.numel() * 2,
                     lambda: L.conv_fwd(stp_all, self._ws_all, self._zero_bias, table_all, Cout=self._ws_rows, ks=1,
                                        w_img_rows=self._ws_rows))
         # GEMM-B form of every table for the K-DYN extension of the SEAN GEMM: [nS][B*2nf][9*16]
         nf2 = self._ws_rows // 9
-        wdyn_all = torch.empty(nS, B * nf2, 9 * 16, device=vec.device, dtype=BF16)
+        # (fp32-split planes: the planes of an instance's filters sit inside its own slice -- see include/dasr.h)
+        wdyn_all = torch.empty(nS, L.planes(), B * nf2, 9 * 16, device=vec.device, dtype=BF16)
         self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
-                    lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, s)))
-        return stp_all, table_all, wdyn_all
+                    lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, B, s)))
+        return stp_all, table_all, wdyn_all[:, 0]
 
     def _sean_actv(self, sean, depth, out=None, ctas_per_sm=0):
         """actv = ReLU(mlp_mask(depth)) of one SEAN instance (normalization.py:37-40,61)."""
@@ -467,7 +471,7 @@ class Engine:
         B, _, H, W = depth.shape
         nf2 = 2 * sean.norm_nc
         s = L.stream_ptr()
-        actv = out if out is not None else torch.empty(B, H, W, nf2, device=depth.device, dtype=BF16)
+        actv = out if out is not None else L.act_empty(B, H, W, nf2, device=depth.device)
         self._timed("actv", "hbm", 0, actv.numel() * 2 + depth.numel() * 4,
                     lambda: L.check(lib.dasr_actv_fwd(L.ptr(depth), L.ptr(sean.mlp_mask[0].weight),
                                                       L.ptr(sean.mlp_mask[0].bias), L.ptr(actv), B, H, W, nf2,
@@ -490,7 +494,7 @@ class Engine:
             self.side = st
             self.main = torch.cuda.current_stream(dev)
             B, _, H, W = depth.shape
-            self.slots = [[torch.empty(B, H, W, nf2, device=dev, dtype=BF16) for _ in range(2)]
+            self.slots = [[L.act_empty(B, H, W, nf2, device=dev) for _ in range(2)]
                           for _ in range(min(ahead, len(blocks)))]
             self.ready = [None] * len(blocks)
             self.k = 0
@@ -533,9 +537,10 @@ class Engine:
         nslots = L.conv_stats_slots(B, H, W, nf, nf)
         stats = torch.empty(2, B, nslots, nf, 2, device=x.device, dtype=torch.float32)
         cur = x
-        out32 = torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32) if self.fp32_residual else None
+        out32 = (torch.empty(B, H, W, nf, device=x.device, dtype=torch.float32)
+                 if self.fp32_residual and L.planes() == 1 else None)
         # actv generated inside the SEAN conv (no actv tensor, no actv launch) when the geometry leaves room for it
-        gen = self.fuse_actv and nf == 64 and lib.dasr_conv_gen_ok(H, W) == 1
+        gen = self.fuse_actv and nf == 64 and lib.dasr_conv_gen_ok(H, W) == 1 and L.planes() == 1
         pre = prefetch.take() if (prefetch is not None and not gen) else None
         for j, sean in ((1, blk.norm1), (2, blk.norm2)):
             n = "%s.norm%d" % (p, j)
@@ -584,7 +589,7 @@ class Engine:
         replayed from a CUDA graph from the third call with the same input shape on (static input / output buffers;
         the result is returned as a copy): 2.7 -> 0.85 ms per 64x64 frame, 2.7 -> 1.3 ms per 1080p frame.  ``cap`` /
         ``profile`` / an ongoing stream capture use the kernel-by-kernel schedule."""
-        if (not self.use_graphs or cap is not None or self.profile is not None or not lq.is_cuda
+        if (not self.use_graphs or cap is not None or self.profile is not None or not lq.is_cuda or L.planes() > 1
                 or lq.shape[0] * lq.shape[2] * lq.shape[3] > self.graph_max_pixels
                 or torch.cuda.is_current_stream_capturing()):
             return self._infer_eager(lq, depth, masks, cap=cap, clamp=clamp)
@@ -636,7 +641,7 @@ class Engine:
 
         # ---- encoder (sftmd_arch.py:771-783)
         enc = net.encoder
-        f0 = torch.empty(B, h, w, 32, device=dev, dtype=BF16)
+        f0 = L.act_empty(B, h, w, 32, device=dev)
         L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g),
                                     L.ptr(enc.layer1.bias), L.ptr(f0), B, h, w, s))
         vec = labels = flag = tables = mask16 = None
@@ -644,7 +649,7 @@ class Engine:
             e2 = self._conv(f0, "encoder.layer2", subsample=2, act=L.ACT_LRELU)
             e3 = self._conv(e2, "encoder.layer3", subsample=2, act=L.ACT_LRELU)
             h3, w3 = e3.shape[1], e3.shape[2]
-            z = torch.empty(B, 2 * h3 - 1, 2 * w3 - 1, 128, device=dev, dtype=BF16)
+            z = L.act_empty(B, 2 * h3 - 1, 2 * w3 - 1, 128, device=dev)
             L.check(lib.dasr_zero_insert2(L.ptr(e3), L.ptr(z), B, h3, w3, 128, s))
             e4 = self._conv(z, "encoder.layer4", act=L.ACT_LRELU)
             e5 = self._conv(e4, "encoder.layer5", subsample=2)
@@ -690,7 +695,7 @@ class Engine:
                     cap["block%d.out" % (i + 1)] = x
         if cap is not None:
             cap["fea_bef"] = fea_bef
-        add = torch.empty_like(x)
+        add = L.act_like(x)
         self._timed("add", "hbm", 0, x.numel() * (2 + 2 + (4 if x32 is not None else 2)),
                     lambda: L.check(lib.dasr_add(L.ptr(x), L.ptr(x32), L.ptr(fea_bef), L.ptr(add), x.numel(), s)))
         x = add
@@ -708,7 +713,7 @@ class Engine:
             # 64 -> 288 convolution (shuffled channel order, LeakyReLU commutes with the permutation), then
             # PixelShuffle(3) as a copy kernel (sftmd_arch.py:904-908)
             u = self._conv(x, "upscale3.0", act=L.ACT_LRELU)
-            x = torch.empty(B, 3 * u.shape[1], 3 * u.shape[2], u.shape[3] // 9, device=dev, dtype=BF16)
+            x = L.act_empty(B, 3 * u.shape[1], 3 * u.shape[2], u.shape[3] // 9, device=dev)
             L.check(lib.dasr_pixel_shuffle(L.ptr(u), L.ptr(x), B, u.shape[1], u.shape[2], u.shape[3] // 9, 3, s))
         else:
             x = self._conv(x, "upscale3.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)

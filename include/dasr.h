@@ -41,6 +41,18 @@ int dasr_check_device(void);
 /* number of kernels this library has launched in the calling process so far (bench.py's gpu_launches) */
 int64_t dasr_launch_count(void);
 
+/* Storage of "act" tensors and packed weights (process-wide switch; TEST INFRASTRUCTURE, default 1):
+ *   1  plain bf16 -- the product configuration (north_star: bf16 operands, fp32 accumulate).
+ *   3  fp32 split: every act tensor / packed weight matrix is 3 consecutive bf16 planes [plane][elements] whose
+ *      sum is the fp32 value (hi, mid, lo); a pointer passed to this library addresses plane 0 and the planes
+ *      follow at a stride of the tensor's own element count.  The SAME kernels then run the 6 cross terms of the
+ *      operand planes through tcgen05 into the same fp32 accumulators, the epilogues and memory-bound kernels read
+ *      plane sums and write plane splits: fp32-class arithmetic (north_star's <= 1e-4 mode) used by the parity
+ *      tests to compare forward and gradients with the fp64 goldens.  ~6x the tensor work; not a product mode.
+ * Exact operands (the mask image of dasr_build_mask16, the auxiliary tensor of dasr_build_aux) stay one plane.   */
+int dasr_set_planes(int n);
+int dasr_get_planes(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (tcgen05 / TMEM / TMA), stride 1, square kernel ks in {1,3,9}, zero padding
  * ks/2.  Replaces nn.Conv2d / weight-normed Conv2d / ConvTranspose2d-as-conv on the hot path
@@ -172,6 +184,8 @@ typedef struct {
     int32_t shuffle_r;    /* 0, or r: destination row = (i*r+j)*(O/r^2) + c for source row c*r^2+i*r+j */
     int32_t row_offset;   /* destination row offset (stack several convs into one B matrix)          */
     int32_t rows_per_tap; /* DASR_PACK_STYLE only                                                    */
+    int64_t dst_plane_stride; /* dasr_set_planes > 1: elements between the planes of dst (its total element count;
+                                 several descriptors may fill row ranges of one dst).  Ignored with 1 plane.  */
 } dasr_pack_desc;
 /* descs: HOST array of n descriptors; scratch: device fp32 [sum of dim0] for the weight-norm scales */
 int dasr_pack_weights(const dasr_pack_desc* descs, int n, float* scratch, void* stream);
@@ -324,9 +338,11 @@ int dasr_dynconv_fwd(const void* table, const uint8_t* labels, const float* mask
 /* K-DYN folded into the SEAN GEMM (dasr_conv_args.dyn_x / dyn_w).  dasr_build_mask16: masks NCHW fp32 [B,K,H,W]
  * (K <= 16) -> NHWC bf16 [B,H,W,16] (one-hot masks are exact in bf16; other values are rounded like every other
  * activation).  dasr_table_to_dynweights: the n = (instances x images) tables bf16 [n][K][9][2nf] -> GEMM-B
- * weights bf16 [n][2nf][9*16] (column tap*16 + k, zero for k >= K).                                          */
+ * weights bf16 [n][2nf][9*16] (column tap*16 + k, zero for k >= K).  group (0 = n): images per weight matrix
+ * (one SEAN instance) -- only matters with dasr_set_planes > 1, where the planes of wdyn sit inside every
+ * group ([n/group][plane][group][2nf][9*16]) so that one instance's slice is a self-contained dyn_w operand.      */
 int dasr_build_mask16(const float* masks, void* mask16, int B, int K, int H, int W, void* stream);
-int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, void* stream);
+int dasr_table_to_dynweights(const void* table, void* wdyn, int n, int K, int nf2, int group, void* stream);
 
 /* InstanceNorm statistics (sftmd_arch.py:813,820 + normalization.py:17,56 = IN applied twice):
  * stats [B][nslots][C][2] (partial sum, sumsq over H*W; summed here in slot order) ->

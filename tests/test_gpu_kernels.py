@@ -58,7 +58,7 @@ def test_sean_conv_with_kdyn_extension_and_fused_finalize(shape):
     mask16 = torch.empty(B, H, W, 16, device=dev, dtype=torch.bfloat16)
     L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(mask16), B, K, H, W, s))
     wdyn = torch.empty(B * 2 * nf, 9 * 16, device=dev, dtype=torch.bfloat16)
-    L.check(lib.dasr_table_to_dynweights(L.ptr(table), L.ptr(wdyn), B, K, 2 * nf, s))
+    L.check(lib.dasr_table_to_dynweights(L.ptr(table), L.ptr(wdyn), B, K, 2 * nf, 0, s))
     # the SEAN convolution itself
     actv = rnd(B, 2 * nf, H, W)
     wgb, bgb = rnd(2 * nf, 2 * nf, 3, 3) / 34, rnd(2 * nf) * 0.1
