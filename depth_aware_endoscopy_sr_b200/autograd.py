@@ -49,6 +49,13 @@ class _T:
         return 0.0 if self.act == "relu" else 0.2
 
 
+def _dbg_mask(eng, key, t):
+    """tests / probes (Engine.debug): the activation pattern of the NHWC act tensor ``t`` as an NCHW bool tensor --
+    which units of this ReLU / LeakyReLU are on.  The backward kernels switch on exactly this (stored value > 0)."""
+    if eng.debug is not None:
+        eng.debug["mask:" + key] = (L.act_value(t) > 0).permute(0, 3, 1, 2).contiguous()
+
+
 class Tape:
     def __init__(self, eng):
         self.eng = eng
@@ -207,6 +214,8 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
     else:
         out = eng._conv(x.data, name, act=acts[act], subsample=subsample)
         o = _T(out, act)
+    if act != "none":
+        _dbg_mask(eng, name, o.data)
     target = convt_src if convt_src is not None else x
     if need_dgrad:
         tp.use(target)
@@ -275,6 +284,8 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
                         dyn_x=mask16, dyn_w=wdyn, resid=resid.data, gamma_out=gamma)
     del table, stats
     o = _T(out, "handled")
+    _dbg_mask(eng, n + ".actv", actv)
+    _dbg_mask(eng, n + ".out", out)
     tp.use(cur)
     if resid is not None:
         tp.use(resid)
@@ -283,6 +294,9 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         HW = H * W
         dout = o.grad
         o.grad = None
+        if eng.debug is not None:      # tests / probes: gradient w.r.t. this SEAN's output and its forward value
+            eng.debug[n + ".dout"] = L.act_value(dout)
+            eng.debug[n + ".out"] = L.act_value(out)
         slots = lib.dasr_sean_bwd_slots(HW)
         dgb = L.act_empty(B, H, W, nf2, device=dev)
         dn = L.act_empty(B, H, W, nf, device=dev)
@@ -337,6 +351,7 @@ def _forward_train(eng, lq, depth, masks):
     L.check(lib.dasr_conv_first(L.ptr(lq), L.ptr(enc.layer1.weight_v), L.ptr(enc.layer1.weight_g), L.ptr(enc.layer1.bias),
                                 L.ptr(f0d), B, h, w, s))
     f0 = _T(f0d, "lrelu")
+    _dbg_mask(eng, "encoder.layer1", f0d)
 
     def bwd_first():
         dy = tp.take(f0)
@@ -443,6 +458,7 @@ def _forward_train(eng, lq, depth, masks):
         pk = eng._packed[p + ".block.2"]
         outd = eng._conv(f.data, p + ".block.2", act=L.ACT_RELU, resid=x.data)
         o = _T(outd, "relu")
+        _dbg_mask(eng, p + ".out", outd)
         tp.use(f)
         tp.use(x)
 
@@ -466,6 +482,8 @@ def _forward_train(eng, lq, depth, masks):
 
     def bwd_add():
         g = tp.take(add)
+        if eng.debug is not None:
+            eng.debug["feat_add1.dout"] = L.act_value(g)
         tp.accum(xa, g)
         tp.accum(xb, g)
 

@@ -196,6 +196,25 @@ __device__ __forceinline__ void store16p(__nv_bfloat16* p, size_t ps, int npl, c
     }
 }
 
+// TMEM read-out of 16 accumulator columns.  PREC kernels keep TWO accumulator sets per tile, ACC_COLS columns apart:
+// set 0 = the hi x hi plane term, set 1 = every lower-order cross term (2^-8 .. 2^-16 of the magnitude).  tcgen05
+// accumulates with truncation, ~1 ulp of the ACCUMULATOR per MMA step: keeping the small terms out of the large sum
+// leaves K/16 truncations of the main term instead of 6 K/16 (measured: 1e-5 -> 2e-6 relative on a 3x3 conv); the two
+// sets are added here in fp32 round-to-nearest.  (issues the loads AND waits for them)
+template <bool PREC, int ACC_COLS>
+__device__ __forceinline__ void tmem_ld16_acc(uint32_t taddr, uint32_t (&v)[16]) {
+    tmem_ld16(taddr, v);
+    if (PREC) {
+        uint32_t w[16];
+        tmem_ld16(taddr + ACC_COLS, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    } else {
+        tmem_ld_wait();
+    }
+}
+
 // Reduce 16 per-thread values over the 32 lanes of a warp (recursive halving).  On return lane L holds in
 // v[0] the warp-wide sum of column  8*b4 + 4*b3 + 2*b2 + b1  (bN = bit N of L); lanes L and L^1 agree.
 __device__ __forceinline__ void warp_colsum16(float* v, int lane) {
@@ -288,9 +307,14 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
             sean_load<N_TILE, NB>(p, ops[(it + 1) & 1], img, q0, w0, m, (it + 1) / CH, half * 16 + ((it + 1) % CH) * 32);
         const SeanOps& o = ops[it & 1];
         uint32_t vg[16], vb[16];
-        tmem_ld16(t_acc + blk * N_TILE + c0, vg);
-        tmem_ld16(t_acc + blk * N_TILE + NF + c0, vb);
-        tmem_ld_wait();
+        if (PREC) {
+            tmem_ld16_acc<true, NB * N_TILE>(t_acc + blk * N_TILE + c0, vg);
+            tmem_ld16_acc<true, NB * N_TILE>(t_acc + blk * N_TILE + NF + c0, vb);
+        } else {
+            tmem_ld16(t_acc + blk * N_TILE + c0, vg);
+            tmem_ld16(t_acc + blk * N_TILE + NF + c0, vb);
+            tmem_ld_wait();
+        }
         if (!o.valid) continue;
         float yv[16], gs[16], f[16];
         unpack8(o.y0, yv);
@@ -391,8 +415,7 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
 #pragma unroll
         for (int blk = 0; blk < NB; blk++) {
             uint32_t v[16];
-            tmem_ld16(t_acc + blk * N_TILE + c0, v);
-            tmem_ld_wait();
+            tmem_ld16_acc<PREC, NB * N_TILE>(t_acc + blk * N_TILE + c0, v);
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_t[c0 + j];
@@ -446,7 +469,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     constexpr int KC = SWZ / 2;          // channels per K chunk (one swizzle span per pixel row)
     constexpr int KSTEPS = SWZ / 32;     // UMMA K = 16 bf16 = 32 bytes
     constexpr int ACC_COLS = NB * N_TILE;
-    constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;
+    // (PREC: one tile in flight, its two accumulator sets -- main / low-order terms -- take the place of the double buffer)
+    constexpr int NACC = PREC ? 1 : ((2 * ACC_COLS <= 512) ? 2 : 1);
+    static_assert(!PREC || 2 * ACC_COLS <= 512, "PREC needs two accumulator sets in TMEM");
     constexpr int TMEM_COLS = 512;
 
     extern __shared__ uint8_t smem_raw[];
@@ -633,8 +658,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 mbar_wait(&acc_empty[buf], aph ^ 1);
                 PROF_LAP(0);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+                const uint32_t d_tmem0 = tmem_base + buf * ACC_COLS;
                 for (int c = 0; c < nch_t; c++) {
+                    // PREC: chunks of the lower-order plane terms (c >= nch) accumulate into the second set
+                    const bool low = PREC && c >= p.nch;
+                    const uint32_t d_tmem = d_tmem0 + (low ? ACC_COLS : 0);
+                    const int c_rel = low ? c - p.nch : c;
                     const int sa = a_it % p.SA;
                     PROF_LAP(3);
                     mbar_wait(&a_full[sa], (a_it / p.SA) & 1);
@@ -655,7 +684,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                                 for (int k = 0; k < KSTEPS; k++)
                                     umma_bf16_lohi(d_tmem + blk * N_TILE, a_lo + blk * BLK_LO + k * 2, b_lo + k * 2,
-                                                   desc_hi, idesc, (c | tap | k) != 0);
+                                                   desc_hi, idesc, (c_rel | tap | k) != 0);
                             }
                         }
                     } else {
@@ -673,7 +702,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
                                 for (int k = 0; k < KSTEPS; k++)
                                     umma_bf16_lohi(d_tmem + blk * N_TILE, a_lo + blk * BLK_LO + k * 2, b_lo + k * 2,
-                                                   desc_hi, idesc, (c | tap | k) != 0);
+                                                   desc_hi, idesc, (c_rel | tap | k) != 0);
                             }
                             umma_commit(&b_empty[sb]);
                             b_it++;
@@ -692,6 +721,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
                     for (int ti = 0; ti < (PREC ? p.taps * p.npl : p.taps); ti++) {
                         const int tap = PREC ? ti % p.taps : ti;
+                        const uint32_t d_tmem = d_tmem0 + ((PREC && ti >= p.taps) ? ACC_COLS : 0);   // lower filter planes
                         const int sb = b_it % p.SB;
                         PROF_LAP(3);
                         mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
@@ -909,8 +939,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         if (rp && valid && !DBG(p, 1)) ldg256(rp + c0, r0, r1);
                         if (mp && valid && !DBG(p, 1)) ldg256(mp + c0, m0, m1);
                         uint32_t v[16];
-                        tmem_ld16(t_blk + c0, v);
-                        tmem_ld_wait();
+                        tmem_ld16_acc<PREC, ACC_COLS>(t_blk + c0, v);
                         float f[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_t[c0 + j];
@@ -940,8 +969,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
                     for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
                         uint32_t v[16];
-                        tmem_ld16(t_blk + c0, v);
-                        tmem_ld_wait();
+                        tmem_ld16_acc<PREC, ACC_COLS>(t_blk + c0, v);
                         if (valid) {
                             const int n0 = nt * N_TILE + c0;  // permuted row: n0 = s*Cq + c
                             const int s = n0 / Cq, c = n0 - s * Cq;

@@ -112,17 +112,20 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             mbar_wait(&w_full, 0);
             tc_fence_after();
             uint32_t it = 0, ia = 0;
+            const bool pl = p.npl > 1;      // fp32-split planes: one tile in flight; accumulator set 1 = low-order terms
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
-                const int s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
+                const int s = pl ? 0 : (it & 1);
+                const uint32_t ph = pl ? (it & 1) : ((it >> 1) & 1);
                 mbar_wait(&acc_empty[s], ph ^ 1);
-                const uint32_t d_base = tmem_base + s * 256;
+                const uint32_t d_base0 = tmem_base + s * 256;
                 for (int term = 0; term < p.n_terms; term++, ia++) {
                     const int sa = ia % p.a_stages;
                     mbar_wait(&a_full[sa], (ia / p.a_stages) & 1);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(a_smem + (size_t)sa * A_BYTES);
                     const uint32_t wt_base = w_base + (uint32_t)p.tb[term] * 9 * W_TAP_BYTES;
+                    const uint32_t d_base = d_base0 + (term > 0 ? 256 : 0);
+                    const int term_rel = term > 1 ? 1 : 0;          // first term of its accumulator set: overwrite
 #pragma unroll 1
                     for (int blk = 0; blk < NBLK; blk++) {
 #pragma unroll
@@ -132,7 +135,7 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                 const uint32_t aa = a_base + (uint32_t)(blk * 128 + t * PW) * 64 + k * 32;
                                 const uint32_t bb = wt_base + t * W_TAP_BYTES + k * 32;
                                 umma_bf16(d_base + blk * NCOL, desc_hi | ((aa & 0x3FFFFu) >> 4),
-                                          desc_hi | ((bb & 0x3FFFFu) >> 4), idesc, (term | t | k) != 0);
+                                          desc_hi | ((bb & 0x3FFFFu) >> 4), idesc, (term_rel | t | k) != 0);
                             }
                         }
                     }
@@ -151,8 +154,9 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int img = tile / tiles_per_img;
             const int r = tile - img * tiles_per_img;
             const int row = r / p.n_strips, strip = r - row * p.n_strips;
-            const int s = it & 1;
-            mbar_wait(&acc_full[s], (it >> 1) & 1);
+            const bool pl = p.npl > 1;
+            const int s = pl ? 0 : (it & 1);
+            mbar_wait(&acc_full[s], pl ? (it & 1) : ((it >> 1) & 1));
             tc_fence_after();
             const uint32_t t_acc = tmem_base + s * 256 + (uint32_t(ew * 32) << 16);
             const int jj = m & 63;
@@ -162,6 +166,13 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 uint32_t v[32];
                 tmem_ld32(t_acc + blk * NCOL, v);
                 tmem_ld_wait();
+                if (pl) {          // add the low-order accumulator set (fp32 round-to-nearest)
+                    uint32_t w[32];
+                    tmem_ld32(t_acc + 256 + blk * NCOL, w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; c++) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(w[c]));
+                }
                 asm volatile("bar.sync 1, 128;\n" ::: "memory");   // previous block's readers are done
 #pragma unroll
                 for (int c = 0; c < 27; c++) zs[m * ZS_STRIDE + c] = __uint_as_float(v[c]);

@@ -90,6 +90,7 @@ class Engine:
         # bench.py's instrumented pass: when a list, every launch appends
         # {family, bound, flops, bytes, e0, e1} with CUDA events recorded on the launching stream
         self.profile = None
+        self.debug = None           # tests / probes: a dict that receives intermediate gradients of the training backward
 
     def _timed(self, family, bound, flops, nbytes, fn):
         if self.profile is None:

@@ -3,10 +3,9 @@
 There is no network for datasets or checkpoints, so every benchmark / parity case is driven by
 tensors generated here from a seed (CPU generator => identical on every box).
 
-* ``depth_masks``  follows the reference data pipeline
-  (/root/reference/codes/data/LQGTker_Depth_dataset.py:204-226, ``getDepthMask`` with
-  ``depthFixedRange=False``): per image, ``interval=(max-min)/K`` and
-  ``mask_k = (d >= min+k*interval) & (d < min+(k+1)*interval)`` evaluated in fp32.
+* ``depth_masks``  bins every depth map into K equal-width one-hot masks over its own range (the input convention
+  of the reference data pipeline, codes/data/LQGTker_Depth_dataset.py:204-226; pinned to the reference function by
+  tests/test_io_golden_cpu.py).
 * ``synthetic_inputs`` follows SURVEY.md section 8(d): LQ in [0,1), depth in [0.01,10), GT in [0,1).
 * ``fill_state_dict`` fills a DepthNet ``state_dict`` *layout* (names + shapes) with seeded values.  It is
   deliberately harsher than the default init: ``weight_g != ||weight_v||`` so that the weight-norm path
@@ -24,22 +23,18 @@ import torch
 
 
 def depth_masks(depth: torch.Tensor, num: int = 10) -> torch.Tensor:
-    """depth [B,1,h,w] fp32 -> one-hot float masks [B,num,h,w] (reference getDepthMask, per image)."""
-    out = []
-    for b in range(depth.shape[0]):
-        d = depth[b, 0]
-        max_val = torch.max(d)
-        min_val = torch.min(d)
-        interval = (max_val - min_val) / num
-        planes = []
-        for i in range(num):
-            start_v = min_val + interval * i
-            end_v = min_val + interval * (i + 1)
-            m = torch.zeros(d.shape, dtype=torch.float32)
-            m[(d >= start_v) & (d < end_v)] = 1
-            planes.append(m)
-        out.append(torch.stack(planes, 0))
-    return torch.stack(out, 0)
+    """depth [B,1,h,w] fp32 -> one-hot fp32 masks [B,num,h,w]: ``num`` equal-width bins over every image's own
+    [min, max) -- the input convention of the reference's data pipeline.  A vectorised generator for synthetic inputs;
+    the checker for the device kernel ``io.depth_masks`` is the golden vector recorded from the reference's own
+    ``getDepthMask`` (tests/golden/io_golden.npz) and its restatement in oracle/depthnet_oracle.py."""
+    d = depth[:, 0].float()
+    lo = d.amin(dim=(1, 2), keepdim=True)
+    step = (d.amax(dim=(1, 2), keepdim=True) - lo) / num
+    k = torch.arange(num, dtype=torch.float32).view(1, num, 1, 1)
+    start = lo.unsqueeze(1) + step.unsqueeze(1) * k
+    end = lo.unsqueeze(1) + step.unsqueeze(1) * (k + 1)
+    dd = d.unsqueeze(1)
+    return ((dd >= start) & (dd < end)).float()
 
 
 def synthetic_inputs(batch: int, h: int, w: int, scale: int = 8, num_masks: int = 10, seed: int = 0,

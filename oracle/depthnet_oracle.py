@@ -88,6 +88,63 @@ def lrelu(x):
     return F.leaky_relu(x, 0.2)
 
 
+# --------------------------------------------------------------------------------------------- activation patterns
+# DepthNet is piecewise smooth: ReLU / LeakyReLU masks, the final clamp and the sign of the L1 loss switch the
+# gradient discontinuously.  An implementation whose forward differs by eps flips the units within eps of a switching
+# point, and each flip changes the gradient by O(1) of that unit's contribution -- so gradients of two correct
+# implementations differ by ~sqrt(flipped fraction), not by eps (the reference's own fp32 gradients deviate from
+# its fp64 gradients by up to 20 % on single parameters this way, tests/golden/*.npz ``grad_dev32``).  To compare
+# gradients ON THE SAME SMOOTH PIECE the oracle can (a) record its activation pattern and (b) be evaluated with a
+# pattern recorded elsewhere (the CUDA run): ``with activation_pattern(record=d)`` / ``activation_pattern(force=d)``.
+# Keys: the prefix of the convolution in front of the activation ("head.0", "upscale2.0", "<block>.block.0"),
+# "<sean>.actv", "<sean>.out" (ReLU after norm1 / after the residual add of norm2), "<classic block>.out", "clamp"
+# and "l1.sign".  Without a context every function below is the plain reference arithmetic.
+_PATTERN = {"record": None, "force": None}
+
+
+class activation_pattern:
+    def __init__(self, record: Optional[dict] = None, force: Optional[dict] = None):
+        self.new = {"record": record, "force": force}
+
+    def __enter__(self):
+        self.old = dict(_PATTERN)
+        _PATTERN.update(self.new)
+        return self
+
+    def __exit__(self, *exc):
+        _PATTERN.update(self.old)
+        return False
+
+
+def _act(x, key, slope=0.0):
+    """ReLU (slope 0) / LeakyReLU(slope) of the call site ``key``."""
+    if _PATTERN["record"] is not None:
+        _PATTERN["record"][key] = (x > 0).detach()
+    m = None if _PATTERN["force"] is None else _PATTERN["force"].get(key)
+    if m is None:
+        return F.leaky_relu(x, slope) if slope else F.relu(x)
+    m = m.to(x.dtype)
+    return x * (m + slope * (1.0 - m))
+
+
+def _clamp01(x, key="clamp"):
+    if _PATTERN["record"] is not None:
+        _PATTERN["record"][key] = ((x > 0) & (x < 1)).detach()
+    m = None if _PATTERN["force"] is None else _PATTERN["force"].get(key)
+    if m is None:
+        return torch.clamp(x, 0.0, 1.0)
+    return torch.where(m, x, torch.clamp(x, 0.0, 1.0).detach())
+
+
+def _abs(d, key="l1.sign"):
+    if _PATTERN["record"] is not None:
+        _PATTERN["record"][key] = (d > 0).detach()
+    m = None if _PATTERN["force"] is None else _PATTERN["force"].get(key)
+    if m is None:
+        return d.abs()
+    return d * (2.0 * m.to(d.dtype) - 1.0)
+
+
 # --------------------------------------------------------------------------------------------- encoder
 def region_pool(feat: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """RegionWiseAvgPooling.forward (models/modules/sftmd_arch.py:714-733) -> [B,K,C]."""
@@ -102,15 +159,16 @@ def region_pool(feat: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
 def encoder_forward(sd, x, mask, cap=None):
     """Encoder.forward (models/modules/sftmd_arch.py:771-783), weight_norm branch 743-749."""
     e1 = _wn_conv(sd, "encoder.layer1", x)
-    e2 = _wn_conv(sd, "encoder.layer2", lrelu(e1), stride=2)
-    e3 = _wn_conv(sd, "encoder.layer3", lrelu(e2), stride=2)
+    f0 = _act(e1, "encoder.layer1", 0.2)
+    e2 = _wn_conv(sd, "encoder.layer2", f0, stride=2)
+    e3 = _wn_conv(sd, "encoder.layer3", _act(e2, "encoder.layer2", 0.2), stride=2)
     w4 = weight_norm(sd["encoder.layer4.weight_g"], sd["encoder.layer4.weight_v"])
-    e4 = F.conv_transpose2d(lrelu(e3), w4, sd["encoder.layer4.bias"], stride=2, padding=1)
-    e5 = _wn_conv(sd, "encoder.layer5", lrelu(e4), stride=2)
+    e4 = F.conv_transpose2d(_act(e3, "encoder.layer3", 0.2), w4, sd["encoder.layer4.bias"], stride=2, padding=1)
+    e5 = _wn_conv(sd, "encoder.layer5", _act(e4, "encoder.layer4", 0.2), stride=2)
     vec = region_pool(e5, mask)
     if cap is not None:
         cap.update(e1=e1, e2=e2, e3=e3, e4=e4, e5=e5, depthVec=vec)
-    return lrelu(e1), vec
+    return f0, vec
 
 
 # --------------------------------------------------------------------------------------------- SEAN
@@ -118,7 +176,7 @@ def sean_gamma_beta(sd, p, depth_map, depth_mask, st, size):
     """gamma/beta of SEAN.forward (models/modules/normalization.py:58-88), literal form."""
     depth_map = F.interpolate(depth_map, size=size, mode="nearest")
     depth_mask = F.interpolate(depth_mask, size=size, mode="nearest")
-    actv = F.relu(F.conv2d(depth_map, sd[p + ".mlp_mask.0.weight"], sd[p + ".mlp_mask.0.bias"], padding=1))
+    actv = _act(F.conv2d(depth_map, sd[p + ".mlp_mask.0.weight"], sd[p + ".mlp_mask.0.bias"], padding=1), p + ".actv")
     beta_o = F.conv2d(actv, sd[p + ".mlp_beta_o.weight"], sd[p + ".mlp_beta_o.bias"], padding=1)
     gamma_o = F.conv2d(actv, sd[p + ".mlp_gamma_o.weight"], sd[p + ".mlp_gamma_o.bias"], padding=1)
     # A_i_j: 1x1 conv over the label axis (normalization.py:80)
@@ -158,10 +216,10 @@ def dynconv_apply(table: torch.Tensor, bias: torch.Tensor, mask: torch.Tensor) -
 def dgb_forward(sd, p, x, depth_map, depth_mask, st, cap=None):
     """Depth_Residual_Block_Mask.forward (models/modules/sftmd_arch.py:826-834)."""
     y1 = instance_norm(F.conv2d(x, sd[p + ".conv1.0.weight"], sd[p + ".conv1.0.bias"], padding=1))
-    a = F.relu(sean_forward(sd, p + ".norm1", y1, depth_map, depth_mask, st))
+    a = _act(sean_forward(sd, p + ".norm1", y1, depth_map, depth_mask, st), p + ".norm1.out")
     y2 = instance_norm(F.conv2d(a, sd[p + ".conv2.0.weight"], sd[p + ".conv2.0.bias"], padding=1))
     z = sean_forward(sd, p + ".norm2", y2, depth_map, depth_mask, st)
-    out = F.relu(x + z)
+    out = _act(x + z, p + ".norm2.out")
     if cap is not None:
         cap[p + ".a"] = a
         cap[p + ".out"] = out
@@ -171,8 +229,8 @@ def dgb_forward(sd, p, x, depth_map, depth_mask, st, cap=None):
 def classic_forward(sd, p, x):
     """Classic_Residual_Block.forward, weight_norm branch (models/modules/sftmd_arch.py:131-136,147-151)."""
     f = _wn_conv(sd, p + ".block.0", x)
-    f = _wn_conv(sd, p + ".block.2", F.relu(f))
-    return F.relu(x + f)
+    f = _wn_conv(sd, p + ".block.2", _act(f, p + ".block.0"))
+    return _act(x + f, p + ".out")
 
 
 def _block(sd, idx, which, x, depth_map, depth_mask, vec, cap):
@@ -186,7 +244,7 @@ def depthnet_forward(sd: Dict[str, torch.Tensor], lq, depth_map, depth_mask, sca
                      which=tuple(range(14)), cap: Optional[dict] = None, clamp=True):
     """DepthNet.forward (models/modules/sftmd_arch.py:912-950)."""
     f0, vec = encoder_forward(sd, lq, depth_mask, cap)
-    fea_bef = lrelu(_wn_conv(sd, "head.2", lrelu(_wn_conv(sd, "head.0", f0))))
+    fea_bef = _act(_wn_conv(sd, "head.2", _act(_wn_conv(sd, "head.0", f0), "head.0", 0.2)), "head.2", 0.2)
     x = fea_bef
     for i in range(nb - 3):
         x = _block(sd, i, which, x, depth_map, depth_mask, vec, cap)
@@ -195,20 +253,20 @@ def depthnet_forward(sd: Dict[str, torch.Tensor], lq, depth_map, depth_mask, sca
         cap["fea_bef"] = fea_bef
         cap["feat_add1"] = x
     if scale == 8:
-        x = lrelu(F.pixel_shuffle(_wn_conv(sd, "upscale1.0", x), 2))
-        x = lrelu(_wn_conv(sd, "upscale1.3", x))
+        x = _act(F.pixel_shuffle(_wn_conv(sd, "upscale1.0", x), 2), "upscale1.0", 0.2)
+        x = _act(_wn_conv(sd, "upscale1.3", x), "upscale1.3", 0.2)
     x = _block(sd, nb - 2, which, x, depth_map, depth_mask, vec, cap)
     if scale >= 4:
-        x = lrelu(F.pixel_shuffle(_wn_conv(sd, "upscale2.0", x), 2))
-        x = lrelu(_wn_conv(sd, "upscale2.3", x))
+        x = _act(F.pixel_shuffle(_wn_conv(sd, "upscale2.0", x), 2), "upscale2.0", 0.2)
+        x = _act(_wn_conv(sd, "upscale2.3", x), "upscale2.3", 0.2)
     x = _block(sd, nb - 1, which, x, depth_map, depth_mask, vec, cap)
     r = 3 if scale == 3 else 2
-    x = lrelu(F.pixel_shuffle(_wn_conv(sd, "upscale3.0", x), r))
+    x = _act(F.pixel_shuffle(_wn_conv(sd, "upscale3.0", x), r), "upscale3.0", 0.2)
     out = F.conv2d(x, sd["conv_output.weight"], sd["conv_output.bias"], padding=4)
     if cap is not None:
         cap["feat_up3"] = x
         cap["pre_clamp"] = out
-    return torch.clamp(out, 0.0, 1.0) if clamp else out
+    return _clamp01(out) if clamp else out
 
 
 # --------------------------------------------------------------------------------------------- loss
@@ -227,7 +285,7 @@ def dynamic_mask_loss(sr, hr, masks, trainable_weight, l_w=10.0):
 
 def training_loss(sr, hr, masks, trainable_weight, l_pix_w=1.0, l_dyn_w=10.0):
     """F_Model_depthCond.optimize_parameters loss (models/F_model_depthCond.py:163-190)."""
-    l_pix = l_pix_w * (sr - hr).abs().mean()
+    l_pix = l_pix_w * _abs(sr - hr).mean()
     raw, l_dyn, sw = dynamic_mask_loss(sr, hr, masks, trainable_weight, l_dyn_w)
     return l_pix + l_dyn, l_pix, l_dyn, raw
 
@@ -294,3 +352,19 @@ def state_layout(scale=8, nb=16, which=tuple(range(14)), latent=256, K=10):
     wn("upscale3.0", 32 * r * r, ch3)
     conv("conv_output", 3, 32, 9)
     return L
+
+
+# --------------------------------------------------------------------------------------------- input preparation
+def get_depth_mask(depth_map: torch.Tensor, fixed_range: bool = True, num: int = 10) -> torch.Tensor:
+    """``LQGTKerDepthDataset.getDepthMask`` (data/LQGTker_Depth_dataset.py:204-226) for ONE depth map [1,h,w] or
+    [h,w]: ``num`` one-hot fp32 planes [num,h,w]; bin i = [min + i*interval, min + (i+1)*interval) evaluated in the
+    tensor's dtype (0-dim tensors for the per-image range, python floats for the fixed [0,1] range)."""
+    d = torch.squeeze(depth_map)
+    hi, lo = (1, 0) if fixed_range else (torch.max(d), torch.min(d))
+    interval = (hi - lo) / num
+    planes = []
+    for i in range(num):
+        m = torch.zeros(d.shape)
+        m[(d >= lo + interval * i) & (d < lo + interval * (i + 1))] = 1
+        planes.append(m)
+    return torch.stack(planes, 0)

@@ -88,6 +88,13 @@ def run_case(name, scale, which, latent, B, h, w, seed, stride, init="synthetic"
         sr = net(lq, depth, masks)          # fp32, as the reference runs it
     for hk in hooks:
         hk.remove()
+    # the reference's own fp32 gradients (what codes/train.py computes), kept only as their per-parameter deviation
+    # from the fp64 gradients below: the conditioning of this gradient (``grad_dev32``)
+    dyn32 = dynamic_weight_mask_loss({"dynamic_criterion": "smoothl1", "dynamic_weight": 10.0}, device="cpu")
+    sr32 = net(lq, depth, masks)
+    (1.0 * torch.nn.L1Loss()(sr32, gt) + dyn32(sr32, gt, masks)[2]).backward()
+    g32 = {k: (p.grad.detach().double().clone() if p.grad is not None else None) for k, p in net.named_parameters()}
+    net.zero_grad(set_to_none=True)
     # loss + gradients in fp64 (the same reference modules, .double()): sums such as d(alpha) cancel heavily and
     # their fp32 value depends on the summation order, so the pin for gradients is the fp64 value.
     # Loss exactly as F_Model_depthCond.optimize_parameters builds it (pixel_weight 1, dynamic_weight 10).
@@ -121,6 +128,13 @@ def run_case(name, scale, which, latent, B, h, w, seed, stride, init="synthetic"
         sigs.append(grad_signature(k, p.grad) if p.grad is not None else np.full(4, np.nan))
     out["grad_names"] = np.array(names)
     out["grad_sig"] = np.stack(sigs)
+    dev = []
+    for k, p in net.named_parameters():
+        if p.grad is None or g32[k] is None or p.grad.norm().item() < 1e-12:
+            dev.append(np.nan)
+        else:
+            dev.append(((g32[k] - p.grad).norm() / p.grad.norm()).item())
+    out["grad_dev32"] = np.array(dev)
     out["sr64_absdiff_max"] = np.array([(sr64.detach().float() - sr).abs().max().item()])
     # a few complete gradients (small tensors) for element-wise checks
     params = dict(net.named_parameters())

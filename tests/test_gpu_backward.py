@@ -1,14 +1,10 @@
 """B200 tests of the backward pass (through the C ABI).
 
-Three levels:
  1. every backward kernel against torch autograd of the op it differentiates, on identical (bf16-rounded) inputs;
- 2. whole-network gradients of a SHALLOW DepthNet (one depth-guided block) against the fp32 CPU oracle -- tight;
- 3. whole-network gradients at full depth.  DepthNet's gradient is ill-conditioned: rounding the convolution
-    operands of the REFERENCE to bf16 (oracle.bf16_operands, what torch.autocast would do) already moves its own
-    early-layer gradients by 30-40 % while the output moves by 4e-3.  So at full depth the criterion is
-    "no worse than the bf16-operand reference": the deviation from the fp32 oracle must stay within 1.35x of the
-    deviation the bf16-operand oracle itself shows, and the layers behind the trunk (tail, output conv) -- which
-    are well conditioned -- must match the fp32 oracle to 2 %.
+ 2. whole-network gradients at full depth in the product arithmetic (bf16), PER PARAMETER, against the fp64 oracle
+    on the same smooth piece of the network (oracle.activation_pattern: DepthNet is piecewise smooth, and comparing
+    across ReLU / clamp / L1-sign flips measures the flips, not the implementation);
+ 3. the fp32-class statement (every gradient within 1e-4 of fp64, x8 / x4 / x2 / x3) lives in test_gpu_precise.py.
 """
 import importlib.util
 import os
@@ -67,98 +63,76 @@ def test_small_backward_kernels(kb):
 
 
 # ------------------------------------------------------------------------------------------------ whole network
-def _grads(meta, sd, inputs, nb=16, emulate=None):
-    """(CUDA grads, oracle grads) for the reference training loss (L1 + dynamic depth-mask loss)."""
-    import depth_aware_endoscopy_sr_b200 as dasr
-    lq, depth, masks, gt = inputs
-    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    wdyn = torch.ones(10, requires_grad=True)
-
-    def ref():
-        sr = oracle.depthnet_forward(sdr, lq, depth, masks, scale=meta["scale"], nb=nb, which=meta["which"])
-        total, *_ = oracle.training_loss(sr, gt, masks, wdyn)
-        total.backward()
-        return sr
-
-    if emulate:
-        with oracle.bf16_operands():
-            ref()
-    else:
-        ref()
-    gref = {k: v.grad for k, v in sdr.items()}
-    net = dasr.DepthNet(which_ResBlk_depth=list(meta["which"]), scale=meta["scale"], depth_latent_ch=meta["latent"], nb=nb,
-                        nf=64, depthRangeNum=10)
-    net.load_state_dict(sd, strict=True)
-    net = net.cuda().train()
-    wd = torch.ones(10, device="cuda", requires_grad=True)
-    sr = net(lq.cuda(), depth.cuda(), masks.cuda())
-    total, *_ = oracle.training_loss(sr, gt.cuda(), masks.cuda(), wd)
-    total.backward()
-    torch.cuda.synchronize()
-    g = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in net.named_parameters()}
-    return g, gref, net
+# (the tolerance-class statement about the backward ALGORITHM is tests/test_gpu_precise.py: every parameter gradient
+# of the full-depth x8 / x4 / x2 / x3 networks within 1e-4 of fp64 in the fp32-split mode of the same kernels.)
+# per-parameter bounds of the bf16 product arithmetic, relative to what bf16 rounding does to the REFERENCE itself on
+# the same smooth piece (oracle.bf16_operands: conv operands rounded to bf16, everything else fp64):
+#   tensors:  err <= 3.5 * err_emulated + 0.03      (measured: ratio median 1.0, max 2.9 over 5 cases x ~440 tensors)
+#   one-element blend scalars (differences of two cancelling full reductions: their relative error is unbounded as the
+#   sum approaches zero): ABSOLUTE error <= 0.75 * rms of the reference's blend-scalar gradients of the case
+BF16_TENSOR_FACTOR, BF16_TENSOR_FLOOR, BF16_SCALAR_ABS = 3.5, 0.03, 0.75
 
 
-def _rel(g, gref):
-    out = {}
-    for k, r in gref.items():
-        # a conv bias in front of an InstanceNorm has an exactly-zero gradient (only fp32 round-off in the oracle)
-        if r is None or r.norm() < 1e-9 or ".conv1.0.bias" in k or ".conv2.0.bias" in k:
-            continue
-        out[k] = ((g[k] - r).norm() / r.norm()).item()
-    return out
-
-
-def test_shallow_network_gradients_match_fp32_oracle():
-    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
-    meta = dict(scale=8, latent=256, which=(0,))
-    torch.manual_seed(3)
-    import warnings
-    from depth_aware_endoscopy_sr_b200.arch import DepthNet
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        sd = {k: v.detach().clone() for k, v in DepthNet(which_ResBlk_depth=[0], scale=8, nb=4).state_dict().items()}
-    inputs = synthetic_inputs(2, 32, 32, scale=8, seed=3, with_gt=True)
-    g, gref, _ = _grads(meta, sd, inputs, nb=4)
-    rel = _rel(g, gref)
-    worst = sorted(rel.items(), key=lambda kv: -kv[1])[:8]
-    print("shallow net: median %.4f max %.4f  worst %s" % (np.median(list(rel.values())), worst[0][1], worst[:4]))
+@pytest.mark.parametrize("name", ["x8_b2_32_init", "x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24"])
+def test_full_depth_bf16_gradients_per_parameter(name):
+    """Product arithmetic (bf16 operands and activations, fp32 accumulate): every parameter gradient of the full-depth
+    network against the fp64 oracle evaluated ON THE SAME SMOOTH PIECE (the activation pattern of the CUDA run,
+    oracle.activation_pattern) -- what is left is the effect of bf16 rounding itself, bounded PER PARAMETER:
+    see the bounds above.  The free comparison (different pieces: bf16 flips ~1e-3 of the ReLU / clamp units, and each flip
+    moves the gradient discontinuously) is reported for reference; so is the same measurement for the oracle with
+    bf16-rounded conv operands (what torch.autocast does to the reference)."""
+    import json
+    from common import cuda_train_grads, oracle_grads64, skip_grad_param
+    z, meta = load_golden(name)
+    sd, inputs = case_tensors(meta)
+    g, _gw, loss, pattern = cuda_train_grads(meta, sd, inputs)
+    np.testing.assert_allclose(loss[:3], z["loss"][:3], rtol=2e-2)
+    rec = {}
+    gfree, _ = oracle_grads64(meta, sd, inputs, record=rec)
+    assert not (set(rec) - set(pattern))
+    flips = sum(int((rec[k] != pattern[k]).sum()) for k in rec)
+    units = sum(rec[k].numel() for k in rec)
+    gref, _ = oracle_grads64(meta, sd, inputs, pattern=pattern)
+    with oracle.bf16_operands():
+        gemu, _ = oracle_grads64(meta, sd, inputs, pattern=pattern)
+    rows = []
     for k, r in gref.items():
         if r is None:
             assert g[k] is None, "%s: the reference leaves this gradient None" % k
+            continue
+        assert g[k] is not None, "missing gradient for " + k
+        if skip_grad_param(k, r):
+            continue
+        rows.append((k, r.numel(), ((g[k] - r).norm() / r.norm()).item(), ((g[k] - gfree[k]).norm() / gfree[k].norm()).item(),
+                     ((gemu[k] - r).norm() / r.norm()).item()))
+    sc_keys = [k for k, n, *_ in rows if n == 1]
+    sc_rms = float(np.sqrt(np.mean([gref[k].item() ** 2 for k in sc_keys])))
+    sc_abs = max(abs(g[k].item() - gref[k].item()) for k in sc_keys) / sc_rms
+    ratio = max(a / (BF16_TENSOR_FACTOR * c + BF16_TENSOR_FLOOR) for k, n, a, b, c in rows if n > 1)
+    ten = np.array([r[2] for r in rows if r[1] > 1])
+    sca = np.array([r[2] for r in rows if r[1] == 1])
+    emu = np.array([r[4] for r in rows if r[1] > 1])
+    free = np.array([r[3] for r in rows if r[1] > 1])
+    wt = max((r for r in rows if r[1] > 1), key=lambda r: r[2])
+    print("%s bf16 gradients: %d of %d units (%.1e) on a different piece\n   same piece, tensors: median %.3g max %.3g (%s);"
+          " scalars: median %.3g max %.3g\n   bf16-operand ORACLE on the same piece, tensors: median %.3g max %.3g\n"
+          "   free comparison, tensors: median %.3g max %.3g" % (
+              name, flips, units, flips / units, np.median(ten), ten.max(), wt[0], np.median(sca), sca.max(),
+              np.median(emu), emu.max(), np.median(free), free.max()))
+    print("   worst tensor err / bound %.2f ; worst blend-scalar abs err / rms %.3f (bound %.2f)" % (ratio, sc_abs, BF16_SCALAR_ABS))
+    out_dir = os.environ.get("DASR_PARITY_OUT")
+    if out_dir:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "grad_parity_bf16_%s.json" % name), "w") as fh:
+            json.dump(dict(case=name, flipped_units=flips, units=units,
+                           params=[dict(param=k, numel=n, rel_l2_same_piece=a, rel_l2_free=b, bf16_operand_oracle_same_piece=c)
+                                   for k, n, a, b, c in rows]), fh, indent=0)
+    for k, n, a, b, c in rows:
+        if n > 1:
+            assert a <= BF16_TENSOR_FACTOR * c + BF16_TENSOR_FLOOR, (k, a, c)
         else:
-            assert g[k] is not None, "missing gradient for " + k
-    assert np.median(list(rel.values())) <= 0.02
-    # 1-element blend scalars are cancellation-dominated full reductions (5 % already between fp32 and fp64)
-    for k, v in rel.items():
-        assert v <= (0.25 if gref[k].numel() == 1 else 0.15), (k, v)
-
-
-@pytest.mark.parametrize("name", ["x8_b2_32_init"])
-def test_full_depth_gradients_are_in_the_bf16_class(name):
-    _z, meta = load_golden(name)
-    sd, inputs = case_tensors(meta)
-    g, gref, net = _grads(meta, sd, inputs)
-    rel = _rel(g, gref)
-    # what rounding the conv operands of the reference itself does to its gradients
-    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    wdyn = torch.ones(10, requires_grad=True)
-    lq, depth, masks, gt = inputs
-    with oracle.bf16_operands():
-        sr = oracle.depthnet_forward(sdr, lq, depth, masks, scale=meta["scale"], which=meta["which"])
-        total, *_ = oracle.training_loss(sr, gt, masks, wdyn)
-        total.backward()
-    rel_emu = _rel({k: v.grad for k, v in sdr.items()}, gref)
-    med, med_emu = np.median(list(rel.values())), np.median(list(rel_emu.values()))
-    print("full depth: median rel err vs fp32 oracle %.4f ; bf16-operand oracle vs fp32 oracle %.4f" % (med, med_emu))
-    assert med <= 1.35 * med_emu + 0.01
-    for k in rel:
-        if k.startswith(("conv_output", "upscale", "classic-residual")):
-            assert rel[k] <= 0.02, (k, rel[k])
-    # parameters the reference never uses get no gradient at all (SURVEY.md headline fact 5)
-    for k, r in gref.items():
-        assert (g[k] is None) == (r is None), k
-    assert g["depth-residual14.conv1.0.weight"] is None
+            assert abs(g[k].item() - gref[k].item()) <= BF16_SCALAR_ABS * sc_rms, (k, g[k].item(), gref[k].item(), sc_rms)
+    assert g["depth-residual14.conv1.0.weight"] is None       # never used by the reference either (SURVEY fact 5)
 
 
 def test_side_stream_backward_equals_the_one_stream_backward():

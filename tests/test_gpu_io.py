@@ -1,77 +1,56 @@
-"""B200 tests of the input / output steps either side of the generator: bit-exact against
-the reference formulas (getDepthMask as restated in synthetic.depth_masks; tensor2img as in codes/utils/util.py)."""
+"""B200 tests of the steps either side of the generator against golden vectors recorded
+by executing the REAL reference functions (tests/golden/make_io_golden.py -> tests/golden/io_golden.npz):
+``getDepthMask`` (codes/data/LQGTker_Depth_dataset.py:204-226), ``tensor2img`` / ``calculate_psnr``
+(codes/utils/util.py:566-590,646-653) and ``pytorch_ssim.ssim`` (codes/pytorch_ssim/__init__.py:65-72).
+Integer / byte outputs are bit-exact; PSNR to 1e-9 relative (float64), SSIM to 2e-5 (fp32 window sums)."""
+import math
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from depth_aware_endoscopy_sr_b200.synthetic import depth_masks as ref_depth_masks
+from common import GOLDEN, IO_DEPTH_SHAPES, io_depth_input, io_frames_input
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("shape", [(3, 16, 24), (2, 64, 64), (1, 135, 240)])
-def test_depth_masks_are_bit_exact(shape):
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "io_golden.npz"))
+
+
+@pytest.mark.parametrize("shape", IO_DEPTH_SHAPES)
+def test_depth_masks_are_bit_exact_against_the_reference_function(shape, gold):
     from depth_aware_endoscopy_sr_b200 import io as bio
     B, h, w = shape
-    g = torch.Generator().manual_seed(B * 1000 + h)
-    depth = 0.01 + 9.99 * torch.rand(B, 1, h, w, generator=g)
-    depth[0, 0, 0, :4] = depth[0].max()                   # several pixels at the (exclusive) upper edge
-    ref = ref_depth_masks(depth, 10)                       # the reference's torch fp32 expression, per image
-    masks, labels = bio.depth_masks(depth.cuda(), 10)
-    assert torch.equal(masks.cpu(), ref)
-    lab_ref = torch.where(ref.sum(1) > 0, ref.argmax(1), torch.full_like(ref.argmax(1), 255)).to(torch.uint8)
-    assert torch.equal(labels.cpu(), lab_ref)
-    assert (labels.cpu() == 255).sum().item() >= 1        # the maximum belongs to no bin
-    # depthFixedRange=True: bins over [0,1] with python-double edges
-    d01 = torch.rand(B, 1, h, w, generator=g)
-    m2, _ = bio.depth_masks(d01.cuda(), 10, fixed_range=True)
-    exp = torch.stack([((d01[:, 0] >= (0 + 0.1 * i)) & (d01[:, 0] < (0 + 0.1 * (i + 1)))).float() for i in range(10)], 1)
-    assert torch.equal(m2.cpu(), exp)
+    depth, d01 = io_depth_input(B, h, w)
+    for tag, src, fixed in (("range", depth, False), ("fixed", d01, True)):
+        ref_lab = torch.from_numpy(gold["labels_%s_%dx%dx%d" % (tag, B, h, w)])
+        masks, labels = bio.depth_masks(src.cuda(), 10, fixed_range=fixed)
+        assert torch.equal(labels.cpu(), ref_lab), tag
+        ref_masks = torch.stack([(ref_lab == k).float() for k in range(10)], 1)     # one-hot planes of the label map
+        assert torch.equal(masks.cpu(), ref_masks), tag
+    assert (torch.from_numpy(gold["labels_range_%dx%dx%d" % (B, h, w)]) == 255).sum().item() >= 1   # the maximum is in no bin
 
 
-def test_tensor2img_matches_reference_conversion():
+def test_tensor2img_is_bit_exact_against_the_reference_function(gold):
     from depth_aware_endoscopy_sr_b200 import io as bio
-    g = torch.Generator().manual_seed(0)
-    sr = torch.rand(2, 3, 40, 56, generator=g) * 1.4 - 0.2         # values outside [0,1] are clamped
-    sr.view(-1)[:512] = (torch.arange(512) // 2).float() / 255.0 + (torch.arange(512) % 2) * 0.5 / 255.0   # exact .5 ties
+    sr, _gt = io_frames_input()
     out = bio.tensor2img(sr.cuda()).cpu().numpy()
-    for b in range(2):
-        t = sr[b].clone().clamp_(0, 1)
-        t = (t - 0) / (1 - 0)
-        ref = np.transpose(t.numpy()[[2, 1, 0], :, :], (1, 2, 0))
-        ref = (ref * 255.0).round().astype(np.uint8)
-        assert np.array_equal(out[b], ref)
+    assert out.dtype == np.uint8 and np.array_equal(out, gold["tensor2img_sr"])
     one = bio.tensor2img(sr[0].cuda())
-    assert one.shape == (40, 56, 3) and np.array_equal(one.cpu().numpy(), out[0])
+    assert one.shape == (72, 100, 3) and np.array_equal(one.cpu().numpy(), gold["tensor2img_sr"][0])
 
 
-def test_psnr_and_ssim_match_the_reference_formulas():
-    import math
-    import torch.nn.functional as F
+def test_psnr_and_ssim_match_the_reference_functions(gold):
     from depth_aware_endoscopy_sr_b200 import io as bio
-    g = torch.Generator().manual_seed(3)
-    gt = torch.rand(2, 3, 72, 100, generator=g)
-    sr = (gt + 0.05 * torch.randn(gt.shape, generator=g)).clamp(0, 1)
-    # PSNR as train.py:251-257 computes it from the tensor2img frames with a border crop of `scale` pixels
+    sr, gt = io_frames_input()
     sr8, gt8 = bio.tensor2img(sr.cuda()), bio.tensor2img(gt.cuda())
-    got = bio.psnr(sr8, gt8, crop=8).cpu().numpy()
-    for f in range(2):
-        a = sr8[f].cpu().numpy().astype(np.float64)[8:-8, 8:-8, :]
-        b = gt8[f].cpu().numpy().astype(np.float64)[8:-8, 8:-8, :]
-        ref = 20 * math.log10(255.0 / math.sqrt(np.mean((a - b) ** 2)))
-        assert abs(got[f] - ref) <= 1e-9 * ref
-    assert math.isinf(bio.psnr(gt8, gt8).cpu()[0].item())
-    # SSIM: pytorch_ssim._ssim restated with torch ops (window = outer product of the normalised 1-D Gaussian)
-    w1 = torch.tensor([math.exp(-(x - 5) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)])
-    w1 = (w1 / w1.sum()).unsqueeze(1)
-    win = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous().double()
-    x, y = sr.double(), gt.double()
-    mu1, mu2 = F.conv2d(x, win, padding=5, groups=3), F.conv2d(y, win, padding=5, groups=3)
-    s1 = F.conv2d(x * x, win, padding=5, groups=3) - mu1 ** 2
-    s2 = F.conv2d(y * y, win, padding=5, groups=3) - mu2 ** 2
-    s12 = F.conv2d(x * y, win, padding=5, groups=3) - mu1 * mu2
-    smap = ((2 * mu1 * mu2 + 0.01 ** 2) * (2 * s12 + 0.03 ** 2)) / ((mu1 ** 2 + mu2 ** 2 + 0.01 ** 2) * (s1 + s2 + 0.03 ** 2))
-    got = bio.ssim(sr.cuda(), gt.cuda(), size_average=False).cpu().double()
-    ref = smap.mean(dim=(1, 2, 3))
-    assert (got - ref).abs().max().item() <= 2e-5
-    assert abs(bio.ssim(sr.cuda(), gt.cuda()).item() - smap.mean().item()) <= 2e-5
+    got = bio.psnr(sr8, gt8, crop=8).cpu().numpy()          # the border crop of train.py:251-257
+    np.testing.assert_allclose(got, gold["psnr_crop8"], rtol=1e-9)
+    assert math.isinf(gold["psnr_identical_is_inf"][0]) and math.isinf(bio.psnr(gt8, gt8).cpu()[0].item())
+    x = sr.clamp(0, 1)
+    per = bio.ssim(x.cuda(), gt.cuda(), size_average=False).cpu().numpy()
+    assert np.abs(per - gold["ssim_per_frame"]).max() <= 2e-5
+    assert abs(bio.ssim(x.cuda(), gt.cuda()).item() - gold["ssim_mean"][0]) <= 2e-5

@@ -123,7 +123,10 @@ def test_fused_adam_matches_torch_adam():
 
 
 def _torch_step_reference(sd, meta, inputs, steps, lr):
-    """The same optimize_parameters step assembled from our generator + torch criteria + torch.optim.Adam."""
+    """The same optimize_parameters step assembled from OUR generator + torch criteria + torch.optim.Adam: isolates the
+    K-LOSS / K-ADAM kernels and the step plumbing (the generator is shared, so this says nothing about ITS gradients --
+    those are pinned to the fp64 oracle / the reference goldens in test_gpu_precise.py and test_gpu_backward.py,
+    including three optimizer steps against the oracle: test_precise_train_steps_follow_the_oracle_trajectory)."""
     import depth_aware_endoscopy_sr_b200 as dasr
     lq, depth, masks, gt = [t.cuda() for t in inputs]
     with warnings.catch_warnings():

@@ -75,3 +75,38 @@ def test_dynamic_conv_restatement_is_exact():
     ref = torch.nn.functional.conv2d(style_map, w, b, padding=1)
     got = oracle.dynconv_apply(oracle.style_table(w, stp), b, mask)
     assert (ref - got).abs().max().item() < 1e-11
+
+
+@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24"])
+def test_forced_activation_pattern_is_the_same_function(name):
+    """oracle.activation_pattern: recording the pattern of a run and forcing it back reproduces the run exactly (so
+    a forced evaluation IS the reference function on that smooth piece), every nonlinearity has a key, and forcing
+    a pattern with a few flipped units changes the gradient discontinuously (what the GPU gradient tests avoid)."""
+    _z, meta = load_golden(name)
+    sd, (lq, depth, masks, gt) = case_tensors(meta)
+
+    def run(force=None, record=None):
+        sdr = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+        wd = torch.ones(10, dtype=torch.float64, requires_grad=True)
+        with oracle.activation_pattern(force=force, record=record):
+            sr = oracle.depthnet_forward(sdr, lq.double(), depth.double(), masks.double(), scale=meta["scale"],
+                                         which=meta["which"])
+            total, *_ = oracle.training_loss(sr, gt.double(), masks.double(), wd)
+        total.backward()
+        return total.item(), {k: v.grad for k, v in sdr.items() if v.grad is not None}
+
+    rec = {}
+    t0, g0 = run(record=rec)
+    n_dgb = len([i for i in meta["which"] if i < 13 or meta["scale"] <= 3 or i >= 13])
+    assert "clamp" in rec and "l1.sign" in rec and "head.2" in rec and "depth-residual1.norm1.actv" in rec
+    assert sum(k.endswith(".actv") for k in rec) == 2 * sum(1 for k in rec if k.endswith(".norm2.out")) > 0 and n_dgb
+    t1, g1 = run(force=rec)
+    assert t1 == t0
+    for k in g0:
+        assert torch.equal(g0[k], g1[k]), k
+    flipped = {k: v.clone() for k, v in rec.items()}
+    m = flipped["depth-residual13.norm2.out"] if "depth-residual13.norm2.out" in flipped else flipped["head.2"]
+    m.view(-1)[::97] ^= True
+    _t2, g2 = run(force=flipped)
+    k = "head.0.weight_v"
+    assert ((g2[k] - g0[k]).norm() / g0[k].norm()).item() > 1e-3
