@@ -188,5 +188,18 @@ class DepthNet(nn.Module):
             self._engine = _engine.Engine(self)
         return self._engine
 
+    def _replicate_for_data_parallel(self):
+        """``nn.DataParallel`` over SEVERAL devices (the reference's default wrapper when ``opt['dist']`` is false,
+        F_model_depthCond.py:35) replicates the module per device and runs the replicas in threads.  A replica
+        shallow-copies ``__dict__``, i.e. it would share this module's Engine -- packed weights, flat gradient
+        buffers and recorded graphs bound to the parameters of device 0.  The B200 path is one process per GPU
+        (``parallel.FlatDataParallel`` / ``install_ddp``: the reference's own ``--launcher pytorch`` mode), so a
+        multi-device replicate is refused with the way out; a single-device DataParallel never replicates."""
+        raise RuntimeError(
+            "DepthNet (B200) does not run under multi-device nn.DataParallel: its engine (packed weights, flat "
+            "gradient buffers, CUDA graphs) is bound to one device.  Use one process per GPU -- torchrun + "
+            "codes/train.py --launcher pytorch with depth_aware_endoscopy_sr_b200.install_ddp() (INTEGRATION.md, "
+            "section 3), or set gpu_ids to a single device.")
+
     def forward(self, input, depthMap, depthMask):
         return self.engine().forward(input, depthMap, depthMask)

@@ -113,7 +113,9 @@ class dynamic_weight_mask_loss(nn.Module):
     the scale), ``num_trainable_para`` = depthMaskNum.  forward -> (loss_list, weighted_loss_list, weighted_loss,
     softmax_weight)."""
 
-    def __init__(self, opt, num_trainable_para: int = 10):
+    def __init__(self, opt, device=None, num_trainable_para: int = 10):
+        # (``device`` is accepted and ignored exactly like the reference's constructor, mask_loss.py:50: the module is
+        # moved with .to(device) by its owner)
         super().__init__()
         loss_type = opt["dynamic_criterion"]
         if loss_type != "smoothl1":

@@ -65,7 +65,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat[gi] = st
         return st
 
-    def _segments(self, st):
+    def _segments(self, st, weight_decay=0.0):
         """[(offset, n, grad tensor)] covering the flat parameter buffer.  Parameters whose gradients are views of
         ONE flat buffer with this optimiser's layout (``Engine.last_flat_grad``, registered with its layout
         {id(param): offset} in ``_lib.flat_grads()``; zero where the network leaves a gradient None) are stepped as a single segment straight
@@ -85,7 +85,27 @@ class FusedAdam(torch.optim.Optimizer):
                            for p in params[i0:i1 + 1])
             if same_layout and in_place and any(p.grad is not None for p in params[i0:i1 + 1]) \
                     and (base.data_ptr() + 4 * g0) % 16 == 0 and g0 + n <= base.numel() and base.device == st["p"].device:
-                segs.append((offsets[i0], n, base[g0:g0 + n], list(range(i0, i1 + 1))))
+                # A parameter the network never uses has a zero slice in the flat buffer.  Without weight decay a zero
+                # gradient on zero Adam state is a no-op, so the whole range is ONE launch; with weight decay the
+                # kernel's g += wd * p would decay it (torch.optim.Adam skips grad-None parameters entirely), so
+                # the range is split into the runs of parameters that do have a gradient.
+                if weight_decay:
+                    runs, cur = [], []
+                    for i in idx:
+                        if params[i].grad is not None:
+                            cur.append(i)
+                        elif cur:
+                            runs.append(cur)
+                            cur = []
+                    if cur:
+                        runs.append(cur)
+                else:
+                    runs = [idx]
+                for run in runs:
+                    r0, r1 = run[0], run[-1]
+                    gr = lay[id(params[r0])]
+                    nr = offsets[r1] + params[r1].numel() - offsets[r0]
+                    segs.append((offsets[r0], nr, base[gr:gr + nr], list(run)))
                 covered.update(range(i0, i1 + 1))
         for i, p in enumerate(params):
             if i in covered or p.grad is None:
@@ -123,7 +143,7 @@ class FusedAdam(torch.optim.Optimizer):
             st = self._ensure_flat(gi, group)
             if st is None:
                 continue
-            segs = self._segments(st)
+            segs = self._segments(st, group["weight_decay"])
             if not segs:
                 continue
             b1, b2 = group["betas"]
@@ -150,20 +170,56 @@ class FusedAdam(torch.optim.Optimizer):
             torch.autograd.graph.increment_version(st["params"])
         return loss
 
+    # ------------------------------------------------------------------ checkpoint interchange with torch.optim.Adam
+    def _param_indices(self):
+        """{id(param): index} in the numbering of Optimizer.state_dict() (group order, every parameter counted)."""
+        out, n = {}, 0
+        for group in self.param_groups:
+            for p in group["params"]:
+                out[id(p)] = n
+                n += 1
+        return out
+
     def state_dict(self):
+        """The layout of ``torch.optim.Adam.state_dict()``: ``state[index] = {step, exp_avg, exp_avg_sq}`` per
+        parameter that has been stepped -- a reference ``*.state`` file written by this optimiser resumes under
+        torch.optim.Adam and vice versa (codes/models/base_model.py resume_training -> optimizer.load_state_dict)."""
         sd = super().state_dict()
-        sd["flat"] = {gi: dict(step=st["step"], pstep=list(st["pstep"]), exp_avg=st["m"].clone(),
-                               exp_avg_sq=st["v"].clone())
-                      for gi, st in self._flat.items()}
+        index = self._param_indices()
+        state = {}
+        for st in self._flat.values():
+            for j, (p, off) in enumerate(zip(st["params"], st["offsets"])):
+                if st["pstep"][j] <= 0:
+                    continue
+                n = p.numel()
+                state[index[id(p)]] = dict(step=torch.tensor(float(st["pstep"][j])),
+                                           exp_avg=st["m"][off:off + n].view(p.shape).clone(),
+                                           exp_avg_sq=st["v"][off:off + n].view(p.shape).clone())
+        sd["state"] = state
         return sd
 
     def load_state_dict(self, state_dict):
+        """Accepts this class's own state_dict, a ``torch.optim.Adam`` state_dict (per-parameter moments are copied
+        into the flat buffers) and the ``flat`` layout of earlier versions of this class."""
         flat = state_dict.get("flat", {})
         super().load_state_dict({k: v for k, v in state_dict.items() if k != "flat"})
         for gi, group in enumerate(self.param_groups):
+            st = self._ensure_flat(gi, group)
+            if st is None:
+                continue
             if gi in flat:
-                st = self._ensure_flat(gi, group)
                 st["step"] = int(flat[gi]["step"])
                 st["pstep"] = list(flat[gi].get("pstep", [st["step"]] * len(st["params"])))
                 st["m"].copy_(flat[gi]["exp_avg"])
                 st["v"].copy_(flat[gi]["exp_avg_sq"])
+                continue
+            for j, (p, off) in enumerate(zip(st["params"], st["offsets"])):
+                ps = self.state.get(p)
+                if not ps:
+                    continue
+                n = p.numel()
+                st["m"][off:off + n].copy_(ps["exp_avg"].reshape(-1))
+                st["v"][off:off + n].copy_(ps["exp_avg_sq"].reshape(-1))
+                st["pstep"][j] = int(float(ps["step"]))
+            st["step"] = max(st["pstep"]) if st["pstep"] else 0
+        self.state.clear()       # the moments live in the flat buffers

@@ -82,8 +82,13 @@ def broadcast_parameters_(module: nn.Module, src: int = 0, group=None) -> None:
     if world(group)[1] == 1:
         return
     with torch.no_grad():
-        for t in list(module.parameters()) + list(module.buffers()):
+        ts = list(module.parameters()) + list(module.buffers())
+        for t in ts:
             dist.broadcast(t.data, src=src, group=group)
+        # written through .data: advance the version counters like an in-place op would, so that weight caches keyed
+        # on them (Engine.pack, the recorded inference graphs) are refreshed on the ranks that received new values
+        if ts:
+            torch.autograd.graph.increment_version(ts)
 
 
 class FlatDataParallel(nn.Module):

@@ -46,6 +46,10 @@ class TrainStep:
         params = [p for p in net.parameters() if p.requires_grad] + list(self.dynamic_loss.parameters())
         self.optimizer = FusedAdam(params, lr=lr, betas=betas, weight_decay=weight_decay, capturable=graph)
         self.graph = bool(graph)
+        if self.graph and int(warmup) < 1:
+            # the first call re-homes the parameters into FusedAdam's flat buffers and allocates its device scalars:
+            # that must not happen inside the capture
+            raise ValueError("TrainStep(graph=True) needs warmup >= 1 eager step before the capture")
         self._warmup = int(warmup)
         self._calls = 0
         self._g = None
@@ -98,7 +102,10 @@ class TrainStep:
         vec = _loss.loss_vector(sr, gt, masks, self.dynamic_loss.trainable_weight, w_pix=self.l_pix_w,
                                 w_dyn=self.l_dyn_w, sums_hook=self._hook, n_scale=self._nscale)
         vec[_loss.O_TOTAL].backward()
-        if self.distributed:
-            _par.sync_extra_grads_(self.dynamic_loss.parameters(), self.group, average=(self.mode == "ddp"))
+        if self.distributed and self.mode == "ddp":
+            # per-rank losses: average the gradients of the 10 loss weights like every other gradient.  In "global"
+            # mode the loss partial sums were all-reduced BEFORE dasr_loss_finalize, so every rank already holds the
+            # gradient of the global-batch loss w.r.t. the loss weights (identical on all ranks): nothing to reduce.
+            _par.sync_extra_grads_(self.dynamic_loss.parameters(), self.group, average=True)
         self.optimizer.step()
         return vec.detach()

@@ -81,10 +81,44 @@ def test_forward_matches_oracle_full_frame(name):
         ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"])
         sr = _build(meta, sd)(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
     err = (sr - ref).abs().max().item()
-    dp = abs(psnr(sr, gt) - psnr(ref, gt))
-    print("%s: max|sr-oracle|=%.4g  PSNR delta=%.5f dB" % (name, err, dp))
+    # PSNR delta the way north_star means it: both outputs scored against the SAME ground truth, and a ground truth the
+    # reference output is close to (reference + 2 % noise, ~34 dB) -- against an unrelated image (MSE ~0.3) a 4e-3 pixel
+    # error moves PSNR by 1e-4 dB and the check could not fail.  Also the PSNR of the CUDA output against the reference
+    # output itself (>= 48 dB <=> rms error <= 4e-3).
+    g = torch.Generator().manual_seed(meta["seed"] + 1000)
+    near = (ref + 0.02 * torch.randn(ref.shape, generator=g)).clamp(0, 1)
+    dp = abs(psnr(sr, near) - psnr(ref, near))
+    direct = psnr(sr, ref)
+    print("%s: max|sr-oracle|=%.4g  PSNR delta=%.5f dB (at %.1f dB)  PSNR(cuda, ref)=%.1f dB" % (
+        name, err, dp, psnr(ref, near), direct))
     assert err <= tol
     assert dp <= TOL_PSNR
+    assert direct >= (48.0 if meta["init"] == "default" else 40.0)
+
+
+def test_bench_config_b64_matches_oracle():
+    """BASELINE configs[1] itself: x8, batch 64, 64x64 LR, the reference's own random init -- every frame of the batch
+    against the CPU oracle (max-abs <= 1e-2), not inferred from batch-1 cases."""
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    import warnings
+    import depth_aware_endoscopy_sr_b200 as dasr
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = dasr.DepthNet(which_ResBlk_depth=list(range(14)), scale=8, nb=16, nf=64, depth_latent_ch=256,
+                            depthRangeNum=10)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    lq, depth, masks = synthetic_inputs(64, 64, 64, scale=8, seed=0)
+    with torch.no_grad():
+        sr = net.cuda().eval()(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+        worst = 0.0
+        for b0 in range(0, 64, 8):                      # the oracle in chunks of 8 frames (memory of the CPU path)
+            ref = oracle.depthnet_forward(sd, lq[b0:b0 + 8], depth[b0:b0 + 8], masks[b0:b0 + 8], scale=8,
+                                          which=tuple(range(14)))
+            worst = max(worst, (sr[b0:b0 + 8] - ref).abs().max().item())
+    print("B=64 64x64 x8 (bench config): max|sr-oracle| over all 64 frames = %.4g" % worst)
+    assert tuple(sr.shape) == (64, 3, 512, 512)
+    assert worst <= TOL_PIX
 
 
 def test_other_seeds_and_batch():

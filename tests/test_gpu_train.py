@@ -118,8 +118,61 @@ def test_fused_adam_matches_torch_adam():
         assert p_new[0]._version > v0
     for a, b in zip(p_ref, p_new):
         assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item() + 1e-7
+    # ---- checkpoint interchange (codes/models/base_model.py resume_training -> optimizer.load_state_dict): the state
+    # dict has torch.optim.Adam's layout, so either optimiser resumes from the other's *.state file
     sd = o_new.state_dict()
-    assert sd["flat"][0]["step"] == 6
+    sd_ref = o_ref.state_dict()
+    assert set(sd["state"].keys()) == set(sd_ref["state"].keys()) == set(range(len(shapes)))
+    for i in range(len(shapes)):
+        assert float(sd["state"][i]["step"]) == float(sd_ref["state"][i]["step"]) == (5 if shapes[i] == (7,) else 6)
+        assert (sd["state"][i]["exp_avg"] - sd_ref["state"][i]["exp_avg"]).abs().max().item() <= 2e-6 * sd_ref["state"][i]["exp_avg"].abs().max().item() + 1e-9
+    p_a = [p.detach().clone().requires_grad_(True) for p in p_ref]      # torch Adam resuming from FusedAdam's file
+    p_b = [p.detach().clone().requires_grad_(True) for p in p_ref]      # FusedAdam resuming from torch Adam's file
+    o_a = torch.optim.Adam(p_a, lr=3e-4, betas=(0.9, 0.99))
+    o_b = dasr.FusedAdam(p_b, lr=3e-4, betas=(0.9, 0.99))
+    o_a.load_state_dict(sd)
+    o_b.load_state_dict(sd_ref)
+    for a, b, r in zip(p_a, p_b, p_ref):
+        g = torch.randn_like(a)
+        a.grad, b.grad, r.grad = g.clone(), g.clone(), g.clone()
+    o_a.step(), o_b.step(), o_ref.step()
+    for a, b, r in zip(p_a, p_b, p_ref):
+        assert (a - r).abs().max().item() <= 2e-6 * r.abs().max().item() + 1e-7
+        assert (b - r).abs().max().item() <= 2e-6 * r.abs().max().item() + 1e-7
+
+
+def test_fused_adam_weight_decay_skips_parameters_without_gradient():
+    """train.weight_decay_G > 0: inside the engine's flat gradient buffer a never-used parameter is a zero slice; like
+    torch.optim.Adam (which skips grad-None parameters) it must neither decay nor build moments."""
+    import depth_aware_endoscopy_sr_b200 as dasr
+    from depth_aware_endoscopy_sr_b200 import _lib as L
+    torch.manual_seed(1)
+    shapes = [(8, 4), (16,), (5, 3), (12,)]
+    p_ref = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    p_new = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    o_ref = torch.optim.Adam(p_ref, lr=1e-2, betas=(0.9, 0.99), weight_decay=0.1)
+    o_new = dasr.FusedAdam(p_new, lr=1e-2, betas=(0.9, 0.99), weight_decay=0.1)
+    o_new.step()                                            # re-homes the parameters into the flat buffer (no grads yet)
+    for step in range(3):
+        offs, n = {}, 0
+        for p in p_new:
+            offs[id(p)] = n
+            n += L.flat_pad(p.numel())
+        flat = torch.zeros(n, device="cuda")
+        for i, (a, b) in enumerate(zip(p_ref, p_new)):
+            if i == 1:                                      # "never used": zero slice, grad None
+                a.grad, b.grad = None, None
+                continue
+            g = torch.randn_like(a)
+            a.grad = g.clone()
+            flat[offs[id(b)]:offs[id(b)] + b.numel()] = g.reshape(-1)
+            b.grad = flat[offs[id(b)]:offs[id(b)] + b.numel()].view(b.shape)
+        L.register_flat_grad(flat, offs)
+        o_ref.step()
+        o_new.step()
+    for a, b in zip(p_ref, p_new):
+        assert (a - b).abs().max().item() <= 2e-6 * a.abs().max().item() + 1e-7
+    assert torch.equal(p_new[1].detach(), p_ref[1].detach())                 # untouched
 
 
 def _torch_step_reference(sd, meta, inputs, steps, lr):

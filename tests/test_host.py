@@ -92,3 +92,16 @@ def test_synthetic_masks_follow_get_depth_mask():
     m = depth_masks(d, 10)
     assert m.shape == (2, 10, 8, 8) and set(m.unique().tolist()) <= {0.0, 1.0}
     assert (m.sum(1) <= 1).all() and (m.sum(1) == 1).float().mean() > 0.95
+
+
+def test_multi_device_data_parallel_is_refused_with_the_way_out():
+    """nn.DataParallel over several devices would share one Engine between the replicas: the replicate
+    hook raises and names the one-process-per-GPU path instead."""
+    import warnings
+    import pytest
+    import depth_aware_endoscopy_sr_b200 as dasr
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = dasr.DepthNet(which_ResBlk_depth=[0], scale=8, nb=4)
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        net._replicate_for_data_parallel()

@@ -69,7 +69,7 @@ def _worker(rank, world, port, q):
         sums = torch.full((36,), float(rank + 1))
         par.loss_sums_hook()(sums)
         res["sums"] = sums.clone()
-        q.put((rank, res))
+        q.put((rank, {k: (v.tolist() if torch.is_tensor(v) else v) for k, v in res.items()}))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -84,6 +84,7 @@ def test_two_rank_gloo_data_parallel_plumbing():
     for p in procs:
         p.start()
     out = dict(q.get(timeout=120) for _ in range(world))
+    out = {r: {k: (torch.tensor(v) if k != "frames" else v) for k, v in d.items()} for r, d in out.items()}
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
