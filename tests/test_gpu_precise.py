@@ -173,7 +173,7 @@ def test_precise_train_steps_follow_the_oracle_trajectory(name, precise):
     side.  Adam's first steps are ~lr * sign(g): a discontinuous function of the gradient, so an element whose tiny
     gradient differs in sign moves by 2 lr and the trajectories separate step by step (measured: 2-10 % of the
     elements after three steps).  Bars: the first loss (same parameters) to 1e-5, the second (one Adam step later) to
-    1e-3, the third to 2e-2; >= 85 % of all parameter elements within 0.15 lr of the oracle's after three steps."""
+    1e-3, the third to 2e-2; >= 98 % of all parameter elements within 0.05 lr of the oracle's after the first step."""
     import depth_aware_endoscopy_sr_b200 as dasr
     _z, meta = load_golden(name)
     sd, (lq, depth, masks, gt) = case_tensors(meta)
@@ -182,7 +182,7 @@ def test_precise_train_steps_follow_the_oracle_trajectory(name, precise):
     prm = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
     wd = torch.ones(10, dtype=torch.float64, requires_grad=True)
     opt = torch.optim.Adam(list(prm.values()) + [wd], lr=lr, betas=(0.9, 0.99))
-    ref_losses = []
+    ref_losses, ref_p1 = [], None
     for _ in range(steps):
         opt.zero_grad(set_to_none=True)
         sr = oracle.depthnet_forward(prm, lq.double(), depth.double(), masks.double(), scale=meta["scale"],
@@ -191,16 +191,25 @@ def test_precise_train_steps_follow_the_oracle_trajectory(name, precise):
         total.backward()
         opt.step()
         ref_losses.append(total.item())
+        if ref_p1 is None:
+            ref_p1 = {k: v.detach().clone() for k, v in prm.items() if v.grad is not None}
     # ---- CUDA
     net = _net(meta, sd).train()
     step = dasr.TrainStep(net, num_masks=10, lr=lr, betas=(0.9, 0.99))
     ins = [t.cuda() for t in (lq, depth, masks, gt)]
-    losses = [step(*ins)[0].item() for _ in range(steps)]
+    losses, p1 = [], None
+    for _ in range(steps):
+        losses.append(step(*ins)[0].item())
+        if p1 is None:
+            p1 = {k: p.detach().double().cpu().clone() for k, p in net.named_parameters()}
     print("%s losses: cuda %s  oracle %s" % (name, losses, ref_losses))
     for got, ref, tol in zip(losses, ref_losses, (1e-5, 1e-3, 2e-2)):
         assert abs(got - ref) <= tol * abs(ref), (losses, ref_losses)
-    a = torch.cat([p.detach().double().cpu().reshape(-1) for k, p in net.named_parameters() if prm[k].grad is not None])
-    b = torch.cat([prm[k].detach().reshape(-1) for k, p in net.named_parameters() if prm[k].grad is not None])
-    agree = ((a - b).abs() <= 0.05 * steps * lr).double().mean().item()
-    assert agree >= 0.85, agree
+    # after ONE Adam step (identical starting point): every element moved by ~lr * sign(g); elements whose tiny
+    # gradients differ in sign are 2 lr apart.  Later steps are compared through the losses only (a chaotic map).
+    a = torch.cat([p1[k].reshape(-1) for k in ref_p1])
+    b = torch.cat([ref_p1[k].reshape(-1) for k in ref_p1])
+    agree = ((a - b).abs() <= 0.05 * lr).double().mean().item()
+    print("   elements within 0.05 lr of the oracle's after the first Adam step: %.4f" % agree)
+    assert agree >= 0.98, agree
     assert (step.dynamic_loss.trainable_weight.detach().double().cpu() - wd.detach()).abs().max().item() <= 1e-4
