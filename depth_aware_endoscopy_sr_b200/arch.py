@@ -203,3 +203,26 @@ class DepthNet(nn.Module):
 
     def forward(self, input, depthMap, depthMask):
         return self.engine().forward(input, depthMap, depthMask)
+
+    @torch.no_grad()
+    def infer_frames(self, input, depthMap, depthMask=None, out: str = "uint8", depthFixedRange: bool = False):
+        """LR frames + depth maps -> SR frames, with the steps the reference runs on the CPU either side of the generator
+        done on the device:
+
+        * ``depthMask=None``: the K one-hot depth masks are built from ``depthMap`` by ``io.depth_masks`` --
+          ``LQGTKerDepthDataset.getDepthMask(depth, depthFixedRange, depthRangeNum)`` of the data pipeline
+          (codes/data/LQGTker_Depth_dataset.py:157,204-226; bit-exact) -- so only the LR frame and its depth map
+          (4 fp32 planes instead of 14) have to be uploaded;
+        * ``out="uint8"``: the SR tensor goes through ``io.tensor2img`` (``util.tensor2img`` as codes/test.py:87 calls
+          it: clamp, x255, round, uint8, RGB->BGR, HWC; bit-exact) and the ``[B, sH, sW, 3]`` uint8 frames are returned
+          -- a quarter of the bytes of the fp32 tensor; ``out="float"`` returns what ``forward`` returns.
+
+        Inference only (no autograd); frames are independent, so a stream is sharded over GPUs by frame
+        (``parallel.shard_frames``) with no collective."""
+        from . import io as _io
+        if out not in ("uint8", "float"):
+            raise ValueError("out must be 'uint8' or 'float'")
+        if depthMask is None:
+            depthMask, _labels = _io.depth_masks(depthMap, self.depthRangeNum, fixed_range=depthFixedRange)
+        sr = self.engine().infer(input, depthMap, depthMask)
+        return _io.tensor2img(sr, (self.min, self.max)) if out == "uint8" else sr

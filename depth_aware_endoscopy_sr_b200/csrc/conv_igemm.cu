@@ -41,7 +41,17 @@ __device__ unsigned long long g_prof[16];
 #define PROF_DECL long long prof_t = clock64(); long long prof_acc[4] = {0, 0, 0, 0}
 #define PROF_LAP(i) do { long long n_ = clock64(); prof_acc[i] += n_ - prof_t; prof_t = n_; } while (0)
 #define PROF_FLUSH(base, n) do { for (int i_ = 0; i_ < (n); i_++) atomicAdd(&g_prof[(base) + i_], (unsigned long long)prof_acc[i_]); } while (0)
+// whole-kernel SM cycles (slot 8) and nanoseconds (slot 9) of every CTA: their ratio is the SM clock DURING the kernel
+__device__ __forceinline__ unsigned long long prof_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PROF_KERNEL_BEGIN long long pk_c0 = clock64(); unsigned long long pk_n0 = prof_ns()
+#define PROF_KERNEL_END do { if (threadIdx.x == 0) { atomicAdd(&g_prof[8], (unsigned long long)(clock64() - pk_c0)); atomicAdd(&g_prof[9], prof_ns() - pk_n0); } } while (0)
 #else
+#define PROF_KERNEL_BEGIN
+#define PROF_KERNEL_END
 #define DBG(p, bit) 0
 #define PROF_DECL
 #define PROF_LAP(i)
@@ -389,6 +399,106 @@ __device__ __forceinline__ void sean_epilogue(const ConvK& p, uint32_t t_acc, co
     }
 }
 
+// The same epilogue with ALL global operands of the tile (y and the residual: 4 steps x 2 x 32 bytes per thread)
+// requested up front -- before the statistics finalize and before the accumulator is ready.  One step of look-ahead
+// (sean_epilogue) keeps ~16 KB of loads in flight per SM; at ~1.5 us of loaded-memory latency that is ~6 B/clk/SM, and
+// the epilogue, not the MMA, bounded the CTA-pair kernel (in-kernel accounting: 17.7 k cycles per 256-pixel tile
+// against 13.9 k of MMA).  No gb_s / fp32 residual stream here (the pair kernel's K-DYN extension replaces gb_s).
+template <int N_TILE, int NB>
+struct SeanTileOps {
+    static constexpr int CH = (N_TILE / 2 + 31) / 32;
+    static constexpr int STEPS = NB * CH;
+    uint4 y[STEPS][2], r[STEPS][2];
+    size_t pix[NB];
+    bool valid[NB];
+};
+
+template <int N_TILE, int NB>
+__device__ __forceinline__ void sean_prefetch_tile(const ConvK& p, SeanTileOps<N_TILE, NB>& o, int img, int q0, int w0, int m,
+                                                   int half) {
+    constexpr int NF = N_TILE / 2;
+    constexpr int CH = SeanTileOps<N_TILE, NB>::CH;
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int blk = 0; blk < NB; blk++) {
+        const int q = q0 + blk * 128 + m;
+        const int h = (int)__umulhi((unsigned)q, p.wp_magic);
+        const int wl = q - h * p.Wp;
+        const int w = w0 + wl;
+        o.valid[blk] = (img < p.B) && (h < p.H) && (wl < p.Wt) && (w < p.W);
+        o.pix[blk] = ((size_t)img * p.H + h) * p.W + w;
+#pragma unroll
+        for (int ci = 0; ci < CH; ci++) {
+            const int it = blk * CH + ci, c0 = half * 16 + ci * 32;
+            o.y[it][0] = o.y[it][1] = o.r[it][0] = o.r[it][1] = z4;
+            if (o.valid[blk] && !DBG(p, 1)) {
+                ldg256(p.y + o.pix[blk] * NF + c0, o.y[it][0], o.y[it][1]);
+                if (p.resid) ldg256(p.resid + o.pix[blk] * NF + c0, o.r[it][0], o.r[it][1]);
+            }
+        }
+    }
+}
+
+template <int N_TILE, int NB>
+__device__ __forceinline__ void sean_epilogue_tile(const ConvK& p, const SeanTileOps<N_TILE, NB>& o, uint32_t t_acc,
+                                                   const float* bias_t, const float* norm_s, int half) {
+    constexpr int NF = N_TILE / 2;
+    constexpr int CH = SeanTileOps<N_TILE, NB>::CH;
+    constexpr int STEPS = NB * CH;
+#pragma unroll
+    for (int it = 0; it < STEPS; it++) {
+        const int blk = it / CH, c0 = half * 16 + (it % CH) * 32;
+        uint32_t vg[16], vb[16];
+        tmem_ld16(t_acc + blk * N_TILE + c0, vg);
+        tmem_ld16(t_acc + blk * N_TILE + NF + c0, vb);
+        tmem_ld_wait();
+        if (!o.valid[blk]) continue;
+        float yv[16], gs[16], f[16];
+        unpack8(o.y[it][0], yv);
+        unpack8(o.y[it][1], yv + 8);
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+            const float4 bg = *reinterpret_cast<const float4*>(bias_t + c0 + j4);
+            const float4 bb = *reinterpret_cast<const float4*>(bias_t + NF + c0 + j4);
+            gs[j4] = __uint_as_float(vg[j4]) + bg.x;
+            gs[j4 + 1] = __uint_as_float(vg[j4 + 1]) + bg.y;
+            gs[j4 + 2] = __uint_as_float(vg[j4 + 2]) + bg.z;
+            gs[j4 + 3] = __uint_as_float(vg[j4 + 3]) + bg.w;
+            f[j4] = __uint_as_float(vb[j4]) + bb.x;
+            f[j4 + 1] = __uint_as_float(vb[j4 + 1]) + bb.y;
+            f[j4 + 2] = __uint_as_float(vb[j4 + 2]) + bb.z;
+            f[j4 + 3] = __uint_as_float(vb[j4 + 3]) + bb.w;
+        }
+#pragma unroll
+        for (int j2 = 0; j2 < 16; j2 += 2) {
+            const float4 nm = *reinterpret_cast<const float4*>(norm_s + 2 * (c0 + j2));     // (mean, scale) x 2
+            f[j2] = fmaf((yv[j2] - nm.x) * nm.y, 1.f + gs[j2], f[j2]);
+            f[j2 + 1] = fmaf((yv[j2 + 1] - nm.z) * nm.w, 1.f + gs[j2 + 1], f[j2 + 1]);
+        }
+        if (p.inner_relu) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (DBG(p, 2)) continue;
+        if (p.gamma_out) store16(p.gamma_out + o.pix[blk] * NF + c0, gs);
+        if (p.resid) {
+            float rr[16];
+            unpack8(o.r[it][0], rr);
+            unpack8(o.r[it][1], rr + 8);
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] += rr[j];
+        }
+        if (p.act == DASR_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.act == DASR_ACT_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
+        }
+        store16(p.out + o.pix[blk] * NF + c0, f);
+    }
+}
+
 // STATS epilogue of one tile for one thread: store y = acc + bias (bf16) and accumulate, per column, the sum and the
 // sum of squares of the STORED values over this warp's 32 rows of BOTH M blocks in registers; one butterfly reduction
 // per 16-column chunk and tile (v1 reduced every M block separately: twice the shuffles on the critical epilogue).
@@ -492,6 +602,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    PROF_KERNEL_BEGIN;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.SA; i++) {
@@ -1030,8 +1141,321 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    PROF_KERNEL_END;
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
+
+#ifndef DASR_CONV_PRECISE_TU
+// ------------------------------------------------------------------------------------------------ SEAN conv, CTA pairs
+// The [gamma_o; beta_o] convolution of SEAN (128 -> 128, 3x3, K-DYN extension, SEAN epilogue) on CTA PAIRS:
+// tcgen05.mma.cta_group::2, M = 256.  With one CTA per tile an M128 x N128 x K16 SS-MMA reads 4 KB of A and 4 KB of B
+// from shared memory per 64 tensor cycles -- exactly the 128 B/clk a B200 SM can deliver -- so the TMA fills of the
+// 288 KB weight ring and the epilogue's own shared-memory reads push the MMA to ~110 cycles (ncu, round 1).  A pair
+// shares ONE weight stream: each CTA stages only HALF of every weight tile (rows rank*64..+63), the tensor cores of
+// both SMs read both halves, and each CTA multiplies them with its own 128 pixel rows: 6 KB per MMA and CTA, half the
+// weight fill per CTA.
+//   * Pairing: the two CTAs of a pair work on the SAME tile position of TWO CONSECUTIVE IMAGES (identical geometry,
+//     one set of descriptors).  The main K loop is shared.  The K-DYN extension has per-image filters; it runs as two
+//     passes, pass j with the filters of image j, and every CTA keeps TWO mask-patch buffers at the same offsets: its
+//     own patch in buffer `rank`, zeros in the other -- so the foreign pass adds 0 to its accumulator.
+//   * Only the leader (cluster rank 0) issues MMAs.  Both CTAs run TMA producers; their transaction bytes are counted
+//     on the LEADER's full barriers: the leader's producer posts ONE arrive.expect_tx for the bytes of both CTAs, the
+//     peer's producer only issues its TMA (a remote arrive per stage is a cluster-scope release: ~2000 cycles each,
+//     measured -- it made the kernel 2.2x slower than the single-CTA one).  "Stage free" / "accumulator ready" come from a
+//     multicast tcgen05.commit that arrives on the same barrier in both CTAs; "accumulator drained" is counted on the
+//     leader's acc_empty (8 local + 8 remote epilogue warps).
+//   * Epilogue = sean_epilogue (unchanged), each CTA on its own TMEM half and its own image.
+constexpr int kPairSB = 8;
+template <int N_TILE, int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+sean_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const ConvK p) {
+    constexpr int SWZ = 128, KC = 64, KSTEPS = 4;
+    constexpr int ACC_COLS = NB * N_TILE;
+    constexpr int TMEM_COLS = 512;
+    static_assert(2 * ACC_COLS <= 512, "two accumulator buffers must fit TMEM");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[2], a_empty[2];
+    __shared__ uint64_t b_full[kPairSB], b_empty[kPairSB];
+    __shared__ uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint64_t a2_full, a2_empty;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float norm_s[512];
+    __shared__ __align__(16) float bias_s[N_TILE];
+    __shared__ uint32_t tap_lo_s[9];
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* a_smem = smem;
+    uint8_t* b_smem = smem + 2 * (size_t)p.a_stage_bytes;
+    uint8_t* a2_smem = smem + p.a2_off;                 // two buffers of a2_bytes: [0] image 0's patch, [1] image 1's
+    const uint32_t a2_bytes = (p.a2_tx_bytes + 1023u) & ~1023u;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    PROF_KERNEL_BEGIN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&a_full[i], 1);           // leader only: ONE arrive.expect_tx for the bytes of BOTH CTAs
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 16);       // 8 epilogue warps x 2 CTAs (leader only)
+        }
+        for (int i = 0; i < kPairSB; i++) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        mbar_init(&a2_full, 1);
+        mbar_init(&a2_empty, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        tma_prefetch_desc(&mapA2);
+        tma_prefetch_desc(&mapB2);
+    }
+    if (warp == 2) tmem_alloc_pair<TMEM_COLS>(&tmem_base_s);
+    // the foreign mask-patch buffer stays zero for the whole kernel
+    {
+        uint4* z = reinterpret_cast<uint4*>(a2_smem + (size_t)(1 - rank) * a2_bytes);
+        for (int i = threadIdx.x; i < (int)(a2_bytes / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int i = threadIdx.x; i < N_TILE; i += kThreads) bias_s[i] = __ldg(p.bias + i);
+    if (threadIdx.x < 9) {
+        const int t = threadIdx.x / 3, u = threadIdx.x - t * 3;
+        tap_lo_s[threadIdx.x] = (uint32_t)((t * p.Wp + u) * SWZ) >> 4;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // barriers of both CTAs are initialised before any remote arrive / TMA
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int tiles_per_img = p.n_strips * p.tiles_per_strip;
+    const int n_pairs = gridDim.x >> 1;
+    const int pair_id = blockIdx.x >> 1;
+    // the leader's copies of the barriers the producers of BOTH CTAs signal
+    const uint32_t a2_full_l = mapa_u32(smem_u32(&a2_full), 0);
+
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(DASR_LEAN_ROLE_REGS));
+    if (warp == 0) {
+        // ===================================================== A producer (both CTAs): own image, own patches
+        if (elect_one()) {
+            uint32_t a_it = 0, t_it = 0;
+            for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, t_it++) {
+                const int ip = tile / tiles_per_img;
+                int r = tile - ip * tiles_per_img;
+                const int strip = r / p.tiles_per_strip;
+                const int tps = r - strip * p.tiles_per_strip;
+                const int img = 2 * ip + (int)rank;            // >= B for the odd image out: TMA zero-fills
+                const int q0 = tps * (NB * 128);
+                const int r0 = q0 / p.Wp;
+                const int w0 = strip * p.Wt;
+                for (int c = 0; c < 2; c++, a_it++) {
+                    const int sa = a_it & 1;
+                    mbar_wait(&a_empty[sa], ((a_it >> 1) & 1) ^ 1);
+                    const uint32_t full_l = mapa_u32(smem_u32(&a_full[sa]), 0);
+                    if (leader) mbar_expect_tx(&a_full[sa], 2 * p.a_tx_bytes);
+                    tma_load_4d_pair(a_smem + (size_t)sa * p.a_stage_bytes, &mapA, full_l, c * KC, w0 - p.pad_w,
+                                     r0 - p.pad_h, img);
+                }
+                mbar_wait(&a2_empty, (t_it & 1) ^ 1);
+                if (leader) mbar_expect_tx(&a2_full, 2 * p.a2_tx_bytes);
+                tma_load_4d_pair(a2_smem + (size_t)rank * a2_bytes, &mapA2, a2_full_l, 0, w0 - p.pad_w, r0 - p.pad_h, img);
+            }
+        }
+    } else if (warp == 3) {
+        // ===================================================== B producer (both CTAs): rows rank*64.. of every weight tile
+        if (elect_one()) {
+            uint32_t b_it = 0;
+            for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs) {
+                const int ip = tile / tiles_per_img;
+                for (int c = 0; c < 2; c++)
+                    for (int tap = 0; tap < 9; tap++, b_it++) {
+                        const int sb = b_it % kPairSB;
+                        mbar_wait(&b_empty[sb], ((b_it / kPairSB) & 1) ^ 1);
+                        const uint32_t full_l = mapa_u32(smem_u32(&b_full[sb]), 0);
+                        if (leader) mbar_expect_tx(&b_full[sb], 2 * p.b_tx_bytes);
+                        tma_load_2d_pair(b_smem + (size_t)sb * p.b_stage_bytes, &mapB, full_l, tap * p.Cin + c * KC,
+                                         (int)rank * (N_TILE / 2));
+                    }
+                for (int j = 0; j < 2; j++)             // dynamic filters of image j of the pair, this CTA's half
+                    for (int tap = 0; tap < 9; tap++, b_it++) {
+                        const int sb = b_it % kPairSB;
+                        mbar_wait(&b_empty[sb], ((b_it / kPairSB) & 1) ^ 1);
+                        const uint32_t full_l = mapa_u32(smem_u32(&b_full[sb]), 0);
+                        if (leader) mbar_expect_tx(&b_full[sb], 2 * p.b2_tx_bytes);
+                        tma_load_2d_pair(b_smem + (size_t)sb * p.b_stage_bytes, &mapB2, full_l, tap * 16,
+                                         (2 * ip + j) * N_TILE + (int)rank * (N_TILE / 2));
+                    }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===================================================== MMA issuer (leader CTA, one thread)
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(256, N_TILE);
+            const uint64_t desc0 = make_smem_desc<SWZ>(0, 0);
+            const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
+            const uint32_t lo_flags = (uint32_t)desc0 & ~0x3FFFu;
+            const uint32_t a_lo0 = lo_flags | ((smem_u32(a_smem) & 0x3FFFFu) >> 4);
+            const uint32_t b_lo0 = lo_flags | ((smem_u32(b_smem) & 0x3FFFFu) >> 4);
+            const uint32_t a_stage_lo = p.a_stage_bytes >> 4, b_stage_lo = p.b_stage_bytes >> 4;
+            constexpr uint32_t BLK_LO = (128u * SWZ) >> 4;
+            const uint32_t desc_hi32 = (uint32_t)(make_smem_desc<32>(0, 0) >> 32);
+            const uint32_t a2_lo0 = lo_flags | ((smem_u32(a2_smem) & 0x3FFFFu) >> 4);
+            uint32_t a_it = 0, b_it = 0, acc_it = 0, t_it = 0;
+            PROF_DECL;
+            for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, t_it++, acc_it++) {
+                const int r = tile % tiles_per_img;
+                const int tps = r % p.tiles_per_strip;
+                const int q0 = tps * (NB * 128);
+                const int soff = q0 - (q0 / p.Wp) * p.Wp;
+                const int buf = acc_it & 1;
+                PROF_LAP(3);
+                mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+                PROF_LAP(0);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+                for (int c = 0; c < 2; c++, a_it++) {
+                    const int sa = a_it & 1;
+                    PROF_LAP(3);
+                    mbar_wait(&a_full[sa], (a_it >> 1) & 1);
+                    PROF_LAP(1);
+                    tc_fence_after();
+                    const uint32_t a_lo_tile = a_lo0 + sa * a_stage_lo + (uint32_t)soff * (SWZ >> 4);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; tap++, b_it++) {
+                        const int sb = b_it % kPairSB;
+                        PROF_LAP(3);
+                        mbar_wait(&b_full[sb], (b_it / kPairSB) & 1);
+                        PROF_LAP(2);
+                        tc_fence_after();
+                        const uint32_t a_lo = a_lo_tile + tap_lo_s[tap];
+                        const uint32_t b_lo = b_lo0 + sb * b_stage_lo;
+#pragma unroll
+                        for (int blk = 0; blk < NB; blk++) {
+#pragma unroll
+                            for (int k = 0; k < KSTEPS; k++)
+                                umma_bf16_lohi_pair(d_tmem + blk * N_TILE, a_lo + blk * BLK_LO + k * 2, b_lo + k * 2, desc_hi,
+                                                    idesc, (c | tap | k) != 0);
+                        }
+                        umma_commit_pair(&b_empty[sb]);
+                    }
+                    umma_commit_pair(&a_empty[sa]);
+                }
+                // K-DYN extension, two passes: pass j = filters of image j x mask-patch buffer j (own patch in one
+                // CTA, zeros in the other)
+                mbar_wait(&a2_full, t_it & 1);
+                tc_fence_after();
+                for (int j = 0; j < 2; j++) {
+                    const uint32_t a2_lo_tile = a2_lo0 + ((uint32_t)j * a2_bytes >> 4) + (uint32_t)soff * (32u >> 4);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; tap++, b_it++) {
+                        const int sb = b_it % kPairSB;
+                        mbar_wait(&b_full[sb], (b_it / kPairSB) & 1);
+                        tc_fence_after();
+                        const uint32_t a_lo = a2_lo_tile + (tap_lo_s[tap] * 32u) / SWZ;
+                        const uint32_t b_lo = b_lo0 + sb * b_stage_lo;
+#pragma unroll
+                        for (int blk = 0; blk < NB; blk++)
+                            umma_bf16_lohi_pair(d_tmem + blk * N_TILE, a_lo + blk * ((128u * 32u) >> 4), b_lo, desc_hi32, idesc, 1);
+                        umma_commit_pair(&b_empty[sb]);
+                    }
+                }
+                umma_commit_pair(&a2_empty);
+                umma_commit_pair(&acc_full[buf]);
+            }
+            PROF_LAP(3);
+            PROF_FLUSH(0, 4);
+        }
+    }
+    } else if (warp >= 4 && warp < 12) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(DASR_LEAN_EPI_REGS));
+        // ===================================================== epilogue warps (both CTAs): sean_epilogue on the own image
+        const int ew = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int m = ew * 32 + lane;
+        const int et = threadIdx.x - 128;
+        uint32_t acc_it = 0;
+        PROF_DECL;
+        for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, acc_it++) {
+            const int ip = tile / tiles_per_img;
+            int r = tile - ip * tiles_per_img;
+            const int strip = r / p.tiles_per_strip;
+            const int tps = r - strip * p.tiles_per_strip;
+            const int img = 2 * ip + (int)rank;
+            const bool have = img < p.B;
+            const int q0 = tps * (NB * 128);
+            const int w0 = strip * p.Wt;
+            const int buf = acc_it & 1;
+            constexpr int NF = N_TILE / 2;
+            SeanTileOps<N_TILE, NB> ops;              // every global operand of the tile is requested here
+            sean_prefetch_tile<N_TILE, NB>(p, ops, img, q0, w0, m, half);
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            if (et < NF && have) {
+                // fused double-InstanceNorm finalize of this image (see conv_halo_kernel)
+                const float2* sp = reinterpret_cast<const float2*>(p.stats) + (size_t)img * p.nslots * NF + et;
+                float a1 = 0.f, a2 = 0.f;
+                for (int sl = 0; sl < p.nslots; sl += 8) {
+                    float2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        v[u] = (sl + u < p.nslots) ? __ldg(sp + (size_t)(sl + u) * NF) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        a1 += v[u].x;
+                        a2 += v[u].y;
+                    }
+                }
+                const float inv_hw = 1.f / (float)(p.H * p.W);
+                const float mean = a1 * inv_hw;
+                const float var = fmaxf(a2 * inv_hw - mean * mean, 0.f);
+                const float eps = 1e-5f;
+                const float r1 = rsqrtf(var + eps);
+                const float r2 = rsqrtf(var * r1 * r1 + eps);
+                norm_s[2 * et] = mean;
+                norm_s[2 * et + 1] = r1 * r2;
+                if (p.norm_out && tps == 0 && strip == 0) {
+                    p.norm_out[((size_t)img * NF + et) * 2] = mean;
+                    p.norm_out[((size_t)img * NF + et) * 2 + 1] = r1 * r2;
+                    if (p.normk_out) {
+                        const float a = var + eps, rr = var / a + eps;
+                        p.normk_out[(size_t)img * NF + et] = 1.f / a + eps / (a * a * rr);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            PROF_LAP(1);
+            mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
+            PROF_LAP(0);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
+            if (have && half * 16 < NF) sean_epilogue_tile<N_TILE, NB>(p, ops, t_acc, bias_s, norm_s, half);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+        }
+        PROF_LAP(1);
+#ifdef DASR_PROFILE
+        if (threadIdx.x == 128) PROF_FLUSH(4, 2);
+#endif
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs are done with both TMEM halves and with each other's barriers
+    PROF_KERNEL_END;
+    if (warp == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+}
+#endif  // DASR_CONV_PRECISE_TU
 
 // ------------------------------------------------------------------------------------------------ host
 // DASR_PDL=0 turns programmatic dependent launch off (A/B measurements)
@@ -1112,6 +1536,83 @@ static int dispatch_n(int epi, int n_tile, const CUtensorMap& mA, const CUtensor
     return fail(DASR_ERR_BAD_ARG, "unsupported epilogue %d with N tile %d", epi, n_tile);
 }
 
+#ifndef DASR_CONV_PRECISE_TU
+// DASR_SEAN_PAIR=0: keep the [gamma_o; beta_o] convolution on single CTAs (A/B measurements)
+static int g_sean_pair = -1;        // -1: environment (default on), 0 / 1: dasr_set_sean_pair
+static bool sean_pair_enabled() {
+    if (g_sean_pair >= 0) return g_sean_pair != 0;
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DASR_SEAN_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+// sean_pair_kernel launch: k holds the single-CTA geometry (NB = 2, two A stages); the weight ring and the tile
+// count are re-derived for pairs.  Returns 1 when the geometry does not fit (the caller uses the single-CTA kernel).
+static int launch_sean_pair(const dasr_conv_desc* d, const dasr_conv_args* a, ConvK k, const CUtensorMap& mA,
+                            const CUtensorMap& mA2, cudaStream_t stream, int* used) {
+    constexpr int N_TILE = 128, NB = 2;
+    *used = 0;
+    const uint32_t a2_bytes = (k.a2_tx_bytes + 1023u) & ~1023u;
+    k.b_tx_bytes = (N_TILE / 2) * 128;
+    k.b_stage_bytes = k.b_tx_bytes;
+    k.b2_tx_bytes = (N_TILE / 2) * 32;
+    k.SA = 2;
+    k.SB = kPairSB;
+    k.b_resident = 0;
+    k.a2_off = (uint32_t)(2 * (size_t)k.a_stage_bytes + (size_t)kPairSB * k.b_stage_bytes);
+    const size_t smem_bytes = (size_t)k.a2_off + 2 * (size_t)a2_bytes + 1024;
+    if (smem_bytes > 227 * 1024 - 10 * 1024) return DASR_OK;          // wide strips: single-CTA kernel
+    const int pairs_of_images = (d->B + 1) / 2;
+    k.total_tiles = pairs_of_images * k.n_strips * k.tiles_per_strip;
+    CUtensorMap mB, mB2;
+    {
+        uint64_t dims[2] = {(uint64_t)k.taps * d->Cin, (uint64_t)N_TILE};
+        uint64_t str[1] = {(uint64_t)k.taps * d->Cin * 2};
+        uint32_t box[2] = {64, (uint32_t)(N_TILE / 2)};
+        int rc = encode_tmap_bf16(&mB, a->w, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)k.taps * 16, (uint64_t)d->B * N_TILE};
+        uint64_t str[1] = {(uint64_t)k.taps * 16 * 2};
+        uint32_t box[2] = {16, (uint32_t)(N_TILE / 2)};
+        int rc = encode_tmap_bf16(&mB2, a->dyn_w, 2, dims, str, box, 32);
+        if (rc) return rc;
+    }
+    auto fn = sean_pair_kernel<N_TILE, NB>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    DASR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 10 * 1024));
+        cudaFuncAttributes fa;
+        DASR_CUDA_OK(cudaFuncGetAttributes(&fa, fn));
+        DASR_REQUIRE(fa.numRegs * kThreads >= 128 * DASR_LEAN_ROLE_REGS + 256 * DASR_LEAN_EPI_REGS,
+                     "SEAN pair kernel compiled with %d registers per thread: setmaxnreg cannot be served", fa.numRegs);
+        configured[dev & 63] = true;
+    }
+    int n_pairs = num_sms() / 2;
+    if (n_pairs > k.total_tiles) n_pairs = k.total_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    DASR_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, mA, mB, mA2, mB2, k));
+    DASR_LAUNCH_OK();
+    *used = 1;
+    return DASR_OK;
+}
+#endif
+
 // the kernel instantiations of this translation unit (plain bf16 storage, or -- conv_igemm_precise.cu -- the
 // fp32-split PREC variants): called by dasr_conv_fwd with the finished kernel parameters
 #ifdef DASR_CONV_PRECISE_TU
@@ -1154,6 +1655,11 @@ extern "C" int dasr_prof_read(unsigned long long* host_out, int reset) {
     return DASR_OK;
 }
 #endif
+
+extern "C" int dasr_set_sean_pair(int on) {
+    dasr::g_sean_pair = on < 0 ? -1 : (on ? 1 : 0);
+    return DASR_OK;
+}
 
 // 1 if the SEAN conv of this geometry can generate its A operand in-kernel (two A stages fit), else 0
 extern "C" int dasr_conv_gen_ok(int H, int W) {
@@ -1386,6 +1892,15 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         }
     }
     if (npl > 1) return conv_dispatch_precise(d->epi, n_tile, NB, SWZ, mA, mB, mA2, mB2, k, smem_bytes, stream);
+    // the [gamma_o; beta_o] convolution of SEAN on CTA pairs (cta_group::2) when there are at least two images and
+    // enough pair tiles to occupy every SM pair
+    if (d->epi == DASR_EPI_SEAN && n_tile == 128 && d->Cin == 128 && d->ks == 3 && k.kw == 3 && k.dyn && !gen && !a->norm &&
+        !a->gb_s && !a->resid_f32 && !a->out_aux_f32 && d->B >= 2 && sean_pair_enabled() &&
+        ((d->B + 1) / 2) * k.n_strips * k.tiles_per_strip >= num_sms() / 2) {
+        int used = 0;
+        int rc = launch_sean_pair(d, a, k, mA, mA2, stream, &used);
+        if (rc || used) return rc;
+    }
     return conv_dispatch(d->epi, n_tile, NB, SWZ, mA, mB, mA2, mB2, k, smem_bytes, stream);
 }
 #endif  // DASR_CONV_PRECISE_TU

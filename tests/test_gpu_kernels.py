@@ -92,3 +92,40 @@ def test_sean_conv_with_kdyn_extension_and_fused_finalize(shape):
     assert (_nchw(out32) - ref).abs().max().item() <= 3e-3 * scale
     assert (_nchw(out).float() - ref).abs().max().item() <= 1.5e-2 * scale
     assert (_nchw(gamma).float() - gb[:, :nf]).abs().max().item() <= 1.5e-2 * gb.abs().max().item()
+
+
+@pytest.mark.parametrize("B", [10, 11])
+def test_sean_conv_on_cta_pairs_equals_single_cta_kernel(B):
+    """The [gamma_o; beta_o] convolution on CTA pairs (tcgen05.mma.cta_group::2, two images per pair, K-DYN in two
+    passes against a zero patch) against the single-CTA kernel: whole network, even and odd batch (the odd image's
+    partner CTA runs on zero-filled TMA boxes), inference and training (saved gamma / norm coefficients, gradients)."""
+    import warnings
+    import depth_aware_endoscopy_sr_b200 as dasr
+    from depth_aware_endoscopy_sr_b200 import _lib as L
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    torch.manual_seed(3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = dasr.DepthNet(which_ResBlk_depth=list(range(14)), scale=8, nb=16).cuda()
+    lq, depth, masks, gt = [t.cuda() for t in synthetic_inputs(B, 64, 64, scale=8, seed=B, with_gt=True)]
+    lib = L.load()
+    out = {}
+    try:
+        for on in (0, 1):
+            L.check(lib.dasr_set_sean_pair(on))
+            net.eval()
+            with torch.no_grad():
+                sr = net(lq, depth, masks).clone()
+            net.train()
+            net.zero_grad(set_to_none=True)
+            (net(lq, depth, masks) - gt).abs().mean().backward()
+            torch.cuda.synchronize()
+            out[on] = (sr, {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None})
+    finally:
+        L.check(lib.dasr_set_sean_pair(-1))
+    d = (out[0][0] - out[1][0]).abs().max().item()
+    print("B=%d: max|sr(pairs) - sr(single)| = %.3g (%s)" % (B, d, "bit-identical" if d == 0 else "differs"))
+    assert d <= 1e-5
+    for k, g0 in out[0][1].items():
+        g1 = out[1][1][k]
+        assert (g0 - g1).abs().max().item() <= 1e-3 * g0.abs().max().item() + 1e-9, k

@@ -48,6 +48,8 @@ def run(name, B, H, Cin, Cout, ks, epi, **kw):
     fl = 2.0 * B * H * H * Cout * Cin * ks * ks
     print("== %-34s %.3f ms  %.0f TFLOP/s   per-CTA cycles (avg over 148):" % (name, ms, fl / ms / 1e9))
     print("   " + "  ".join("%s=%dk" % (NAMES[i], buf[i] / 148 / 1000) for i in range(8)), flush=True)
+    print("   whole kernel per CTA: %.1f k cycles in %.1f us -> SM clock during the kernel %.0f MHz" % (
+        buf[8] / 148 / 1e3, buf[9] / 148 / 1e3, 1e3 * buf[8] / max(buf[9], 1)), flush=True)
 
 DBG = int(os.environ.get("DASR_DBG", "0"))
 lib.dasr_prof_set(DBG)
