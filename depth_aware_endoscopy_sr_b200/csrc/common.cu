@@ -3,6 +3,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace dasr {
 
@@ -85,6 +86,23 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static std::atomic<int> g_planes{1};
 int planes() { return g_planes.load(std::memory_order_relaxed); }
 
+// CTA-pair (tcgen05.mma.cta_group::2) kernels: -1 = environment DASR_SEAN_PAIR (default on), 0 / 1 = dasr_set_sean_pair
+// a bit mask: 1 = SEAN convolution, 2 = trunk (STATS) convolution, 4 = conv_out9
+static std::atomic<int> g_pair_mode{-1};
+bool pair_kernels_enabled(int which) {
+    int m = g_pair_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        static int v = -1;
+        if (v < 0) {
+            const char* e = getenv("DASR_SEAN_PAIR");
+            v = e ? atoi(e) : DASR_PAIR_DEFAULT;
+            if (e && e[0] == '1' && e[1] == 0) v = 7;
+        }
+        m = v;
+    }
+    return (m & which) != 0;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -109,6 +127,10 @@ extern "C" int dasr_set_planes(int n) {
     return DASR_OK;
 }
 extern "C" int dasr_get_planes(void) { return dasr::planes(); }
+extern "C" int dasr_set_sean_pair(int on) {
+    dasr::g_pair_mode.store(on < 0 ? -1 : (on == 1 ? 7 : on));
+    return DASR_OK;
+}
 
 extern "C" int dasr_check_device(void) {
     int dev = 0;

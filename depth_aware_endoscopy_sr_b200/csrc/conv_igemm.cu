@@ -502,7 +502,8 @@ __device__ __forceinline__ void sean_epilogue_tile(const ConvK& p, const SeanTil
 // STATS epilogue of one tile for one thread: store y = acc + bias (bf16) and accumulate, per column, the sum and the
 // sum of squares of the STORED values over this warp's 32 rows of BOTH M blocks in registers; one butterfly reduction
 // per 16-column chunk and tile (v1 reduced every M block separately: twice the shuffles on the critical epilogue).
-template <int N_TILE, int NB, bool PREC>
+// (EW = epilogue warps per TMEM lane quadrant: warp `half` of a quadrant takes the 16-column chunks half, half + EW, ...)
+template <int N_TILE, int NB, bool PREC, int EW = 2>
 __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, const float* bias_t, float* red_s, int img,
                                                int q0, int w0, int nt, int m, int half, int ew, int lane) {
     if (half * 16 >= N_TILE) return;
@@ -518,7 +519,7 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
         pix[blk] = ((size_t)img * p.H + h) * p.W + w;
     }
 #pragma unroll 1
-    for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
+    for (int c0 = half * 16; c0 < N_TILE; c0 += 16 * EW) {
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) s1[j] = s2[j] = 0.f;
@@ -1005,11 +1006,102 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
             }
 
+            // STORE epilogue with few pieces per thread (N tile <= 64): the residual and the activation mask of the WHOLE
+            // tile (<= 4 pieces of 32 bytes each) are requested BEFORE the accumulator is awaited -- with the loads issued
+            // piece by piece after the wait their latency was exposed once per piece (the residual convolution of a
+            // classic block took 261 us against 159 us without residual for 1.5x the bytes).
+            constexpr int PRE_CH = (N_TILE + 31) / 32;
+            constexpr bool PRE = (EPI == DASR_EPI_STORE) && !PREC && (NB * PRE_CH <= 4);
+            uint4 pre_r[PRE ? NB * PRE_CH : 1][2], pre_m[PRE ? NB * PRE_CH : 1][2];
+            bool pre_valid[PRE ? NB : 1];
+            __nv_bfloat16* pre_op[PRE ? NB : 1];
+            if (PRE && half * 16 < N_TILE) {
+#pragma unroll
+                for (int blk = 0; blk < NB; blk++) {
+                    const int q = q0 + blk * 128 + m;
+                    const int h = (int)__umulhi((unsigned)q, p.wp_magic);
+                    const int wl = q - h * p.Wp;
+                    const int w = w0 + wl;
+                    bool valid = (h < p.H) && (wl < p.Wt) && (w < p.W);
+                    int ho = h, wo = w;
+                    if (p.subsample == 2) {
+                        valid = valid && !(h & 1) && !(w & 1);
+                        ho = h >> 1;
+                        wo = w >> 1;
+                    }
+                    const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+                    __nv_bfloat16* op = p.out + pix * p.Cout + nt * N_TILE;
+                    if (p.unshuffle)
+                        op = p.out + ((((size_t)img * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1)) * 4 +
+                                      ((ho & 1) * 2 + (wo & 1))) * p.Cout + nt * N_TILE;
+                    pre_valid[blk] = valid;
+                    pre_op[blk] = op;
+#pragma unroll
+                    for (int ci = 0; ci < PRE_CH; ci++) {
+                        const int c0 = half * 16 + ci * 32;
+                        const uint4 z4 = make_uint4(0, 0, 0, 0);
+                        pre_r[blk * PRE_CH + ci][0] = pre_r[blk * PRE_CH + ci][1] = z4;
+                        pre_m[blk * PRE_CH + ci][0] = pre_m[blk * PRE_CH + ci][1] = z4;
+                        if (c0 < N_TILE && valid && !DBG(p, 1)) {
+                            if (p.resid) ldg256(p.resid + pix * p.Cout + nt * N_TILE + c0, pre_r[blk * PRE_CH + ci][0], pre_r[blk * PRE_CH + ci][1]);
+                            if (p.actmask) ldg256(p.actmask + pix * p.Cout + nt * N_TILE + c0, pre_m[blk * PRE_CH + ci][0], pre_m[blk * PRE_CH + ci][1]);
+                        }
+                    }
+                }
+            }
+
             PROF_LAP(1);
             mbar_wait(&acc_full[buf], aph);
             PROF_LAP(0);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
+
+            if (PRE) {
+                if (half * 16 < N_TILE) {
+#pragma unroll
+                    for (int blk = 0; blk < NB; blk++) {
+#pragma unroll
+                        for (int ci = 0; ci < PRE_CH; ci++) {
+                            const int c0 = half * 16 + ci * 32;
+                            if (c0 >= N_TILE) continue;
+                            uint32_t v[16];
+                            tmem_ld16(t_acc + blk * N_TILE + c0, v);
+                            tmem_ld_wait();
+                            float f[16];
+#pragma unroll
+                            for (int j4 = 0; j4 < 16; j4 += 4) {
+                                const float4 bb = *reinterpret_cast<const float4*>(bias_t + c0 + j4);
+                                f[j4] = __uint_as_float(v[j4]) + bb.x;
+                                f[j4 + 1] = __uint_as_float(v[j4 + 1]) + bb.y;
+                                f[j4 + 2] = __uint_as_float(v[j4 + 2]) + bb.z;
+                                f[j4 + 3] = __uint_as_float(v[j4 + 3]) + bb.w;
+                            }
+                            if (p.resid) {
+                                float rr[16];
+                                unpack8(pre_r[blk * PRE_CH + ci][0], rr);
+                                unpack8(pre_r[blk * PRE_CH + ci][1], rr + 8);
+#pragma unroll
+                                for (int j = 0; j < 16; j++) f[j] += rr[j];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; j++) f[j] = apply_act(f[j], p.act);
+                            if (p.actmask) {
+                                float mm[16];
+                                unpack8(pre_m[blk * PRE_CH + ci][0], mm);
+                                unpack8(pre_m[blk * PRE_CH + ci][1], mm + 8);
+#pragma unroll
+                                for (int j = 0; j < 16; j++) f[j] *= (mm[j] > 0.f ? 1.f : p.mask_slope);
+                            }
+                            if (pre_valid[blk] && !DBG(p, 2)) store16(pre_op[blk] + c0, f);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                acc_it++;
+                continue;
+            }
 
             if (EPI == DASR_EPI_SEAN) {
                 sean_epilogue<N_TILE, NB, PREC>(p, t_acc, bias_t, norm_s, img, q0, w0, m, half);
@@ -1455,6 +1547,199 @@ sean_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     PROF_KERNEL_END;
     if (warp == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
 }
+
+// ------------------------------------------------------------------------------------------------ trunk conv, CTA pairs
+// The 64 -> 64 convolution in front of every InstanceNorm (DASR_EPI_STATS) on CTA pairs.  A single CTA issues
+// M128 x N64 x K16 MMAs, which cost max(N/2, (128 + N)/4) = 48 tensor cycles for 32 cycles of math (the A operand's
+// shared-memory reads bound it); a pair issues M256 x N64 in the same ~46 cycles (tools/pair_probe.cu): twice the
+// pixels per dispatch.  Pairing as in sean_pair_kernel: the same tile position of two consecutive images; the weights
+// (9 taps x 64 x 64) stay resident, each CTA holding rows rank*32..+31 of every tap (36 KB).  Statistics slots, store
+// addressing and summation order are those of the single-CTA kernel (bit-identical partial sums).
+// 16 epilogue warps (4 per TMEM lane quadrant, one 16-column chunk each at N = 64): with the MMA time halved the
+// statistics epilogue became the critical path (in-kernel accounting: 5.3 k cycles per tile with 8 warps against 3.3 k
+// of MMA); its cost is the latency chain TMEM load -> round -> store -> butterfly, so more warps shorten it.
+constexpr int kStatsPairEW = 2;
+constexpr int kStatsPairThreads = 128 + 128 * kStatsPairEW;
+template <int N_TILE, int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStatsPairThreads, 1)
+stats_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvK p) {
+    constexpr int SWZ = 128, KSTEPS = 4;
+    constexpr int ACC_COLS = NB * N_TILE;
+    constexpr int TMEM_COLS = 512;
+    constexpr uint32_t B_TAP_BYTES = (N_TILE / 2) * 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[2], a_empty[2], b_full, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float norm_s[512];         // scratch of the per-tile statistics reduction
+    __shared__ __align__(16) float bias_s[N_TILE];
+    __shared__ uint32_t tap_lo_s[9];
+
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* a_smem = smem;
+    uint8_t* b_smem = smem + 2 * (size_t)p.a_stage_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    PROF_KERNEL_BEGIN;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 8 * kStatsPairEW);
+        }
+        mbar_init(&b_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 2) tmem_alloc_pair<TMEM_COLS>(&tmem_base_s);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int i = threadIdx.x; i < N_TILE; i += kStatsPairThreads) bias_s[i] = __ldg(p.bias + i);
+    if (threadIdx.x < 9) {
+        const int t = threadIdx.x / 3, u = threadIdx.x - t * 3;
+        tap_lo_s[threadIdx.x] = (uint32_t)((t * p.Wp + u) * SWZ) >> 4;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const int tiles_per_img = p.n_strips * p.tiles_per_strip;
+    const int n_pairs = gridDim.x >> 1;
+    const int pair_id = blockIdx.x >> 1;
+
+    if (warp == 0) {
+        // ===================================================== producer (both CTAs): half of the weights once, own patches
+        if (elect_one()) {
+            const uint32_t b_full_l = mapa_u32(smem_u32(&b_full), 0);
+            if (leader) mbar_expect_tx(&b_full, 2 * 9 * B_TAP_BYTES);
+            for (int tap = 0; tap < 9; tap++)
+                tma_load_2d_pair(b_smem + (size_t)tap * B_TAP_BYTES, &mapB, b_full_l, tap * p.Cin, (int)rank * (N_TILE / 2));
+            uint32_t a_it = 0;
+            for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, a_it++) {
+                const int ip = tile / tiles_per_img;
+                int r = tile - ip * tiles_per_img;
+                const int strip = r / p.tiles_per_strip;
+                const int tps = r - strip * p.tiles_per_strip;
+                const int img = 2 * ip + (int)rank;
+                const int q0 = tps * (NB * 128);
+                const int sa = a_it & 1;
+                mbar_wait(&a_empty[sa], ((a_it >> 1) & 1) ^ 1);
+                const uint32_t full_l = mapa_u32(smem_u32(&a_full[sa]), 0);
+                if (leader) mbar_expect_tx(&a_full[sa], 2 * p.a_tx_bytes);
+                tma_load_4d_pair(a_smem + (size_t)sa * p.a_stage_bytes, &mapA, full_l, 0, strip * p.Wt - p.pad_w,
+                                 q0 / p.Wp - p.pad_h, img);
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===================================================== MMA issuer (leader CTA, one thread)
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(256, N_TILE);
+            const uint64_t desc0 = make_smem_desc<SWZ>(0, 0);
+            const uint32_t desc_hi = (uint32_t)(desc0 >> 32);
+            const uint32_t lo_flags = (uint32_t)desc0 & ~0x3FFFu;
+            const uint32_t a_lo0 = lo_flags | ((smem_u32(a_smem) & 0x3FFFFu) >> 4);
+            const uint32_t b_lo0 = lo_flags | ((smem_u32(b_smem) & 0x3FFFFu) >> 4);
+            const uint32_t a_stage_lo = p.a_stage_bytes >> 4;
+            constexpr uint32_t BLK_LO = (128u * SWZ) >> 4;
+            uint32_t it = 0;
+            PROF_DECL;
+            mbar_wait(&b_full, 0);
+            tc_fence_after();
+            for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, it++) {
+                const int tps = (tile % tiles_per_img) % p.tiles_per_strip;
+                const int q0 = tps * (NB * 128);
+                const int soff = q0 - (q0 / p.Wp) * p.Wp;
+                const int buf = it & 1;
+                PROF_LAP(3);
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                PROF_LAP(0);
+                mbar_wait(&a_full[buf], (it >> 1) & 1);          // A stage index == accumulator buffer index
+                PROF_LAP(1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+                const uint32_t a_lo_tile = a_lo0 + buf * a_stage_lo + (uint32_t)soff * (SWZ >> 4);
+#pragma unroll 1
+                for (int tap = 0; tap < 9; tap++) {
+                    const uint32_t a_lo = a_lo_tile + tap_lo_s[tap];
+                    const uint32_t b_lo = b_lo0 + tap * (B_TAP_BYTES >> 4);
+#pragma unroll
+                    for (int blk = 0; blk < NB; blk++) {
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; k++)
+                            umma_bf16_lohi_pair(d_tmem + blk * N_TILE, a_lo + blk * BLK_LO + k * 2, b_lo + k * 2, desc_hi, idesc,
+                                                (tap | k) != 0);
+                    }
+                }
+                umma_commit_pair(&a_empty[buf]);
+                umma_commit_pair(&acc_full[buf]);
+            }
+            PROF_LAP(3);
+            PROF_FLUSH(0, 4);
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue warps (both CTAs): stats_epilogue on the own image
+        const int ew = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int m = ew * 32 + lane;
+        const int et = threadIdx.x - 128;
+        uint32_t it = 0;
+        PROF_DECL;
+        for (int tile = pair_id; tile < p.total_tiles; tile += n_pairs, it++) {
+            const int ip = tile / tiles_per_img;
+            int r = tile - ip * tiles_per_img;
+            const int strip = r / p.tiles_per_strip;
+            const int tps = r - strip * p.tiles_per_strip;
+            const int img = 2 * ip + (int)rank;
+            const bool have = img < p.B;
+            const int q0 = tps * (NB * 128);
+            const int w0 = strip * p.Wt;
+            const int buf = it & 1;
+            PROF_LAP(1);
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            PROF_LAP(0);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
+            if (have) stats_epilogue<N_TILE, NB, false, kStatsPairEW>(p, t_acc, bias_s, norm_s, img, q0, w0, 0, m, half, ew, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
+            // one statistics slot per (image, tile): the four row quadrants are added in a fixed order
+            asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kStatsPairEW) : "memory");
+            if (et < N_TILE && have) {
+                float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    a1 += norm_s[(q * N_TILE + et) * 2];
+                    a2 += norm_s[(q * N_TILE + et) * 2 + 1];
+                }
+                const int slot = strip * p.tiles_per_strip + tps;
+                float2* sp = reinterpret_cast<float2*>(p.stats) + ((size_t)img * p.nslots + slot) * p.Cout + et;
+                *sp = make_float2(a1, a2);
+            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kStatsPairEW) : "memory");
+        }
+        PROF_LAP(1);
+#ifdef DASR_PROFILE
+        if (threadIdx.x == 128) PROF_FLUSH(4, 2);
+#endif
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    PROF_KERNEL_END;
+    if (warp == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+}
 #endif  // DASR_CONV_PRECISE_TU
 
 // ------------------------------------------------------------------------------------------------ host
@@ -1538,16 +1823,7 @@ static int dispatch_n(int epi, int n_tile, const CUtensorMap& mA, const CUtensor
 
 #ifndef DASR_CONV_PRECISE_TU
 // DASR_SEAN_PAIR=0: keep the [gamma_o; beta_o] convolution on single CTAs (A/B measurements)
-static int g_sean_pair = -1;        // -1: environment (default on), 0 / 1: dasr_set_sean_pair
-static bool sean_pair_enabled() {
-    if (g_sean_pair >= 0) return g_sean_pair != 0;
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("DASR_SEAN_PAIR");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v != 0;
-}
+static bool sean_pair_enabled() { return pair_kernels_enabled(DASR_PAIR_SEAN); }
 
 // sean_pair_kernel launch: k holds the single-CTA geometry (NB = 2, two A stages); the weight ring and the tile
 // count are re-derived for pairs.  Returns 1 when the geometry does not fit (the caller uses the single-CTA kernel).
@@ -1611,6 +1887,49 @@ static int launch_sean_pair(const dasr_conv_desc* d, const dasr_conv_args* a, Co
     *used = 1;
     return DASR_OK;
 }
+
+// stats_pair_kernel launch (the 64 -> 64 trunk convolution in front of an InstanceNorm on CTA pairs)
+static int launch_stats_pair(const dasr_conv_desc* d, const dasr_conv_args* a, ConvK k, const CUtensorMap& mA,
+                             cudaStream_t stream, int* used) {
+    constexpr int N_TILE = 64, NB = 2;
+    *used = 0;
+    const size_t smem_bytes = 2 * (size_t)k.a_stage_bytes + 9 * (size_t)(N_TILE / 2) * 128 + 1024;
+    if (smem_bytes > 227 * 1024 - 10 * 1024) return DASR_OK;
+    k.SA = 2;
+    k.total_tiles = ((d->B + 1) / 2) * k.n_strips * k.tiles_per_strip;
+    CUtensorMap mB;
+    {
+        uint64_t dims[2] = {(uint64_t)k.taps * d->Cin, (uint64_t)N_TILE};
+        uint64_t str[1] = {(uint64_t)k.taps * d->Cin * 2};
+        uint32_t box[2] = {64, (uint32_t)(N_TILE / 2)};
+        int rc = encode_tmap_bf16(&mB, a->w, 2, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    auto fn = stats_pair_kernel<N_TILE, NB>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    DASR_CUDA_OK(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        DASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 10 * 1024));
+        configured[dev & 63] = true;
+    }
+    int n_pairs = num_sms() / 2;
+    if (n_pairs > k.total_tiles) n_pairs = k.total_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_pairs);
+    cfg.blockDim = dim3(kStatsPairThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    DASR_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, mA, mB, k));
+    DASR_LAUNCH_OK();
+    *used = 1;
+    return DASR_OK;
+}
 #endif
 
 // the kernel instantiations of this translation unit (plain bf16 storage, or -- conv_igemm_precise.cu -- the
@@ -1655,11 +1974,6 @@ extern "C" int dasr_prof_read(unsigned long long* host_out, int reset) {
     return DASR_OK;
 }
 #endif
-
-extern "C" int dasr_set_sean_pair(int on) {
-    dasr::g_sean_pair = on < 0 ? -1 : (on ? 1 : 0);
-    return DASR_OK;
-}
 
 // 1 if the SEAN conv of this geometry can generate its A operand in-kernel (two A stages fit), else 0
 extern "C" int dasr_conv_gen_ok(int H, int W) {
@@ -1899,6 +2213,13 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
         ((d->B + 1) / 2) * k.n_strips * k.tiles_per_strip >= num_sms() / 2) {
         int used = 0;
         int rc = launch_sean_pair(d, a, k, mA, mA2, stream, &used);
+        if (rc || used) return rc;
+    }
+    if (d->epi == DASR_EPI_STATS && n_tile == 64 && d->Cin == 64 && d->Cout == 64 && d->ks == 3 && k.kw == 3 && NB == 2 &&
+        k.subsample == 1 && !d->w_img_rows && d->B >= 2 && pair_kernels_enabled(DASR_PAIR_STATS) &&
+        ((d->B + 1) / 2) * k.n_strips * k.tiles_per_strip >= num_sms() / 2) {
+        int used = 0;
+        int rc = launch_stats_pair(d, a, k, mA, stream, &used);
         if (rc || used) return rc;
     }
     return conv_dispatch(d->epi, n_tile, NB, SWZ, mA, mB, mA2, mB2, k, smem_bytes, stream);

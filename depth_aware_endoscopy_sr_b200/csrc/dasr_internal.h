@@ -43,6 +43,14 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 int num_sms();
+// the CTA-pair (cta_group::2) kernels that may be used (dasr_set_sean_pair / DASR_SEAN_PAIR): bit mask
+#define DASR_PAIR_SEAN 1
+#define DASR_PAIR_STATS 2
+#define DASR_PAIR_OUT9 4
+#ifndef DASR_PAIR_DEFAULT
+#define DASR_PAIR_DEFAULT 5      /* SEAN + conv_out9; the trunk (STATS) pair kernel is faster alone but slower beside the side-stream actv kernel */
+#endif
+bool pair_kernels_enabled(int which);
 void count_launch();   // bumps the counter behind dasr_launch_count()
 
 // ---------------------------------------------------------------------------------------------- fp32-split planes

@@ -123,10 +123,11 @@ typedef struct {
 } dasr_conv_args;
 
 int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, void* stream);
-/* The 3x3, 128 -> 128 DASR_EPI_SEAN convolution with the K-DYN extension runs on CTA PAIRS (tcgen05.mma.cta_group::2,
- * M = 256: two consecutive images share one weight stream) when the batch has >= 2 images and enough tiles to occupy
- * every SM pair.  on = 0 keeps it on single CTAs, 1 allows pairs, -1 = environment DASR_SEAN_PAIR (default: pairs).
- * Both forms compute the same sums in the same order (A/B measurements, tests).                                  */
+/* CTA-pair kernels (tcgen05.mma.cta_group::2, M = 256: the two CTAs of a pair work on the same tile position of two
+ * consecutive images and share one weight stream): the 3x3 128 -> 128 DASR_EPI_SEAN convolution with the K-DYN
+ * extension, the 64 -> 64 DASR_EPI_STATS convolution and dasr_conv_out9 use them when the batch has >= 2 images and
+ * enough tiles to occupy every SM pair.  on = 0 keeps everything on single CTAs, 1 allows pairs, -1 = environment
+ * DASR_SEAN_PAIR (default: pairs).  Both forms compute the same sums in the same order (A/B measurements, tests). */
 int dasr_set_sean_pair(int on);
 /* number of partial-statistics slots per image the DASR_EPI_STATS epilogue writes for this shape (> 0),
  * or a negative dasr_status                                                                         */
