@@ -13,12 +13,20 @@ Prints ONE JSON line:
   e2e        frames/s through the public call ``net(LQ, Depth, DepthMaskList)`` with pinned HOST buffers: the
              host->device copies of the inputs and the device->host read of the SR frames are inside the timed
              region
+  e2e_frames the frame-level public call ``net.infer_frames(LQ, Depth)`` (depth masks built and uint8 BGR frames
+             produced on the device -- getDepthMask / tensor2img of the reference run there): 4 instead of 14 input planes
+             up, a quarter of the output bytes down; also stored as e2e["frames_uint8"]
+  stream_1080p  BASELINE.json configs[4]: 135x240 LR frames -> 1080x1920, frames sharded over the ranks, device-resident
+             and end to end (uint8 frames)
   roofline   the dominant kernel family of the step, measured live with CUDA events in a separate
              instrumented pass (achieved algorithmic TFLOP/s or GB/s against MEASURED_PEAKS.json)
   train      BASELINE.json configs[2] next to the headline: x8 training step (forward + loss + backward + flat
-             NCCL gradient all-reduce + Adam), batch 16 per GPU, images/s over the whole job
+             NCCL gradient all-reduce + Adam), batch 16 per GPU, images/s over the whole job; dp_check = the parameter
+             checksum after the timed steps is identical on every rank
   cpu_baseline  the CPU oracle port of the reference's forward (literal form: 256-channel style-map convs),
-             timed on this box's host cores on a bounded sample (rank 0, N == 1 only)
+             timed on this box's host cores on a bounded sample (rank 0, N == 1 only); the same leg checks the CUDA
+             output of two frames of the timed batch against that oracle (``parity``) and times the same oracle
+             on the GPU with torch's own kernels (``gpu_eager_baseline``: cuDNN / cuBLAS, fp32 and bf16 autocast)
 
 ``--impl reference`` times the reference's own CPU algorithm (the oracle port -- the reference is a Python
 code base that cannot travel to the GPU box) with all host threads on a bounded sample of the same workload.
@@ -60,6 +68,18 @@ LR = 64
 WHICH = tuple(range(14))
 METRIC = "hr_frames_per_sec_x8_sr_64to512"
 UNIT = "frames/s"
+
+
+REF_SAMPLE_B = 2       # frames per step of the bounded CPU sample (reference arm AND cpu_baseline leg)
+
+
+def _config(B, numa=None, n_sets=3):
+    """The ``config`` object of BOTH arms (the reference arm times a bounded sample of this workload)."""
+    return {"workload": "depthNet_SEAN_depthMask x8 inference, batch %d per GPU, synthetic 3x64x64 LR + 1x64x64 depth + "
+                        "10 masks -> 3x512x512, random-init weights" % B,
+            "batch_per_gpu": B, "lr": [LR, LR], "scale": SCALE, "sharding": "frames by rank, no collective",
+            "l2": "no flush: one step streams ~3.5 GB of activations (>> 126 MB L2) and the input batch rotates over "
+                  "%d sets" % n_sets}
 
 
 def _peaks():
@@ -139,8 +159,10 @@ def _make_state(seed=0):
     return net
 
 
-def cpu_reference_rate(seconds_budget=20.0, batch=1, warmup=1, min_iters=3):
-    """frames/s of the CPU oracle port (the reference's algorithm, fp32, all host threads) on B=`batch` frames."""
+def cpu_reference_rate(seconds_budget=20.0, batch=REF_SAMPLE_B, warmup=1, min_iters=3, check=None):
+    """frames/s of the CPU oracle port (the reference's algorithm, fp32, all host threads) on ``batch`` frames.
+    check = (lq, depth, masks, sr_cuda) on the host: the oracle also runs on THESE frames and the max-abs difference
+    to the CUDA output is returned (the oracle as the checker)."""
     import torch
     try:
         torch.set_num_threads(len(os.sched_getaffinity(0)))
@@ -152,7 +174,12 @@ def cpu_reference_rate(seconds_budget=20.0, batch=1, warmup=1, min_iters=3):
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     lq, depth, masks = synthetic_inputs(batch, LR, LR, scale=SCALE, seed=0)
     times = []
+    parity = None
     with torch.no_grad():
+        if check is not None:
+            ref = oracle.depthnet_forward(sd, check[0], check[1], check[2], scale=SCALE, which=WHICH)
+            parity = {"max_abs_vs_oracle": float((check[3] - ref).abs().max()), "frames": int(ref.shape[0]),
+                      "tolerance": 1e-2, "what": "SR of the first frames of the timed batch, CUDA vs the CPU oracle"}
         for _ in range(warmup):
             oracle.depthnet_forward(sd, lq, depth, masks, scale=SCALE, which=WHICH)
         t_all = time.time()
@@ -164,7 +191,75 @@ def cpu_reference_rate(seconds_budget=20.0, batch=1, warmup=1, min_iters=3):
                 break
     times.sort()
     med = times[len(times) // 2]
-    return batch / med, len(times), torch.get_num_threads()
+    return batch / med, len(times), torch.get_num_threads(), parity
+
+
+def gpu_eager_rates(dev, B=64, Bt=16):
+    """The reference's own formulation executed with torch's GPU kernels (cuDNN / cuBLAS on sm_100) -- the practical
+    existing-kernel bar next to the CPU figure.  Same oracle port as the CPU leg: NCHW, 256-channel style-map convs,
+    10 python-level mask loops; fp32 (TF32 off) and bf16 autocast + channels_last; inference B frames and one training
+    step (forward + loss + backward, no optimizer) at Bt images."""
+    import torch
+    from oracle import depthnet_oracle as oracle
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    out = {}
+    net = _make_state(0)
+    sd = {k: v.detach().to(dev) for k, v in net.state_dict().items()}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ("fp32", "bf16_autocast"):
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            lq, depth, masks = [t.to(dev) for t in synthetic_inputs(B, LR, LR, scale=SCALE, seed=0)]
+            if mode != "fp32":
+                lq, depth, masks = [t.contiguous(memory_format=torch.channels_last) for t in (lq, depth, masks)]
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode != "fp32" else torch.autocast("cuda", enabled=False)
+
+            def fwd():
+                with torch.no_grad(), ctx:
+                    return oracle.depthnet_forward(sd, lq, depth, masks, scale=SCALE, which=WHICH)
+
+            for _ in range(3):
+                fwd()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5
+            e0.record()
+            for _ in range(n):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+            out["infer_%s_frames_per_s" % mode] = B * n / (e0.elapsed_time(e1) * 1e-3)
+            # training step (forward + loss + backward)
+            sdt = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            wd = torch.ones(10, device=dev, requires_grad=True)
+            lq2, d2, m2, gt2 = [t.to(dev) for t in synthetic_inputs(Bt, LR, LR, scale=SCALE, seed=1, with_gt=True)]
+
+            def step():
+                for v in sdt.values():
+                    v.grad = None
+                with ctx:
+                    sr = oracle.depthnet_forward(sdt, lq2, d2, m2, scale=SCALE, which=WHICH)
+                total, *_ = oracle.training_loss(sr.float(), gt2, m2, wd)
+                total.backward()
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            out["train_%s_images_per_s" % mode] = Bt * 3 / (e0.elapsed_time(e1) * 1e-3)
+            del sdt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = tf32
+    out["what"] = ("oracle port of the reference executed with torch %s GPU kernels (cuDNN benchmark on): inference B=%d, "
+                   "training step (fwd + loss + bwd) B=%d" % (torch.__version__, B, Bt))
+    return out
 
 
 def run_reference(args):
@@ -182,7 +277,7 @@ def run_reference(args):
         torch.set_num_threads(os.cpu_count() or 1)
     net = _make_state(0)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    sample_b = 2       # frames per step of the bounded sample (the workload is 64 frames per step)
+    sample_b = REF_SAMPLE_B   # frames per step of the bounded sample (the workload is args.batch frames per step)
     lq, depth, masks = synthetic_inputs(sample_b, LR, LR, scale=SCALE, seed=0)
     with torch.no_grad():
         for _ in range(max(W, 1)):
@@ -197,8 +292,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "depthNet_SEAN_depthMask x8 inference, 64x64 LR + depth -> 512x512, CPU oracle "
-                                   "port of the reference forward", "batch_per_step": sample_b, "lr": [LR, LR]},
+            "config": _config(args.batch),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -285,6 +379,13 @@ def run_b200(args):
         launches = _lib.launch_count() - n0
         ms_total = e0.elapsed_time(e1)
 
+        # ------------------------------------------------ per-kernel instrumented pass (same thermal state as the timed
+        # region above) and the frames the cpu_baseline leg will check against the oracle (before any training step
+        # changes the weights)
+        roof = roofline_pass(net, dev_sets, B) if rank == 0 else None
+        nchk = min(2, B)
+        sr_chk = net(*[t[:nchk].contiguous() for t in dev_sets[0]]).cpu() if rank == 0 else None
+
         # ------------------------------------------------ end to end through the public call, host buffers
         # Every step copies ITS inputs from pinned host memory and reads ITS SR frames back to pinned host memory;
         # the copies run on their own streams so that step i's read-back overlaps step i+1's kernels
@@ -330,21 +431,21 @@ def run_b200(args):
         barrier()
         ms_e2e = f0.elapsed_time(f1)
 
-        # ------------------------------------------------ the same with the output step of codes/test.py on the
-        # device: tensor2img (clamp / x255 / round / uint8 / BGR) before the read-back, so a
-        # quarter of the bytes crosses PCIe (reported next to e2e, not instead of it)
-        from depth_aware_endoscopy_sr_b200 import io as dio
+        # ------------------------------------------------ frame-level public call: net.infer_frames(LQ, Depth)
+        # getDepthMask and tensor2img of the reference run on the device: only the LR frame and
+        # its depth map go up (4 planes instead of 14), uint8 BGR frames come back (a quarter of the fp32 bytes)
         out_u8 = [torch.empty(B, SCALE * LR, SCALE * LR, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        h2d_frames = sum(t.numel() * t.element_size() for t in host_sets[0][:2])
 
         def e2e_u8_step(i):
             slot = i % 2
             with torch.cuda.stream(s_in):
                 s_in.wait_event(ev_done[slot])
-                for d, h in zip(dev_in[slot], host_sets[i % n_sets]):
+                for d, h in zip(dev_in[slot][:2], host_sets[i % n_sets][:2]):
                     d.copy_(h, non_blocking=True)
                 ev_in[slot].record(s_in)
             cur.wait_event(ev_in[slot])
-            img = dio.tensor2img(net(*dev_in[slot]))
+            img = net.infer_frames(dev_in[slot][0], dev_in[slot][1])
             ev_done[slot].record(cur)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[slot])
@@ -363,6 +464,9 @@ def run_b200(args):
         g1.record()
         barrier()
         ms_e2e_u8 = g0.elapsed_time(g1)
+
+        # ------------------------------------------------ BASELINE.json configs[4]: 1080p stream, frames sharded by rank
+        stream = stream_pass(args, net, dev, rank, world, barrier, s_in, s_out) if args.stream_steps > 0 else None
         clocks = sampler.stop(clk_mark) if rank == 0 else None      # samples span the timed regions
 
     train = train_pass(args, net, dev, rank, world, barrier) if args.train_steps > 0 else None
@@ -374,36 +478,109 @@ def run_b200(args):
     value = B * world * K / (ms_total * 1e-3)
     e2e = B * world * K / (ms_e2e * 1e-3)
 
-    roof = None
     cpu = None
+    parity = None
+    eager = None
     if rank == 0:
-        roof = roofline_pass(net, dev_sets, B)
         if world == 1 and not args.no_cpu:
-            fps, iters, cores = cpu_reference_rate(seconds_budget=args.cpu_seconds)
+            check = tuple(t[:nchk] for t in host_sets[0]) + (sr_chk,)
+            fps, iters, cores, parity = cpu_reference_rate(seconds_budget=args.cpu_seconds, check=check)
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d forwards of 1 frame (x8, 64x64 LR -> 512x512), median" % iters}
+                   "sample": "%d forwards of %d frames (x8, 64x64 LR -> 512x512) of the %d-frame batch, median" % (
+                       iters, REF_SAMPLE_B, B)}
+            if not args.no_eager:
+                try:
+                    eager = gpu_eager_rates(dev, B=B, Bt=args.train_batch)
+                except Exception as e:      # a baseline must not take the benchmark down
+                    eager = {"error": "%s: %s" % (type(e).__name__, e)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    frames = {"value": B * world * K / (ms_e2e_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_frames,
+              "d2h_bytes_per_step": out_u8[0].numel(), "ms_per_step": ms_e2e_u8 / K,
+              "call": "net.infer_frames(LQ, Depth) -> uint8 BGR frames (depth masks and tensor2img on the device)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "depthNet_SEAN_depthMask x8 inference, batch %d per GPU, synthetic 3x64x64 LR + "
-                                   "1x64x64 depth + 10 masks -> 3x512x512, random-init weights" % B,
-                       "batch_per_gpu": B, "lr": [LR, LR], "scale": SCALE, "sharding": "frames by rank, no collective",
-                       "host_affinity": numa,
-                       "l2": "no flush: one step streams ~3.5 GB of activations (>> 126 MB L2) and the input batch "
-                             "rotates over %d sets" % n_sets},
+            "config": _config(B),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / K},
-            "e2e_uint8_frames": {"value": B * world * K / (ms_e2e_u8 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                                 "d2h_bytes_per_step": out_u8[0].numel(), "ms_per_step": ms_e2e_u8 / K,
-                                 "note": "net(...) + device-side tensor2img (uint8 BGR frames, what codes/test.py "
-                                         "writes) read back instead of the fp32 tensor"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train}
+                    "ms_per_step": ms_e2e / K, "call": "net(LQ, Depth, DepthMaskList) -> fp32 SR tensor",
+                    "frames_uint8": frames},
+            "e2e_frames": frames, "stream_1080p": stream, "host_affinity": numa,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "gpu_eager_baseline": eager, "train": train}
     _emit(line)
+
+
+def stream_pass(args, net, dev, rank, world, barrier, s_in, s_out):
+    """1080p-HR endoscopy stream: 135x240 LR frames + depth -> 1080x1920, ``--stream-frames`` frames per call and
+    rank (frame f of the stream -> rank f mod N, parallel.shard_frames; no collective).  Device-resident rate and the
+    end-to-end rate through net.infer_frames with pinned host buffers (LR + depth up, uint8 frames down)."""
+    import torch
+    import torch.distributed as dist
+    from depth_aware_endoscopy_sr_b200.synthetic import synthetic_inputs
+    F_, Ks = args.stream_frames, args.stream_steps
+    h, w = 135, 240
+    sets_h = [tuple(t.pin_memory() for t in synthetic_inputs(F_, h, w, scale=SCALE, seed=7000 + 10 * rank + i)[:2])
+              for i in range(2)]
+    sets_d = [tuple(t.to(dev) for t in hs) for hs in sets_h]
+    out_h = [torch.empty(F_, SCALE * h, SCALE * w, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    dev_in = [tuple(torch.empty_like(t, device=dev) for t in sets_h[0]) for _ in range(2)]
+    cur = torch.cuda.current_stream()
+    for i in range(3):
+        net.infer_frames(*sets_d[i % 2])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ks):
+        net.infer_frames(*sets_d[i % 2])
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+
+    def step(i):
+        slot = i % 2
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_done[slot])
+            for d, hh in zip(dev_in[slot], sets_h[i % 2]):
+                d.copy_(hh, non_blocking=True)
+            ev_in[slot].record(s_in)
+        cur.wait_event(ev_in[slot])
+        img = net.infer_frames(*dev_in[slot])
+        ev_done[slot].record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_done[slot])
+            out_h[slot].copy_(img, non_blocking=True)
+            img.record_stream(s_out)
+
+    for i in range(3):
+        step(i)
+    cur.wait_stream(s_in)
+    cur.wait_stream(s_out)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(Ks):
+        step(i)
+    cur.wait_stream(s_in)
+    cur.wait_stream(s_out)
+    f1.record()
+    barrier()
+    t = torch.tensor([ms_dev, f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    h2d = sum(x.numel() * x.element_size() for x in sets_h[0])
+    return {"metric": "hr_frames_per_sec_x8_sr_1080p_stream", "unit": UNIT, "value": F_ * world * Ks / (ms_dev * 1e-3),
+            "ms_per_call": ms_dev / Ks, "frames_per_call_per_gpu": F_, "steps": Ks, "lr": [h, w], "hr": [SCALE * h, SCALE * w],
+            "sharding": "frame f -> rank f mod %d, no collective" % world,
+            "e2e": {"value": F_ * world * Ks / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_call": ms_e2e / Ks,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_h[0].numel(),
+                    "call": "net.infer_frames(LQ, Depth) -> uint8 BGR frames"}}
 
 
 def train_pass(args, net, dev, rank, world, barrier):
@@ -437,6 +614,16 @@ def train_pass(args, net, dev, rank, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     loss = float(vec[0].item())
+    # data-parallel consistency: after the same number of steps every rank must hold the SAME parameters (they start
+    # from rank 0's weights and apply the same averaged gradients); a silent divergence would show up here
+    chk = torch.stack([torch.cat([p.detach().double().reshape(-1) for p in net.parameters()]).sum(),
+                       torch.cat([p.detach().double().abs().reshape(-1) for p in net.parameters()]).sum()])
+    dp_check = None
+    if world > 1:
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        dp_check = {"param_checksum_identical_on_all_ranks": bool(all(torch.equal(allc[0], c) for c in allc)),
+                    "checksum": [float(v) for v in allc[0].tolist()], "ranks": world, "after_steps": Kt + 4}
     net.eval()
     nparam = sum(p.numel() for p in net.parameters())
     return {"metric": "train_images_per_sec_x8_64to512", "value": Bt * world * Kt / (ms * 1e-3), "unit": "images/s",
@@ -444,7 +631,7 @@ def train_pass(args, net, dev, rank, world, barrier):
             "loss": "L1 + dynamic depth-mask (SmoothL1), Adam lr 1e-3 betas (0.9, 0.99)", "last_loss": loss,
             "gradient_allreduce": None if world == 1 else "one NCCL all-reduce (AVG) of the flat fp32 buffer, %.1f MB"
                                                              % (nparam * 4 / 1e6),
-            "cuda_graph": not args.no_graph,
+            "cuda_graph": not args.no_graph, "dp_check": dp_check,
             "gpu_launches": int(launches)}
 
 
@@ -516,7 +703,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step (BASELINE configs[1]: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--train-steps", type=int, default=8, help="timed steps of the training leg (0 = skip it)")
+    ap.add_argument("--train-steps", type=int, default=50, help="timed steps of the training leg (0 = skip it)")
+    ap.add_argument("--stream-steps", type=int, default=20, help="timed calls of the 1080p stream leg (0 = skip it)")
+    ap.add_argument("--stream-frames", type=int, default=8, help="1080p frames per call and GPU")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (torch kernels on the GPU)")
     ap.add_argument("--no-graph", action="store_true", help="issue the training step kernel by kernel (no CUDA graph)")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per training step (BASELINE configs[2])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
