@@ -637,20 +637,20 @@ def train_pass(args, net, dev, rank, world, barrier):
 
 def _ncu_traffic(kernel_family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/r01_conv_ncu_full_v6_summary.csv), or None."""
-    col = {"conv3x3_128to128_sean": 2}.get(kernel_family)
-    path = os.path.join(ROOT, "profiles", "r01_conv_ncu_full_v6_summary.csv")
-    if col is None or not os.path.exists(path):
+    `ncu --set full` capture (profiles/r02_sean_pair_v2_ncu_full_summary.csv, first captured launch), or None."""
+    path = {"conv3x3_128to128_sean": os.path.join(ROOT, "profiles", "r02_sean_pair_v2_ncu_full_summary.csv")}.get(kernel_family)
+    if path is None or not os.path.exists(path):
         return None
     import csv
-    rd = wr = None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    seen = 0
     with open(path) as f:
         for row in csv.reader(f):
-            if row and row[0] == "dram__bytes_read.sum":
-                rd = float(row[1 + col]) * (1e6 if row[1] == "Mbyte" else 1.0)
-            if row and row[0] == "dram__bytes_write.sum":
-                wr = float(row[1 + col]) * (1e6 if row[1] == "Mbyte" else 1.0)
-    return None if rd is None or wr is None else rd + wr
+            if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and len(row) > 2:
+                tot += float(row[2]) * scale.get(row[1], 1.0)
+                seen += 1
+    return tot if seen == 2 else None
 
 
 def roofline_pass(net, dev_sets, B):

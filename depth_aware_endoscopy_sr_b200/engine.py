@@ -75,9 +75,12 @@ class Engine:
         self._wg_streams = {}
         self.use_graphs = os.environ.get("DASR_INFER_GRAPH", "1") != "0"   # replay inference from a CUDA graph (see infer)
         self.max_graphs = 3
-        # larger batches are device-bound when issued kernel by kernel (B=64 at 64x64: 6.3 ms of kernels against 2.7 ms
-        # of host time); a graph would only add the output copy and pin 3.5 GB of activations
-        self.graph_max_pixels = 32 * 64 * 64
+        # Up to the bench shape (B=64 at 64x64, or eight 135x240 frames of a 1080p stream): measured at B=64, kernel by
+        # kernel 5.63 ms per step with 4.3 ms of host time to issue it (the device waits on the host at every short
+        # kernel of the encoder / table stage), replayed 5.53 ms including the 0.06 ms copy of the result out of the
+        # graph's static buffer (tools/hostbound.py).  A recorded shape pins its activations (3.5 GB at B=64, at most
+        # ``max_graphs`` shapes); larger batches stay kernel by kernel.
+        self.graph_max_pixels = 64 * 64 * 64
         self._graphs = {}
         self._graph_state = None
         self.always_pack = False    # CUDA-graph capture of a training step: repack inside every forward
