@@ -250,20 +250,22 @@ def _conv_train(tp: Tape, x: _T, name: str, *, act="none", subsample=1, shuffle=
     return o
 
 
-def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, masks, flag, vec, dvec, aux, tables,
-                mask16, dT_all, scr_all, *, first: bool, resid: Optional[_T], actv_pre=None) -> _T:
-    """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure."""
+def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, ctx, tables, dT_all, scr_all, *, first: bool,
+                resid: Optional[_T], actv_pre=None) -> _T:
+    """conv -> IN -> IN -> SEAN modulate -> ReLU (first) | + resid -> ReLU (second), with the backward closure.
+    ``ctx``: Engine.mask_context of this feature-map resolution (depth map, masks, labels, flag, aux, mask image)."""
     eng, lib, s = tp.eng, tp.lib, tp.s
     x = cur.data
     B, H, W, nf = x.shape
     nf2 = 2 * nf
     K, lat = sean.label_nc, sean.len_latent
     dev = x.device
+    depth, masks, flag, aux, mask16 = ctx["depth"], ctx["masks"], ctx["flag"], ctx["aux"], ctx["mask16"]
     # ---- forward (same kernels as Engine._dgb, plus the tensors the backward needs)
-    sidx = eng._sean_index[n]
-    stp, table = tables[0][sidx], tables[1][sidx]        # all instances were computed in two launches
-    pkt = eng._packed[n + ".table"]
-    wdyn = tables[2][sidx]                                # K-DYN runs inside the SEAN GEMM as a K extension
+    grp = eng._sean_group[n]
+    sidx = grp.index[n]
+    # all instances of a width group were computed in two launches; K-DYN runs inside the SEAN GEMM as a K extension
+    _stp, table, wdyn = eng.sean_tables(tables, n)
     nslots = L.conv_stats_slots(B, H, W, nf, nf)
     stats = torch.empty(B, nslots, nf, 2, device=dev, dtype=torch.float32)
     norm = torch.empty(B, nf, 2, device=dev, dtype=torch.float32)
@@ -315,8 +317,8 @@ def _sean_train(tp: Tape, n: str, sean, cur: _T, conv_name: str, depth, labels, 
         pkd = eng._packed[n + ".gb_o.dg"]
         dA = L.act_empty(B, H, W, nf2, device=dev)
         gw, gb = eng._grad_view(n + ".mlp_mask.0.weight"), eng._grad_view(n + ".mlp_mask.0.bias")
-        scr = scr_all[sidx]          # zeroed once per step for all instances
-        dT = dT_all[sidx]
+        scr = scr_all[grp][sidx]     # zeroed once per step for all instances
+        dT = dT_all[grp][sidx]
         # everything below only reaches parameter gradients (mlp_mask, the style tables): a leaf chain
         with tp.leaf(dgb, actv, dA) as s2:
             L.conv_fwd(dgb, pkd.w, eng._zero_bias, dA, Cout=nf2, ks=3, actmask=actv, mask_slope=0.0)
@@ -361,7 +363,8 @@ def _forward_train(eng, lq, depth, masks):
 
     tp.ops.append(bwd_first)
 
-    vec = labels = flag = dvec = aux = tables = mask16 = dT_all = scr_all = None
+    vec = dvec = tables = dT_all = scr_all = None
+    ctxs = {}        # Engine.mask_context per feature-map resolution of the depth-guided blocks
     if not net.isBaseline:
         e2 = _conv_train(tp, f0, "encoder.layer2", act="lrelu", subsample=2)
         e3 = _conv_train(tp, e2, "encoder.layer3", act="lrelu", subsample=2)
@@ -382,31 +385,29 @@ def _forward_train(eng, lq, depth, masks):
         tp.use(e5)
 
         def bwd_pool():
-            # style branch of ALL SEAN instances: dWs = dT^T stp, dstp = dT Ws, then the A_i_j backward (batched)
+            # style branch of ALL SEAN instances: dWs = dT^T stp, dstp = dT Ws, then the A_i_j backward (batched per
+            # width group)
             tp.sync_leaves()             # dT_all is complete once the K-DYN leaf chains have run
-            nS = len(eng._sean_names)
-            N = eng._ws_rows
-            dWs_all = eng._dw_flat[eng._wg_tables_off:eng._wg_tables_off + nS * N * lat]
-            dstp_all = torch.empty(nS, B * K, lat, device=dev, dtype=torch.float32)
-            L.check(lib.dasr_table_bwd_batched(L.ptr(dT_all), L.ptr(tables[0]), L.ptr(eng._ws_all), L.ptr(dWs_all),
-                                               L.ptr(dstp_all), nS, B * K, N, lat, tp.s))
-            L.check(lib.dasr_style_mix_bwd_batched(L.ptr(dstp_all), L.ptr(vec), L.ptr(eng._A_ptrs), L.ptr(eng._dA_ptrs),
-                                                   L.ptr(eng._da_ptrs), L.ptr(dvec), nS, B, K, lat, tp.s))
+            for grp in eng._sean_groups:
+                nS = len(grp.names)
+                N = grp.ws_rows
+                dWs_all = eng._dw_flat[grp.wg_tables_off:grp.wg_tables_off + nS * N * lat]
+                dstp_all = torch.empty(nS, B * K, lat, device=dev, dtype=torch.float32)
+                L.check(lib.dasr_table_bwd_batched(L.ptr(dT_all[grp]), L.ptr(tables[grp][0]), L.ptr(grp.ws_all),
+                                                   L.ptr(dWs_all), L.ptr(dstp_all), nS, B * K, N, lat, tp.s))
+                L.check(lib.dasr_style_mix_bwd_batched(L.ptr(dstp_all), L.ptr(vec), L.ptr(grp.A_ptrs), L.ptr(grp.dA_ptrs),
+                                                       L.ptr(grp.da_ptrs), L.ptr(dvec), nS, B, K, lat, tp.s))
             de5 = L.act_like(e5.data)
             L.check(lib.dasr_region_pool_bwd(L.ptr(dvec), L.ptr(msel), L.ptr(cnt), L.ptr(de5), B, P, lat, K, s))
             tp.accum(e5, de5)
 
         tp.ops.append(bwd_pool)
-        labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
-        flag = torch.zeros(1, device=dev, dtype=torch.int32)
-        L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
         tables = eng.style_tables(vec)
-        dT_all = torch.zeros(len(eng._sean_names), B * K, eng._ws_rows, device=dev, dtype=torch.float32)
-        scr_all = torch.zeros(len(eng._sean_names), eng._ws_rows // 9, 9 * L.AUX_CH, device=dev, dtype=torch.float32)
-        mask16 = torch.empty(B, h, w, 16, device=dev, dtype=BF16)
-        L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(mask16), B, K, h, w, s))
-        aux = torch.empty(B, h, w, L.AUX_CH, device=dev, dtype=BF16)
-        L.check(lib.dasr_build_aux(L.ptr(labels), L.ptr(depth), L.ptr(aux), B, K, h, w, s))
+        dT_all = {g: torch.zeros(len(g.names), B * K, g.ws_rows, device=dev, dtype=torch.float32)
+                  for g in eng._sean_groups}
+        scr_all = {g: torch.zeros(len(g.names), 2 * g.nf, 9 * L.AUX_CH, device=dev, dtype=torch.float32)
+                   for g in eng._sean_groups}
+        ctxs[(h, w)] = eng.mask_context(depth, masks, h, w, training=True)
 
     # ---- head + trunk
     h1 = _conv_train(tp, f0, "head.0", act="lrelu")
@@ -418,7 +419,7 @@ def _forward_train(eng, lq, depth, masks):
     # (Engine._ActvPrefetch is the inference counterpart with rotating buffers)
     actv_pre = {}
     if eng.actv_overlap and not net.isBaseline:
-        dgb_blocks = [i for i, _pos in order if i in net.which_ResBlk_depth]
+        dgb_blocks = [i for i, _pos in order if i in net.which_ResBlk_depth and eng.block_scale(i) == 1]
         side = eng._side_streams.get(dev.index)
         if side is None:
             side = eng._side_streams[dev.index] = torch.cuda.Stream(device=dev)
@@ -440,18 +441,22 @@ def _forward_train(eng, lq, depth, masks):
 
     def run_block(i, x):
         if i in net.which_ResBlk_depth:
-            if x.data.shape[1] != h or x.data.shape[2] != w:
-                raise NotImplementedError("depth-guided blocks above LR resolution are not implemented")
+            res = (x.data.shape[1], x.data.shape[2])
+            if res not in ctxs:
+                # a depth-guided block above LR resolution: depth map and masks resized to its feature map
+                # (normalization.py:58-59)
+                ctxs[res] = eng.mask_context(depth, masks, res[0], res[1], training=True)
+            ctx = ctxs[res]
             p = "depth-residual%d" % (i + 1)
             blk = net.block(i)
             pre = (None, None)
             if i in actv_pre:
                 pre, ev = actv_pre.pop(i)
                 torch.cuda.current_stream(dev).wait_event(ev)
-            a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", depth, labels, masks, flag, vec, dvec, aux,
-                            tables, mask16, dT_all, scr_all, first=True, resid=None, actv_pre=pre[0])
-            return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", depth, labels, masks, flag, vec, dvec, aux,
-                               tables, mask16, dT_all, scr_all, first=False, resid=x, actv_pre=pre[1])
+            a = _sean_train(tp, p + ".norm1", blk.norm1, x, p + ".conv1.0", ctx, tables, dT_all, scr_all, first=True,
+                            resid=None, actv_pre=pre[0])
+            return _sean_train(tp, p + ".norm2", blk.norm2, a, p + ".conv2.0", ctx, tables, dT_all, scr_all, first=False,
+                               resid=x, actv_pre=pre[1])
         p = "classic-residual%d" % (i + 1)
         f = _conv_train(tp, x, p + ".block.0", act="relu")
         # relu(x + conv(f)): the residual add is the conv epilogue; its backward = lazy ReLU mask, then both paths

@@ -2108,7 +2108,9 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     if ((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes > budget) k.SA = 1;
     DASR_REQUIRE((size_t)k.SA * k.a_stage_bytes + 2 * (size_t)k.b_stage_bytes <= budget,
                  "A tile (%u bytes) does not fit in shared memory", k.a_stage_bytes);
-    const bool may_reside = (k.ntn == 1) && (d->w_img_rows == 0) && npl == 1;    // per-image weights always stream
+    // per-image weights always stream; so does a GEMM with the K-DYN extension (its dynamic filters share the weight ring:
+    // with Cin = 64 -- a SEAN instance of a 32-channel block -- the static weights alone would fit)
+    const bool may_reside = (k.ntn == 1) && (d->w_img_rows == 0) && npl == 1 && !k.dyn;
     if (may_reside && k.nch * k.taps <= kMaxBStages &&
         (size_t)k.SA * k.a_stage_bytes + all_b <= budget) {
         k.b_resident = 1;

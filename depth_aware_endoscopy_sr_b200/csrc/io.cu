@@ -87,6 +87,20 @@ __global__ void tensor2img_kernel(const float* __restrict__ sr, uint8_t* __restr
     }
 }
 
+// F.interpolate(x, size=(Ho, Wo), mode='nearest') for integer ratios (normalization.py:58-59: a SEAN instance above LR
+// resolution resizes the depth map and the depth masks to its feature map): out[b,c,Y,X] = in[b,c,Y/ry,X/rx]
+__global__ void __launch_bounds__(256) nearest_up_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+                                                         int W, int ry, int rx, size_t total) {
+    const int Wo = W * rx, Ho = H * ry;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % Wo);
+        const size_t r = i / Wo;
+        const int Y = (int)(r % Ho);
+        const size_t plane = r / Ho;
+        out[i] = __ldg(in + (plane * H + Y / ry) * W + X / rx);
+    }
+}
+
 }  // namespace dasr
 
 using namespace dasr;
@@ -96,6 +110,19 @@ extern "C" int dasr_depth_masks(const float* depth, uint8_t* labels, float* mask
     DASR_REQUIRE(depth && labels && B > 0 && H > 0 && W > 0, "bad arguments");
     DASR_REQUIRE(K >= 1 && K <= DASR_LOSS_KMAX, "depth masks: 1..%d bins (got %d)", DASR_LOSS_KMAX, K);
     depth_masks_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(depth, labels, masks, range_out, K, H * W, fixed_range);
+    DASR_LAUNCH_OK();
+    return DASR_OK;
+}
+
+extern "C" int dasr_nearest_up(const float* in, float* out, int planes, int H, int W, int Ho, int Wo, void* stream) {
+    DASR_REQUIRE(in && out && planes > 0 && H > 0 && W > 0, "bad arguments");
+    DASR_REQUIRE(Ho >= H && Wo >= W && Ho % H == 0 && Wo % W == 0, "nearest resize: integer ratios only (%dx%d -> %dx%d)", H, W,
+                 Ho, Wo);
+    const size_t total = (size_t)planes * Ho * Wo;
+    size_t grid = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (grid > cap) grid = cap;
+    nearest_up_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W, Ho / H, Wo / W, total);
     DASR_LAUNCH_OK();
     return DASR_OK;
 }

@@ -37,6 +37,21 @@ class _Packed:
         self.w, self.bias, self.cout, self.cin, self.ks = w, bias, cout, cin, ks
 
 
+class _SeanGroup:
+    """The SEAN instances of one width (norm_nc, latent size) in execution order: their style-table operands
+    (``ws_all`` [n * 9*2nf, latent]), A_i_j pointer tables and weight-gradient slices are contiguous, so the per-image
+    filter tables of the whole group (and their backward) are ONE launch each."""
+
+    def __init__(self, nf: int, lat: int):
+        self.nf, self.lat = nf, lat
+        self.ws_rows = 9 * 2 * nf
+        self.names: List[str] = []
+        self.seans: list = []
+        self.index: Dict[str, int] = {}
+        self.ws_all = self.A_ptrs = self.a_ptrs = self.dA_ptrs = self.da_ptrs = None
+        self.wg_tables_off = 0
+
+
 class Engine:
     def __init__(self, net):
         self.net = net
@@ -128,23 +143,31 @@ class Engine:
         self._used_params = set()
         rows_total = 0
         rows_bwd = 0
-        # every active SEAN instance, in execution order: their style-table GEMM operands live in ONE buffer so that
-        # the 26 table GEMMs are a single launch with per-image weights (dasr_conv_desc.w_img_rows)
+        # every active SEAN instance, in execution order, grouped by width (nf = 64 in the trunk, 32 for the blocks
+        # behind upscale1 / upscale2 when which_ResBlk_depth selects them): the style-table GEMM operands of a group
+        # live in ONE buffer so that its table GEMMs are a single launch with per-image weights
+        # (dasr_conv_desc.w_img_rows)
         sean_names = []
         for i, _pos in net.block_order():
             if i in net.which_ResBlk_depth:
                 sean_names += ["depth-residual%d.norm%d" % (i + 1, j) for j in (1, 2)]
         self._sean_names = sean_names
-        self._sean_index = {n: k for k, n in enumerate(sean_names)}
-        self._ws_all = None
-        if sean_names:
-            blk0 = net.block(next(i for i, _ in net.block_order() if i in net.which_ResBlk_depth))
-            nf0, lat0 = blk0.nf, blk0.norm1.len_latent
-            self._ws_rows = 9 * 2 * nf0
-            self._ws_all = L.act_zeros(len(sean_names) * self._ws_rows, lat0, device=device)
-            seans = [getattr(net.block(int(n.split(".")[0][len("depth-residual"):]) - 1), n.split(".")[1]) for n in sean_names]
-            self._A_ptrs = torch.tensor([m.A_i_j.weight.data_ptr() for m in seans], dtype=torch.int64, device=device)
-            self._a_ptrs = torch.tensor([m.A_i_j.bias.data_ptr() for m in seans], dtype=torch.int64, device=device)
+        self._sean_groups = []
+        self._sean_group = {}
+        for n in sean_names:
+            m = getattr(net.block(int(n.split(".")[0][len("depth-residual"):]) - 1), n.split(".")[1])
+            g = next((g for g in self._sean_groups if g.nf == m.norm_nc and g.lat == m.len_latent), None)
+            if g is None:
+                g = _SeanGroup(m.norm_nc, m.len_latent)
+                self._sean_groups.append(g)
+            g.index[n] = len(g.names)
+            g.names.append(n)
+            g.seans.append(m)
+            self._sean_group[n] = g
+        for g in self._sean_groups:
+            g.ws_all = L.act_zeros(len(g.names) * g.ws_rows, g.lat, device=device)
+            g.A_ptrs = torch.tensor([m.A_i_j.weight.data_ptr() for m in g.seans], dtype=torch.int64, device=device)
+            g.a_ptrs = torch.tensor([m.A_i_j.bias.data_ptr() for m in g.seans], dtype=torch.int64, device=device)
 
         def reserve(name, rows, kdim):
             self._wg[name] = (self._wg_total, rows, kdim)
@@ -237,25 +260,25 @@ class Engine:
                     self._used_params.update([n + ".mlp_mask.0.weight", n + ".mlp_mask.0.bias", n + ".A_i_j.weight",
                                               n + ".A_i_j.bias"])
                     # style-table GEMM operand: rows = tap * 2nf + [gamma | beta], K = latent, scaled by alpha
-                    if 9 * 2 * nf != self._ws_rows or lat != self._ws_all.shape[1]:
-                        raise NotImplementedError("depth-guided blocks with different widths in one network")
-                    k0 = self._sean_index[n] * self._ws_rows
-                    ws = self._ws_all[k0:k0 + self._ws_rows]
+                    grp = self._sean_group[n]
+                    k0 = grp.index[n] * grp.ws_rows
+                    ws = grp.ws_all[k0:k0 + grp.ws_rows]
                     for off, x, al in ((0, "gamma", ag), (nf, "beta", ab)):
                         self._descs.append(L.pack_desc(P("%s.mlp_%s_s.weight" % (n, x)), ws, alpha=al, alpha_mode=1,
                                                        mode=L.PACK_STYLE, row_offset=off, rows_per_tap=2 * nf,
-                                                       dst_stride=self._ws_all.numel()))
+                                                       dst_stride=grp.ws_all.numel()))
                         rows_total += nf
                     self._packed[n + ".table"] = _Packed(ws, None, 9 * 2 * nf, lat, 1)
             else:
                 p = "classic-residual%d" % (i + 1)
                 add_wn(p + ".block.0")
                 add_wn(p + ".block.2")
-        # weight gradients of the style-table GEMMs: one contiguous [nS][9*2nf][lat] block (batched backward)
-        self._wg_tables_off = self._wg_total
-        for n in sean_names:
-            self._wg[n + ".table"] = (self._wg_total, self._ws_rows, self._ws_all.shape[1])
-            self._wg_total += self._ws_rows * self._ws_all.shape[1]
+        # weight gradients of the style-table GEMMs: one contiguous [nS][9*2nf][lat] block per group (batched backward)
+        for grp in self._sean_groups:
+            grp.wg_tables_off = self._wg_total
+            for n in grp.names:
+                self._wg[n + ".table"] = (self._wg_total, grp.ws_rows, grp.lat)
+                self._wg_total += grp.ws_rows * grp.lat
         if net.scale == 8:
             add_wn("upscale1.0", shuffle_r=2)
             add_wn("upscale1.3")
@@ -386,12 +409,12 @@ class Engine:
                 U(self._dw_view("conv_output"), P("conv_output.weight"), G("conv_output.weight"), mode=L.PACK_ROWTAPS)
         self._unpack_descs = (L.UnpackDesc * len(descs))(*descs)
         # gradient pointer tables of the batched A_i_j backward (dasr_style_mix_bwd_batched)
-        if self._sean_names:
-            dev = self._g_flat.device
-            self._dA_ptrs = torch.tensor([self._grad_view(n + ".A_i_j.weight").data_ptr() for n in self._sean_names],
-                                         dtype=torch.int64, device=dev)
-            self._da_ptrs = torch.tensor([self._grad_view(n + ".A_i_j.bias").data_ptr() for n in self._sean_names],
-                                         dtype=torch.int64, device=dev)
+        dev = self._g_flat.device
+        for grp in self._sean_groups:
+            grp.dA_ptrs = torch.tensor([self._grad_view(n + ".A_i_j.weight").data_ptr() for n in grp.names],
+                                       dtype=torch.int64, device=dev)
+            grp.da_ptrs = torch.tensor([self._grad_view(n + ".A_i_j.bias").data_ptr() for n in grp.names],
+                                       dtype=torch.int64, device=dev)
 
     def _finish_backward(self):
         """Packed-layout gradients -> parameter gradients; returns one tensor (or None) per parameter, all of them
@@ -444,30 +467,66 @@ class Engine:
                                               subsample=subsample, **kw))
 
     def style_tables(self, vec):
-        """The per-image dynamic-filter tables of ALL SEAN instances in two launches:
+        """The per-image dynamic-filter tables of ALL SEAN instances, two launches per width group:
         stp[s] = A_i_j^(s)(depthVec) (dasr_style_mix_batched) and T[s] = alpha^(s) W_s^(s) . stp[s] (one 1x1
-        dasr_conv_fwd over the batch of instances with per-image weights).  Returns (stp_all [nS,1,B*K,L],
-        table_all [nS,1,B*K,9*2nf]); instance ``n`` uses index ``self._sean_index[n]``."""
+        dasr_conv_fwd over the instances of the group with per-image weights).  Returns {group: (stp_all [nS,1,B*K,L],
+        table_all [nS,1,B*K,9*2nf], wdyn_all [nS,B*2nf,9*16])}; ``sean_tables(tables, n)`` picks instance ``n``."""
         lib = L.load()
-        nS = len(self._sean_names)
         B, K, lat = vec.shape
         s = L.stream_ptr()
-        stp_all = L.act_empty(nS, 1, B * K, lat, device=vec.device)
-        self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp_all.numel() * 2,
-                    lambda: L.check(lib.dasr_style_mix_batched(L.ptr(vec), L.ptr(self._A_ptrs), L.ptr(self._a_ptrs),
-                                                               L.ptr(stp_all), nS, B, K, lat, s)))
-        table_all = L.act_empty(nS, 1, B * K, self._ws_rows, device=vec.device)
-        self._timed("style_table_gemm", "tensor", 2.0 * nS * B * K * lat * self._ws_rows,
-                    stp_all.numel() * 2 + table_all.numel() * 2 + self._ws_all.numel() * 2,
-                    lambda: L.conv_fwd(stp_all, self._ws_all, self._zero_bias, table_all, Cout=self._ws_rows, ks=1,
-                                       w_img_rows=self._ws_rows))
-        # GEMM-B form of every table for the K-DYN extension of the SEAN GEMM: [nS][B*2nf][9*16]
-        nf2 = self._ws_rows // 9
-        # (fp32-split planes: the planes of an instance's filters sit inside its own slice -- see include/dasr.h)
-        wdyn_all = torch.empty(nS, L.planes(), B * nf2, 9 * 16, device=vec.device, dtype=BF16)
-        self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
-                    lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, B, s)))
-        return stp_all, table_all, wdyn_all[:, 0]
+        res = {}
+        for grp in self._sean_groups:
+            nS = len(grp.names)
+            stp_all = L.act_empty(nS, 1, B * K, lat, device=vec.device)
+            self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp_all.numel() * 2,
+                        lambda: L.check(lib.dasr_style_mix_batched(L.ptr(vec), L.ptr(grp.A_ptrs), L.ptr(grp.a_ptrs),
+                                                                   L.ptr(stp_all), nS, B, K, lat, s)))
+            table_all = L.act_empty(nS, 1, B * K, grp.ws_rows, device=vec.device)
+            self._timed("style_table_gemm", "tensor", 2.0 * nS * B * K * lat * grp.ws_rows,
+                        stp_all.numel() * 2 + table_all.numel() * 2 + grp.ws_all.numel() * 2,
+                        lambda: L.conv_fwd(stp_all, grp.ws_all, self._zero_bias, table_all, Cout=grp.ws_rows, ks=1,
+                                           w_img_rows=grp.ws_rows))
+            # GEMM-B form of every table for the K-DYN extension of the SEAN GEMM: [nS][B*2nf][9*16]
+            nf2 = 2 * grp.nf
+            # (fp32-split planes: the planes of an instance's filters sit inside its own slice -- see include/dasr.h)
+            wdyn_all = torch.empty(nS, L.planes(), B * nf2, 9 * 16, device=vec.device, dtype=BF16)
+            self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
+                        lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, B,
+                                                                     s)))
+            res[grp] = (stp_all, table_all, wdyn_all[:, 0])
+        return res
+
+    def sean_tables(self, tables, n: str):
+        """(stp, table, wdyn) of SEAN instance ``n`` out of ``style_tables``' result."""
+        grp = self._sean_group[n]
+        t = tables[grp]
+        k = grp.index[n]
+        return t[0][k], t[1][k], t[2][k]
+
+    def mask_context(self, depth, masks, H: int, W: int, training: bool = False):
+        """What the SEAN instances of one resolution read of the depth map and the depth masks: at LR resolution the
+        inputs themselves, above it their nearest-neighbour resize (normalization.py:58-59) -- plus the derived
+        operands: the bf16 mask image of the K-DYN extension and, for the backward, labels / general-mask flag / aux."""
+        lib = L.load()
+        s = L.stream_ptr()
+        B, K, h, w = masks.shape
+        dev = masks.device
+        if (H, W) != (h, w):
+            d_up = torch.empty(B, 1, H, W, device=dev, dtype=torch.float32)
+            m_up = torch.empty(B, K, H, W, device=dev, dtype=torch.float32)
+            L.check(lib.dasr_nearest_up(L.ptr(depth), L.ptr(d_up), B, h, w, H, W, s))
+            L.check(lib.dasr_nearest_up(L.ptr(masks), L.ptr(m_up), B * K, h, w, H, W, s))
+            depth, masks = d_up, m_up
+        ctx = dict(depth=depth, masks=masks)
+        ctx["mask16"] = torch.empty(B, H, W, 16, device=dev, dtype=BF16)
+        L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(ctx["mask16"]), B, K, H, W, s))
+        if training:
+            ctx["labels"] = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+            ctx["flag"] = torch.zeros(1, device=dev, dtype=torch.int32)
+            L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(ctx["labels"]), L.ptr(ctx["flag"]), B, K, H, W, s))
+            ctx["aux"] = torch.empty(B, H, W, L.AUX_CH, device=dev, dtype=BF16)
+            L.check(lib.dasr_build_aux(L.ptr(ctx["labels"]), L.ptr(depth), L.ptr(ctx["aux"]), B, K, H, W, s))
+        return ctx
 
     def _sean_actv(self, sean, depth, out=None, ctas_per_sm=0):
         """actv = ReLU(mlp_mask(depth)) of one SEAN instance (normalization.py:37-40,61)."""
@@ -550,7 +609,7 @@ class Engine:
             n = "%s.norm%d" % (p, j)
             # conv + per-tile statistics; the double-InstanceNorm coefficients are finalised inside the SEAN conv
             y = self._conv(cur, "%s.conv%d.0" % (p, j), epi=L.EPI_STATS, stats=stats[j - 1])
-            wdyn = tables[2][self._sean_index[n]]     # K-DYN runs inside the SEAN GEMM as a K extension
+            wdyn = self.sean_tables(tables, n)[2]     # K-DYN runs inside the SEAN GEMM as a K extension
             if gen:
                 actv = None
                 akw = dict(shape=(B, H, W, 2 * nf), gen_depth=depth, gen_w=sean.mlp_mask[0].weight,
@@ -571,6 +630,15 @@ class Engine:
         if pre is not None:
             prefetch.done()
         return cur, out32
+
+    def block_scale(self, i: int) -> int:
+        """Resolution of block ``i``'s feature map relative to the LR input (sftmd_arch.py:932-944): the trunk runs at
+        LR resolution, block nb-2 behind upscale1 (x2 at scale 8), block nb-1 behind upscale2 (x2 at scale 4, x4 at 8)."""
+        net = self.net
+        pos = dict(net.block_order()).get(i, "trunk")
+        up1 = 2 if net.scale == 8 else 1
+        up2 = up1 * (2 if net.scale >= 4 else 1)
+        return {"trunk": 1, "up1": up1, "up2": up2}[pos]
 
     def _classic(self, p: str, x):
         """Classic_Residual_Block.forward (sftmd_arch.py:147-151)."""
@@ -661,13 +729,12 @@ class Engine:
             vec = torch.empty(B, K, lat, device=dev, dtype=torch.float32)
             L.check(lib.dasr_region_pool_fwd(L.ptr(e5), L.ptr(masks), L.ptr(vec), None, None, B, e5.shape[1],
                                              e5.shape[2], lat, K, h, w, s))
-            labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
-            flag = torch.zeros(1, device=dev, dtype=torch.int32)
-            L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
             tables = self.style_tables(vec)
-            mask16 = torch.empty(B, h, w, 16, device=dev, dtype=BF16)
-            L.check(lib.dasr_build_mask16(L.ptr(masks), L.ptr(mask16), B, K, h, w, s))
+            mask16 = self.mask_context(depth, masks, h, w)["mask16"]
             if cap is not None:
+                labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
+                flag = torch.zeros(1, device=dev, dtype=torch.int32)
+                L.check(lib.dasr_mask_labels(L.ptr(masks), L.ptr(labels), L.ptr(flag), B, K, h, w, s))
                 cap.update(e5=e5, depthVec=vec, labels=labels, flag=flag)
 
         # ---- head + trunk (sftmd_arch.py:920-931)
@@ -679,17 +746,20 @@ class Engine:
         # (the instrumented pass of bench.py times kernels one by one: no overlap there unless forced by a probe)
         if (self.actv_overlap and (self.profile is None or self.actv_overlap == "force") and cap is None
                 and not self.fuse_actv):
-            blocks = [(net.block(i).norm1, net.block(i).norm2) for i, _pos in order if i in net.which_ResBlk_depth]
+            # (the instances at LR resolution; a depth-guided block behind upscale1 / upscale2 produces its own actv)
+            blocks = [(net.block(i).norm1, net.block(i).norm2) for i, _pos in order
+                      if i in net.which_ResBlk_depth and self.block_scale(i) == 1]
             if blocks:
                 prefetch = Engine._ActvPrefetch(self, blocks, depth, 2 * blocks[0][0].norm_nc)
 
         def run_block(i, x, x32):
             if i in net.which_ResBlk_depth:
+                p = "depth-residual%d" % (i + 1)
                 if x.shape[1] != h or x.shape[2] != w:
-                    raise NotImplementedError("depth-guided blocks above LR resolution (which_ResBlk_depth containing "
-                                              "%d at x%d) are not implemented yet" % (i, net.scale))
-                return self._dgb("depth-residual%d" % (i + 1), net.block(i), x, x32, depth, mask16, tables,
-                                 prefetch=prefetch)
+                    # a depth-guided block above LR resolution: depth map and masks resized to its feature map
+                    hr = self.mask_context(depth, masks, x.shape[1], x.shape[2])
+                    return self._dgb(p, net.block(i), x, x32, hr["depth"], hr["mask16"], tables)
+                return self._dgb(p, net.block(i), x, x32, depth, mask16, tables, prefetch=prefetch)
             return self._classic("classic-residual%d" % (i + 1), x), None
 
         for i, pos in order:

@@ -406,6 +406,10 @@ int dasr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, doub
  * [0,1]); otherwise per-image (min,max), written to range_out [B][2] when not NULL.  Same fp32 roundings as torch. */
 int dasr_depth_masks(const float* depth, uint8_t* labels, float* masks, float* range_out, int B, int K, int H, int W,
                      int fixed_range, void* stream);
+/* F.interpolate(x, size=(Ho,Wo), mode='nearest') with integer ratios, NCHW fp32 planes [planes][H][W] ->
+ * [planes][Ho][Wo]: what a SEAN instance above LR resolution applies to the depth map and the depth masks
+ * (codes/models/modules/normalization.py:58-59; which_ResBlk_depth containing nb-2 / nb-1 at x8 / x4).            */
+int dasr_nearest_up(const float* in, float* out, int planes, int H, int W, int Ho, int Wo, void* stream);
 /* tensor2img (codes/utils/util.py:566-590) per frame: sr NCHW fp32 [B,3,H,W] RGB -> img u8 [B,H,W,3] BGR,
  * round_half_even((clamp(x, lo, hi) - lo) / (hi - lo) * 255)                                                     */
 int dasr_tensor2img(const float* sr, uint8_t* img, int B, int H, int W, float lo, float hi, void* stream);

@@ -15,6 +15,9 @@ from oracle import depthnet_oracle as oracle  # noqa: E402  (the checker; tests 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 INIT_CASES = ["x8_b1_64_init", "x8_b2_32_init"]   # the reference's own random init (strict tolerance)
 CASES = ["x8_b2_16", "x8_b1_64", "x8_b1_24x40", "x4_b1_24", "x2_b1_32", "x3_b1_24"]
+# depth-guided blocks ABOVE LR resolution (which_ResBlk_depth = 0..15: the 32-channel blocks behind upscale1 / upscale2
+# are depth-guided too and resize depth map / masks, normalization.py:58-59)
+HR_CASES = ["x8_b1_16_hr", "x4_b2_16_hr"]
 
 
 def load_golden(name):

@@ -42,6 +42,11 @@ CASES = {
     "x2_b1_32": (2, list(range(16)), 32, 1, 32, 32, 4, 1),
     # x3 (options/train/train_depthNet_SEAN_depthMask_endoscene_x3.yml:48-63): 16 depth-guided blocks, PixelShuffle(3)
     "x3_b1_24": (3, list(range(16)), 256, 1, 24, 24, 5, 1),
+    # depth-guided blocks ABOVE LR resolution (which_ResBlk_depth containing nb-2 / nb-1): 32-channel blocks behind
+    # upscale1 / upscale2 whose SEAN instances resize depth map and masks (normalization.py:58-59).  No shipped yml
+    # selects them; the reference builds and runs them.
+    "x8_b1_16_hr": (8, list(range(16)), 256, 1, 16, 16, 6, 1),
+    "x4_b2_16_hr": (4, list(range(16)), 64, 2, 16, 16, 8, 1, "default"),
 }
 
 
@@ -80,6 +85,9 @@ def run_case(name, scale, which, latent, B, h, w, seed, stride, init="synthetic"
     hooks.append(getattr(net, "depth-residual1").register_forward_hook(grab("dgb1_out")))
     hooks.append(getattr(net, "depth-residual1").norm1.register_forward_hook(grab("dgb1_norm1_out")))
     hooks.append(getattr(net, "depth-residual13").register_forward_hook(grab("dgb13_out")))
+    for i in (15, 16):      # blocks nb-2 / nb-1 when they are depth-guided
+        if hasattr(net, "depth-residual%d" % i):
+            hooks.append(getattr(net, "depth-residual%d" % i).register_forward_hook(grab("dgb%d_out" % i)))
     hooks.append(net.upscale3.register_forward_hook(grab("feat_up3")))
     hooks.append(net.conv_output.register_forward_hook(grab("pre_clamp")))
 
@@ -122,6 +130,9 @@ def run_case(name, scale, which, latent, B, h, w, seed, stride, init="synthetic"
         "loss": np.array([total.item(), l_pix.item(), l_dyn.item()] + [r.item() for r in raw]),
         "dyn_weight_grad": dyn.trainable_weight.grad.numpy(),
     }
+    for i in (15, 16):
+        if "dgb%d_out" % i in cap:
+            out["dgb%d_out" % i] = cap["dgb%d_out" % i].numpy()[:, ::4]
     names, sigs = [], []
     for k, p in net.named_parameters():
         names.append(k)
@@ -140,7 +151,10 @@ def run_case(name, scale, which, latent, B, h, w, seed, stride, init="synthetic"
     params = dict(net.named_parameters())
     for k in ("conv_output.bias", "depth-residual1.norm1.alpha_gamma", "depth-residual1.norm1.alpha_beta",
               "depth-residual1.norm1.A_i_j.weight", "depth-residual7.conv2.0.bias", "encoder.layer5.bias",
-              "head.0.weight_g", "upscale3.0.bias", "depth-residual13.norm2.mlp_mask.0.weight"):
+              "head.0.weight_g", "upscale3.0.bias", "depth-residual13.norm2.mlp_mask.0.weight",
+              "depth-residual15.norm1.A_i_j.weight", "depth-residual15.norm2.alpha_gamma",
+              "depth-residual16.norm2.mlp_mask.0.weight", "depth-residual16.norm1.alpha_beta",
+              "depth-residual16.conv1.0.weight"):
         if k in params and params[k].grad is not None:
             out["grad:" + k] = params[k].grad.numpy()
     path = os.path.join(HERE, name + ".npz")

@@ -73,7 +73,7 @@ def test_small_backward_kernels(kb):
 BF16_TENSOR_FACTOR, BF16_TENSOR_FLOOR, BF16_SCALAR_ABS = 3.5, 0.03, 0.75
 
 
-@pytest.mark.parametrize("name", ["x8_b2_32_init", "x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24"])
+@pytest.mark.parametrize("name", ["x8_b2_32_init", "x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24", "x8_b1_16_hr", "x4_b2_16_hr"])
 def test_full_depth_bf16_gradients_per_parameter(name):
     """Product arithmetic (bf16 operands and activations, fp32 accumulate): every parameter gradient of the full-depth
     network against the fp64 oracle evaluated ON THE SAME SMOOTH PIECE (the activation pattern of the CUDA run,

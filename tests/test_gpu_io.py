@@ -76,3 +76,18 @@ def test_infer_frames_builds_masks_and_uint8_frames_on_the_device():
     sr = net.infer_frames(lq, depth, out="float")
     with torch.no_grad():
         assert torch.equal(sr, net(lq, depth, masks))
+
+
+@pytest.mark.parametrize("shape,ratio", [((2, 10, 16, 16), (2, 2)), ((1, 1, 24, 40), (4, 4)), ((3, 10, 9, 7), (2, 4))])
+def test_nearest_resize_equals_torch_interpolate(shape, ratio):
+    """dasr_nearest_up == F.interpolate(mode='nearest') -- what a SEAN instance above LR resolution applies to the depth
+    map and the masks (codes/models/modules/normalization.py:58-59); bit-exact (a copy)."""
+    from depth_aware_endoscopy_sr_b200 import _lib as L
+    B, C, h, w = shape
+    g = torch.Generator().manual_seed(h * 100 + w)
+    x = torch.randn(B, C, h, w, generator=g).cuda()
+    H, W = h * ratio[0], w * ratio[1]
+    out = torch.empty(B, C, H, W, device="cuda")
+    L.check(L.load().dasr_nearest_up(L.ptr(x), L.ptr(out), B * C, h, w, H, W, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, torch.nn.functional.interpolate(x, size=(H, W), mode="nearest"))

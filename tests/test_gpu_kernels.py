@@ -20,13 +20,14 @@ def _nchw(x):
     return x.permute(0, 3, 1, 2).contiguous()
 
 
+@pytest.mark.parametrize("nf", [64, 32])      # 32: a depth-guided block behind upscale1 / upscale2 (which_ResBlk_depth 14, 15)
 @pytest.mark.parametrize("shape", [(2, 64, 64), (3, 24, 40), (1, 135, 240)])
-def test_sean_conv_with_kdyn_extension_and_fused_finalize(shape):
+def test_sean_conv_with_kdyn_extension_and_fused_finalize(shape, nf):
     from depth_aware_endoscopy_sr_b200 import _lib as L
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     B, H, W = shape
-    nf, K = 64, 10
+    K = 10
     dev = torch.device("cuda:0")
     lib = L.load()
     s = L.stream_ptr()

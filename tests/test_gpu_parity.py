@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import CASES, INIT_CASES, case_tensors, load_golden, oracle, psnr
+from common import CASES, HR_CASES, INIT_CASES, case_tensors, load_golden, oracle, psnr
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +29,19 @@ def stress_tol(pre_clamp_absmax):
     return TOL_PIX_STRESS * max(1.0, float(pre_clamp_absmax) / 2.0)
 
 
+def hr_tol(meta, sd, lq, depth, masks):
+    """HR_CASES (all 16 blocks depth-guided, no shipped yml): the 32-channel SEAN blocks behind upscale1 / upscale2
+    amplify operand rounding -- the pre-clamp output spans +-2.4 at the reference's own init instead of [0, 0.14] -- so
+    the bound is what bf16 operands do to the REFERENCE ITSELF: 1.5 x the deviation of the bf16-operand oracle from the
+    fp32 oracle (measured: oracle 0.069 / CUDA 0.078 at x4, 0.042 / 0.035 at x8) + 5e-3.  The fp32-split mode of the same
+    kernels meets 1e-4 on these cases too (test_gpu_precise.py)."""
+    with torch.no_grad():
+        ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"])
+        with oracle.bf16_operands():
+            emu = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"])
+    return 1.5 * (emu - ref).abs().max().item() + 5e-3
+
+
 def _build(meta, sd):
     import depth_aware_endoscopy_sr_b200 as dasr
     net = dasr.DepthNet(which_ResBlk_depth=list(meta["which"]), in_nc=3, out_nc=3, nf=64, nb=16, scale=meta["scale"],
@@ -42,11 +55,13 @@ def _nchw(t):
     return t.float().permute(0, 3, 1, 2).contiguous().cpu()
 
 
-@pytest.mark.parametrize("name", INIT_CASES + CASES)
+@pytest.mark.parametrize("name", INIT_CASES + CASES + HR_CASES)
 def test_forward_matches_reference_golden(name):
     z, meta = load_golden(name)
     tol = TOL_PIX if meta["init"] == "default" else stress_tol(np.abs(z["pre_clamp"]).max())
     sd, (lq, depth, masks, gt) = case_tensors(meta)
+    if name in HR_CASES:
+        tol = hr_tol(meta, sd, lq, depth, masks)
     net = _build(meta, sd)
     cap = {}
     with torch.no_grad():
@@ -73,12 +88,14 @@ def test_forward_matches_reference_golden(name):
     assert err_pre <= 2 * tol * max(1.0, np.abs(z["pre_clamp"]).max())
 
 
-@pytest.mark.parametrize("name", INIT_CASES + ["x8_b2_16", "x8_b1_24x40", "x4_b1_24", "x2_b1_32", "x3_b1_24"])
+@pytest.mark.parametrize("name", INIT_CASES + ["x8_b2_16", "x8_b1_24x40", "x4_b1_24", "x2_b1_32", "x3_b1_24"] + HR_CASES)
 def test_forward_matches_oracle_full_frame(name):
     """Full-resolution comparison + PSNR delta against the CPU oracle (itself pinned to the goldens)."""
     _z, meta = load_golden(name)
     tol = TOL_PIX if meta["init"] == "default" else stress_tol(np.abs(_z["pre_clamp"]).max())
     sd, (lq, depth, masks, gt) = case_tensors(meta)
+    if name in HR_CASES:
+        tol = hr_tol(meta, sd, lq, depth, masks)
     with torch.no_grad():
         ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=meta["scale"], which=meta["which"])
         sr = _build(meta, sd)(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
@@ -94,7 +111,7 @@ def test_forward_matches_oracle_full_frame(name):
     print("%s: max|sr-oracle|=%.4g  PSNR delta=%.5f dB (at %.1f dB)  PSNR(cuda, ref)=%.1f dB" % (
         name, err, dp, psnr(ref, near), direct))
     assert err <= tol
-    if meta["init"] == "default":        # north_star's configuration: the reference's own random init
+    if meta["init"] == "default" and name not in HR_CASES:   # north_star's configuration: the reference's own random init
         assert dp <= TOL_PSNR
         assert direct >= 48.0
     else:

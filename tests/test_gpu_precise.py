@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import (CASES, INIT_CASES, case_tensors, cuda_net as _net, cuda_train_grads as _train_grads, load_golden,
+from common import (CASES, HR_CASES, INIT_CASES, case_tensors, cuda_net as _net, cuda_train_grads as _train_grads, load_golden,
                     oracle, oracle_grads64 as _oracle_grads64, skip_grad_param as _skip_param)
 
 pytestmark = pytest.mark.gpu
@@ -56,7 +56,7 @@ def test_plane_split_is_exact_and_mode_switches_back(precise):
     assert torch.equal(L.act_value(out), x)
 
 
-@pytest.mark.parametrize("name", INIT_CASES + CASES)
+@pytest.mark.parametrize("name", INIT_CASES + CASES + HR_CASES)
 def test_precise_forward_matches_reference_fp32(name, precise):
     """north_star's fp32 bar: max-abs <= 1e-4 on [0,1] pixels against the golden recorded from the real reference."""
     z, meta = load_golden(name)
@@ -76,7 +76,7 @@ def test_precise_forward_matches_reference_fp32(name, precise):
     assert err_pre <= 1e-4 * max(1.0, np.abs(ref_pre).max())
 
 
-@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24", "x8_b2_32_init", "x8_b1_24x40"])
+@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24", "x8_b2_32_init", "x8_b1_24x40"] + HR_CASES)
 def test_precise_gradients_match_reference_fp64(name, precise):
     """Every parameter gradient of the full-depth network against fp64: relative L2 error <= 1e-4 per tensor, <= 1e-3
     for the one-element blend scalars.

@@ -4,10 +4,10 @@ import numpy as np
 import pytest
 import torch
 
-from common import CASES, INIT_CASES, case_tensors, load_golden, oracle
+from common import CASES, HR_CASES, INIT_CASES, case_tensors, load_golden, oracle
 
 
-@pytest.mark.parametrize("name", INIT_CASES + CASES)
+@pytest.mark.parametrize("name", INIT_CASES + CASES + HR_CASES)
 def test_oracle_forward_matches_reference(name):
     z, meta = load_golden(name)
     sd, (lq, depth, masks, gt) = case_tensors(meta)
@@ -22,12 +22,16 @@ def test_oracle_forward_matches_reference(name):
     np.testing.assert_allclose(cap["fea_bef"].numpy()[:, ::4], z["fea_bef"], atol=2e-5, rtol=1e-5)
     np.testing.assert_allclose(cap["depth-residual1.out"].numpy()[:, ::4], z["dgb1_out"], atol=2e-4, rtol=1e-4)
     np.testing.assert_allclose(cap["depth-residual13.out"].numpy()[:, ::4], z["dgb13_out"], atol=2e-3, rtol=1e-4)
+    for i in (15, 16):      # depth-guided blocks behind upscale1 / upscale2 (HR_CASES)
+        if "dgb%d_out" % i in z.files:
+            np.testing.assert_allclose(cap["depth-residual%d.out" % i].numpy()[:, ::4], z["dgb%d_out" % i], atol=2e-3,
+                                       rtol=1e-4)
     np.testing.assert_allclose(cap["pre_clamp"].numpy()[:, :, ::st, ::st], z["pre_clamp"], atol=1e-4, rtol=1e-4)
     # the tolerance north_star states for fp32: max-abs <= 1e-4 on [0,1] pixels
     assert np.abs(sr.numpy()[:, :, ::st, ::st] - z["sr"]).max() <= 1e-4
 
 
-@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24"])
+@pytest.mark.parametrize("name", ["x8_b2_16", "x4_b1_24", "x2_b1_32", "x3_b1_24"] + HR_CASES)
 def test_oracle_loss_and_gradients_match_reference(name):
     z, meta = load_golden(name)
     sd, (lq, depth, masks, gt) = case_tensors(meta)
