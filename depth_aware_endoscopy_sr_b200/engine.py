@@ -72,6 +72,8 @@ class Engine:
         # actv of the next SEAN instances is produced on a low-priority side stream while the trunk convolutions run
         # (it depends on the depth map only); three rotating buffers.  DASR_ACTV_OVERLAP=0 keeps one stream.
         self.actv_overlap = os.environ.get("DASR_ACTV_OVERLAP", "1") == "1"
+        # inference: the style-table chain on its own side stream beside the head convolutions (style_tables)
+        self.tables_overlap = os.environ.get("DASR_TABLES_OVERLAP", "1") == "1"
         self._side_streams = {}
         # Training backward: the weight gradients (leaves of the backward) are issued round-robin on side streams, so
         # their CTAs fill the wave tails of the data-gradient chain (256 tiles on 148 SMs at B=16) and their launch /
@@ -466,34 +468,58 @@ class Engine:
                            lambda: L.conv_fwd(x, pk.w, pk.bias, out, Cout=pk.cout, ks=pk.ks, epi=epi, act=act,
                                               subsample=subsample, **kw))
 
-    def style_tables(self, vec):
-        """The per-image dynamic-filter tables of ALL SEAN instances, two launches per width group:
-        stp[s] = A_i_j^(s)(depthVec) (dasr_style_mix_batched) and T[s] = alpha^(s) W_s^(s) . stp[s] (one 1x1
-        dasr_conv_fwd over the instances of the group with per-image weights).  Returns {group: (stp_all [nS,1,B*K,L],
-        table_all [nS,1,B*K,9*2nf], wdyn_all [nS,B*2nf,9*16])}; ``sean_tables(tables, n)`` picks instance ``n``."""
+    def style_tables(self, vec, side=None):
+        """The per-image dynamic-filter tables of ALL SEAN instances, three launches per width group:
+        stp[s] = A_i_j^(s)(depthVec) (dasr_style_mix_batched), T[s] = alpha^(s) W_s^(s) . stp[s] (one 1x1
+        dasr_conv_fwd over the instances of the group with per-image weights) and its GEMM-B form for the K-DYN
+        extension.  Returns {group: (stp_all [nS,1,B*K,L], table_all [nS,1,B*K,9*2nf], wdyn_all [nS,B*2nf,9*16])};
+        ``sean_tables(tables, n)`` picks instance ``n``.
+
+        ``side``: a stream to run the launches on (forked from the current stream here; the CALLER joins with
+        ``tables["ready"]`` before the first consumer).  The chain depends on the encoder output only, so in inference it
+        runs beside the head convolutions and the first trunk convolution instead of in front of them.  All buffers
+        are allocated on the current stream, like Engine._ActvPrefetch's."""
         lib = L.load()
         B, K, lat = vec.shape
-        s = L.stream_ptr()
         res = {}
+        bufs = []
         for grp in self._sean_groups:
             nS = len(grp.names)
             stp_all = L.act_empty(nS, 1, B * K, lat, device=vec.device)
-            self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp_all.numel() * 2,
-                        lambda: L.check(lib.dasr_style_mix_batched(L.ptr(vec), L.ptr(grp.A_ptrs), L.ptr(grp.a_ptrs),
-                                                                   L.ptr(stp_all), nS, B, K, lat, s)))
             table_all = L.act_empty(nS, 1, B * K, grp.ws_rows, device=vec.device)
-            self._timed("style_table_gemm", "tensor", 2.0 * nS * B * K * lat * grp.ws_rows,
-                        stp_all.numel() * 2 + table_all.numel() * 2 + grp.ws_all.numel() * 2,
-                        lambda: L.conv_fwd(stp_all, grp.ws_all, self._zero_bias, table_all, Cout=grp.ws_rows, ks=1,
-                                           w_img_rows=grp.ws_rows))
             # GEMM-B form of every table for the K-DYN extension of the SEAN GEMM: [nS][B*2nf][9*16]
-            nf2 = 2 * grp.nf
             # (fp32-split planes: the planes of an instance's filters sit inside its own slice -- see include/dasr.h)
-            wdyn_all = torch.empty(nS, L.planes(), B * nf2, 9 * 16, device=vec.device, dtype=BF16)
-            self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
-                        lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K, nf2, B,
-                                                                     s)))
+            wdyn_all = torch.empty(nS, L.planes(), B * 2 * grp.nf, 9 * 16, device=vec.device, dtype=BF16)
+            bufs.append((grp, stp_all, table_all, wdyn_all))
             res[grp] = (stp_all, table_all, wdyn_all[:, 0])
+
+        def launch():
+            s = L.stream_ptr()
+            for grp, stp_all, table_all, wdyn_all in bufs:
+                nS = len(grp.names)
+                self._timed("style_mix", "hbm", 0, vec.numel() * 4 + stp_all.numel() * 2,
+                            lambda: L.check(lib.dasr_style_mix_batched(L.ptr(vec), L.ptr(grp.A_ptrs), L.ptr(grp.a_ptrs),
+                                                                       L.ptr(stp_all), nS, B, K, lat, s)))
+                self._timed("style_table_gemm", "tensor", 2.0 * nS * B * K * lat * grp.ws_rows,
+                            stp_all.numel() * 2 + table_all.numel() * 2 + grp.ws_all.numel() * 2,
+                            lambda: L.conv_fwd(stp_all, grp.ws_all, self._zero_bias, table_all, Cout=grp.ws_rows, ks=1,
+                                               w_img_rows=grp.ws_rows))
+                self._timed("table_to_dynweights", "hbm", 0, table_all.numel() * 2 + wdyn_all.numel() * 2,
+                            lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K,
+                                                                         2 * grp.nf, B, s)))
+
+        if side is None:
+            launch()
+            return res
+        main = torch.cuda.current_stream(vec.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            launch()
+            ready = torch.cuda.Event()
+            ready.record(side)
+        res["ready"] = ready
         return res
 
     def sean_tables(self, tables, n: str):
@@ -729,7 +755,13 @@ class Engine:
             vec = torch.empty(B, K, lat, device=dev, dtype=torch.float32)
             L.check(lib.dasr_region_pool_fwd(L.ptr(e5), L.ptr(masks), L.ptr(vec), None, None, B, e5.shape[1],
                                              e5.shape[2], lat, K, h, w, s))
-            tables = self.style_tables(vec)
+            # the style-table chain (three small launches, ~130 us at B = 64) runs beside the head convolutions
+            tside = None
+            if self.tables_overlap and self.profile is None and cap is None:
+                tside = self._side_streams.get(("tables", dev.index))
+                if tside is None:
+                    tside = self._side_streams[("tables", dev.index)] = torch.cuda.Stream(device=dev)
+            tables = self.style_tables(vec, side=tside)
             mask16 = self.mask_context(depth, masks, h, w)["mask16"]
             if cap is not None:
                 labels = torch.empty(B, h, w, device=dev, dtype=torch.uint8)
@@ -755,6 +787,9 @@ class Engine:
         def run_block(i, x, x32):
             if i in net.which_ResBlk_depth:
                 p = "depth-residual%d" % (i + 1)
+                ready = tables.pop("ready", None)
+                if ready is not None:       # join the style-table side stream in front of the first SEAN instance
+                    torch.cuda.current_stream(dev).wait_event(ready)
                 if x.shape[1] != h or x.shape[2] != w:
                     # a depth-guided block above LR resolution: depth map and masks resized to its feature map
                     hr = self.mask_context(depth, masks, x.shape[1], x.shape[2])

@@ -231,5 +231,10 @@ wq, bq = pack9(w, b)
 out = torch.empty(64, 3, 512, 512, device=dev)
 ms = timeit(lambda: L.check(L.load().dasr_conv_out9(x.data_ptr(), wq.data_ptr(), bq.data_ptr(), out.data_ptr(), 64, 512, 512, 3, 1, L.stream_ptr())), n=5)
 print("time conv_out9 B64@512: %.3f ms (%.1f real TFLOP/s, %.0f GB/s algorithmic)" % (ms, 2.0 * 64 * 512 * 512 * 3 * 32 * 81 / ms / 1e9, (x.numel() * 2 + out.numel() * 4) / ms / 1e6))
+xt = x.permute(0, 3, 1, 2)          # NHWC storage viewed NCHW = channels_last
+wt = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+torch.backends.cudnn.benchmark = True
+ms2 = timeit(lambda: F.conv2d(xt, wt, None, padding=4), n=5)
+print("     cudnn bf16 channels_last 9x9 32->3   %.3f ms  %.1f TFLOP/s" % (ms2, 2.0 * 64 * 512 * 512 * 3 * 32 * 81 / ms2 / 1e9), flush=True)
 
 print("ALL PASS" if allok else "SOME FAILED")
