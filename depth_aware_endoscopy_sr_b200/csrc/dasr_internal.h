@@ -48,7 +48,7 @@ int num_sms();
 #define DASR_PAIR_STATS 2
 #define DASR_PAIR_OUT9 4
 #ifndef DASR_PAIR_DEFAULT
-#define DASR_PAIR_DEFAULT 5      /* SEAN + conv_out9; the trunk (STATS) pair kernel is faster alone but slower beside the side-stream actv kernel */
+#define DASR_PAIR_DEFAULT 7      /* all three; measured through bench.py (two alternating runs each): mask 7 5.68 ms per step, mask 5 (no trunk pair kernel) 5.70 ms, trunk conv 34 vs 37 us per launch; equal in the power-bound steady state */
 #endif
 bool pair_kernels_enabled(int which);
 void count_launch();   // bumps the counter behind dasr_launch_count()
