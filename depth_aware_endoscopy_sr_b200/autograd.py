@@ -532,6 +532,7 @@ class _DepthNetFn(torch.autograd.Function):
         masks = masks.detach().contiguous().float()
         eng.pack(training=True, force=eng.always_pack)
         sr, tp = _forward_train(eng, lq, depth, masks)
+        eng.wait_pack_bwd()       # the dgrad weight copies were packed beside this forward (Engine.pack)
         ctx.eng = eng
         ctx.tape = tp
         ctx.n_params = len(params)
@@ -544,6 +545,7 @@ class _DepthNetFn(torch.autograd.Function):
             raise RuntimeError("DepthNet backward called twice (activations are released after the first pass)")
         ctx.tape = None
         dsr = dsr.contiguous().float()
+        eng.wait_pack_bwd()
         tp.begin_backward(dsr.device)
         eng._begin_backward(dsr.device)
         tp.bwd_out(dsr)

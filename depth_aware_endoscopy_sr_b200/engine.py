@@ -74,6 +74,9 @@ class Engine:
         self.actv_overlap = os.environ.get("DASR_ACTV_OVERLAP", "1") == "1"
         # inference: the style-table chain on its own side stream beside the head convolutions (style_tables)
         self.tables_overlap = os.environ.get("DASR_TABLES_OVERLAP", "1") == "1"
+        # captured training step: the data-gradient weight copies are packed on a side stream beside the forward
+        self.pack_overlap = os.environ.get("DASR_PACK_OVERLAP", "1") == "1"
+        self._pack_bwd_ready = None
         self._side_streams = {}
         # Training backward: the weight gradients (leaves of the backward) are issued round-robin on side streams, so
         # their CTAs fill the wave tails of the data-gradient chain (256 tiles on 148 SMs at B=16) and their launch /
@@ -303,6 +306,7 @@ class Engine:
         self._unpack_specs.append(dict(kind="out9"))
         self._used_params.update(["conv_output.weight", "conv_output.bias"])
         self._scratch = torch.zeros(max(rows_total, rows_bwd), device=device, dtype=torch.float32)
+        self._scratch_bwd = torch.zeros(max(rows_bwd, 1), device=device, dtype=torch.float32)
         self._dw_flat = None          # allocated on the first backward
         self._unpack_descs = None
         self._zero_bias = torch.zeros(9 * 2 * 64, device=device, dtype=torch.float32)
@@ -331,8 +335,30 @@ class Engine:
             L.pack_weights(self._descs, self._scratch)
             self._key = key
         if training and key != self._key_bwd:
-            L.pack_weights(self._descs_bwd, self._scratch)
+            # the data-gradient copies are first read by the backward: inside the captured training step they are packed
+            # on a side stream beside the forward (65 us at x8) and joined by wait_pack_bwd() at the end of the forward
+            self._pack_bwd_ready = None
+            if self.pack_overlap and torch.cuda.is_current_stream_capturing():
+                side = self._side_streams.get(("pack", device.index))
+                if side is None:
+                    side = self._side_streams[("pack", device.index)] = torch.cuda.Stream(device=device)
+                fork = torch.cuda.Event()
+                fork.record(torch.cuda.current_stream(device))
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    L.pack_weights(self._descs_bwd, self._scratch_bwd)
+                    self._pack_bwd_ready = torch.cuda.Event()
+                    self._pack_bwd_ready.record(side)
+            else:
+                L.pack_weights(self._descs_bwd, self._scratch_bwd)
             self._key_bwd = key
+
+    def wait_pack_bwd(self):
+        """The current stream waits for the data-gradient weight copies packed on the side stream (see pack)."""
+        ev = getattr(self, "_pack_bwd_ready", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._pack_bwd_ready = None
 
     # ------------------------------------------------------------------------------------------ backward support
     def _dw_view(self, name):
