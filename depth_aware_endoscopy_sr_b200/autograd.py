@@ -402,7 +402,13 @@ def _forward_train(eng, lq, depth, masks):
             tp.accum(e5, de5)
 
         tp.ops.append(bwd_pool)
-        tables = eng.style_tables(vec)
+        # (inside the captured step the style-table chain runs on its own side stream beside the head convolutions)
+        tside = None
+        if eng.tables_overlap and torch.cuda.is_current_stream_capturing():
+            tside = eng._side_streams.get(("tables", dev.index))
+            if tside is None:
+                tside = eng._side_streams[("tables", dev.index)] = torch.cuda.Stream(device=dev)
+        tables = eng.style_tables(vec, side=tside)
         dT_all = {g: torch.zeros(len(g.names), B * K, g.ws_rows, device=dev, dtype=torch.float32)
                   for g in eng._sean_groups}
         scr_all = {g: torch.zeros(len(g.names), 2 * g.nf, 9 * L.AUX_CH, device=dev, dtype=torch.float32)
@@ -441,6 +447,9 @@ def _forward_train(eng, lq, depth, masks):
 
     def run_block(i, x):
         if i in net.which_ResBlk_depth:
+            ready = tables.pop("ready", None)
+            if ready is not None:       # join the style-table side stream in front of the first SEAN instance
+                torch.cuda.current_stream(dev).wait_event(ready)
             res = (x.data.shape[1], x.data.shape[2])
             if res not in ctxs:
                 # a depth-guided block above LR resolution: depth map and masks resized to its feature map

@@ -534,7 +534,7 @@ class Engine:
                             lambda: L.check(lib.dasr_table_to_dynweights(L.ptr(table_all), L.ptr(wdyn_all), nS * B, K,
                                                                          2 * grp.nf, B, s)))
 
-        if side is None:
+        if side is None or not bufs:
             launch()
             return res
         main = torch.cuda.current_stream(vec.device)
