@@ -74,6 +74,7 @@ def load() -> C.CDLL:
         "dasr_get_planes": [],
         "dasr_conv_fwd": [C.POINTER(ConvDesc), C.POINTER(ConvArgs), vp],
         "dasr_conv_out9": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+        "dasr_conv_out9_frames": [vp, vp, vp, vp, i32, i32, i32, C.c_float, C.c_float, vp],
         "dasr_conv_wgrad": [C.POINTER(WgradDesc), vp, vp, vp, vp, vp],
         "dasr_pack_weights": [C.POINTER(PackDesc), i32, vp, vp],
         "dasr_conv_first": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
@@ -133,7 +134,7 @@ def load() -> C.CDLL:
     return lib
 
 
-EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_set_planes", "dasr_get_planes", "dasr_set_sean_pair", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_gen_ok", "dasr_conv_out9", "dasr_conv_wgrad", "dasr_pack_weights",
+EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_device", "dasr_set_planes", "dasr_get_planes", "dasr_set_sean_pair", "dasr_conv_fwd", "dasr_conv_stats_slots", "dasr_conv_gen_ok", "dasr_conv_out9", "dasr_conv_out9_frames", "dasr_conv_wgrad", "dasr_pack_weights",
             "dasr_conv_first", "dasr_zero_insert2", "dasr_add", "dasr_region_pool_fwd", "dasr_mask_labels",
             "dasr_actv_fwd", "dasr_style_mix", "dasr_dynconv_fwd", "dasr_instats_finalize", "dasr_unpack_grads",
             "dasr_sean_bwd_slots", "dasr_sean_bwd1", "dasr_sean_bwd2", "dasr_colsum",

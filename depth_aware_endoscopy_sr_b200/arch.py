@@ -213,9 +213,10 @@ class DepthNet(nn.Module):
           ``LQGTKerDepthDataset.getDepthMask(depth, depthFixedRange, depthRangeNum)`` of the data pipeline
           (codes/data/LQGTker_Depth_dataset.py:157,204-226; bit-exact) -- so only the LR frame and its depth map
           (4 fp32 planes instead of 14) have to be uploaded;
-        * ``out="uint8"``: the SR tensor goes through ``io.tensor2img`` (``util.tensor2img`` as codes/test.py:87 calls
-          it: clamp, x255, round, uint8, RGB->BGR, HWC; bit-exact) and the ``[B, sH, sW, 3]`` uint8 frames are returned
-          -- a quarter of the bytes of the fp32 tensor; ``out="float"`` returns what ``forward`` returns.
+        * ``out="uint8"``: ``util.tensor2img`` as codes/test.py:87 calls it (clamp, x255, round, uint8, RGB->BGR, HWC;
+          bit-exact) runs in the store of the output convolution and the ``[B, sH, sW, 3]`` uint8 frames are returned
+          -- a quarter of the bytes of the fp32 tensor, which is never written; ``out="float"`` returns what ``forward``
+          returns.
 
         Inference only (no autograd); frames are independent, so a stream is sharded over GPUs by frame
         (``parallel.shard_frames``) with no collective."""
@@ -224,5 +225,6 @@ class DepthNet(nn.Module):
             raise ValueError("out must be 'uint8' or 'float'")
         if depthMask is None:
             depthMask, _labels = _io.depth_masks(depthMap, self.depthRangeNum, fixed_range=depthFixedRange)
-        sr = self.engine().infer(input, depthMap, depthMask)
-        return _io.tensor2img(sr, (self.min, self.max)) if out == "uint8" else sr
+        # uint8: tensor2img is fused into the store of the output convolution (dasr_conv_out9_frames; bit-identical to
+        # io.tensor2img of the fp32 tensor, which then never exists in HBM)
+        return self.engine().infer(input, depthMap, depthMask, frames=(out == "uint8"))

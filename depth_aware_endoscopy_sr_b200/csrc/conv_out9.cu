@@ -45,10 +45,27 @@ struct Out9K {
     int clamp01;
     const float* bias;
     float* out;
+    // frame output (dasr_conv_out9_frames): tensor2img of the clamped value fused into the store -- uint8 BGR HWC
+    uint8_t* out_u8;
+    float lo, hi;
     // fp32-split planes (dasr_internal.h): cross terms of the x / weight planes, a_stages patch buffers
     int npl, n_terms, a_stages;
     unsigned char ta[6], tb[6];
 };
+
+// util.tensor2img (codes/utils/util.py:566-590) of one pixel, fused into the output store: clamp to [lo, hi], scale to
+// [0, 255], round half to even, RGB -> BGR.  The same fp32 operations, in the same order, as tensor2img_kernel (io.cu),
+// so the fused frames are bit-identical to conv_out9 followed by dasr_tensor2img.
+__device__ __forceinline__ void store_frame_pixel(uint8_t* d, float r, float g, float b, float lo, float hi) {
+    const float inv = hi - lo;
+    const float v[3] = {r, g, b};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float x = fminf(fmaxf(v[c], lo), hi);
+        x = __fdiv_rn(__fsub_rn(x, lo), inv);
+        d[2 - c] = (uint8_t)__float2int_rn(__fmul_rn(x, 255.0f));
+    }
+}
 
 // PL: the fp32-split planes form (dasr_set_planes > 1; test infrastructure).  A template parameter so that the product
 // kernel keeps compile-time stage counts (with run-time ones it went from 515 to 565 us at batch 64).
@@ -194,6 +211,9 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         o1 += zp[1];
                         o2 += zp[2];
                     }
+                    if (p.out_u8) {
+                        store_frame_pixel(p.out_u8 + ((size_t)img * plane + (size_t)h * p.W + w) * 3, o0, o1, o2, p.lo, p.hi);
+                    } else {
                     if (p.clamp01) {
                         o0 = fminf(fmaxf(o0, 0.f), 1.f);
                         o1 = fminf(fmaxf(o1, 0.f), 1.f);
@@ -203,6 +223,7 @@ conv_out9_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                     op[0] = o0;
                     if (p.Cout > 1) op[plane] = o1;
                     if (p.Cout > 2) op[2 * plane] = o2;
+                    }
                 }
             }
             tc_fence_before();
@@ -360,6 +381,9 @@ conv_out9_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                         o1 += zp[1];
                         o2 += zp[2];
                     }
+                    if (p.out_u8) {
+                        store_frame_pixel(p.out_u8 + ((size_t)img * plane + (size_t)h * p.W + w) * 3, o0, o1, o2, p.lo, p.hi);
+                    } else {
                     if (p.clamp01) {
                         o0 = fminf(fmaxf(o0, 0.f), 1.f);
                         o1 = fminf(fmaxf(o1, 0.f), 1.f);
@@ -369,6 +393,7 @@ conv_out9_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
                     op[0] = o0;
                     if (p.Cout > 1) op[plane] = o1;
                     if (p.Cout > 2) op[2 * plane] = o2;
+                    }
                 }
             }
             tc_fence_before();
@@ -387,11 +412,11 @@ conv_out9_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
 
 using namespace dasr;
 
-extern "C" int dasr_conv_out9(const void* x, const void* wq, const float* bias, float* out, int B, int H, int W,
-                              int Cout, int clamp01, void* stream_) {
+static int conv_out9_launch(const void* x, const void* wq, const float* bias, float* out, uint8_t* out_u8, float lo,
+                            float hi, int B, int H, int W, int Cout, int clamp01, void* stream_) {
     using namespace out9;
     cudaStream_t stream = (cudaStream_t)stream_;
-    DASR_REQUIRE(x && wq && bias && out, "null tensor pointer");
+    DASR_REQUIRE(x && wq && bias && (out || out_u8), "null tensor pointer");
     DASR_REQUIRE(B > 0 && H > 0 && W > 0 && Cout == 3, "bad shape (the output conv has Cout == 3)");
     Out9K k;
     k.B = B; k.H = H; k.W = W; k.Cout = Cout;
@@ -401,6 +426,9 @@ extern "C" int dasr_conv_out9(const void* x, const void* wq, const float* bias, 
     k.clamp01 = clamp01;
     k.bias = bias;
     k.out = out;
+    k.out_u8 = out_u8;
+    k.lo = lo;
+    k.hi = hi;
     k.npl = planes();
     k.a_stages = k.npl > 1 ? 1 : 2;
     {
@@ -464,4 +492,16 @@ extern "C" int dasr_conv_out9(const void* x, const void* wq, const float* bias, 
     else conv_out9_kernel<false><<<grid, kThreads, SMEM_BYTES, stream>>>(mA, mW, k);
     DASR_LAUNCH_OK();
     return DASR_OK;
+}
+
+extern "C" int dasr_conv_out9(const void* x, const void* wq, const float* bias, float* out, int B, int H, int W,
+                              int Cout, int clamp01, void* stream) {
+    DASR_REQUIRE(out, "null tensor pointer");
+    return conv_out9_launch(x, wq, bias, out, nullptr, 0.f, 1.f, B, H, W, Cout, clamp01, stream);
+}
+
+extern "C" int dasr_conv_out9_frames(const void* x, const void* wq, const float* bias, uint8_t* img, int B, int H, int W,
+                                     float lo, float hi, void* stream) {
+    DASR_REQUIRE(img && hi > lo, "bad arguments");
+    return conv_out9_launch(x, wq, bias, nullptr, img, lo, hi, B, H, W, 3, 0, stream);
 }

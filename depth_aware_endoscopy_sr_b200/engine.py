@@ -707,18 +707,20 @@ class Engine:
 
     @torch.no_grad()
     def infer(self, lq: torch.Tensor, depth: torch.Tensor, masks: torch.Tensor, cap: dict = None,
-              clamp: bool = True) -> torch.Tensor:
+              clamp: bool = True, frames: bool = False) -> torch.Tensor:
         """Inference.  A forward is ~100 kernel launches; issued from Python that is 2.7 ms of host time, more than
         the kernels of a single 1080p frame need (1.5 ms), so for small batches (``graph_max_pixels``) the schedule is
         replayed from a CUDA graph from the third call with the same input shape on (static input / output buffers;
         the result is returned as a copy): 2.7 -> 0.85 ms per 64x64 frame, 2.7 -> 1.3 ms per 1080p frame.  ``cap`` /
-        ``profile`` / an ongoing stream capture use the kernel-by-kernel schedule."""
+        ``profile`` / an ongoing stream capture use the kernel-by-kernel schedule.
+        ``frames``: return uint8 BGR frames [B, sH, sW, 3] -- ``util.tensor2img`` fused into the store of the output
+        convolution (dasr_conv_out9_frames) -- instead of the fp32 SR tensor."""
         if (not self.use_graphs or cap is not None or self.profile is not None or not lq.is_cuda or L.planes() > 1
                 or lq.shape[0] * lq.shape[2] * lq.shape[3] > self.graph_max_pixels
                 or torch.cuda.is_current_stream_capturing()):
-            return self._infer_eager(lq, depth, masks, cap=cap, clamp=clamp)
+            return self._infer_eager(lq, depth, masks, cap=cap, clamp=clamp, frames=frames)
         self.pack()
-        key = (tuple(lq.shape), tuple(masks.shape), lq.device.index, bool(clamp), self.fp32_residual)
+        key = (tuple(lq.shape), tuple(masks.shape), lq.device.index, bool(clamp), self.fp32_residual, bool(frames))
         if self._graph_state != self._key:            # parameters changed: every recorded schedule is stale
             self._graphs.clear()
             self._graph_state = self._key
@@ -730,14 +732,14 @@ class Engine:
         ent["calls"] += 1
         if ent["graph"] is None:
             if ent["calls"] <= 2:
-                return self._infer_eager(lq, depth, masks, clamp=clamp)
+                return self._infer_eager(lq, depth, masks, clamp=clamp, frames=frames)
             ins = [torch.empty(t.shape, device=t.device, dtype=torch.float32) for t in (lq, depth, masks)]
             for d, src in zip(ins, (lq, depth, masks)):
                 d.copy_(src)
             g = torch.cuda.CUDAGraph()
             n0 = int(L.load().dasr_launch_count())
             with torch.cuda.graph(g):
-                out = self._infer_eager(*ins, clamp=clamp)
+                out = self._infer_eager(*ins, clamp=clamp, frames=frames)
             ent.update(graph=g, ins=ins, out=out, launches=int(L.load().dasr_launch_count()) - n0)
         for d, src in zip(ent["ins"], (lq, depth, masks)):
             d.copy_(src)
@@ -747,7 +749,7 @@ class Engine:
 
     @torch.no_grad()
     def _infer_eager(self, lq: torch.Tensor, depth: torch.Tensor, masks: torch.Tensor, cap: dict = None,
-                     clamp: bool = True) -> torch.Tensor:
+                     clamp: bool = True, frames: bool = False) -> torch.Tensor:
         """Inference schedule, kernel by kernel.  ``cap`` (tests only) receives intermediate tensors in the engine's
         own layouts (NHWC bf16 activations); ``clamp=False`` returns the pre-clamp output of conv_output."""
         net = self.net
@@ -852,13 +854,20 @@ class Engine:
             L.check(lib.dasr_pixel_shuffle(L.ptr(u), L.ptr(x), B, u.shape[1], u.shape[2], u.shape[3] // 9, 3, s))
         else:
             x = self._conv(x, "upscale3.0", epi=L.EPI_SHUFFLE2, act=L.ACT_LRELU)
-        out = torch.empty(B, 3, x.shape[1], x.shape[2], device=dev, dtype=torch.float32)
         if net.min != 0.0 or net.max != 1.0:
             raise NotImplementedError("the fused output epilogue clamps to [0,1] (the only range define_G builds)")
         if cap is not None:
             cap["feat_up3"] = x
         pk = self._packed["conv_output"]
         Bo, Ho, Wo, _ = x.shape
+        if frames:
+            # conv_output + clamp + util.tensor2img in one kernel: no fp32 frames in HBM
+            out = torch.empty(B, Ho, Wo, 3, device=dev, dtype=torch.uint8)
+            self._timed("conv_out9", "tensor", 2.0 * Bo * Ho * Wo * 3 * 32 * 81, x.numel() * 2 + out.numel(),
+                        lambda: L.check(lib.dasr_conv_out9_frames(L.ptr(x), L.ptr(pk.w), L.ptr(pk.bias), L.ptr(out), Bo, Ho,
+                                                                  Wo, float(net.min), float(net.max), s)))
+            return out
+        out = torch.empty(B, 3, Ho, Wo, device=dev, dtype=torch.float32)
         # algorithmic bytes: read feat_up3 once + write the fp32 frames
         self._timed("conv_out9", "tensor", 2.0 * Bo * Ho * Wo * 3 * 32 * 81, x.numel() * 2 + out.numel() * 4,
                     lambda: L.check(lib.dasr_conv_out9(L.ptr(x), L.ptr(pk.w), L.ptr(pk.bias), L.ptr(out), Bo, Ho, Wo, 3,

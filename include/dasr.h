@@ -156,6 +156,12 @@ int dasr_conv_wgrad(const dasr_wgrad_desc* d, const void* dy, const void* x, flo
  * out NCHW fp32 [B,3,H,W] = clamp01 ? clamp(conv + bias, 0, 1) : conv + bias                          */
 int dasr_conv_out9(const void* x, const void* wq, const float* bias, float* out, int B, int H, int W,
                    int Cout, int clamp01, void* stream);
+/* The same convolution with util.tensor2img (codes/utils/util.py:566-590, as codes/test.py:87 calls it) fused into
+ * the store: img u8 [B,H,W,3] BGR = round_half_even((clamp(conv + bias, lo, hi) - lo) / (hi - lo) * 255) -- bit-identical
+ * to dasr_conv_out9 followed by dasr_tensor2img, without the fp32 frames in HBM (201 MB written and read back per
+ * 64-frame batch).                                                                                              */
+int dasr_conv_out9_frames(const void* x, const void* wq, const float* bias, uint8_t* img, int B, int H, int W,
+                          float lo, float hi, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight preparation: weight-norm (w = g*v/||v||, sftmd_arch.py:740,851), alpha folding and repacking

@@ -56,9 +56,11 @@ def test_psnr_and_ssim_match_the_reference_functions(gold):
     assert abs(bio.ssim(x.cuda(), gt.cuda()).item() - gold["ssim_mean"][0]) <= 2e-5
 
 
-def test_infer_frames_builds_masks_and_uint8_frames_on_the_device():
-    """net.infer_frames(LQ, Depth): getDepthMask and tensor2img run on the device around the generator -- the frames
-    equal tensor2img(net(LQ, Depth, host-built masks)) bit for bit, only 4 of the 14 input planes are uploaded."""
+@pytest.mark.parametrize("B", [3, 1])       # 3: conv_output on CTA pairs, 1: the single-CTA kernel
+def test_infer_frames_builds_masks_and_uint8_frames_on_the_device(B):
+    """net.infer_frames(LQ, Depth): getDepthMask runs on the device in front of the generator and tensor2img inside the
+    store of its output convolution (dasr_conv_out9_frames) -- the frames equal tensor2img(net(LQ, Depth, host-built
+    masks)) bit for bit, only 4 of the 14 input planes are uploaded and the fp32 frames are never written."""
     import warnings
     import depth_aware_endoscopy_sr_b200 as dasr
     from depth_aware_endoscopy_sr_b200 import io as bio
@@ -67,11 +69,11 @@ def test_infer_frames_builds_masks_and_uint8_frames_on_the_device():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         net = dasr.DepthNet(which_ResBlk_depth=list(range(14)), scale=8, nb=16).cuda().eval()
-    lq, depth, masks = [t.cuda() for t in synthetic_inputs(3, 24, 40, scale=8, seed=6)]
+    lq, depth, masks = [t.cuda() for t in synthetic_inputs(B, 24, 40, scale=8, seed=6)]
     with torch.no_grad():
         ref = bio.tensor2img(net(lq, depth, masks))
     frames = net.infer_frames(lq, depth)
-    assert frames.dtype == torch.uint8 and tuple(frames.shape) == (3, 192, 320, 3)
+    assert frames.dtype == torch.uint8 and tuple(frames.shape) == (B, 192, 320, 3)
     assert torch.equal(frames, ref)
     sr = net.infer_frames(lq, depth, out="float")
     with torch.no_grad():
