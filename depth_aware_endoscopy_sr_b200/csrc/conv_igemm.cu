@@ -503,7 +503,9 @@ __device__ __forceinline__ void sean_epilogue_tile(const ConvK& p, const SeanTil
 // sum of squares of the STORED values over this warp's 32 rows of BOTH M blocks in registers; one butterfly reduction
 // per 16-column chunk and tile (v1 reduced every M block separately: twice the shuffles on the critical epilogue).
 // (EW = epilogue warps per TMEM lane quadrant: warp `half` of a quadrant takes the 16-column chunks half, half + EW, ...)
-template <int N_TILE, int NB, bool PREC, int EW = 2>
+// (UNROLL: the pair kernel unrolls the chunk loop, so that the butterflies of one chunk overlap the TMEM load, the store
+// and the accumulation of the next -- each is a latency chain of its own)
+template <int N_TILE, int NB, bool PREC, int EW = 2, bool UNROLL = false>
 __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, const float* bias_t, float* red_s, int img,
                                                int q0, int w0, int nt, int m, int half, int ew, int lane) {
     if (half * 16 >= N_TILE) return;
@@ -518,8 +520,11 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
         valid[blk] = (h < p.H) && (wl < p.Wt) && (w < p.W);
         pix[blk] = ((size_t)img * p.H + h) * p.W + w;
     }
-#pragma unroll 1
-    for (int c0 = half * 16; c0 < N_TILE; c0 += 16 * EW) {
+    constexpr int NCHUNK = (N_TILE + 16 * EW - 1) / (16 * EW);
+#pragma unroll(UNROLL ? NCHUNK : 1)
+    for (int ck = 0; ck < NCHUNK; ck++) {
+        const int c0 = half * 16 + ck * 16 * EW;
+        if (c0 >= N_TILE) break;
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) s1[j] = s2[j] = 0.f;
@@ -547,8 +552,10 @@ __device__ __forceinline__ void stats_epilogue(const ConvK& p, uint32_t t_acc, c
                 }
             }
         }
+        if (!DBG(p, 4)) {
         warp_colsum16(s1, lane);
         warp_colsum16(s2, lane);
+        }
         if (!(lane & 1)) {
             const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
             // per-tile partials of this warp's row quadrant: (ew, column) has exactly one owner lane -> deterministic
@@ -1558,7 +1565,10 @@ sean_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // 16 epilogue warps (4 per TMEM lane quadrant, one 16-column chunk each at N = 64): with the MMA time halved the
 // statistics epilogue became the critical path (in-kernel accounting: 5.3 k cycles per tile with 8 warps against 3.3 k
 // of MMA); its cost is the latency chain TMEM load -> round -> store -> butterfly, so more warps shorten it.
-constexpr int kStatsPairEW = 2;
+#ifndef DASR_STATS_PAIR_EW
+#define DASR_STATS_PAIR_EW 2
+#endif
+constexpr int kStatsPairEW = DASR_STATS_PAIR_EW;
 constexpr int kStatsPairThreads = 128 + 128 * kStatsPairEW;
 template <int N_TILE, int NB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kStatsPairThreads, 1)
@@ -1709,13 +1719,13 @@ stats_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             PROF_LAP(0);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + buf * ACC_COLS + (uint32_t(ew * 32) << 16);
-            if (have) stats_epilogue<N_TILE, NB, false, kStatsPairEW>(p, t_acc, bias_s, norm_s, img, q0, w0, 0, m, half, ew, lane);
+            if (have) stats_epilogue<N_TILE, NB, false, kStatsPairEW, true>(p, t_acc, bias_s, norm_s, img, q0, w0, 0, m, half, ew, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[buf]), 0));
             // one statistics slot per (image, tile): the four row quadrants are added in a fixed order
-            asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kStatsPairEW) : "memory");
-            if (et < N_TILE && have) {
+            if (!DBG(p, 16)) asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kStatsPairEW) : "memory");
+            if (et < N_TILE && have && !DBG(p, 8)) {
                 float a1 = 0.f, a2 = 0.f;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -1726,7 +1736,7 @@ stats_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 float2* sp = reinterpret_cast<float2*>(p.stats) + ((size_t)img * p.nslots + slot) * p.Cout + et;
                 *sp = make_float2(a1, a2);
             }
-            asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kStatsPairEW) : "memory");
+            if (!DBG(p, 16)) asm volatile("bar.sync 1, %0;\n" ::"n"(128 * kStatsPairEW) : "memory");
         }
         PROF_LAP(1);
 #ifdef DASR_PROFILE
