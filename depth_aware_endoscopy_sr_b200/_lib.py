@@ -92,6 +92,7 @@ def load() -> C.CDLL:
         "dasr_table_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_style_mix_bwd": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "dasr_table_bwd_batched": [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
+        "dasr_table_bwd_parts": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
         "dasr_style_mix_bwd_batched": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_region_pool_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
         "dasr_actv_bwd": [vp, vp, vp, vp, i32, i32, i32, i32, vp],
@@ -141,7 +142,7 @@ EXPORTED = ["dasr_last_error", "dasr_version", "dasr_launch_count", "dasr_check_
             "dasr_dynconv_bwd", "dasr_table_bwd", "dasr_style_mix_bwd", "dasr_region_pool_bwd", "dasr_actv_bwd",
             "dasr_unshuffle_actgrad", "dasr_pixel_shuffle", "dasr_out9_bwd_prep", "dasr_nchw3_to_nhwc32", "dasr_actgrad",
             "dasr_zero_insert2_to", "dasr_loss_rows", "dasr_loss_fwd", "dasr_loss_finalize", "dasr_loss_bwd",
-            "dasr_adam_step", "dasr_table_bwd_batched", "dasr_style_mix_bwd_batched", "dasr_build_aux", "dasr_build_mask16", "dasr_table_to_dynweights", "dasr_depth_masks", "dasr_tensor2img", "dasr_nearest_up", "dasr_sqdiff_u8", "dasr_psnr_u8", "dasr_ssim_tiles", "dasr_ssim", "dasr_style_mix_batched", "dasr_dynconv_bwd_tc", "dasr_actv_bwd_tc"]
+            "dasr_adam_step", "dasr_table_bwd_batched", "dasr_table_bwd_parts", "dasr_style_mix_bwd_batched", "dasr_build_aux", "dasr_build_mask16", "dasr_table_to_dynweights", "dasr_depth_masks", "dasr_tensor2img", "dasr_nearest_up", "dasr_sqdiff_u8", "dasr_psnr_u8", "dasr_ssim_tiles", "dasr_ssim", "dasr_style_mix_batched", "dasr_dynconv_bwd_tc", "dasr_actv_bwd_tc"]
 AUX_CH = 32
 LOSS_KMAX, LOSS_ROW = 16, 36
 

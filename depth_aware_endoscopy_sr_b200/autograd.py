@@ -393,8 +393,13 @@ def _forward_train(eng, lq, depth, masks):
                 N = grp.ws_rows
                 dWs_all = eng._dw_flat[grp.wg_tables_off:grp.wg_tables_off + nS * N * lat]
                 dstp_all = torch.empty(nS, B * K, lat, device=dev, dtype=torch.float32)
-                L.check(lib.dasr_table_bwd_batched(L.ptr(dT_all[grp]), L.ptr(tables[grp][0]), L.ptr(grp.ws_all),
-                                                   L.ptr(dWs_all), L.ptr(dstp_all), nS, B * K, N, lat, tp.s))
+                # the weight gradient dWs only reaches parameter gradients: a leaf (side stream); the data gradient dstp
+                # feeds the A_i_j / encoder chain on the main stream
+                with tp.leaf(dT_all[grp], tables[grp][0]) as s2:
+                    L.check(lib.dasr_table_bwd_parts(L.ptr(dT_all[grp]), L.ptr(tables[grp][0]), None, L.ptr(dWs_all), None,
+                                                     nS, B * K, N, lat, 1, s2))
+                L.check(lib.dasr_table_bwd_parts(L.ptr(dT_all[grp]), None, L.ptr(grp.ws_all), None, L.ptr(dstp_all), nS,
+                                                 B * K, N, lat, 2, tp.s))
                 L.check(lib.dasr_style_mix_bwd_batched(L.ptr(dstp_all), L.ptr(vec), L.ptr(grp.A_ptrs), L.ptr(grp.dA_ptrs),
                                                        L.ptr(grp.da_ptrs), L.ptr(dvec), nS, B, K, lat, tp.s))
             de5 = L.act_like(e5.data)

@@ -736,30 +736,45 @@ extern "C" int dasr_dynconv_bwd(const void* dgb, const uint8_t* labels, const fl
 }
 
 // nS independent instances in one call (strides between instances: dT BK*N, stp BK*L, Ws / dWs N*L, dstp BK*L)
+// parts: 1 = the weight gradient dWs only, 2 = the data gradient dstp only, 3 = both.  dWs only reaches parameter
+// gradients (a leaf of the backward: the training step runs it on a side stream), dstp feeds the A_i_j / encoder chain.
+extern "C" int dasr_table_bwd_parts(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int nS,
+                                    int BK, int N, int L, int parts, void* stream) {
+    DASR_REQUIRE(dT && nS > 0 && (parts & 3) && !(parts & ~3), "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (parts & 1) {
+        DASR_REQUIRE(stp && dWs, "bad arguments");
+        // dWs [N][L] = dT^T [N][BK] * stp [BK][L]
+        gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, nS), 256, 0, st>>>(
+            dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0, 1, (long long)BK * N, (long long)BK * L,
+            (long long)N * L, planes(), (size_t)nS * BK * L);
+        DASR_LAUNCH_OK();
+    }
+    if (parts & 2) {
+        DASR_REQUIRE(Ws && dstp, "bad arguments");
+        // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles per instance -> split the reduction over N
+        const int tiles = ((L + 63) / 64) * ((BK + 63) / 64) * nS;
+        // ~8 resident blocks per SM: the kernel has no software pipelining, so it needs the warps to hide its load
+        // latency (2 blocks per SM: 147 us for the 26 instances of a training step at B = 16; 8: 110 - 135 us)
+        int splits = (8 * num_sms() + tiles - 1) / tiles;
+        if (splits > (N + 63) / 64) splits = (N + 63) / 64;
+        if (splits < 1) splits = 1;
+        const int kps = (((N + splits - 1) / splits) + 15) / 16 * 16;
+        splits = (N + kps - 1) / kps;
+        DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)nS * BK * L * sizeof(float), st));
+        gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, nS * splits), 256, 0, st>>>(
+            dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1, splits, (long long)BK * N, (long long)N * L,
+            (long long)BK * L, planes(), (size_t)nS * N * L);
+        DASR_LAUNCH_OK();
+    }
+    return DASR_OK;
+}
+
+// nS independent instances in one call (strides between instances: dT BK*N, stp BK*L, Ws / dWs N*L, dstp BK*L)
 extern "C" int dasr_table_bwd_batched(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int nS,
                                       int BK, int N, int L, void* stream) {
     DASR_REQUIRE(dT && stp && Ws && dWs && dstp && nS > 0, "bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    // dWs [N][L] = dT^T [N][BK] * stp [BK][L]
-    gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, nS), 256, 0, st>>>(
-        dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0, 1, (long long)BK * N, (long long)BK * L,
-        (long long)N * L, planes(), (size_t)nS * BK * L);
-    DASR_LAUNCH_OK();
-    // dstp [BK][L] = dT [BK][N] * Ws [N][L]; few output tiles per instance -> split the reduction over N
-    const int tiles = ((L + 63) / 64) * ((BK + 63) / 64) * nS;
-    // ~8 resident blocks per SM: the kernel has no software pipelining, so it needs the warps to hide its load latency
-    // (2 blocks per SM: 147 us for the 26 instances of a training step at B = 16; 8: 110 - 135 us)
-    int splits = (8 * num_sms() + tiles - 1) / tiles;
-    if (splits > (N + 63) / 64) splits = (N + 63) / 64;
-    if (splits < 1) splits = 1;
-    const int kps = (((N + splits - 1) / splits) + 15) / 16 * 16;
-    splits = (N + kps - 1) / kps;
-    DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)nS * BK * L * sizeof(float), st));
-    gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, nS * splits), 256, 0, st>>>(
-        dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1, splits, (long long)BK * N, (long long)N * L,
-        (long long)BK * L, planes(), (size_t)nS * N * L);
-    DASR_LAUNCH_OK();
-    return DASR_OK;
+    return dasr_table_bwd_parts(dT, stp, Ws, dWs, dstp, nS, BK, N, L, 3, stream);
 }
 
 extern "C" int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int BK, int N,

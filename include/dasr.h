@@ -265,6 +265,10 @@ int dasr_table_bwd(const float* dT, const void* stp, const void* Ws, float* dWs,
 /* the same for nS SEAN instances at once (instance strides: dT BK*N, stp BK*L, Ws / dWs N*L, dstp BK*L)      */
 int dasr_table_bwd_batched(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int nS, int BK,
                            int N, int L, void* stream);
+/* The two GEMMs of dasr_table_bwd_batched separately (parts: 1 = dWs, 2 = dstp, 3 = both): dWs only reaches parameter
+ * gradients, so the training step issues it on a side stream beside the dstp -> A_i_j -> encoder chain.            */
+int dasr_table_bwd_parts(const float* dT, const void* stp, const void* Ws, float* dWs, float* dstp, int nS, int BK,
+                         int N, int L, int parts, void* stream);
 /* A_i_j backward: dA += , da += , dvec += (accumulating over the SEAN instances)                        */
 int dasr_style_mix_bwd(const float* dstp, const float* vec, const float* A, float* dA, float* da, float* dvec, int B,
                        int K, int L, void* stream);
