@@ -281,17 +281,19 @@ __global__ void __launch_bounds__(128) dynconv_bwd_kernel(const __nv_bfloat16* _
 // T[bk][n] = sum_c stp[bk][c] * Ws[n][c]  (n = tap*C2 + o2)
 //   dWs[n][c]   = sum_bk dT[bk][n] * stp[bk][c]      (A = dT read transposed, B = stp)
 //   dstp[bk][c] = sum_n  dT[bk][n] * Ws[n][c]        (A = dT, B = Ws; split-K with fp32 atomics)
-// Both are small fp32 x bf16 GEMMs (94 MFLOP at B = 16): one shared-memory tiled kernel, 64x64x16 tiles, 4x4
-// outputs per thread.  C[m][n] (+)= sum_k A(m,k) * B[k][n];  A(m,k) = AT ? A[k*lda + m] : A[m*lda + k].
-template <bool AT>
+// Both are small fp32 x bf16 GEMMs (94 MFLOP per instance at B = 16, 26 instances per step): one shared-memory tiled
+// kernel, (16 TM) x 64 x 16 tiles, TM x 4 outputs per thread, operands read from shared memory as 128-bit vectors, the
+// next K tile prefetched into registers while the current one is multiplied (two shared-memory buffers, one barrier
+// per K tile).  C[m][n] (+)= sum_k A(m,k) * B[k][n];  A(m,k) = AT ? A[k*lda + m] : A[m*lda + k].
+template <bool AT, int TM>
 __global__ void __launch_bounds__(256) gemm_f32_bf16_kernel(const float* __restrict__ A, const __nv_bfloat16* __restrict__ Bm,
                                                             float* __restrict__ C, int M, int N, int K, int lda, int ldb,
                                                             int ldc, int k_per_split, int atomic, int splits,
                                                             long long sA, long long sB, long long sC, int npl,
                                                             size_t psB) {
-    constexpr int BM = 64, BN = 64, BK = 16;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
+    constexpr int BM = 16 * TM, BN = 64, BK = 16;
+    __shared__ __align__(16) float As[2][BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][BK][BN + 4];
     // blockIdx.z = batch * splits + split (a batch of independent GEMMs with strides sA / sB / sC)
     const int batch = blockIdx.z / splits, split = blockIdx.z - batch * splits;
     A += (size_t)batch * sA;
@@ -300,43 +302,75 @@ __global__ void __launch_bounds__(256) gemm_f32_bf16_kernel(const float* __restr
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = split * k_per_split, kend = min(K, kbeg + k_per_split);
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    float acc[4][4];
+    float acc[TM][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < TM; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    float ra[TM], rb[4];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < TM; i++) {
+            const int idx = threadIdx.x + i * 256;
+            int r, kk;
+            if (AT) { kk = idx / BM; r = idx - kk * BM; } else { r = idx >> 4; kk = idx & 15; }
+            const int m = m0 + r, k = k0 + kk;
+            ra[i] = 0.f;
+            if (m < M && k < kend) ra[i] = AT ? __ldg(A + (size_t)k * lda + m) : __ldg(A + (size_t)m * lda + k);
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int idx = threadIdx.x + i * 256;
-            int r, kk;
-            if (AT) { kk = idx >> 6; r = idx & 63; } else { r = idx >> 4; kk = idx & 15; }
-            const int m = m0 + r, k = k0 + kk;
-            float v = 0.f;
-            if (m < M && k < kend) v = AT ? __ldg(A + (size_t)k * lda + m) : __ldg(A + (size_t)m * lda + k);
-            As[kk][r] = v;
-            const int kb = idx >> 6, c = idx & 63;
-            const int kq = k0 + kb, n = n0 + c;
-            Bs[kb][c] = (kq < kend && n < N) ? pl_load1(Bm, (size_t)kq * ldb + n, psB, npl) : 0.f;
+            const int kq = k0 + (idx >> 6), n = n0 + (idx & 63);
+            rb[i] = (kq < kend && n < N) ? pl_load1(Bm, (size_t)kq * ldb + n, psB, npl) : 0.f;
         }
-        __syncthreads();
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < TM; i++) {
+            const int idx = threadIdx.x + i * 256;
+            int r, kk;
+            if (AT) { kk = idx / BM; r = idx - kk * BM; } else { r = idx >> 4; kk = idx & 15; }
+            As[buf][kk][r] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = threadIdx.x + i * 256;
+            Bs[buf][idx >> 6][idx & 63] = rb[i];
+        }
+    };
+    if (kbeg < kend) {
+        gload(kbeg);
+        sstore(0);
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += BK, cur ^= 1) {
+        const bool more = k0 + BK < kend;
+        if (more) gload(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; kk++) {
-            float a[4], b[4];
+            float a[TM];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+            for (int i4 = 0; i4 < TM; i4 += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(&As[cur][kk][ty * TM + i4]);
+                a[i4] = v.x; a[i4 + 1] = v.y; a[i4 + 2] = v.z; a[i4 + 3] = v.w;
+            }
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < TM; i++) {
+                acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+                acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+                acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+            }
         }
+        if (more) sstore(cur ^ 1);
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; i++) {
+        const int m = m0 + ty * TM + i;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -745,7 +779,7 @@ extern "C" int dasr_table_bwd_parts(const float* dT, const void* stp, const void
     if (parts & 1) {
         DASR_REQUIRE(stp && dWs, "bad arguments");
         // dWs [N][L] = dT^T [N][BK] * stp [BK][L]
-        gemm_f32_bf16_kernel<true><<<dim3((L + 63) / 64, (N + 63) / 64, nS), 256, 0, st>>>(
+        gemm_f32_bf16_kernel<true, 8><<<dim3((L + 63) / 64, (N + 127) / 128, nS), 256, 0, st>>>(
             dT, (const __nv_bfloat16*)stp, dWs, N, L, BK, N, L, L, BK, 0, 1, (long long)BK * N, (long long)BK * L,
             (long long)N * L, planes(), (size_t)nS * BK * L);
         DASR_LAUNCH_OK();
@@ -762,7 +796,7 @@ extern "C" int dasr_table_bwd_parts(const float* dT, const void* stp, const void
         const int kps = (((N + splits - 1) / splits) + 15) / 16 * 16;
         splits = (N + kps - 1) / kps;
         DASR_CUDA_OK(cudaMemsetAsync(dstp, 0, (size_t)nS * BK * L * sizeof(float), st));
-        gemm_f32_bf16_kernel<false><<<dim3((L + 63) / 64, (BK + 63) / 64, nS * splits), 256, 0, st>>>(
+        gemm_f32_bf16_kernel<false, 4><<<dim3((L + 63) / 64, (BK + 63) / 64, nS * splits), 256, 0, st>>>(
             dT, (const __nv_bfloat16*)Ws, dstp, BK, L, N, N, L, L, kps, 1, splits, (long long)BK * N, (long long)N * L,
             (long long)BK * L, planes(), (size_t)nS * N * L);
         DASR_LAUNCH_OK();
