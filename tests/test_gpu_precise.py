@@ -214,3 +214,28 @@ def test_precise_train_steps_follow_the_oracle_trajectory(name, precise):
     assert agree >= 0.98, agree
     # the 10 loss weights move by ~lr per step; after three steps of a separating trajectory they agree to a fraction of it
     assert (step.dynamic_loss.trainable_weight.detach().double().cpu() - wd.detach()).abs().max().item() <= 0.5 * lr
+
+
+@pytest.mark.parametrize("scale,B,h,w", [(8, 2, 24, 40), (4, 1, 40, 24)])
+def test_precise_hr_blocks_on_non_square_frames_match_the_oracle(scale, B, h, w, precise):
+    """Depth-guided blocks above LR resolution (which_ResBlk_depth = 0..15) on non-square frames with several images:
+    the nearest-resized depth map / masks, the 32-channel SEAN instances and their style-table group against the fp32
+    oracle (pinned to the reference for this configuration by the goldens x8_b1_16_hr / x4_b2_16_hr): <= 1e-4."""
+    from depth_aware_endoscopy_sr_b200.synthetic import fill_state_dict, synthetic_inputs
+    meta = dict(scale=scale, latent=64, which=tuple(range(16)))
+    sd = fill_state_dict(oracle.state_layout(scale=scale, nb=16, which=meta["which"], latent=64, K=10), seed=11)
+    lq, depth, masks = synthetic_inputs(B, h, w, scale=scale, seed=12)
+    net = _net(meta, sd).eval()
+    with torch.no_grad():
+        ref = oracle.depthnet_forward(sd, lq, depth, masks, scale=scale, which=meta["which"])
+        pre_ref = {}
+        oracle.depthnet_forward(sd, lq, depth, masks, scale=scale, which=meta["which"], cap=pre_ref)
+        sr = net(lq.cuda(), depth.cuda(), masks.cuda()).cpu()
+        pre = net.engine().infer(lq.cuda(), depth.cuda(), masks.cuda(), clamp=False).cpu()
+    err = (sr - ref).abs().max().item()
+    err_pre = (pre - pre_ref["pre_clamp"]).abs().max().item()
+    rng = pre_ref["pre_clamp"].abs().max().item()
+    print("x%d B=%d %dx%d which=0..15 precise: max|sr - oracle| %.3g  max|pre_clamp - oracle| %.3g (range %.3g)" % (
+        scale, B, h, w, err, err_pre, rng))
+    assert err <= 1e-4
+    assert err_pre <= 1e-4 * max(1.0, rng)
