@@ -84,9 +84,12 @@ class Engine:
         # many CTAs (half the partial-dW flushes and SM-microseconds, twice the latency -- hidden by the four
         # streams).  Measured at B=16: 7.72 (one stream) -> 7.44 (1 side stream) -> 7.25 ms (4 streams, split / 2);
         # split / 3 and / 4 are slower again (7.66, 7.78).  DASR_WGRAD_OVERLAP=0 keeps one stream.
+        # Round 2, with the leaf chains on the side streams too (below): more streams take a third of the split-K CTAs
+        # per launch without exposing the latency -- 6 streams, split / 2: 6.50 ms; 16 streams, split / 3: 6.39 ms
+        # (12 / 3: 6.42, 24 / 4: 6.40, 16 / 4: 6.51).
         self.wgrad_overlap = os.environ.get("DASR_WGRAD_OVERLAP", "1") == "1"
-        self.wgrad_streams = max(1, int(os.environ.get("DASR_WGRAD_STREAMS", "6")))
-        self.wgrad_ksplit_div = max(1, int(os.environ.get("DASR_WG_KSPLIT_DIV", "2")))
+        self.wgrad_streams = max(1, int(os.environ.get("DASR_WGRAD_STREAMS", "16")))
+        self.wgrad_ksplit_div = max(1, int(os.environ.get("DASR_WG_KSPLIT_DIV", "3")))
         # the other leaf chains of a SEAN backward (gamma_o/beta_o data gradient -> mlp_mask gradient, K-DYN backward)
         # go to the side streams as well: the critical chain of an instance is then sean_bwd1 -> sean_bwd2 -> one
         # 64 -> 64 data gradient.  7.31 -> 6.83 ms (4 streams), 6.77 ms (6 streams).  DASR_LEAF_OVERLAP=0: main stream.
