@@ -74,6 +74,10 @@ class Engine:
         self.actv_overlap = os.environ.get("DASR_ACTV_OVERLAP", "1") == "1"
         # inference: the style-table chain on its own side stream beside the head convolutions (style_tables)
         self.tables_overlap = os.environ.get("DASR_TABLES_OVERLAP", "1") == "1"
+        # side-stream actv: blocks produced ahead of the main stream, resident actv blocks per SM
+        # (ahead: 1 -> 6.07 ms per B = 64 step, 2 -> 5.62, 3 -> 5.58, 4 .. 13 like 3; two resident blocks: 5.78)
+        self.actv_ahead = max(1, int(os.environ.get("DASR_ACTV_AHEAD", "3")))
+        self.actv_ctas = max(1, int(os.environ.get("DASR_ACTV_CTAS", "1")))
         # captured training step: the data-gradient weight copies are packed on a side stream beside the forward
         self.pack_overlap = os.environ.get("DASR_PACK_OVERLAP", "1") == "1"
         self._pack_bwd_ready = None
@@ -603,8 +607,9 @@ class Engine:
         buffers back for block k + ahead.  One cross-stream wait and one record per BLOCK: the four convolutions of a
         block stay an unbroken programmatic-dependent-launch chain."""
 
-        def __init__(self, eng, blocks, depth, nf2, ahead=2):
+        def __init__(self, eng, blocks, depth, nf2, ahead=None):
             dev = depth.device
+            ahead = eng.actv_ahead if ahead is None else ahead
             self.eng, self.blocks, self.depth = eng, blocks, depth
             st = eng._side_streams.get(dev.index)
             if st is None:
@@ -626,7 +631,7 @@ class Engine:
             with torch.cuda.stream(self.side):
                 for sean, buf in zip(self.blocks[i], self.slots[i % len(self.slots)]):
                     # one block per SM: it fits beside the convolution kernels and never keeps their blocks waiting
-                    self.eng._sean_actv(sean, self.depth, out=buf, ctas_per_sm=1)
+                    self.eng._sean_actv(sean, self.depth, out=buf, ctas_per_sm=self.eng.actv_ctas)
                 ev = torch.cuda.Event()
                 ev.record(self.side)
             self.ready[i] = ev
