@@ -22,8 +22,10 @@ Prints ONE JSON line:
              the end-to-end figure; e2e_frames repeats e2e under its round-1 name
   stream_1080p  BASELINE.json configs[4]: 135x240 LR frames -> 1080x1920, frames sharded over the ranks, device-resident
              and end to end (uint8 frames)
-  roofline   the dominant kernel family of the step, measured live with CUDA events in a separate
-             instrumented pass (achieved algorithmic TFLOP/s or GB/s against MEASURED_PEAKS.json)
+  roofline   the dominant kernel family of the step, measured live with CUDA events around every launch in two
+             instrumented passes that bracket the timed region (3 steps right before it, 3 right after: the board
+             heats up over the timed steps and reaches its power cap) -- achieved algorithmic TFLOP/s or GB/s of the
+             average launch against MEASURED_PEAKS.json; ms_per_launch_before_after gives both ends
   train      BASELINE.json configs[2] next to the headline: x8 training step (forward + loss + backward + flat
              NCCL gradient all-reduce + Adam), batch 16 per GPU, images/s over the whole job; dp_check = the parameter
              checksum after the timed steps is identical on every rank
@@ -371,6 +373,8 @@ def run_b200(args):
             sampler.start()
         for i in range(W):
             net(*dev_sets[i % n_sets])
+        # per-kernel instrumented pass, first half (the second follows the timed region)
+        roof_recs = [roofline_records(net, dev_sets)] if rank == 0 else []
         barrier()
         clk_mark = sampler.mark()
         n0 = _lib.launch_count()
@@ -383,10 +387,13 @@ def run_b200(args):
         launches = _lib.launch_count() - n0
         ms_total = e0.elapsed_time(e1)
 
-        # ------------------------------------------------ per-kernel instrumented pass (same thermal state as the timed
-        # region above) and the frames the cpu_baseline leg will check against the oracle (before any training step
-        # changes the weights)
-        roof = roofline_pass(net, dev_sets, B) if rank == 0 else None
+        # ------------------------------------------------ per-kernel instrumented pass, second half (the two halves
+        # bracket the timed region: its thermal / power state at the start and at the end) and the frames the
+        # cpu_baseline leg will check against the oracle (before any training step changes the weights)
+        roof = None
+        if rank == 0:
+            roof_recs.append(roofline_records(net, dev_sets))
+            roof = roofline_pass(roof_recs)
         nchk = min(2, B)
         sr_chk = net(*[t[:nchk].contiguous() for t in dev_sets[0]]).cpu() if rank == 0 else None
 
@@ -675,31 +682,40 @@ def _ncu_traffic(kernel_family):
     return tot if seen == 2 else None
 
 
-def roofline_pass(net, dev_sets, B):
-    """Instrumented pass: CUDA events around every kernel launch of the engine (on the launching stream),
-    grouped by kernel family; reports the family that takes the largest share of the step."""
+def roofline_records(net, dev_sets, reps=3):
+    """Instrumented forwards: CUDA events around every kernel launch of the engine (on the launching stream); returns
+    the per-launch records of ``reps`` steps."""
     import torch
     eng = net.engine()
-    peaks = _peaks()
     with torch.no_grad():
         eng.profile = []
         for i in range(2):
             net(*dev_sets[i % len(dev_sets)])
         torch.cuda.synchronize()
         eng.profile = []
-        reps = 3
         for i in range(reps):
             net(*dev_sets[i % len(dev_sets)])
         torch.cuda.synchronize()
         recs = eng.profile
         eng.profile = None
+    return recs, reps
+
+
+def roofline_pass(passes):
+    """``passes``: roofline_records taken right BEFORE and right AFTER the timed region (the board heats up over the 50
+    timed steps and runs into its power cap; one pass alone sees only one end of that).  Launch durations are grouped
+    by kernel family and averaged over both passes; reports the family that takes the largest share of the step."""
+    peaks = _peaks()
     fam = {}
-    for r in recs:
-        f = fam.setdefault(r["family"], dict(ms=0.0, n=0, flops=0.0, bytes=0.0, bound=r["bound"]))
-        f["ms"] += r["e0"].elapsed_time(r["e1"])
-        f["n"] += 1
-        f["flops"] += r["flops"]
-        f["bytes"] += r["bytes"]
+    reps = 0
+    for recs, n in passes:
+        reps += n
+        for r in recs:
+            f = fam.setdefault(r["family"], dict(ms=0.0, n=0, flops=0.0, bytes=0.0, bound=r["bound"]))
+            f["ms"] += r["e0"].elapsed_time(r["e1"])
+            f["n"] += 1
+            f["flops"] += r["flops"]
+            f["bytes"] += r["bytes"]
     total = sum(f["ms"] for f in fam.values())
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])
     name, f = top
@@ -711,9 +727,15 @@ def roofline_pass(net, dev_sets, B):
         ach, peak, unit = f["flops"] / f["ms"] / 1e9, peaks["tc_sustained"], "TFLOP/s"
     else:
         ach, peak, unit = f["bytes"] / f["ms"] / 1e6, peaks["hbm"], "GB/s"
+    per_pass = []
+    for recs, n in passes:
+        ms = sum(r["e0"].elapsed_time(r["e1"]) for r in recs if r["family"] == name)
+        cnt = sum(1 for r in recs if r["family"] == name)
+        per_pass.append(ms / max(cnt, 1))
     return {"kernel": name, "bound": "tensor" if f["bound"] == "tensor" else "hbm", "achieved": ach, "peak": peak,
             "unit": unit, "frac": ach / peak, "traffic": _ncu_traffic(name), "peak_source": peaks["src"],
-            "ms_per_launch": f["ms"] / f["n"], "share_of_step": f["ms"] / total, "families": table}
+            "ms_per_launch": f["ms"] / f["n"], "ms_per_launch_before_after": per_pass,
+            "share_of_step": f["ms"] / total, "families": table}
 
 
 def main():
