@@ -1753,6 +1753,22 @@ stats_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #endif  // DASR_CONV_PRECISE_TU
 
 // ------------------------------------------------------------------------------------------------ host
+// Widest strip of a frame one tile row covers (wider frames are cut into equal strips).  The trunk convolutions of a
+// depth-guided block (STATS / SEAN epilogue -- the producer's statistics slots and the consumer's finalize must agree on
+// the strips) use strips of at most 96 pixels, so that two A stages and the CTA-pair kernels fit in shared memory at
+// W = 128 (x4: 4.90 -> 4.15 ms per 16-frame forward) and W = 240 (1080p frames: +1.6 %); everything else keeps 128
+// (narrower strips only add halo columns there).  DASR_MAX_WT overrides both (measurements).
+static int max_strip_width(int epi) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DASR_MAX_WT");
+        v = e ? atoi(e) : 0;
+        if (v < 16 || v > 128) v = 0;
+    }
+    if (v) return v;
+    return (epi == DASR_EPI_STATS || epi == DASR_EPI_SEAN) ? 96 : 128;
+}
+
 // DASR_PDL=0 turns programmatic dependent launch off (A/B measurements)
 static bool pdl_enabled() {
     static int v = -1;
@@ -1987,7 +2003,7 @@ extern "C" int dasr_prof_read(unsigned long long* host_out, int reset) {
 
 // 1 if the SEAN conv of this geometry can generate its A operand in-kernel (two A stages fit), else 0
 extern "C" int dasr_conv_gen_ok(int H, int W) {
-    const int NB = 2, max_wt = 128;
+    const int NB = 2, max_wt = max_strip_width(DASR_EPI_SEAN);
     const int n_strips = (W + max_wt - 1) / max_wt;
     const int Wt = (W + n_strips - 1) / n_strips;
     const int Wp = Wt + 2;
@@ -2001,7 +2017,7 @@ extern "C" int dasr_conv_gen_ok(int H, int W) {
 
 extern "C" int dasr_conv_stats_slots(const dasr_conv_desc* d) {
     DASR_REQUIRE(d && d->W > 0 && d->H > 0 && (d->ks == 1 || d->ks == 3 || d->ks == 9), "bad descriptor");
-    const int NB = 2, max_wt = 128;
+    const int NB = 2, max_wt = max_strip_width(DASR_EPI_STATS);
     const int n_strips = (d->W + max_wt - 1) / max_wt;
     const int Wt = (d->W + n_strips - 1) / n_strips;
     const int Wp = Wt + (d->kw > 0 ? d->kw : d->ks) - 1;
@@ -2077,7 +2093,7 @@ extern "C" int dasr_conv_fwd(const dasr_conv_desc* d, const dasr_conv_args* a, v
     // TMEM still double-buffers (2 x 4 x 32 columns).
     // Measured: 32->32 at 256x256 160 -> 139 us; with Cin = 64 (K = 576) it is slower, so only Cin = 32 layers use it.
     const int NB = (n_tile <= 32 && d->Cin == 32 && d->epi == DASR_EPI_STORE && d->H * d->W >= 128 * 128) ? 4 : 2;
-    const int max_wt = 128;
+    const int max_wt = max_strip_width(d->epi);
     k.n_strips = (d->W + max_wt - 1) / max_wt;
     k.Wt = (d->W + k.n_strips - 1) / k.n_strips;
     k.Wp = k.Wt + k.kw - 1;
