@@ -1757,7 +1757,7 @@ stats_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // depth-guided block (STATS / SEAN epilogue -- the producer's statistics slots and the consumer's finalize must agree on
 // the strips) use strips of at most 96 pixels, so that two A stages and the CTA-pair kernels fit in shared memory at
 // W = 128 (x4: 4.90 -> 4.15 ms per 16-frame forward) and W = 240 (1080p frames: +1.6 %); everything else keeps 128
-// (narrower strips only add halo columns there).  DASR_MAX_WT overrides both (measurements).
+// (narrower strips only add halo columns there).  DASR_MAX_WT overrides both, DASR_TRUNK_WT the trunk width (measurements).
 static int max_strip_width(int epi) {
     static int v = -1;
     if (v < 0) {
@@ -1766,7 +1766,13 @@ static int max_strip_width(int epi) {
         if (v < 16 || v > 128) v = 0;
     }
     if (v) return v;
-    return (epi == DASR_EPI_STATS || epi == DASR_EPI_SEAN) ? 96 : 128;
+    static int trunk = -1;
+    if (trunk < 0) {
+        const char* e = getenv("DASR_TRUNK_WT");
+        trunk = e ? atoi(e) : 96;
+        if (trunk < 16 || trunk > 128) trunk = 96;
+    }
+    return (epi == DASR_EPI_STATS || epi == DASR_EPI_SEAN) ? trunk : 128;
 }
 
 // DASR_PDL=0 turns programmatic dependent launch off (A/B measurements)
