@@ -105,3 +105,22 @@ def test_multi_device_data_parallel_is_refused_with_the_way_out():
         net = dasr.DepthNet(which_ResBlk_depth=[0], scale=8, nb=4)
     with pytest.raises(RuntimeError, match="one process per GPU"):
         net._replicate_for_data_parallel()
+
+
+def test_block_scale_of_the_blocks_behind_the_upsamplers():
+    """Engine.block_scale: the feature-map resolution (relative to the LR input) of every block forward() runs
+    (sftmd_arch.py:923-944): the trunk at x1, block nb-2 behind upscale1 (only x8 has one), block nb-1 behind upscale2
+    (x8 and x4) -- what decides whether a depth-guided block resizes depth map and masks (normalization.py:58-59)."""
+    import warnings
+    import depth_aware_endoscopy_sr_b200 as dasr
+    expect = {8: (2, 4), 4: (1, 2), 2: (1, 1), 3: (1, 1)}
+    for scale, (s14, s15) in expect.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            net = dasr.DepthNet(which_ResBlk_depth=list(range(16)), scale=scale, nb=16, depth_latent_ch=32)
+        eng = net.engine()
+        assert [eng.block_scale(i) for i in range(13)] == [1] * 13
+        assert (eng.block_scale(14), eng.block_scale(15)) == (s14, s15)
+        # the blocks above LR resolution are the 32-channel ones
+        assert net.block(14).nf == (32 if scale == 8 else 64)
+        assert net.block(15).nf == (32 if scale >= 4 else 64)
