@@ -666,8 +666,8 @@ def train_pass(args, net, dev, rank, world, barrier):
 
 def _ncu_traffic(kernel_family):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
-    `ncu --set full` capture (profiles/r02_sean_pair_v2_ncu_full_summary.csv, first captured launch), or None."""
-    path = {"conv3x3_128to128_sean": os.path.join(ROOT, "profiles", "r02_sean_pair_v2_ncu_full_summary.csv")}.get(kernel_family)
+    `ncu --set full` capture (profiles/r02_sean_pair_v3_ncu_full_summary.csv, first captured launch), or None."""
+    path = {"conv3x3_128to128_sean": os.path.join(ROOT, "profiles", "r02_sean_pair_v3_ncu_full_summary.csv")}.get(kernel_family)
     if path is None or not os.path.exists(path):
         return None
     import csv
